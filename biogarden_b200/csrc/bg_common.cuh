@@ -1,0 +1,53 @@
+// bg_common.cuh -- shared device/host definitions of the alignment engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bg {
+
+// "minus infinity" for the X / Y borders.  The reference uses i32::MIN with saturating_add
+// (aligner.rs:49-50,443,447); all that matters is that the border never wins a max and never
+// ties with a real value.  bg_api.cu refuses (BG_EUNSUPPORTED) parameter ranges for which a
+// real score could come within 2^28 of it.
+constexpr int32_t NEG_INF = -(1 << 29);
+
+// Direction nibble, one per DP cell: everything backtrack() reads.
+//   bits 1:0  m_trace  0 = 'R', 1 = 'X', 2 = 'Y', 3 = STOP (local mode only: M == 0, which implies 'Y')
+//   bit  2    x_trace == 'M'  (gap in seq2 was opened here; aligner.rs:444)
+//   bit  3    y_trace == 'M'  (aligner.rs:448)
+constexpr uint32_t TR_R = 0, TR_X = 1, TR_Y = 2, TR_STOP = 3, TR_XOPEN = 4, TR_YOPEN = 8;
+
+enum Mode : int { M_GLOBAL = 0, M_LOCAL = 1, M_SEMIGLOBAL = 2, M_FITTING = 3, M_OVERLAP = 4 };
+
+// One launch slot = one sequence pair placed in a warp's lane group.  Built by the host in
+// launch order (pairs of one length class, longest first); 64 bytes.
+struct __align__(16) PairDesc {
+    uint64_t a_off;      // seq1 bytes at residues + a_off
+    uint64_t b_off;      // seq2 bytes
+    uint64_t trace_off;  // uint32-word offset of the WARP's trace block
+    uint64_t bnd_off;    // int2 offset of this pair's band-boundary column scratch (multi-band only)
+    uint64_t pad_off;    // byte offset of this pair's padded output slot (2 * (n + m) bytes)
+    uint32_t n, m;       // len1, len2
+    uint32_t steps;      // systolic steps per band for this warp = max n in the warp + L - 1
+    uint32_t pair_id;    // index in the caller's batch; 0xFFFFFFFF = empty slot
+    uint32_t nbands;     // column bands of L*C columns
+    uint32_t pad_;
+};
+static_assert(sizeof(PairDesc) == 64, "PairDesc layout");
+
+// Where the walk starts and what it returns, per slot.
+struct __align__(16) EndCell {
+    int32_t score;
+    uint32_t k, l;   // start cell
+    uint32_t flags;  // bit 0: semiglobal column branch (aligner.rs:389)
+};
+
+constexpr uint32_t WALK_UNDERFLOW = 1;  // reference would index seq[usize::MAX] (A.6)
+constexpr uint32_t WALK_HANG = 2;       // step bound exceeded (cannot happen with well-formed traces)
+
+// Geometry of the trace block of a warp: word (t, k, lane) of band bd lives at
+//   trace_off + ((bd * steps + t) * K + k) * 32 + lane,   K = ceil(C / 8) words per lane-step.
+// Every warp-wide store of one k is a fully coalesced 128-byte line.
+__host__ __device__ inline uint32_t words_per_lane_step(int C) { return (uint32_t)((C + 7) / 8); }
+
+}  // namespace bg

@@ -1,0 +1,287 @@
+// k1_fill.cuh -- K1: inter-sequence affine-gap DP fill for sm_100a.
+//
+// Replaces compute_scores_global / compute_scores_local plus the mode-specific border
+// initialisation and end-cell selection of the reference (aligner.rs:437-509, 98-104, 163,
+// 233-237, 299, 360, 112, 173-176, 247-251, 308-312, 369-380).
+//
+// Work decomposition (one lane group of L lanes per pair, 32/L pairs per warp):
+//   * the (len2) columns are cut into bands of L*C columns; inside a band lane p owns the C
+//     consecutive columns p*C .. p*C+C-1 and keeps M[i-1][j], X[i-1][j] for them in registers;
+//   * rows stream through the lanes systolically: at step t lane p computes row t-p, so the
+//     only cross-lane traffic is (M, Y, row residue) of the strip's last column, handed to
+//     lane p+1 with __shfl_up_sync -- no shared-memory round trip on the recurrence;
+//   * per cell the recurrence is the DPX forms VIADDMNMX / VIMNMX3 plus the tie tests that
+//     become the 4-bit direction code (bg_common.cuh); one 32-bit word of codes per lane-step
+//     is written to HBM with a fully coalesced 128-byte warp store (layout in bg_common.cuh);
+//   * substitution scores: for <= 4-letter row alphabets with |s| <= 127 every column keeps a
+//     packed byte profile in a register and a single PRMT (byte select + sign extend) yields
+//     s(row residue, column residue); otherwise the dense table sits in shared memory.
+//   * pairs longer than one band loop over bands; the band's last column (M, Y) per row goes
+//     through a small global scratch column (written by lane L-1, prefetched by lane 0).
+#pragma once
+#include "bg_common.cuh"
+
+namespace bg {
+
+struct FillArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* residues;
+    const int32_t* table;      // n_rows x n_cols (device)
+    int32_t n_rows, n_cols;
+    const uint8_t* row_code;   // [256] (device)
+    const uint8_t* col_code;   // [256]
+    int32_t a, b;              // gap open / extend
+    int32_t mode;
+    int32_t want_trace;
+    uint32_t* trace;
+    int2* bnd;
+    EndCell* end;
+    uint32_t* err_flag;        // bit 0: residue without a table row/column
+};
+
+__device__ __forceinline__ int32_t prmt_sx(uint32_t packed, uint32_t sel) {
+    int32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(packed), "r"(0u), "r"(sel));
+    return d;
+}
+
+// M[0][j] and M[i][0].
+__device__ __forceinline__ int32_t border_row(bool row_gap, int32_t a, int32_t b, uint32_t j) {
+    return (row_gap && j > 0) ? a + (int32_t)(j - 1) * b : 0;
+}
+__device__ __forceinline__ int32_t border_col(bool col_gap, int32_t a, int32_t b, uint32_t i) {
+    return (col_gap && i > 0) ? a + (int32_t)(i - 1) * b : 0;
+}
+
+template <int L, int C, bool IS_LOCAL, bool PROF4>
+__global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
+    constexpr int G = 32 / L;
+    constexpr int K = (C + 7) / 8;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t* s_row = smem_raw;            // [256]
+    uint8_t* s_col = smem_raw + 256;      // [256]
+    int32_t* s_tab = reinterpret_cast<int32_t*>(smem_raw + 512);   // n_rows x (n_cols + 1), last column = 0 (padding)
+
+    const int ncol1 = A.n_cols + 1;
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) { s_row[x] = A.row_code[x]; s_col[x] = A.col_code[x]; }
+    for (int x = threadIdx.x; x < A.n_rows * ncol1; x += blockDim.x) {
+        const int r = x / ncol1, c = x - r * ncol1;
+        s_tab[x] = (c < A.n_cols) ? A.table[r * A.n_cols + c] : 0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / L, p = lane % L;
+    const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t slot = warp_global * G + g;
+
+    PairDesc d;
+    d.n = 0; d.m = 0; d.steps = 0; d.nbands = 0; d.pair_id = 0xFFFFFFFFu;
+    d.a_off = d.b_off = d.trace_off = d.bnd_off = d.pad_off = 0;
+    if (slot < A.n_slots) d = A.desc[slot];
+    const bool has_pair = d.pair_id != 0xFFFFFFFFu;
+    const uint32_t n = has_pair ? d.n : 0, m = has_pair ? d.m : 0;
+    const uint32_t my_nbands = has_pair ? d.nbands : 0;
+    const uint32_t steps_w = __reduce_max_sync(FULL, has_pair ? d.steps : 0u);
+    const uint32_t nbands_w = __reduce_max_sync(FULL, my_nbands);
+
+    const int32_t a = A.a, b = A.b;
+    const int mode = A.mode;
+    const bool row_gap = (mode == M_GLOBAL || mode == M_FITTING);
+    const bool col_gap = (mode == M_GLOBAL);
+    const bool track_col = (mode == M_SEMIGLOBAL || mode == M_FITTING);
+    const bool track_row = (mode == M_SEMIGLOBAL || mode == M_OVERLAP);
+    const uint8_t* sa = A.residues + d.a_off;
+    const uint8_t* sb = A.residues + d.b_off;
+    bool bad_residue = false;
+
+    // column-m bookkeeping (last-column scan / global corner)
+    const uint32_t band_cols = (uint32_t)(L * C);
+    const uint32_t mcol0 = m ? m - 1 : 0;
+    const uint32_t bd_m = mcol0 / band_cols;
+    const uint32_t p_m = (mcol0 % band_cols) / C;
+    const uint32_t c_m = mcol0 % C;
+    const bool col_lane = (m > 0) && ((uint32_t)p == p_m);
+
+    // running end-cell state
+    int32_t best = 0; uint32_t bi = 0, bj = 0;                          // local: first max, row-major (aligner.rs:173-176)
+    int32_t rbest = INT32_MIN; uint32_t rj = 0;                         // last row, last max (>=)
+    int32_t cbest = border_row(row_gap, a, b, m); uint32_t ci = 0;      // last column, first max (>); row 0 candidate
+    int32_t corner = border_col(col_gap, a, b, n);                      // M[n][m] when m == 0
+    if (p == 0) { rbest = border_col(col_gap, a, b, n); rj = 0; }       // row n, column 0 candidate
+
+    for (uint32_t bd = 0; bd < nbands_w; ++bd) {
+        const bool band_on = has_pair && bd < my_nbands;
+        const uint32_t jbase = bd * band_cols + (uint32_t)p * C;   // 0-based index of this lane's first column
+        const bool lane_has_cols = band_on && jbase < m;
+        const bool last_band_for_pair = (bd + 1 == my_nbands);
+
+        // per-column constants: packed score profile (PROF4) or byte offset of the table column
+        uint32_t cprof[C];
+        int32_t Mu[C], Xu[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const uint32_t j0 = jbase + c;
+            uint32_t code = (uint32_t)A.n_cols;   // padding column (score 0)
+            if (band_on && j0 < m) {
+                code = s_col[sb[j0]];
+                if (code == 0xFFu) { bad_residue = true; code = 0; }
+            }
+            if (PROF4) {
+                uint32_t pk = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int32_t sv = (r < A.n_rows) ? s_tab[r * ncol1 + code] : 0;
+                    pk |= ((uint32_t)sv & 0xffu) << (8 * r);
+                }
+                cprof[c] = pk;
+            } else {
+                cprof[c] = code * 4u;
+            }
+            Mu[c] = border_row(row_gap, a, b, j0 + 1);
+            Xu[c] = NEG_INF;
+        }
+        int32_t Mdiag = border_row(row_gap, a, b, jbase);
+        int32_t Mlast = 0, Ylast = NEG_INF;
+        uint32_t rcur = 0;
+
+        // row residues: each lane of the group fetches one every L steps, lane 0 consumes one per step
+        auto load_rows = [&](uint32_t base) -> uint32_t {
+            const uint32_t idx = base + (uint32_t)p;
+            uint32_t cd = 0;
+            if (band_on && idx < n) {
+                cd = s_row[sa[idx]];
+                if (cd == 0xFFu) { bad_residue = true; cd = 0; }
+            }
+            return cd;
+        };
+        uint32_t cur_blk = 0, next_blk = load_rows(0);
+        int2 bnd_in = make_int2(0, NEG_INF);
+        if (bd > 0 && p == 0 && band_on && n > 0) bnd_in = __ldcg(A.bnd + d.bnd_off);
+
+        for (uint32_t t = 0; t < steps_w; ++t) {
+            if ((t & (L - 1)) == 0) { cur_blk = next_blk; next_blk = load_rows(t + L); }
+            const uint32_t r0 = __shfl_sync(FULL, cur_blk, (int)(t & (L - 1)), L);
+            int32_t Ml = __shfl_up_sync(FULL, Mlast, 1, L);
+            int32_t Yl = __shfl_up_sync(FULL, Ylast, 1, L);
+            uint32_t r = __shfl_up_sync(FULL, rcur, 1, L);
+            const uint32_t i0 = t - (uint32_t)p;          // 0-based row; wraps (inactive) while t < p
+            const bool active = band_on && i0 < n;
+            if (p == 0) {
+                r = r0;
+                if (bd == 0) { Ml = border_col(col_gap, a, b, i0 + 1); Yl = NEG_INF; }
+                else {
+                    Ml = bnd_in.x; Yl = bnd_in.y;
+                    if (band_on && i0 + 1 < n) bnd_in = __ldcg(A.bnd + d.bnd_off + i0 + 1);
+                }
+            }
+            rcur = r;
+            if (active) {
+                int32_t diag = Mdiag, left = Ml, Y = Yl;
+                uint32_t w[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) w[k] = 0;
+                uint32_t sel; const unsigned char* rowp;
+                if (PROF4) sel = r * 0x1111u + 0x8880u;
+                else rowp = reinterpret_cast<const unsigned char*>(s_tab) + r * (uint32_t)(ncol1 * 4);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int32_t up = Mu[c];
+                    // aligner.rs:443-444 / 477-480
+                    const int32_t xo = up + a;
+                    int32_t X = __viaddmax_s32(Xu[c], b, xo);
+                    uint32_t nib = (X == xo) ? TR_XOPEN : 0u;
+                    // aligner.rs:447-448 / 483-486
+                    const int32_t yo = left + a;
+                    Y = __viaddmax_s32(Y, b, yo);
+                    nib |= (Y == yo) ? TR_YOPEN : 0u;
+                    if (IS_LOCAL) { X = max(X, 0); Y = max(Y, 0); }
+                    // aligner.rs:451-466 / 489-506
+                    int32_t s;
+                    if (PROF4) s = prmt_sx(cprof[c], sel);
+                    else s = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
+                    const int32_t mx = __vimax3_s32(diag + s, X, Y);
+                    uint32_t code = (mx == Y) ? TR_Y : ((mx == X) ? TR_X : TR_R);
+                    if (IS_LOCAL) {
+                        if (mx == 0) code = TR_STOP;      // mx >= 0 here; M == 0 implies m_trace == 'Y' (A.3)
+                        if (mx > best) { best = mx; bi = i0 + 1; bj = jbase + c + 1; }
+                    }
+                    nib |= code;
+                    w[c >> 3] |= nib << (4 * (c & 7));
+                    diag = up; left = mx;
+                    Mu[c] = mx; Xu[c] = X;
+                }
+                Mlast = left; Ylast = Y; Mdiag = Ml;
+                if (A.want_trace && lane_has_cols) {
+                    uint32_t* tp = A.trace + d.trace_off + ((uint64_t)(bd * d.steps + t) * K) * 32u + lane;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) tp[k * 32] = w[k];
+                }
+                if (track_col && bd == bd_m) {
+                    int32_t v = Mu[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c) v = (c_m == (uint32_t)c) ? Mu[c] : v;
+                    if (col_lane && v > cbest) { cbest = v; ci = i0 + 1; }
+                }
+                if (p == L - 1 && !last_band_for_pair) A.bnd[d.bnd_off + i0] = make_int2(Mlast, Ylast);
+            }
+        }
+        // Mu[] now holds row n of this band (row 0 borders if n == 0)
+        if (band_on) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint32_t j = jbase + c + 1;
+                if (j <= m) {
+                    if (track_row && Mu[c] >= rbest) { rbest = Mu[c]; rj = j; }
+                    if (j == m) corner = Mu[c];
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    if (bad_residue) atomicOr(A.err_flag, 1u);
+
+    // ---- end-cell selection across the lane group ------------------------------------
+    if (track_row) {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            const int32_t ov = __shfl_xor_sync(FULL, rbest, o, L);
+            const uint32_t oj = __shfl_xor_sync(FULL, rj, o, L);
+            if (ov > rbest || (ov == rbest && oj > rj)) { rbest = ov; rj = oj; }   // last max
+        }
+    }
+    if (IS_LOCAL) {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            const int32_t ov = __shfl_xor_sync(FULL, best, o, L);
+            const uint32_t oi = __shfl_xor_sync(FULL, bi, o, L);
+            const uint32_t oj = __shfl_xor_sync(FULL, bj, o, L);
+            if (ov > best || (ov == best && (oi < bi || (oi == bi && oj < bj)))) { best = ov; bi = oi; bj = oj; }
+        }
+    }
+    // column-m owner -> lane 0 of the group
+    const int src = g * L + (int)p_m;
+    const int32_t cbest0 = __shfl_sync(FULL, cbest, src);
+    const uint32_t ci0 = __shfl_sync(FULL, ci, src);
+    const int32_t corner0 = __shfl_sync(FULL, corner, src);
+
+    if (p == 0 && has_pair) {
+        EndCell e; e.flags = 0;
+        switch (mode) {
+        case M_GLOBAL: e.score = corner0; e.k = n; e.l = m; break;
+        case M_LOCAL: e.score = best; e.k = bi; e.l = bj; break;
+        case M_FITTING: e.score = cbest0; e.k = ci0; e.l = m; break;
+        case M_OVERLAP: e.score = rbest; e.k = n; e.l = rj; break;
+        default:  // M_SEMIGLOBAL, aligner.rs:389
+            if (cbest0 > rbest) { e.score = cbest0; e.k = ci0; e.l = m; e.flags = 1; }
+            else { e.score = rbest; e.k = n; e.l = rj; }
+            break;
+        }
+        A.end[slot] = e;
+    }
+}
+
+}  // namespace bg

@@ -1,0 +1,146 @@
+// k3_walk.cuh -- K3: on-device traceback walk + aligned-string assembly.
+//
+// Replaces SequenceAligner::backtrack (aligner.rs:511-592) and the semiglobal tail / prefix
+// assembly (aligner.rs:382-432).  The walk is the reference's state machine verbatim
+// (SURVEY A.4), including its late read of x_trace / y_trace: after an M->X move the walker
+// consults the open/extend bit of the cell it ARRIVED at.  The emitted path is therefore
+// defined by the stored direction codes alone and is reproduced bit for bit.
+//
+// One thread per pair: the walk is a serial chain of dependent 4-byte loads, so the way to
+// keep the machine busy is many independent walks per SM, not lanes cooperating on one.
+// Characters are produced back to front into a padded slot of 2*(n+m) bytes; k_gather then
+// packs all strings densely (offsets from a device-side scan of the lengths).
+#pragma once
+#include "bg_common.cuh"
+
+namespace bg {
+
+struct WalkArgs {
+    const PairDesc* desc;
+    const EndCell* end;
+    uint32_t n_slots;
+    const uint8_t* residues;
+    const uint32_t* trace;
+    int32_t mode;
+    int32_t L, C;           // geometry K1 used for this launch
+    uint8_t* pad;           // padded output slots
+    int32_t* score;         // [pair]
+    uint8_t* walk_flags;    // [pair]
+    uint64_t* lens2;        // [2*pairs + 1]: lens2[2p] = lens2[2p+1] = aligned length
+};
+
+__global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const EndCell e = A.end[slot];
+    const uint32_t n = d.n, m = d.m;
+    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
+    const uint32_t K = (C + 7) / 8;
+    const uint32_t band_cols = L * C;
+    const uint32_t lane_base = (slot % (32u / L)) * L;
+    const uint8_t* sa = A.residues + d.a_off;
+    const uint8_t* sb = A.residues + d.b_off;
+    uint8_t* outA = A.pad + d.pad_off;
+    uint8_t* outB = outA + (n + m);
+    uint32_t pos = n + m;
+    const int mode = A.mode;
+
+    auto push = [&](uint8_t x, uint8_t y) { --pos; outA[pos] = x; outB[pos] = y; };
+    auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
+        const uint32_t j0 = j - 1;
+        const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
+        const uint32_t p = rr / C, c = rr - p * C;
+        const uint32_t t = (i - 1) + p;
+        const uint64_t idx = d.trace_off + ((uint64_t)(bd * d.steps + t) * K + (c >> 3)) * 32u + lane_base + p;
+        return (__ldg(A.trace + idx) >> ((c & 7u) * 4u)) & 15u;
+    };
+
+    uint32_t k = e.k, l = e.l, flags = 0;
+    const bool colbr = (e.flags & 1u) != 0;
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
+        if (colbr) { for (uint32_t i = n; i > k; --i) push(sa[i - 1], '-'); }
+        else       { for (uint32_t i = m; i > l; --i) push('-', sb[i - 1]); }
+    }
+    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
+    const uint64_t bound = 2ull * ((uint64_t)n + m) + 8;
+    uint64_t it = 0;
+    for (;; ++it) {
+        if (it > bound) { flags |= WALK_HANG; break; }
+        const bool interior = (k != 0 && l != 0);
+        uint32_t nib = 0;
+        if (interior) nib = nib_at(k, l);
+        bool valid;
+        switch (mode) {
+            case M_GLOBAL: valid = (k != 0 || l != 0); break;                                   // aligner.rs:117
+            case M_LOCAL: valid = interior && (nib & 3u) != TR_STOP; break;                     // aligner.rs:181 (borders are 0)
+            case M_SEMIGLOBAL: valid = interior; break;                                         // aligner.rs:409
+            default: valid = (l != 0); break;                                                 // aligner.rs:256,317
+        }
+        if (!valid) break;
+        if (cur == 0) {
+            uint32_t t;   // m_trace borders: column 0 'X', then row 0 'Y' (aligner.rs:107-108)
+            if (l == 0) t = TR_X; else if (k == 0) t = TR_Y; else t = nib & 3u;
+            if (t == TR_R) { push(sa[k - 1], sb[l - 1]); --k; --l; }
+            else if (t == TR_X) { push(sa[k - 1], '-'); --k; cur = 1; }
+            else { push('-', sb[l - 1]); --l; cur = 2; }
+        } else if (cur == 1) {
+            if (interior && (nib & TR_XOPEN)) cur = 0;                 // x_trace borders stay 'I' (aligner.rs:52)
+            else if (k == 0) { flags |= WALK_UNDERFLOW; break; }      // reference: seq1[usize::MAX] -> panic
+            else { push(sa[k - 1], '-'); --k; }
+        } else {
+            if (interior && (nib & TR_YOPEN)) cur = 0;
+            else if (l == 0) { flags |= WALK_UNDERFLOW; break; }
+            else { push('-', sb[l - 1]); --l; }
+        }
+    }
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
+        if (colbr) { for (uint32_t i = k; i > 0; --i) push(sa[i - 1], '-'); }
+        else       { for (uint32_t i = l; i > 0; --i) push('-', sb[i - 1]); }
+    }
+    const uint32_t len = n + m - pos;
+    A.score[d.pair_id] = e.score;
+    A.walk_flags[d.pair_id] = (uint8_t)flags;
+    A.lens2[2ull * d.pair_id] = len;
+    A.lens2[2ull * d.pair_id + 1] = len;
+}
+
+// Score-only epilogue when no traceback is requested.
+__global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t n_slots, int32_t* score,
+                              uint8_t* walk_flags) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const uint32_t id = desc[slot].pair_id;
+    if (id == 0xFFFFFFFFu) return;
+    score[id] = end[slot].score;
+    walk_flags[id] = 0;
+}
+
+// Dense packing: one warp per slot copies a_align then b_align to arena[off[2p]..], arena[off[2p+1]..].
+struct GatherArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* pad;
+    const uint64_t* off;   // exclusive scan of lens2
+    uint8_t* arena;
+};
+
+__global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const uint64_t o0 = A.off[2ull * d.pair_id], o1 = A.off[2ull * d.pair_id + 1];
+    const uint32_t len = (uint32_t)(o1 - o0);
+    const uint32_t cap = d.n + d.m;
+    const uint8_t* srcA = A.pad + d.pad_off + (cap - len);
+    const uint8_t* srcB = srcA + cap;
+    for (uint32_t x = lane; x < len; x += 32) {
+        A.arena[o0 + x] = srcA[x];
+        A.arena[o1 + x] = srcB[x];
+    }
+}
+
+}  // namespace bg

@@ -1,0 +1,311 @@
+"""ctypes binding of libbgalign.so (include/bgalign.h).
+
+There is no fallback of any kind: if the shared library is missing, or there is no CUDA device,
+every compute entry point raises.  The library is built in-tree by `__graft_entry__.build()` /
+`make -C biogarden_b200/csrc`."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .error import EngineError, InvalidArgumentRange, InvalidInputSize
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbgalign.so")
+
+BG_OK, BG_EINVAL_RANGE, BG_EINVAL_SIZE, BG_ECUDA, BG_ENOMEM, BG_EINVAL_ARG, BG_EINVAL_RESIDUE, BG_ENODEVICE, \
+    BG_EUNSUPPORTED = range(9)
+MODES = {"global": 0, "local": 1, "semiglobal": 2, "fitting": 3, "overlap": 4}
+F_SCORE_ONLY = 1
+ST_OK, ST_REF_UNDEFINED = 0, 1
+
+
+class bg_batch(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("residues", C.c_void_p), ("seq_off", C.c_void_p)]
+
+
+class bg_params(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("flags", C.c_uint32),
+                ("table", C.c_void_p), ("n_rows", C.c_int32), ("n_cols", C.c_int32),
+                ("row_code", C.c_void_p), ("col_code", C.c_void_p)]
+
+
+class bg_result(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("score", C.c_void_p), ("status", C.c_void_p), ("arena", C.c_void_p),
+                ("off", C.c_void_p), ("owner_", C.c_void_p)]
+
+
+class bg_timing(C.Structure):
+    _fields_ = [("encode_ms", C.c_double), ("fill_ms", C.c_double), ("walk_ms", C.c_double),
+                ("compact_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_uint64),
+                ("launches", C.c_uint64), ("trace_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/bgalign.h declares (tests check the library exports all of them)
+SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_version", "bg_align_batch",
+           "bg_result_free", "bg_edit_distance_batch", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
+           "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
+           "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
+           "bg_set_trace_budget", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
+
+_lib = None
+
+
+def lib():
+    """Load libbgalign.so; raises (never falls back) when it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError("libbgalign.so not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C biogarden_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64, ci = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_int
+    L.bg_create.restype = ci; L.bg_create.argtypes = [C.POINTER(ci), ci, C.POINTER(vp)]
+    L.bg_destroy.restype = None; L.bg_destroy.argtypes = [vp]
+    L.bg_strerror.restype = C.c_char_p; L.bg_strerror.argtypes = [ci]
+    L.bg_last_error.restype = C.c_char_p; L.bg_last_error.argtypes = [vp]
+    L.bg_version.restype = ci
+    L.bg_align_batch.restype = ci
+    L.bg_align_batch.argtypes = [vp, C.POINTER(bg_batch), C.POINTER(bg_params), C.POINTER(bg_result)]
+    L.bg_result_free.restype = None; L.bg_result_free.argtypes = [C.POINTER(bg_result)]
+    L.bg_edit_distance_batch.restype = ci; L.bg_edit_distance_batch.argtypes = [vp, C.POINTER(bg_batch), vp]
+    L.bg_batch_upload.restype = ci; L.bg_batch_upload.argtypes = [vp, ci, C.POINTER(bg_batch), C.POINTER(vp)]
+    L.bg_dbatch_free.restype = None; L.bg_dbatch_free.argtypes = [vp]
+    L.bg_align_device.restype = ci; L.bg_align_device.argtypes = [vp, vp, C.POINTER(bg_params), C.POINTER(vp)]
+    L.bg_edit_distance_device.restype = ci; L.bg_edit_distance_device.argtypes = [vp, vp, C.POINTER(vp)]
+    L.bg_dresult_download.restype = ci; L.bg_dresult_download.argtypes = [vp, vp, C.POINTER(bg_result)]
+    L.bg_dresult_download_u64.restype = ci; L.bg_dresult_download_u64.argtypes = [vp, vp, vp]
+    L.bg_dresult_free.restype = None; L.bg_dresult_free.argtypes = [vp]
+    L.bg_sync.restype = ci; L.bg_sync.argtypes = [vp]
+    L.bg_stream.restype = vp; L.bg_stream.argtypes = [vp, ci]
+    L.bg_device_ordinal.restype = ci; L.bg_device_ordinal.argtypes = [vp, ci]
+    L.bg_last_timing.restype = ci; L.bg_last_timing.argtypes = [vp, C.POINTER(bg_timing)]
+    L.bg_batch_prepare.restype = ci; L.bg_batch_prepare.argtypes = [vp, vp, ci]
+    L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
+    L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
+    L.bg_score_table26.restype = C.POINTER(C.c_int8); L.bg_score_table26.argtypes = [C.c_char_p]
+    L.bg_residue_histogram.restype = ci; L.bg_residue_histogram.argtypes = [C.POINTER(bg_batch), vp, vp]
+    L.bg_ref_status.restype = ci; L.bg_ref_status.argtypes = [ci, u64, u64, i32, ci]
+    L.bg_synth_pairs.restype = ci
+    L.bg_synth_pairs.argtypes = [u64, u64, u64, C.c_char_p, ci, u32, u32, ci, vp, vp, C.POINTER(u64)]
+    _lib = L
+    return L
+
+
+def check(rc, ctx=None):
+    if rc == BG_OK:
+        return
+    L = lib()
+    msg = L.bg_strerror(rc).decode()
+    if ctx is not None:
+        extra = L.bg_last_error(ctx).decode()
+        if extra:
+            msg += ": " + extra
+    if rc == BG_EINVAL_RANGE:
+        raise InvalidArgumentRange(msg)
+    if rc == BG_EINVAL_SIZE:
+        raise InvalidInputSize(msg)
+    raise EngineError("bgalign error %d: %s" % (rc, msg))
+
+
+def score_table26(name: str) -> np.ndarray:
+    p = lib().bg_score_table26(name.encode())
+    if not p:
+        raise KeyError(name)
+    return np.ctypeslib.as_array(p, shape=(26, 26)).astype(np.int32)
+
+
+class Batch:
+    """Host-side batch in the C ABI's layout (keeps the numpy arrays alive)."""
+
+    def __init__(self, residues: np.ndarray, seq_off: np.ndarray):
+        self.residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        self.seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        assert self.seq_off.ndim == 1 and len(self.seq_off) % 2 == 1
+        self.n_pairs = (len(self.seq_off) - 1) // 2
+        self.c = bg_batch(self.n_pairs, self.residues.ctypes.data if self.residues.size else None,
+                          self.seq_off.ctypes.data)
+
+    @classmethod
+    def from_sequences(cls, seqs):
+        """seqs: flat list of bytes-like, pair p = (seqs[2p], seqs[2p+1])."""
+        if len(seqs) % 2:
+            raise InvalidInputSize("a Tile of pairs needs an even number of sequences")
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+        off = np.zeros(len(seqs) + 1, np.uint64)
+        np.cumsum(lens, out=off[1:])
+        res = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8) if len(seqs) else np.zeros(0, np.uint8)
+        return cls(res, off)
+
+    def lengths(self):
+        d = np.diff(self.seq_off)
+        return d[0::2], d[1::2]
+
+    def cells(self) -> int:
+        n, m = self.lengths()
+        return int(np.sum(n.astype(np.float64) * m.astype(np.float64)))
+
+    def histograms(self):
+        ha = np.zeros(256, np.uint64)
+        hb = np.zeros(256, np.uint64)
+        check(lib().bg_residue_histogram(C.byref(self.c), ha.ctypes.data, hb.ctypes.data))
+        return ha, hb
+
+
+class Params:
+    """bg_params plus the arrays it points to."""
+
+    def __init__(self, mode, gap_open, gap_extend, table, row_code, col_code, score_only=False):
+        self.table = np.ascontiguousarray(table, dtype=np.int32)
+        self.row_code = np.ascontiguousarray(row_code, dtype=np.uint8)
+        self.col_code = np.ascontiguousarray(col_code, dtype=np.uint8)
+        assert self.table.ndim == 2 and self.row_code.shape == (256,) and self.col_code.shape == (256,)
+        m = MODES[mode] if isinstance(mode, str) else int(mode)
+        self.c = bg_params(m, int(gap_open), int(gap_extend), F_SCORE_ONLY if score_only else 0,
+                           self.table.ctypes.data, self.table.shape[0], self.table.shape[1],
+                           self.row_code.ctypes.data, self.col_code.ctypes.data)
+
+
+class Result:
+    """Owns a bg_result; numpy views are valid until close()."""
+
+    def __init__(self, c_res: bg_result):
+        self._c = c_res
+        n = int(c_res.n_pairs)
+        self.n_pairs = n
+
+        def view(ptr, dtype, count):
+            if count == 0 or not ptr:
+                return np.zeros(0, dtype)
+            buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=count)
+        self.score = view(c_res.score, np.int32, n)
+        self.status = view(c_res.status, np.uint8, n)
+        self.off = view(c_res.off, np.uint64, 2 * n + 1)
+        total = int(self.off[-1]) if n else 0
+        self.arena = view(c_res.arena, np.uint8, total)
+
+    def strings(self, p):
+        o0, o1, o2 = int(self.off[2 * p]), int(self.off[2 * p + 1]), int(self.off[2 * p + 2])
+        return bytes(self.arena[o0:o1]), bytes(self.arena[o1:o2])
+
+    def close(self):
+        if self._c is not None:
+            lib().bg_result_free(C.byref(self._c))
+            self._c = None
+            self.score = self.status = self.off = self.arena = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """bg_ctx: one engine instance (SequenceAligner::new, aligner.rs:44)."""
+
+    def __init__(self, devices=None):
+        L = lib()
+        h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = L.bg_create(arr, len(devices), C.byref(h))
+        else:
+            rc = L.bg_create(None, 0, C.byref(h))
+        if rc == BG_ENODEVICE:
+            raise EngineError("no usable CUDA device: the alignment engine has no CPU path")
+        check(rc)
+        self.h = h
+        self.n_devices = len(devices) if devices else 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host-buffer path ----
+    def align_batch(self, batch: Batch, params: Params) -> Result:
+        r = bg_result()
+        check(lib().bg_align_batch(self.h, C.byref(batch.c), C.byref(params.c), C.byref(r)), self.h)
+        return Result(r)
+
+    def edit_distance_batch(self, batch: Batch) -> np.ndarray:
+        out = np.zeros(batch.n_pairs, np.uint64)
+        check(lib().bg_edit_distance_batch(self.h, C.byref(batch.c), out.ctypes.data), self.h)
+        return out
+
+    # ---- device-resident path ----
+    def upload(self, batch: Batch, dev_index=0, prepare=None):
+        h = C.c_void_p()
+        check(lib().bg_batch_upload(self.h, dev_index, C.byref(batch.c), C.byref(h)), self.h)
+        if prepare is not None:
+            check(lib().bg_batch_prepare(self.h, h, 1 if prepare == "edit" else 0), self.h)
+        return h
+
+    def free_batch(self, h):
+        lib().bg_dbatch_free(h)
+
+    def align_device(self, dbatch, params: Params):
+        h = C.c_void_p()
+        check(lib().bg_align_device(self.h, dbatch, C.byref(params.c), C.byref(h)), self.h)
+        return h
+
+    def edit_distance_device(self, dbatch):
+        h = C.c_void_p()
+        check(lib().bg_edit_distance_device(self.h, dbatch, C.byref(h)), self.h)
+        return h
+
+    def download(self, dres) -> Result:
+        r = bg_result()
+        check(lib().bg_dresult_download(self.h, dres, C.byref(r)), self.h)
+        return Result(r)
+
+    def download_u64(self, dres, n) -> np.ndarray:
+        out = np.zeros(n, np.uint64)
+        check(lib().bg_dresult_download_u64(self.h, dres, out.ctypes.data), self.h)
+        return out
+
+    def free_result(self, dres):
+        lib().bg_dresult_free(dres)
+
+    def sync(self):
+        check(lib().bg_sync(self.h), self.h)
+
+    def stream(self, dev_index=0):
+        return lib().bg_stream(self.h, dev_index)
+
+    def timing(self) -> dict:
+        t = bg_timing()
+        check(lib().bg_last_timing(self.h, C.byref(t)), self.h)
+        return t.as_dict()
+
+    def set_shape(self, L_, C_):
+        check(lib().bg_set_shape(self.h, L_, C_), self.h)
+
+    def set_trace_budget(self, nbytes):
+        check(lib().bg_set_trace_budget(self.h, nbytes), self.h)
+
+
+def synth_pairs(seed, first_pair, n_pairs, alphabet: bytes, len_lo, len_hi, resize_b=True) -> Batch:
+    """Deterministic synthetic workload (SURVEY 8d generator)."""
+    L = lib()
+    off = np.zeros(2 * n_pairs + 1, np.uint64)
+    tot = C.c_uint64(0)
+    check(L.bg_synth_pairs(seed, first_pair, n_pairs, alphabet, len(alphabet), len_lo, len_hi, int(resize_b), None,
+                           off.ctypes.data, C.byref(tot)))
+    res = np.zeros(max(1, tot.value), np.uint8)
+    check(L.bg_synth_pairs(seed, first_pair, n_pairs, alphabet, len(alphabet), len_lo, len_hi, int(resize_b),
+                           res.ctypes.data, off.ctypes.data, C.byref(tot)))
+    return Batch(res[:tot.value], off)

@@ -1,0 +1,190 @@
+/*
+ * bgalign.h -- C ABI of the B200 batched pairwise-alignment engine (libbgalign.so).
+ *
+ * This is the drop-in boundary for biogarden's alignment hot path.  The reference
+ * (robsndr/biogarden, Rust) has no FFI today; each entry point below names the
+ * reference interface it stands behind (file:line in the reference checkout).  A Rust
+ * caller binds these with a plain `extern "C"` block (INTEGRATION.md shows the stub and
+ * the patched SequenceAligner methods); this repository drives the same symbols from C++
+ * (include/biogarden.hpp) and Python ctypes (biogarden_b200/native.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary;
+ *   - inputs are borrowed for the duration of a call and never written;
+ *   - outputs are library-owned pinned host memory until bg_result_free();
+ *   - every function returns a bg_err code (0 = ok); nothing panics or hangs across the ABI;
+ *   - a bg_ctx is used by one caller thread at a time (mirrors `&mut self`, aligner.rs:84);
+ *   - all arithmetic runs in CUDA kernels built for sm_100a.  There is no CPU path: with no
+ *     usable device bg_create() fails with BG_ENODEVICE.
+ */
+#ifndef BGALIGN_H
+#define BGALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_API_VERSION 1
+
+typedef struct bg_ctx bg_ctx;
+
+/* Alignment flavour = which public SequenceAligner method is being replaced:
+ *   BG_GLOBAL     global_alignment      aligner.rs:84-121
+ *   BG_LOCAL      local_alignment       aligner.rs:150-185
+ *   BG_SEMIGLOBAL semiglobal_alignment  aligner.rs:351-435
+ *   BG_FITTING    fitting_alignment     aligner.rs:216-260
+ *   BG_OVERLAP    overlap_alignment     aligner.rs:290-321 */
+typedef enum { BG_GLOBAL = 0, BG_LOCAL = 1, BG_SEMIGLOBAL = 2, BG_FITTING = 3, BG_OVERLAP = 4 } bg_mode;
+
+/* Call-level return codes.  BG_EINVAL_RANGE / BG_EINVAL_SIZE map 1:1 onto
+ * BioError::InvalidArgumentRange / InvalidInputSize (error.rs:9-10) and are returned under
+ * exactly the reference's conditions (aligner.rs:87-89,153-155,219-225; semiglobal and overlap
+ * do NOT check the sign of the penalties, aligner.rs:290-296,351-357). */
+typedef enum {
+    BG_OK = 0,
+    BG_EINVAL_RANGE = 1,   /* a > 0 || b > 0 in global / local / fitting */
+    BG_EINVAL_SIZE = 2,    /* fitting with len1 < len2 in some pair; odd Tile length */
+    BG_ECUDA = 3,          /* CUDA runtime / launch failure (bg_last_error has the text) */
+    BG_ENOMEM = 4,         /* host or device allocation failed */
+    BG_EINVAL_ARG = 5,     /* NULL pointer, unknown mode, malformed offsets ... */
+    BG_EINVAL_RESIDUE = 6, /* a residue byte has no row/column in the score table (the shipped
+                              scorers panic on such bytes, score.rs:40,79,115) */
+    BG_ENODEVICE = 7,      /* no CUDA device / library built without the requested device */
+    BG_EUNSUPPORTED = 8    /* penalties or scores outside the engine's 32-bit-safe range */
+} bg_err;
+
+/* Per-pair status.  BG_ST_REF_UNDEFINED: the reference itself panics or never returns on
+ * this input; score / strings are then the engine's documented
+ * extension (the recurrence restricted to the (len1+1)x(len2+1) rectangle). */
+typedef enum { BG_ST_OK = 0, BG_ST_REF_UNDEFINED = 1 } bg_status;
+
+/* A batch of sequence pairs in Tile order (ds/tile.rs:9-11): sequence s occupies
+ * residues[seq_off[s] .. seq_off[s+1]); pair p = (sequence 2p, sequence 2p+1), the layout of
+ * every alignment fixture (tests/integration.rs:236-242) and of examples/from_file.rs:26-27.
+ * Raw bytes, exactly what Sequence::chain holds (ds/sequence.rs:10-13). */
+typedef struct {
+    uint64_t n_pairs;
+    const uint8_t* residues;
+    const uint64_t* seq_off; /* 2*n_pairs + 1 entries, non-decreasing */
+} bg_batch;
+
+#define BG_F_SCORE_ONLY 1u /* skip traceback: result.arena / off stay empty */
+
+/* Parameters of one alignment call.  The score callback of the reference
+ * (`&dyn Fn(&u8,&u8)->i32`, aligner.rs:85) cannot cross the ABI; the caller materialises it
+ * once, on its own thread, over the residues present in the batch:
+ *   table[row_code[x] * n_cols + col_code[y]] = score(x, y),  x from a seq1, y from a seq2.
+ * Argument order is (seq1 residue, seq2 residue) as in aligner.rs:451; no symmetry is assumed.
+ * Codes 0xFF mark bytes that must not occur. */
+typedef struct {
+    int32_t mode;       /* bg_mode */
+    int32_t gap_open;   /* `a` */
+    int32_t gap_extend; /* `b` */
+    uint32_t flags;
+    const int32_t* table;
+    int32_t n_rows, n_cols;
+    const uint8_t* row_code; /* [256] */
+    const uint8_t* col_code; /* [256] */
+} bg_params;
+
+/* Result of bg_align_batch: what the reference returns per call, `(i32, Sequence, Sequence)`
+ * (aligner.rs:85), for every pair.  a_align of pair p = arena[off[2p] .. off[2p+1]),
+ * b_align = arena[off[2p+1] .. off[2p+2]); both have the same length. */
+typedef struct {
+    uint64_t n_pairs;
+    int32_t* score;  /* [n_pairs] */
+    uint8_t* status; /* [n_pairs] bg_status */
+    uint8_t* arena;
+    uint64_t* off;   /* [2*n_pairs + 1] */
+    void* owner_;    /* private */
+} bg_result;
+
+/* Phase timings of the most recent device pass, measured with CUDA events on the engine's
+ * own stream (milliseconds; kernels only, no host<->device copies). */
+typedef struct {
+    double encode_ms;   /* residue validation + recoding */
+    double fill_ms;     /* DP fill kernels (K1/K2) incl. end-cell selection */
+    double walk_ms;     /* traceback walk (K3) */
+    double compact_ms;  /* aligned-string compaction */
+    double total_ms;    /* first launch -> last kernel end */
+    uint64_t cells;     /* sum over pairs of len1*len2 */
+    uint64_t launches;  /* kernels launched */
+    uint64_t trace_bytes; /* bytes of packed direction codes written */
+    uint64_t h2d_bytes, d2h_bytes; /* of the last host-buffer call */
+} bg_timing;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* SequenceAligner::new (aligner.rs:44-55).  devices = CUDA ordinals to shard batches over
+ * (NULL / n_dev == 0 -> the current device only). */
+int bg_create(const int* devices, int n_dev, bg_ctx** out);
+void bg_destroy(bg_ctx* ctx);
+const char* bg_strerror(int err);
+const char* bg_last_error(const bg_ctx* ctx);
+int bg_version(void);
+
+/* ---- the hot path, host buffers (what a drop-in caller uses) ---------------------- */
+/* global/local/semiglobal/fitting/overlap_alignment for every pair of the batch
+ * (aligner.rs:84,150,216,290,351).  H2D of the batch, all kernels, D2H of the results. */
+int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_result* out);
+void bg_result_free(bg_result* r);
+
+/* analysis::seq::edit_distance for every pair (seq.rs:105-130): out[p] = distance.  Never
+ * fails on any byte content (the reference never errs). */
+int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out);
+
+/* ---- the hot path, device-resident (benchmarks: inputs already in HBM) ------------- */
+typedef struct bg_dbatch bg_dbatch;   /* batch resident on one device of the context */
+typedef struct bg_dresult bg_dresult; /* results resident on that device */
+
+int bg_batch_upload(bg_ctx* ctx, int dev_index, const bg_batch* in, bg_dbatch** out);
+void bg_dbatch_free(bg_dbatch* b);
+/* Runs encode + fill + walk + compaction on the batch's device, asynchronously on the
+ * context's stream for that device; *out stays on the device. */
+int bg_align_device(bg_ctx* ctx, const bg_dbatch* in, const bg_params* p, bg_dresult** out);
+int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* in, bg_dresult** out);
+int bg_dresult_download(bg_ctx* ctx, bg_dresult* r, bg_result* out); /* syncs */
+int bg_dresult_download_u64(bg_ctx* ctx, bg_dresult* r, uint64_t* out);
+void bg_dresult_free(bg_dresult* r);
+int bg_sync(bg_ctx* ctx);
+/* cudaStream_t of device dev_index (so a harness can bracket calls with its own events) */
+void* bg_stream(bg_ctx* ctx, int dev_index);
+int bg_device_ordinal(bg_ctx* ctx, int dev_index);
+int bg_last_timing(const bg_ctx* ctx, bg_timing* out);
+/* Build the launch plan (length classes, trace layout) of an uploaded batch now instead of
+ * inside the first align / edit-distance call. */
+int bg_batch_prepare(bg_ctx* ctx, bg_dbatch* b, int for_edit);
+/* Tuning knobs (tests, experiments): force one kernel shape (lanes per pair, columns per lane;
+ * 0,0 = automatic by length class) and bound the per-launch trace buffer. */
+int bg_set_shape(bg_ctx* ctx, int lanes_per_pair, int cols_per_lane);
+int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes);
+
+/* ---- helpers for host mirrors ------------------------------------------------------ */
+/* The shipped scorers' 26x26 tables, indexed [a-'A'][b-'A'] (score.rs:5-35,45-75,82-111).
+ * name = "blosum62" | "pam250" | "unit"; returns NULL for anything else. */
+const int8_t* bg_score_table26(const char* name);
+
+/* Byte histograms of the seq1 / seq2 sides of a batch (which residues a score callback has to
+ * be evaluated on).  hist_a / hist_b: [256]. */
+int bg_residue_histogram(const bg_batch* in, uint64_t* hist_a, uint64_t* hist_b);
+
+/* Whether the REFERENCE defines a result for (mode, len1, len2) given the outcome the engine
+ * computed; used by host mirrors that want reference-identical failure behaviour. Returns a
+ * bg_status. (fresh-aligner semantics.) */
+int bg_ref_status(int mode, uint64_t len1, uint64_t len2, int32_t score, int walk_flags);
+
+/* Deterministic synthetic workloads (SURVEY 8d generator: splitmix64 stream; a uniform over
+ * the alphabet, b = a mutated with P(sub)=.05, P(ins)=.01, P(del)=.01 for 90% of pairs,
+ * independent uniform for the rest).  Lengths uniform in [len_lo, len_hi]; if fix_b_len != 0,
+ * b is truncated / padded with random residues to exactly the drawn length of its own.
+ * Call with residues == NULL to size: returns total residues in *n_residues. */
+int bg_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, const char* alphabet, int alphabet_len,
+                   uint32_t len_lo, uint32_t len_hi, int resize_b,
+                   uint8_t* residues, uint64_t* seq_off, uint64_t* n_residues);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGALIGN_H */

@@ -1,0 +1,291 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libbgalign.so) via the host mirror; the oracle is only the checker."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import _cmp
+import _oracle as orc
+from biogarden_b200 import native, score as score_mod
+from biogarden_b200.aligner import SequenceAligner
+from biogarden_b200.fasta import read_tile
+from biogarden_b200.sequence import Sequence, Tile
+from biogarden_b200 import seq as seqmod
+from biogarden_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(32, 2), (32, 4), (32, 5), (32, 8), (32, 12), (32, 16), (16, 10), (8, 19)]
+
+
+@pytest.fixture(scope="module")
+def aligner():
+    return SequenceAligner()
+
+
+def _fixture(golden_dir, name):
+    inp = read_tile(os.path.join(golden_dir, "fasta", "input", name + ".fasta"))
+    outp = os.path.join(golden_dir, "fasta", "output", name + ".fasta")
+    return inp, (read_tile(outp) if os.path.exists(outp) else None)
+
+
+def test_doctests(aligner, kat):
+    for t in kat["doctests"]:
+        f = getattr(aligner, t["mode"] + "_alignment")
+        sc, a, b = f(Sequence(t["s1"]), Sequence(t["s2"]), _cmp.SCORERS[t["scorer"]], t["a"], t["b"])
+        assert (sc, bytes(a), bytes(b)) == (t["score"], t["a_align"].encode(), t["b_align"].encode()), t["ref"]
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_integration_goldens(aligner, kat, golden_dir, idx):
+    t = kat["integration"][idx]
+    inp, out = _fixture(golden_dir, t["fixture"])
+    f = getattr(aligner, t["mode"] + "_alignment")
+    sc, a, b = f(inp[0], inp[1], _cmp.SCORERS[t["scorer"]], t["a"], t["b"])
+    assert sc == t["score"]
+    assert a == out[0], "a_align differs (len %d vs %d)" % (len(a), len(out[0]))
+    assert b == out[1]
+
+
+def test_config1_from_file_example(aligner, golden_dir):
+    """BASELINE config #1: examples/from_file.rs:20-31 (blosum62, open -1, enlarge -2)."""
+    inp, _ = _fixture(golden_dir, "semiglobal_alignment")
+    sc, a, b = aligner.semiglobal_alignment(inp[0], inp[1], score_mod.blosum62, -1, -2)
+    st, osc, oa, ob = orc.align("semiglobal", bytes(inp[0]), bytes(inp[1]), "blosum62", -1, -2, lean=True)
+    assert st == orc.OK
+    assert sc == osc == 31188
+    assert bytes(a) == oa and bytes(b) == ob and len(a) == 11242
+
+
+def test_edit_distance(kat, golden_dir):
+    d = kat["edit_distance_doctest"]
+    assert seqmod.edit_distance(Sequence(d["s1"]), Sequence(d["s2"])) == d["distance"]
+    t = kat["edit_distance_integration"]
+    inp, _ = _fixture(golden_dir, t["fixture"])
+    assert seqmod.edit_distance(inp[0], inp[1]) == t["distance"]
+    assert seqmod.edit_distance_batch(Tile([inp[0], inp[1], inp[1], inp[0], Sequence(""), inp[0]])) == \
+        [t["distance"], t["distance"], len(inp[0])]
+
+
+def _random_batch(rng, n_pairs, alpha, max_len, edge=False):
+    seqs = []
+    for _ in range(n_pairs):
+        n = rng.randint(0, max_len) if not edge else rng.choice([0, 1, 2, 3, max_len])
+        s1 = bytes(rng.choice(alpha) for _ in range(n))
+        if rng.random() < 0.7 and n > 0:
+            s2 = bytearray()
+            for c in s1:
+                r = rng.random()
+                if r < 0.08:
+                    s2.append(rng.choice(alpha))
+                elif r < 0.12:
+                    continue
+                elif r < 0.16:
+                    s2.append(c); s2.append(rng.choice(alpha))
+                else:
+                    s2.append(c)
+            s2 = bytes(s2)
+        else:
+            m = rng.randint(0, max_len) if not edge else rng.choice([0, 1, 2, max_len])
+            s2 = bytes(rng.choice(alpha) for _ in range(m))
+        seqs += [s1, s2]
+    return native.Batch.from_sequences(seqs)
+
+
+PARAMS = [
+    ("global", "blosum62", -11, -1), ("global", "unit", -2, -1), ("global", "unit", -1, -1),
+    ("local", "blosum62", -11, -1), ("local", "unit", -1, -1), ("local", "pam250", -5, -2), ("local", "unit", 0, 0),
+    ("semiglobal", "unit", -1, -1), ("semiglobal", "blosum62", -1, -2), ("semiglobal", "unit", 1, -1),
+    ("fitting", "unit", -1, -1), ("fitting", "blosum62", -11, -1),
+    ("overlap", "unit", -2, -2), ("overlap", "blosum62", -3, -1),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES + [None])
+def test_random_vs_oracle_all_modes(aligner, shape):
+    """Small random pairs (incl. empty sequences and ties-heavy 2-letter alphabets), every mode,
+    every compiled kernel shape: scores, strings and reference-undefined status must match."""
+    rng = random.Random(1234 + (shape[0] * 100 + shape[1] if shape else 0))
+    ctx = aligner.context
+    if shape:
+        ctx.set_shape(*shape)
+    try:
+        problems = []
+        for mode, scorer, a, b in PARAMS:
+            for alpha, max_len in ((b"ACGT", 70), (b"AC", 40), (b"ACDEFGHIKLMNPQRSTVWY", 150)):
+                batch = _random_batch(rng, 96, alpha, max_len)
+                if mode == "fitting":   # reference returns Err for len1 < len2; keep the batch inside the Ok domain
+                    seqs = []
+                    for p in range(batch.n_pairs):
+                        s = [bytes(batch.residues[int(batch.seq_off[2 * p + k]):int(batch.seq_off[2 * p + k + 1])]) for k in (0, 1)]
+                        seqs += s if len(s[0]) >= len(s[1]) else s[::-1]
+                    batch = native.Batch.from_sequences(seqs)
+                eng = _cmp.engine_align(aligner, batch, mode, scorer, a, b)
+                ora = _cmp.oracle_align(batch, mode, scorer, a, b, lean=False, threads=8)
+                problems += _cmp.diff(batch, eng, ora, "%s/%s/%d/%d/%s" % (mode, scorer, a, b, alpha.decode()[:4]))
+                eng.close()
+        assert not problems, "\n".join(problems[:40])
+    finally:
+        ctx.set_shape(0, 0)
+
+
+def test_edge_lengths_and_multiband(aligner):
+    """Lengths around the reference's 1024 buffer edge (A.6) and pairs spanning several column
+    bands; lean oracle (the literal one agrees with it, tests/test_oracle_forms.py)."""
+    rng = random.Random(7)
+    seqs = []
+    for n, m in [(1023, 1023), (1024, 5), (5, 1024), (1025, 1025), (1030, 600), (300, 2100), (2100, 300), (513, 512),
+                 (512, 513), (1, 700), (700, 1), (0, 600), (600, 0), (33, 33), (161, 159)]:
+        s1 = bytes(rng.choice(b"ACGT") for _ in range(n))
+        s2 = bytearray(s1[:m]) if m <= n else bytearray(s1 + bytes(rng.choice(b"ACGT") for _ in range(m - n)))
+        for k in range(0, len(s2), 11):
+            s2[k] = rng.choice(b"ACGT")
+        seqs += [s1, bytes(s2)]
+    batch = native.Batch.from_sequences(seqs)
+    problems = []
+    for mode, scorer, a, b in [("global", "unit", -2, -1), ("local", "blosum62", -11, -1), ("semiglobal", "unit", -1, -1),
+                               ("overlap", "unit", -2, -2)]:
+        eng = _cmp.engine_align(aligner, batch, mode, scorer, a, b)
+        ora = _cmp.oracle_align(batch, mode, scorer, a, b, lean=True)
+        problems += _cmp.diff(batch, eng, ora, "%s/%s" % (mode, scorer))
+        eng.close()
+    assert not problems, "\n".join(problems)
+
+
+def test_error_behaviour(aligner):
+    from biogarden_b200.error import InvalidArgumentRange, InvalidInputSize
+    s1, s2 = Sequence("ACGTACGT"), Sequence("ACGTTT")
+    for f in (aligner.global_alignment, aligner.local_alignment, aligner.fitting_alignment):
+        with pytest.raises(InvalidArgumentRange):
+            f(s1, s2, score_mod.unit, 1, -1)
+        with pytest.raises(InvalidArgumentRange):
+            f(s1, s2, score_mod.unit, -1, 2)
+    with pytest.raises(InvalidInputSize):
+        aligner.fitting_alignment(s2, s1, score_mod.unit, -1, -1)
+    # semiglobal / overlap accept positive penalties (aligner.rs:290-296,351-357)
+    aligner.semiglobal_alignment(s1, s2, score_mod.unit, 1, 1)
+    with pytest.raises(InvalidInputSize):
+        aligner.align_batch(Tile([s1, s2, s1]), "global", score_mod.unit, -1, -1)
+    # a residue the shipped scorer cannot index (score.rs:40) never reaches the device
+    from biogarden_b200.error import ReferenceUndefined
+    with pytest.raises(ReferenceUndefined):
+        aligner.global_alignment(Sequence("AC-T"), s2, score_mod.unit, -1, -1)
+    # raw C-ABI call with a code map that lacks a residue -> BG_EINVAL_RESIDUE
+    batch = native.Batch.from_sequences([b"ACGT", b"ACGX"])
+    rc = np.full(256, 0xFF, np.uint8); rc[[65, 67, 71, 84]] = [0, 1, 2, 3]
+    prm = native.Params("global", -1, -1, np.eye(4, dtype=np.int32), rc, rc)
+    from biogarden_b200.error import EngineError
+    with pytest.raises(EngineError):
+        aligner.context.align_batch(batch, prm)
+
+
+def test_cfg2_sample_vs_oracle(aligner):
+    """BASELINE config #2 shape (150 bp DNA, global, +1/-1, a=-2, b=-1): a 20k-pair prefix of the
+    seeded stream against the oracle, digest compare of all strings + exact compare of a few."""
+    batch = synth.make("cfg2_dna150_global", n_pairs=20000)
+    for shape in (None, (8, 19), (16, 10)):
+        if shape:
+            aligner.context.set_shape(*shape)
+        try:
+            eng = _cmp.engine_align(aligner, batch, "global", "unit", -2, -1)
+        finally:
+            aligner.context.set_shape(0, 0)
+        ora = _cmp.oracle_align(batch, "global", "unit", -2, -1, lean=True, want_strings=False)
+        assert np.all(ora["status"] == orc.OK)
+        assert np.array_equal(eng.score, ora["score"]), "shape %r" % (shape,)
+        assert np.all(eng.status == 0)
+        assert np.array_equal(_cmp.fnv_pairs(eng), ora["hash"]), "shape %r" % (shape,)
+        eng.close()
+
+
+def test_cfg4_sample_vs_oracle(aligner):
+    """Config #4 shape: protein 200-1000 aa, local, blosum62 -11/-1 (integration.rs:258 parameters)."""
+    batch = synth.make("cfg4_protein_local", n_pairs=300)
+    eng = _cmp.engine_align(aligner, batch, "local", "blosum62", -11, -1)
+    ora = _cmp.oracle_align(batch, "local", "blosum62", -11, -1, lean=True)
+    problems = _cmp.diff(batch, eng, ora, "cfg4")
+    eng.close()
+    assert not problems, "\n".join(problems)
+
+
+def test_cfg3_sample_vs_oracle():
+    batch = synth.make("cfg3_edit_100_300", n_pairs=20000)
+    ctx = native.Context()
+    got = ctx.edit_distance_batch(batch)
+    want, _ = orc.edit_distance_batch(batch.residues, batch.seq_off, threads=orc.hw_threads(), lean=True)
+    assert np.array_equal(got, want)
+    # protein + arbitrary bytes (the reference compares raw bytes)
+    rng = random.Random(5)
+    seqs = [bytes(rng.randrange(256) for _ in range(rng.randint(0, 400))) for _ in range(400)]
+    b2 = native.Batch.from_sequences(seqs)
+    want2, _ = orc.edit_distance_batch(b2.residues, b2.seq_off, threads=4, lean=False)
+    assert np.array_equal(ctx.edit_distance_batch(b2), want2)
+    ctx.close()
+
+
+def test_cfg5_small_long_pair(aligner):
+    """Config #5 shape at a size the lean oracle finishes in seconds: one 6-9 kbp DNA pair, semiglobal."""
+    batch = native.synth_pairs(5, 0, 2, b"ACGT", 6000, 9000, False)
+    eng = _cmp.engine_align(aligner, batch, "semiglobal", "unit", -1, -1)
+    ora = _cmp.oracle_align(batch, "semiglobal", "unit", -1, -1, lean=True)
+    problems = _cmp.diff(batch, eng, ora, "cfg5-small")
+    eng.close()
+    assert not problems, "\n".join(problems)
+
+
+def test_full_size_properties_cfg2(aligner):
+    """Config #2 at full size (1M pairs): size-independent properties + a random sample vs the oracle.
+      * global alignment strings, with '-' removed, are exactly the inputs; equal lengths; no column
+        of two gaps;
+      * score-only pass == scores of the traceback pass;
+      * chunking (trace budget) does not change a single output byte."""
+    n_pairs = 1_000_000
+    batch = synth.make("cfg2_dna150_global", n_pairs=n_pairs)
+    eng = _cmp.engine_align(aligner, batch, "global", "unit", -2, -1)
+    assert eng.n_pairs == n_pairs and np.all(eng.status == 0)
+    off = eng.off.astype(np.int64)
+    la = off[1::2] - off[0:-1:2]; lb = off[2::2] - off[1::2]
+    assert np.array_equal(la, lb)
+    arena = eng.arena
+    # gap-free projection of all a_align strings equals all seq1 concatenated (same for b / seq2)
+    is_a = np.zeros(len(arena), bool)
+    starts = off[0:-1:2]; ends = off[1::2]
+    marks = np.zeros(len(arena) + 1, np.int32)
+    np.add.at(marks, starts, 1); np.add.at(marks, ends, -1)
+    is_a = np.cumsum(marks[:-1]) > 0
+    a_chars = arena[is_a]; b_chars = arena[~is_a]
+    assert not np.any((a_chars == 45) & (b_chars == 45))
+    so = batch.seq_off.astype(np.int64)
+    in_a = np.zeros(len(batch.residues) + 1, np.int32)
+    np.add.at(in_a, so[0:-1:2], 1); np.add.at(in_a, so[1::2], -1)
+    in_a = np.cumsum(in_a[:-1]) > 0
+    assert np.array_equal(a_chars[a_chars != 45], batch.residues[in_a])
+    assert np.array_equal(b_chars[b_chars != 45], batch.residues[~in_a])
+    score_full = eng.score.copy()
+    digest_full = (int(np.sum(arena.astype(np.uint64) * (np.arange(len(arena), dtype=np.uint64) % 1000003))), len(arena))
+    # sample vs oracle
+    rng = np.random.RandomState(11)
+    idx = np.sort(rng.choice(n_pairs, 3000, replace=False))
+    seqs = []
+    for p in idx:
+        seqs += [bytes(batch.residues[so[2 * p]:so[2 * p + 1]]), bytes(batch.residues[so[2 * p + 1]:so[2 * p + 2]])]
+    sub = native.Batch.from_sequences(seqs)
+    ora = _cmp.oracle_align(sub, "global", "unit", -2, -1, lean=True)
+    for q, p in enumerate(idx):
+        assert int(ora["score"][q]) == int(eng.score[p])
+        assert orc.batch_strings(ora, sub.seq_off, q) == eng.strings(int(p))
+    eng.close()
+    so_res = _cmp.engine_align(aligner, batch, "global", "unit", -2, -1, score_only=True)
+    assert np.array_equal(so_res.score, score_full)
+    so_res.close()
+    aligner.context.set_trace_budget(1 << 30)
+    try:
+        eng2 = _cmp.engine_align(aligner, batch, "global", "unit", -2, -1)
+    finally:
+        aligner.context.set_trace_budget(8 << 30)
+    a2 = eng2.arena
+    assert np.array_equal(eng2.score, score_full)
+    assert (int(np.sum(a2.astype(np.uint64) * (np.arange(len(a2), dtype=np.uint64) % 1000003))), len(a2)) == digest_full
+    eng2.close()
