@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- GCUPS of the alignment hot path on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (DP fill with 4-bit direction codes -> on-device traceback
+walk -> dense packing of the aligned strings) over one batch of synthetic pairs.  At N = 1 the
+workload is BASELINE config #2: 1,000,000 synthetic DNA pairs of 150 bp, global affine-gap
+alignment (+1/-1, open -2, extend -1) with traceback.  For N > 1 every rank gets its own batch of
+the same size from the same seeded stream (weak scaling; pairs are independent, so there is no
+collective on the data path -- torch.distributed is used only for the barrier and the max-over-ranks
+of the device times).
+
+  value     : cells / s with the batch already resident in HBM (CUDA events on the engine's stream)
+  e2e       : same metric through bg_align_batch() with HOST buffers: H2D of the residues,
+              all kernels, D2H of scores + offsets + aligned strings, every step
+  roofline  : DP fill kernel against the SM integer pipe (12 algorithmic int ops per cell,
+              SURVEY 8d) -- peak measured by tools/int32_peak.cu, recorded in profiles/
+  cpu_baseline : the literal CPU restatement of the reference (oracle/) on a bounded sample,
+              all host threads, timed on this box (rank 0, N = 1 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name -> (synth config, pairs per GPU)
+    "cfg2": ("cfg2_dna150_global", 1_000_000),
+    "cfg4": ("cfg4_protein_local", 100_000),
+    "cfg3": ("cfg3_edit_100_300", 1_250_000),
+}
+ALG_OPS_PER_CELL = {"global": 12, "semiglobal": 12, "local": 15, "edit": 4}
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous pair range of `rank` when a workload of n_total pairs is dealt over `world` ranks."""
+    lo = n_total * rank // world
+    hi = n_total * (rank + 1) // world
+    return lo, hi
+
+
+def int32_peak():
+    """(Top/s, source): measured VIADDMNMX-class issue rate x SMs x clock from profiles/, else nominal."""
+    p = os.path.join(ROOT, "profiles", "int32_peak_r01.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            rates = {o["op"]: o for o in d["ops"]}
+            r = rates["viaddmnmx_s32"]
+            return r["tera_lane_instr_per_s"], "measured (profiles/int32_peak_r01.json: viaddmnmx_s32 %.1f lane-instr/clk/SM at load clocks)" % r["lane_instr_per_clk_per_sm"]
+        except Exception:
+            pass
+    return 148 * 64 * 1.965e9 / 1e12, "fallback (nominal 148 SM x 64 lanes/clk x 1.965 GHz; not yet measured)"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def pinned_batch(batch):
+    """Copy a native.Batch into pinned host memory (so the e2e leg's H2D is a true async DMA)."""
+    import numpy as np
+    import torch
+    from biogarden_b200 import native
+    r = torch.empty(max(1, batch.residues.size), dtype=torch.uint8, pin_memory=True)
+    o = torch.empty(batch.seq_off.size, dtype=torch.int64, pin_memory=True)
+    rn = r.numpy()[:batch.residues.size]
+    rn[:] = batch.residues
+    on = o.numpy().view(np.uint64)
+    on[:] = batch.seq_off
+    nb = native.Batch.__new__(native.Batch)
+    nb.residues, nb.seq_off, nb.n_pairs = rn, on, batch.n_pairs
+    nb._keep = (r, o)
+    nb.c = native.bg_batch(nb.n_pairs, rn.ctypes.data, on.ctypes.data)
+    return nb
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation (literal restatement, oracle/) on the host
+    cores, same metric / config; each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as orc
+    from biogarden_b200 import synth
+    cfg_name, _ = WORKLOADS[args.workload]
+    cfg = synth.CONFIGS[cfg_name]
+    cores = orc.hw_threads()
+    sample = args.ref_pairs or (2500 * cores if args.workload == "cfg2" else 40 * cores)
+    batch = synth.make(cfg_name, n_pairs=sample)
+    cells = batch.cells()
+
+    def step():
+        if cfg["mode"] == "edit":
+            _, secs = orc.edit_distance_batch(batch.residues, batch.seq_off, threads=cores, lean=False)
+        else:
+            secs = orc.align_batch(cfg["mode"], batch.residues, batch.seq_off, cfg["scorer"], cfg["a"], cfg["b"],
+                                   threads=cores, lean=False, want_strings=True)["seconds"]
+        return secs
+    for _ in range(args.warmup):
+        step()
+    t = [step() for _ in range(args.steps)]
+    tot = sum(t)
+    value = cells * args.steps / tot / 1e9
+    line = {
+        "impl": "reference", "metric": "GCUPS (cell updates/s, with traceback)", "value": value, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, cfg, sample, note="bounded sample of the workload on host cores"),
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": "port",
+                         "sample": "%d pairs (%d cells) per step of the same seeded stream" % (sample, cells)},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, pairs_per_gpu, note=None):
+    c = {"workload": "%s: %d synthetic %s pairs per GPU, len %d-%d, %s, scorer %s, open %d, extend %d, %s" % (
+        args.workload, pairs_per_gpu, "DNA" if cfg["alphabet"] == b"ACGT" else "protein", cfg["lo"], cfg["hi"],
+        cfg["mode"], cfg["scorer"], cfg["a"], cfg["b"], "score only" if cfg["mode"] == "edit" else "with traceback"),
+        "pairs_per_gpu": pairs_per_gpu, "seed": cfg["seed"], "parallelism": "independent pairs sharded per GPU, no collective",
+        "l2": "inputs + trace larger than L2 (no flush needed)"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's full size)")
+    ap.add_argument("--ref-pairs", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", default="", help="force kernel shape L,C (experiments)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from biogarden_b200 import native, score, synth
+    from biogarden_b200.aligner import SequenceAligner
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg_name, full_pairs = WORKLOADS[args.workload]
+    cfg = synth.CONFIGS[cfg_name]
+    pairs = args.pairs or full_pairs
+    # weak scaling: rank r owns pairs [r*pairs, (r+1)*pairs) of the seeded stream
+    batch = pinned_batch(synth.make(cfg_name, n_pairs=pairs, first_pair=rank * pairs))
+    cells = batch.cells()
+    is_edit = cfg["mode"] == "edit"
+
+    al = SequenceAligner([local_rank])
+    ctx = al.context
+    if args.shape:
+        l_, c_ = (int(x) for x in args.shape.split(","))
+        ctx.set_shape(l_, c_)
+    scorer = getattr(score, cfg["scorer"]) if cfg["scorer"] else None
+    params = None if is_edit else al.make_params(batch, cfg["mode"], scorer, cfg["a"], cfg["b"])
+
+    # ---------------- device-resident leg: `value` ----------------
+    dbatch = ctx.upload(batch, 0, prepare="edit" if is_edit else "align")
+    ctx.sync()
+    stream = torch.cuda.ExternalStream(ctx.stream(0), device=torch.device("cuda", local_rank))
+
+    def device_step():
+        r = ctx.edit_distance_device(dbatch) if is_edit else ctx.align_device(dbatch, params)
+        return r
+
+    for _ in range(args.warmup):
+        r = device_step(); ctx.sync(); ctx.free_result(r)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fill_ms = walk_ms = compact_ms = 0.0
+    launches = 0
+    e0.record(stream)
+    results = []
+    for _ in range(args.steps):
+        results.append(device_step())
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    t = ctx.timing()                       # phases of the last step (events on the same stream)
+    fill_ms, walk_ms, compact_ms, launches = t["fill_ms"], t["walk_ms"], t["compact_ms"], int(t["launches"])
+    trace_bytes = int(t["trace_bytes"])
+    for r in results:
+        ctx.free_result(r)
+    ctx.free_batch(dbatch)
+
+    # ---------------- end-to-end leg: host buffers through the C ABI ----------------
+    def e2e_step():
+        if is_edit:
+            out = ctx.edit_distance_batch(batch)
+            return int(out[0]), batch.n_pairs * 8
+        res = ctx.align_batch(batch, params)
+        tt = ctx.timing()
+        s = int(res.score[0])
+        res.close()
+        return s, int(tt["d2h_bytes"])
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        _, d2h = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    h2d = int(ctx.timing()["h2d_bytes"]) if not is_edit else int(batch.residues.size + 64 * batch.n_pairs)
+    barrier()
+
+    # ---------------- reduce over ranks ----------------
+    vals = torch.tensor([dev_ms, e2e_s * 1e3, float(cells)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max, e2e_ms_max, cells_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        dev_ms_max, e2e_ms_max, cells_total = dev_ms, e2e_s * 1e3, float(cells)
+
+    if rank == 0:
+        ms_per_step = dev_ms_max / args.steps
+        value = cells_total * args.steps / (dev_ms_max * 1e-3) / 1e9
+        e2e_value = cells_total * args.steps / (e2e_ms_max * 1e-3) / 1e9
+        ops = ALG_OPS_PER_CELL.get(cfg["mode"], 12)
+        peak, peak_src = int32_peak()
+        achieved = ops * cells / (fill_ms * 1e-3) / 1e12 if fill_ms > 0 else None
+        hbm, hbm_src = hbm_peak()
+        line = {
+            "metric": "GCUPS (cell updates/s, with traceback)" if not is_edit else "GCUPS (cell updates/s, score only)",
+            "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, cfg, pairs),
+            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_max / args.steps, "timed": "host wall clock around bg_align_batch (pinned host buffers in, pinned results out)"},
+            "gpu_launches": launches * args.steps,
+            "clocks": clocks,
+            "phases_ms_last_step": {"fill": fill_ms, "walk": walk_ms, "compact": compact_ms},
+            "roofline": {
+                "bound": "int32", "kernel": "k1_fill (DP fill + direction codes)",
+                "achieved": achieved, "peak": peak, "unit": "Tops/s (int32 lane-ops)",
+                "frac": (achieved / peak) if achieved else None,
+                "ops_per_cell": ops, "gcups_fill_only": cells / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None,
+                "peak_source": peak_src, "traffic": None,
+                "hbm": {"trace_bytes_per_launch_set": trace_bytes,
+                        "achieved_gbs": trace_bytes / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None,
+                        "peak_gbs": hbm, "peak_source": hbm_src},
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cfg_name, cfg)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, cfg_name, cfg):
+    """Literal CPU restatement of the reference (oracle/) on a bounded sample, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as orc
+    from biogarden_b200 import synth
+    cores = orc.hw_threads()
+    per_core = {"cfg2": 1500, "cfg3": 300, "cfg4": 12}.get(args.workload, 100)
+    sample = per_core * cores
+    batch = synth.make(cfg_name, n_pairs=sample)
+    t0 = time.perf_counter()
+    if cfg["mode"] == "edit":
+        _, secs = orc.edit_distance_batch(batch.residues, batch.seq_off, threads=cores, lean=False)
+    else:
+        secs = orc.align_batch(cfg["mode"], batch.residues, batch.seq_off, cfg["scorer"], cfg["a"], cfg["b"],
+                               threads=cores, lean=False, want_strings=True)["seconds"]
+    return {"value": batch.cells() / secs / 1e9, "unit": "GCUPS", "cores": cores, "kind": "port",
+            "sample": "%d pairs (%.3g cells) of the same seeded stream, literal 6-matrix layout, %.1f s" % (
+                sample, batch.cells(), time.perf_counter() - t0)}
+
+
+if __name__ == "__main__":
+    main()

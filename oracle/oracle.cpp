@@ -520,21 +520,23 @@ double orc_align_batch(int mode, const uint8_t* residues, const uint64_t* seq_of
                        uint8_t* arena, const uint64_t* out_off) {
     ScoreFn fn = pick_scorer(scorer);
     return run_threads(n_pairs, n_threads, [&](int, uint64_t lo, uint64_t hi) {
-        orc_aligner* al = lean ? nullptr : new orc_aligner();
+        const bool fresh = (lean & 2) != 0; const bool lean_form = (lean & 1) != 0;
+        orc_aligner* al = lean_form ? nullptr : new orc_aligner();
         std::vector<uint8_t> o1, o2;
         for (uint64_t p = lo; p < hi; ++p) {
+            if (!lean_form && fresh && p != lo) { delete al; al = new orc_aligner(); }
             Seq s1{residues + seq_off[2 * p], (size_t)(seq_off[2 * p + 1] - seq_off[2 * p])};
             Seq s2{residues + seq_off[2 * p + 1], (size_t)(seq_off[2 * p + 2] - seq_off[2 * p + 1])};
             int32_t sc = 0; o1.clear(); o2.clear();
             int st = guarded([&] {
-                return lean ? lean_run(mode, s1, s2, fn, table, a, b, &sc, o1, o2)
+                return lean_form ? lean_run(mode, s1, s2, fn, table, a, b, &sc, o1, o2)
                             : al->run(mode, s1, s2, fn, table, a, b, &sc, o1, o2);
             });
             if (st == ORC_PANIC || st == ORC_HANG) {
                 // a panicking aligner is gone in Rust; start over with a fresh one
-                if (!lean) { delete al; al = new orc_aligner(); }
+                if (!lean_form) { delete al; al = new orc_aligner(); }
                 o1.clear(); o2.clear();
-            } else if (!lean && (al->R != 1024 || al->C != 1024)) {
+            } else if (!lean_form && (al->R != 1024 || al->C != 1024)) {
                 // keep "fresh aligner" semantics across pairs (A.6: dims persist across calls)
                 delete al; al = new orc_aligner();
             }

@@ -64,6 +64,8 @@ int orc_edit_distance_lean(const uint8_t* s1, size_t n, const uint8_t* s2, size_
  * dealt statically.  Outputs: score[p], status[p], aligned strings in a padded
  * arena: a_align of pair p at arena[out_off[p] ..), b_align right after it at
  * arena[out_off[p] + cap_p ..) with cap_p = n_p + m_p; len[p] = aligned length.
+ * lean: bit 0 = lean form, bit 1 = (literal form only) a brand-new aligner for every pair, i.e.
+ * "fresh aligner" semantics even where stale buffer contents would otherwise leak (A.6).
  * arena / out_off may be NULL (then strings are hashed only): hash[p] = FNV-1a-64
  * over a_align, then b_align.  Returns wall seconds of the compute section. */
 double orc_align_batch(int mode, const uint8_t* residues, const uint64_t* seq_off, uint64_t n_pairs,

@@ -22,13 +22,14 @@ def engine_align(aligner, batch, mode, scorer, a, b, match_mismatch=None, score_
     return aligner.align_batch_raw(batch, mode, sc, a, b, score_only=score_only)
 
 
-def oracle_align(batch, mode, scorer, a, b, match_mismatch=None, lean=True, threads=None, want_strings=True):
+def oracle_align(batch, mode, scorer, a, b, match_mismatch=None, lean=True, threads=None, want_strings=True,
+                 fresh=True):
     if match_mismatch:
         return orc.align_batch(mode, batch.residues, batch.seq_off, "table", a, b,
                                table=table256_for(scorer, match_mismatch), threads=threads or orc.hw_threads(),
-                               lean=lean, want_strings=want_strings)
+                               lean=lean, want_strings=want_strings, fresh=fresh)
     return orc.align_batch(mode, batch.residues, batch.seq_off, scorer, a, b, threads=threads or orc.hw_threads(),
-                           lean=lean, want_strings=want_strings)
+                           lean=lean, want_strings=want_strings, fresh=fresh)
 
 
 def fnv_pairs(res: native.Result):

@@ -87,7 +87,8 @@ def edit_distance(s1, s2, lean=False):
     return out.value
 
 
-def align_batch(mode, residues, seq_off, scorer, a, b, table=None, threads=1, lean=False, want_strings=True):
+def align_batch(mode, residues, seq_off, scorer, a, b, table=None, threads=1, lean=False, want_strings=True,
+                fresh=False):
     """Batch driver. residues: uint8 array; seq_off: uint64[2n+1].
     Returns dict(score, status, len, hash, arena, out_off, seconds)."""
     L = lib()
@@ -108,7 +109,7 @@ def align_batch(mode, residues, seq_off, scorer, a, b, table=None, threads=1, le
         arena = np.zeros(int(out_off[-1]) + 1, np.uint8)
         ap, op = arena.ctypes.data, out_off.ctypes.data
     secs = L.orc_align_batch(MODES[mode], residues.ctypes.data, seq_off.ctypes.data, n, SCORERS[scorer], tp, a, b,
-                             threads, int(lean), score.ctypes.data, status.ctypes.data, ln.ctypes.data,
+                             threads, int(lean) | (2 if fresh else 0), score.ctypes.data, status.ctypes.data, ln.ctypes.data,
                              hs.ctypes.data, ap, op)
     return dict(score=score, status=status, len=ln, hash=hs, arena=arena, out_off=out_off, seconds=secs)
 
