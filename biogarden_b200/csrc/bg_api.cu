@@ -2,8 +2,15 @@
 //
 // Host side is deliberately thin: it cuts a batch into length classes (one kernel shape per
 // class), lays out the trace / output slots, launches K1 (fill) -> K3 (walk) -> scan -> gather
-// on the context's stream and moves bytes.  All arithmetic is in the kernels; there is no CPU
-// path (bg_create fails without a device).
+// and moves bytes.  All arithmetic is in the kernels; there is no CPU path (bg_create fails
+// without a device).
+//
+// Two ways in:
+//   * device-resident (bg_batch_upload / bg_align_device / bg_dresult_download): one pass over a
+//     batch that already sits in HBM, everything asynchronous on work set 0's stream;
+//   * host buffers (bg_align_batch / bg_edit_distance_batch): the batch is cut into chunks that
+//     flow through a 3-deep software pipeline per device (plan on the host | H2D | kernels | D2H),
+//     each stage of chunk c overlapping other stages of chunks c+1, c+2 on separate streams.
 #include "../../include/bgalign.h"
 #include "../../include/bg_score_tables.h"
 
@@ -12,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -41,21 +49,81 @@ namespace {
 struct Shape { int L, C; };
 
 // Kernel shapes compiled in: (lanes per pair, columns per lane).  A band is L*C columns.
-#define BG_SHAPES(X) X(32, 2) X(32, 4) X(32, 5) X(32, 8) X(32, 12) X(32, 16) X(16, 10) X(8, 19)
+#define BG_SHAPES(X) \
+    X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 5) X(32, 8) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
+constexpr int MAX_SHAPES = 16;
+constexpr int PIPE_DEPTH = 3;
+
+// Size-keyed free lists so that steady-state calls never hit cudaMalloc / cudaFree / cudaHostAlloc
+// (each of which synchronises the device or pins pages: milliseconds to 100s of milliseconds).
+struct BlockCache {
+    bool pinned_host = false;
+    std::mutex mu;
+    std::multimap<size_t, void*> free_;
+    void* get(size_t bytes, size_t* got) {
+        if (bytes == 0) bytes = 1;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_.lower_bound(bytes);
+            if (it != free_.end() && it->first <= bytes * 2 + (1 << 20)) {
+                void* p = it->second; *got = it->first; free_.erase(it); return p;
+            }
+        }
+        void* p = nullptr;
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = pinned_host ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            trim();   // give cached blocks back and retry with the exact size
+            want = bytes;
+            e = pinned_host ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        }
+        *got = want;
+        return p;
+    }
+    void put(void* p, size_t bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        free_.emplace(bytes, p);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& kv : free_) { if (pinned_host) cudaFreeHost(kv.second); else cudaFree(kv.second); }
+        free_.clear();
+    }
+};
+
+BlockCache& pinned_cache() { static BlockCache c; c.pinned_host = true; return c; }
 
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want; else { p = nullptr; (void)cudaGetLastError(); }
-        return e;
+    BlockCache* cache = nullptr;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap && p) return true;
+        release();
+        p = cache->get(bytes, &cap);
+        if (!p) { cap = 0; return false; }
+        return true;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() {
+        if (p && cache) cache->put(p, cap);
+        p = nullptr; cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {   // pinned host block from the global cache
+    void* p = nullptr; size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap && p) return true;
+        release();
+        p = pinned_cache().get(bytes, &cap);
+        if (!p) { cap = 0; return false; }
+        return true;
+    }
+    void release() { if (p) pinned_cache().put(p, cap); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -63,8 +131,8 @@ struct Chunk { uint32_t slot_begin, slot_end; uint64_t trace_words; };
 struct LaunchClass { Shape sh; std::vector<Chunk> chunks; };
 
 struct Plan {
-    std::vector<PairDesc> desc;      // all slots, class after class
     std::vector<LaunchClass> classes;
+    size_t n_slots = 0;
     uint64_t max_trace_words = 0, bnd_elems = 0, pad_bytes = 0, cells = 0, total_trace_words = 0;
     uint32_t max_n = 0, max_m = 0;
     bool built = false;
@@ -72,18 +140,45 @@ struct Plan {
 
 struct PhaseEv { cudaEvent_t a, b; int phase; };   // phase: 0 encode, 1 fill, 2 walk, 3 compact
 
-struct Device {
+// Everything one in-flight unit of work needs on one device.
+struct WorkSet {
     int ordinal = 0;
     cudaStream_t stream = nullptr;
-    DevBuf trace, end, bnd, pad, table, codes, err, cubtmp;
+    BlockCache* cache = nullptr;
+    DevBuf trace, end, bnd, pad, table, codes, err, cubtmp;             // scratch + parameters
+    DevBuf residues, desc, score, flags, lens2, off, arena, out64;     // pipeline mode: chunk in / out
+    PinBuf stage;                                                     // descriptor staging
+    PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
+    cudaEvent_t ev_scan = nullptr;
     std::vector<PhaseEv> evs;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    size_t total_mem = 0;
     cudaEvent_t get_event() {
         if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
         return ev_pool[ev_used++];
     }
+    void reset_events() { evs.clear(); ev_used = 0; }
+    std::vector<DevBuf*> all_bufs() {
+        return {&trace, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64};
+    }
+};
+
+struct Device {
+    int ordinal = 0;
+    size_t total_mem = 0;
+    BlockCache* cache = nullptr;   // device blocks of this ordinal
+    WorkSet ws[PIPE_DEPTH];
+};
+
+// Validated, device-independent view of bg_params.
+struct Prepared {
+    int mode = 0; int32_t a = 0, b = 0;
+    bool local = false, prof4 = false, score_only = false;
+    size_t smem = 0;
+    int n_rows = 0, n_cols = 0;
+    std::vector<int32_t> table;
+    uint8_t codes[512];
+    int64_t maxabs = 0;
 };
 
 }  // namespace
@@ -91,10 +186,12 @@ struct Device {
 struct bg_ctx {
     std::vector<Device> devs;
     std::string last_error;
+    std::mutex err_mu;
     bg_timing timing{};
+    std::atomic<uint64_t> h2d{0}, d2h{0}, launches{0};
     uint64_t trace_budget_words = 0;
     int force_L = 0, force_C = 0;
-    void set_error(const std::string& s) { last_error = s; }
+    void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu); last_error = s; }
 };
 
 struct bg_dbatch {
@@ -116,24 +213,40 @@ struct bg_dresult {
 
 namespace {
 
-struct HostResultOwner { std::vector<void*> pinned; };
-
-int pinned_alloc(void** p, size_t bytes) {
-    if (bytes == 0) bytes = 1;
-    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); *p = nullptr; return BG_ENOMEM; }
-    return BG_OK;
-}
+struct HostResultOwner {
+    std::vector<std::pair<void*, size_t>> pinned;
+    void* grab(size_t bytes) {
+        size_t got = 0;
+        void* q = pinned_cache().get(bytes, &got);
+        if (q) pinned.emplace_back(q, got);
+        return q;
+    }
+};
 
 // ------------------------------------------------------------------------------ planning
+// Length class -> kernel shape.  Short pairs use few lanes per pair (the systolic pipeline costs
+// L-1 fill/drain steps per pair) and many columns per lane; wide pairs use a full warp, and pairs
+// wider than 1024 columns loop over bands of the L=32 shape that wastes the fewest padded columns.
 Shape pick_shape(const bg_ctx* ctx, uint32_t m) {
     if (ctx->force_L) return Shape{ctx->force_L, ctx->force_C};
-    if (m <= 64) return Shape{32, 2};
-    if (m <= 128) return Shape{32, 4};
-    if (m <= 160) return Shape{32, 5};
-    if (m <= 256) return Shape{32, 8};
+    if (m <= 64) return Shape{8, 8};
+    if (m <= 96) return Shape{8, 12};
+    if (m <= 128) return Shape{8, 16};
+    if (m <= 152) return Shape{8, 19};
+    if (m <= 192) return Shape{8, 24};
+    if (m <= 256) return Shape{16, 16};
     if (m <= 384) return Shape{32, 12};
-    return Shape{32, 16};
+    if (m <= 512) return Shape{32, 16};
+    if (m <= 640) return Shape{32, 20};
+    if (m <= 768) return Shape{32, 24};
+    if (m <= 1024) return Shape{32, 32};
+    Shape best{32, 32};
+    uint64_t best_cols = ~0ull;
+    for (int c : {32, 24, 20, 16}) {
+        const uint64_t band = 32ull * c, cols = (m + band - 1) / band * band;
+        if (cols < best_cols) { best_cols = cols; best = Shape{32, c}; }
+    }
+    return best;
 }
 
 int shape_index(Shape s) {
@@ -144,90 +257,107 @@ int shape_index(Shape s) {
     return -1;
 }
 
-// Builds launch classes.  with_trace: trace blocks are laid out and chunked by the budget.
-int build_plan(bg_ctx* ctx, const std::vector<uint64_t>& off, uint64_t n_pairs, bool with_trace, Plan& P) {
+size_t plan_desc_capacity(uint64_t n_pairs) { return (size_t)n_pairs + 4 * MAX_SHAPES; }
+
+// Builds launch classes for pairs [0, n_pairs) whose sequence offsets are off[0 .. 2n] (absolute;
+// `base` is subtracted, i.e. the residues of this batch start at device offset 0).  Descriptors go to
+// `dst` (capacity plan_desc_capacity(n_pairs)).  with_trace: trace blocks are laid out and the
+// launches are cut into chunks that fit the trace budget.
+int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs, bool with_trace,
+               uint64_t budget_words, Plan& P, PairDesc* dst) {
     P = Plan();
     if (n_pairs >= 0xFFFFFFF0ull) { ctx->set_error("too many pairs in one device batch"); return BG_EINVAL_ARG; }
-    constexpr int NS = 16;
-    std::vector<uint32_t> per_class[NS];
-    Shape shapes[NS];
+    Shape shapes[MAX_SHAPES];
     int nshape = 0;
 #define X(L_, C_) shapes[nshape++] = Shape{L_, C_};
     BG_SHAPES(X)
 #undef X
+    // pass 1: class of every pair
+    std::vector<uint8_t> cls(n_pairs);
+    size_t count[MAX_SHAPES] = {0};
+    uint32_t last_m = 0xFFFFFFFFu; int last_si = -1;
     for (uint64_t p = 0; p < n_pairs; ++p) {
         const uint64_t n = off[2 * p + 1] - off[2 * p], m = off[2 * p + 2] - off[2 * p + 1];
         if (n > 0x7FFFFFF0ull || m > 0x7FFFFFF0ull) { ctx->set_error("sequence longer than 2^31"); return BG_EUNSUPPORTED; }
-        const int si = shape_index(pick_shape(ctx, (uint32_t)m));
-        if (si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
-        per_class[si].push_back((uint32_t)p);
+        if ((uint32_t)m != last_m) {
+            last_m = (uint32_t)m; last_si = shape_index(pick_shape(ctx, last_m));
+            if (last_si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
+        }
+        cls[p] = (uint8_t)last_si; count[last_si]++;
         P.cells += n * m;
         P.max_n = std::max<uint32_t>(P.max_n, (uint32_t)n);
         P.max_m = std::max<uint32_t>(P.max_m, (uint32_t)m);
     }
+    // pass 2: bucket pair ids per class
+    std::vector<uint32_t> ids(n_pairs);
+    size_t start[MAX_SHAPES + 1]; start[0] = 0;
+    for (int s = 0; s < nshape; ++s) start[s + 1] = start[s] + count[s];
+    {
+        size_t cur[MAX_SHAPES];
+        for (int s = 0; s < nshape; ++s) cur[s] = start[s];
+        for (uint64_t p = 0; p < n_pairs; ++p) ids[cur[cls[p]]++] = (uint32_t)p;
+    }
     uint64_t pad_off = 0, bnd_off = 0;
+    size_t nd = 0;
     for (int si = 0; si < nshape; ++si) {
-        auto& ids = per_class[si];
-        if (ids.empty()) continue;
+        if (!count[si]) continue;
+        uint32_t* cid = ids.data() + start[si];
+        const size_t cn = count[si];
         const Shape sh = shapes[si];
         const uint32_t G = 32 / sh.L, K = words_per_lane_step(sh.C), band_cols = sh.L * sh.C;
-        // longest first (by rows, then columns) so that the lane groups of a warp and the warps of
-        // a wave carry similar work; skipped when the class is uniform.
+        auto len_n = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 1] - off[2 * (uint64_t)id]); };
+        auto len_m = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
+        // longest first so that the lane groups of a warp and the warps of a wave carry similar work;
+        // skipped when the class is uniform.
         bool uniform = true;
-        {
-            const uint64_t n0 = off[2 * (uint64_t)ids[0] + 1] - off[2 * (uint64_t)ids[0]];
-            for (uint32_t id : ids) if (off[2 * (uint64_t)id + 1] - off[2 * (uint64_t)id] != n0) { uniform = false; break; }
-        }
+        const uint32_t n0 = len_n(cid[0]);
+        for (size_t k = 1; k < cn; ++k) if (len_n(cid[k]) != n0) { uniform = false; break; }
         if (!uniform) {
-            std::stable_sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
-                const uint64_t nx = off[2 * (uint64_t)x + 1] - off[2 * (uint64_t)x], ny = off[2 * (uint64_t)y + 1] - off[2 * (uint64_t)y];
-                return nx > ny;
-            });
+            std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) { return len_n(x) > len_n(y); });
         }
         LaunchClass lc; lc.sh = sh;
-        Chunk ch; ch.slot_begin = (uint32_t)P.desc.size(); ch.trace_words = 0;
-        const size_t nwarps = (ids.size() + G - 1) / G;
+        Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
+        const size_t nwarps = (cn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
             uint32_t maxn = 0, maxb = 0;
             for (uint32_t gidx = 0; gidx < G; ++gidx) {
                 const size_t k = w * G + gidx;
-                if (k >= ids.size()) break;
-                const uint64_t id = ids[k];
-                const uint32_t n = (uint32_t)(off[2 * id + 1] - off[2 * id]), m = (uint32_t)(off[2 * id + 2] - off[2 * id + 1]);
-                maxn = std::max(maxn, n);
-                maxb = std::max(maxb, (m + band_cols - 1) / band_cols);
+                if (k >= cn) break;
+                maxn = std::max(maxn, len_n(cid[k]));
+                maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
             }
             const uint32_t steps = maxn + sh.L - 1;
             const uint64_t warp_words = with_trace ? (uint64_t)maxb * steps * K * 32ull : 0;
-            if (with_trace && ch.trace_words > 0 && ch.trace_words + warp_words > ctx->trace_budget_words) {
-                ch.slot_end = (uint32_t)P.desc.size();
+            if (with_trace && ch.trace_words > 0 && ch.trace_words + warp_words > budget_words) {
+                ch.slot_end = (uint32_t)nd;
                 lc.chunks.push_back(ch);
                 P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
                 ch.slot_begin = ch.slot_end; ch.trace_words = 0;
             }
             for (uint32_t gidx = 0; gidx < G; ++gidx) {
                 const size_t k = w * G + gidx;
-                PairDesc d; memset(&d, 0, sizeof d);
+                PairDesc& d = dst[nd++];
+                memset(&d, 0, sizeof d);
                 d.pair_id = 0xFFFFFFFFu; d.steps = steps; d.trace_off = ch.trace_words;
-                if (k < ids.size()) {
-                    const uint64_t id = ids[k];
-                    d.a_off = off[2 * id]; d.b_off = off[2 * id + 1];
+                if (k < cn) {
+                    const uint64_t id = cid[k];
+                    d.a_off = off[2 * id] - base; d.b_off = off[2 * id + 1] - base;
                     d.n = (uint32_t)(off[2 * id + 1] - off[2 * id]); d.m = (uint32_t)(off[2 * id + 2] - off[2 * id + 1]);
                     d.nbands = (d.m + band_cols - 1) / band_cols;
                     d.pair_id = (uint32_t)id;
-                    d.pad_off = pad_off; pad_off += 2ull * ((uint64_t)d.n + d.m);
+                    d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull);
                     if (d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }
                 }
-                P.desc.push_back(d);
             }
             ch.trace_words += warp_words;
             P.total_trace_words += warp_words;
         }
-        ch.slot_end = (uint32_t)P.desc.size();
+        ch.slot_end = (uint32_t)nd;
         lc.chunks.push_back(ch);
         P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
         P.classes.push_back(lc);
     }
+    P.n_slots = nd;
     P.pad_bytes = pad_off; P.bnd_elems = bnd_off;
     P.built = true;
     return BG_OK;
@@ -256,17 +386,165 @@ void dispatch_k4(Shape sh, dim3 grid, cudaStream_t st, const EditArgs& a) {
 }
 
 struct Phase {
-    Device& dv; int phase; cudaEvent_t a;
-    Phase(Device& d, int ph) : dv(d), phase(ph) { a = dv.get_event(); cudaEventRecord(a, dv.stream); }
-    ~Phase() { cudaEvent_t b = dv.get_event(); cudaEventRecord(b, dv.stream); dv.evs.push_back(PhaseEv{a, b, phase}); }
+    WorkSet& ws; int phase; cudaEvent_t a;
+    Phase(WorkSet& w, int ph) : ws(w), phase(ph) { a = ws.get_event(); cudaEventRecord(a, ws.stream); }
+    ~Phase() { cudaEvent_t b = ws.get_event(); cudaEventRecord(b, ws.stream); ws.evs.push_back(PhaseEv{a, b, phase}); }
 };
 
 int check_batch(bg_ctx* ctx, const bg_batch* in) {
-    if (!in || (in->n_pairs && (!in->seq_off || (!in->residues && in->seq_off[2 * in->n_pairs] != 0)))) {
+    if (!in || (in->n_pairs && (!in->seq_off || (!in->residues && in->seq_off[2 * in->n_pairs] != in->seq_off[0])))) {
         ctx->set_error("null batch pointers"); return BG_EINVAL_ARG;
     }
     for (uint64_t s = 0; s < 2 * in->n_pairs; ++s)
         if (in->seq_off[s + 1] < in->seq_off[s]) { ctx->set_error("seq_off not monotone"); return BG_EINVAL_ARG; }
+    return BG_OK;
+}
+
+// Validates bg_params against the reference's rules and the engine's numeric range.
+int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_t N, Prepared& pp) {
+    const int mode = p->mode;
+    if (mode < BG_GLOBAL || mode > BG_OVERLAP) { ctx->set_error("unknown mode"); return BG_EINVAL_ARG; }
+    // aligner.rs:87-89,153-155,219-221: sign check in global / local / fitting only
+    if ((mode == BG_GLOBAL || mode == BG_LOCAL || mode == BG_FITTING) && (p->gap_open > 0 || p->gap_extend > 0)) return BG_EINVAL_RANGE;
+    if (!p->table || !p->row_code || !p->col_code || p->n_rows <= 0 || p->n_cols <= 0 || p->n_rows > 255 || p->n_cols > 255) {
+        ctx->set_error("score table missing or malformed"); return BG_EINVAL_ARG;
+    }
+    uint64_t max_len_sum = 0;
+    for (uint64_t q = 0; q < N; ++q) {
+        const uint64_t n = off[2 * q + 1] - off[2 * q], m = off[2 * q + 2] - off[2 * q + 1];
+        if (mode == BG_FITTING && n < m) return BG_EINVAL_SIZE;   // aligner.rs:223-225
+        max_len_sum = std::max(max_len_sum, n + m);
+    }
+    pp.mode = mode; pp.a = p->gap_open; pp.b = p->gap_extend;
+    pp.local = (mode == BG_LOCAL); pp.score_only = (p->flags & BG_F_SCORE_ONLY) != 0;
+    pp.n_rows = p->n_rows; pp.n_cols = p->n_cols;
+    pp.table.assign(p->table, p->table + (size_t)p->n_rows * p->n_cols);
+    int64_t maxabs = std::max<int64_t>(llabs((long long)p->gap_open), llabs((long long)p->gap_extend));
+    bool fits8 = true;
+    for (int32_t v : pp.table) {
+        maxabs = std::max<int64_t>(maxabs, llabs((long long)v));
+        if (v < -128 || v > 127) fits8 = false;
+    }
+    // 32-bit safety of the recurrence (bg_common.cuh NEG_INF)
+    if (maxabs > (1 << 20) || (int64_t)(max_len_sum + 2) * maxabs >= (1ll << 28)) {
+        ctx->set_error("scores * length exceed the 32-bit-safe range"); return BG_EUNSUPPORTED;
+    }
+    pp.maxabs = maxabs;
+    pp.smem = 512 + (size_t)p->n_rows * (p->n_cols + 1) * 4;
+    if (pp.smem > 48 * 1024) { ctx->set_error("score table too large for shared memory"); return BG_EUNSUPPORTED; }
+    pp.prof4 = fits8 && p->n_rows <= 4;
+    memcpy(pp.codes, p->row_code, 256); memcpy(pp.codes + 256, p->col_code, 256);
+    for (int i = 0; i < 256; ++i) {
+        if (pp.codes[i] != 0xFF && pp.codes[i] >= p->n_rows) { ctx->set_error("row_code entry out of range"); return BG_EINVAL_ARG; }
+        if (pp.codes[256 + i] != 0xFF && pp.codes[256 + i] >= p->n_cols) { ctx->set_error("col_code entry out of range"); return BG_EINVAL_ARG; }
+    }
+    return BG_OK;
+}
+
+struct AlignIO {
+    const uint8_t* residues; const PairDesc* desc; const Plan* plan; uint64_t N;
+    int32_t* score; uint8_t* flags; uint64_t* lens2; uint64_t* off; uint8_t* arena;
+};
+
+// Uploads the score table / code maps into the work set and clears its error flag.
+int upload_params(bg_ctx* ctx, WorkSet& ws, const Prepared& pp) {
+    if (!ws.table.ensure(pp.table.size() * 4) || !ws.codes.ensure(512) || !ws.err.ensure(4)) {
+        ctx->set_error("device allocation failed (parameters)"); return BG_ENOMEM;
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(ws.table.p, pp.table.data(), pp.table.size() * 4, cudaMemcpyHostToDevice, ws.stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ws.codes.p, pp.codes, 512, cudaMemcpyHostToDevice, ws.stream));
+    CU_TRY(ctx, cudaMemsetAsync(ws.err.p, 0, 4, ws.stream));
+    return BG_OK;
+}
+
+// Enqueues fill -> walk -> scan -> gather for one planned batch on ws.stream.  Asynchronous.
+int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
+    const Plan& P = *io.plan;
+    const uint64_t N = io.N;
+    bool ok = ws.end.ensure(std::max<size_t>(1, P.n_slots) * sizeof(EndCell));
+    ok = ok && ws.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2));
+    if (!pp.score_only) {
+        ok = ok && ws.trace.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4);
+        ok = ok && ws.pad.ensure(std::max<uint64_t>(1, P.pad_bytes));
+    }
+    if (!ok) { ctx->set_error("device allocation failed (trace / scratch buffers)"); return BG_ENOMEM; }
+    cudaStream_t st = ws.stream;
+    if (!pp.score_only) CU_TRY(ctx, cudaMemsetAsync(io.lens2, 0, (2 * N + 1) * 8, st));
+
+    FillArgs fa;
+    fa.desc = nullptr; fa.n_slots = 0;
+    fa.residues = io.residues;
+    fa.table = ws.table.as<int32_t>(); fa.n_rows = pp.n_rows; fa.n_cols = pp.n_cols;
+    fa.row_code = ws.codes.as<uint8_t>(); fa.col_code = ws.codes.as<uint8_t>() + 256;
+    fa.a = pp.a; fa.b = pp.b; fa.mode = pp.mode; fa.want_trace = pp.score_only ? 0 : 1;
+    fa.trace = ws.trace.as<uint32_t>(); fa.bnd = ws.bnd.as<int2>(); fa.end = nullptr; fa.err_flag = ws.err.as<uint32_t>();
+
+    for (const LaunchClass& lc : P.classes) {
+        const uint32_t G = 32 / lc.sh.L;
+        for (const Chunk& ch : lc.chunks) {
+            const uint32_t ns = ch.slot_end - ch.slot_begin;
+            if (!ns) continue;
+            fa.desc = io.desc + ch.slot_begin;
+            fa.end = ws.end.as<EndCell>() + ch.slot_begin;
+            fa.n_slots = ns;
+            const uint32_t nwarps = (ns + G - 1) / G;
+            {
+                Phase ph(ws, 1);
+                dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, st, fa);
+            }
+            CU_TRY(ctx, cudaGetLastError());
+            {
+                Phase ph(ws, 2);
+                if (pp.score_only) {
+                    k_scores_only<<<(ns + 127) / 128, 128, 0, st>>>(fa.desc, fa.end, ns, io.score, io.flags);
+                } else {
+                    WalkArgs wa;
+                    wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
+                    wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C;
+                    wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
+                    k3_walk<<<(ns + 127) / 128, 128, 0, st>>>(wa);
+                }
+            }
+            CU_TRY(ctx, cudaGetLastError());
+            ctx->launches += 2;
+        }
+    }
+    if (!pp.score_only) {
+        Phase ph(ws, 3);
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, io.lens2, io.off, (int)(2 * N + 1), st);
+        if (!ws.cubtmp.ensure(tmp + 16)) { ctx->set_error("device allocation failed (scan)"); return BG_ENOMEM; }
+        cub::DeviceScan::ExclusiveSum(ws.cubtmp.p, tmp, io.lens2, io.off, (int)(2 * N + 1), st);
+        ctx->launches += 2;
+        if (P.n_slots) {
+            GatherArgs ga;
+            ga.desc = io.desc; ga.n_slots = (uint32_t)P.n_slots; ga.pad = ws.pad.as<uint8_t>();
+            ga.off = io.off; ga.arena = io.arena;
+            k_gather<<<(unsigned)((P.n_slots + 3) / 4), 128, 0, st>>>(ga);
+            ctx->launches++;
+        }
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    return BG_OK;
+}
+
+int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* desc, const Plan& P, uint64_t* out) {
+    if (!ws.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2))) { ctx->set_error("device allocation failed"); return BG_ENOMEM; }
+    EditArgs ea;
+    ea.residues = residues; ea.bnd = ws.bnd.as<int32_t>(); ea.out = out;
+    for (const LaunchClass& lc : P.classes) {
+        const uint32_t G = 32 / lc.sh.L;
+        for (const Chunk& ch : lc.chunks) {
+            const uint32_t ns = ch.slot_end - ch.slot_begin;
+            if (!ns) continue;
+            ea.desc = desc + ch.slot_begin; ea.n_slots = ns;
+            const uint32_t nwarps = (ns + G - 1) / G;
+            Phase ph(ws, 1);
+            dispatch_k4(lc.sh, dim3((nwarps + 3) / 4), ws.stream, ea);
+            ctx->launches++;
+        }
+    }
+    CU_TRY(ctx, cudaGetLastError());
     return BG_OK;
 }
 
@@ -294,6 +572,23 @@ const char* bg_strerror(int err) {
 
 const char* bg_last_error(const bg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
+void bg_destroy(bg_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& dv : ctx->devs) {
+        cudaSetDevice(dv.ordinal);
+        for (WorkSet& ws : dv.ws) {
+            if (ws.stream) cudaStreamSynchronize(ws.stream);
+            for (DevBuf* b : ws.all_bufs()) b->release();
+            ws.stage.release(); ws.scalars.release();
+            for (auto e : ws.ev_pool) cudaEventDestroy(e);
+            if (ws.ev_scan) cudaEventDestroy(ws.ev_scan);
+            if (ws.stream) cudaStreamDestroy(ws.stream);
+        }
+        if (dv.cache) { dv.cache->trim(); delete dv.cache; dv.cache = nullptr; }
+    }
+    delete ctx;
+}
+
 int bg_create(const int* devices, int n_dev, bg_ctx** out) {
     if (!out) return BG_EINVAL_ARG;
     *out = nullptr;
@@ -303,13 +598,20 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
     std::vector<int> ords;
     if (!devices || n_dev <= 0) { int cur = 0; cudaGetDevice(&cur); ords.push_back(cur); }
     else ords.assign(devices, devices + n_dev);
-    for (int o : ords) {
-        if (o < 0 || o >= count) { delete ctx; return BG_ENODEVICE; }
-        Device dv; dv.ordinal = o;
-        if (cudaSetDevice(o) != cudaSuccess) { delete ctx; return BG_ENODEVICE; }
-        if (cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BG_ECUDA; }
+    ctx->devs.resize(ords.size());
+    for (size_t i = 0; i < ords.size(); ++i) {
+        const int o = ords[i];
+        Device& dv = ctx->devs[i];
+        if (o < 0 || o >= count || cudaSetDevice(o) != cudaSuccess) { bg_destroy(ctx); return BG_ENODEVICE; }
+        dv.ordinal = o;
         size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); dv.total_mem = tot;
-        ctx->devs.push_back(dv);
+        dv.cache = new BlockCache();
+        for (WorkSet& ws : dv.ws) {
+            ws.ordinal = o; ws.cache = dv.cache;
+            for (DevBuf* b : ws.all_bufs()) b->cache = dv.cache;
+            if (cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ws.ev_scan, cudaEventDisableTiming) != cudaSuccess) { bg_destroy(ctx); return BG_ECUDA; }
+        }
     }
     uint64_t budget_mb = 8192;
     if (const char* e = getenv("BG_TRACE_BUDGET_MB")) budget_mb = strtoull(e, nullptr, 10);
@@ -322,21 +624,9 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
     return BG_OK;
 }
 
-void bg_destroy(bg_ctx* ctx) {
-    if (!ctx) return;
-    for (auto& dv : ctx->devs) {
-        cudaSetDevice(dv.ordinal);
-        cudaStreamSynchronize(dv.stream);
-        for (DevBuf* b : {&dv.trace, &dv.end, &dv.bnd, &dv.pad, &dv.table, &dv.codes, &dv.err, &dv.cubtmp}) b->release();
-        for (auto e : dv.ev_pool) cudaEventDestroy(e);
-        cudaStreamDestroy(dv.stream);
-    }
-    delete ctx;
-}
-
 void* bg_stream(bg_ctx* ctx, int dev_index) {
     if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return nullptr;
-    return (void*)ctx->devs[dev_index].stream;
+    return (void*)ctx->devs[dev_index].ws[0].stream;
 }
 int bg_device_ordinal(bg_ctx* ctx, int dev_index) {
     if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return -1;
@@ -358,7 +648,7 @@ int bg_sync(bg_ctx* ctx) {
     if (!ctx) return BG_EINVAL_ARG;
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.ordinal);
-        CU_TRY(ctx, cudaStreamSynchronize(dv.stream));
+        for (WorkSet& ws : dv.ws) CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
     }
     return BG_OK;
 }
@@ -368,16 +658,18 @@ int bg_last_timing(const bg_ctx* cctx, bg_timing* out) {
     if (!ctx || !out) return BG_EINVAL_ARG;
     bg_timing t = ctx->timing;
     t.encode_ms = t.fill_ms = t.walk_ms = t.compact_ms = t.total_ms = 0;
+    t.h2d_bytes = ctx->h2d; t.d2h_bytes = ctx->d2h; t.launches = ctx->launches;
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.ordinal);
-        CU_TRY(ctx, cudaStreamSynchronize(dv.stream));
-        double ph[4] = {0, 0, 0, 0};
-        for (auto& ev : dv.evs) {
-            float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
-            ph[ev.phase] += ms;
+        double ph[4] = {0, 0, 0, 0}, tot = 0;
+        for (WorkSet& ws : dv.ws) {
+            CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+            for (auto& ev : ws.evs) {
+                float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
+                ph[ev.phase] += ms;
+            }
+            if (!ws.evs.empty()) { float ms = 0; cudaEventElapsedTime(&ms, ws.evs.front().a, ws.evs.back().b); tot = std::max<double>(tot, ms); }
         }
-        double tot = 0;
-        if (!dv.evs.empty()) { float ms = 0; cudaEventElapsedTime(&ms, dv.evs.front().a, dv.evs.back().b); tot = ms; }
         // devices run concurrently: report the slowest
         t.encode_ms = std::max(t.encode_ms, ph[0]); t.fill_ms = std::max(t.fill_ms, ph[1]);
         t.walk_ms = std::max(t.walk_ms, ph[2]); t.compact_ms = std::max(t.compact_ms, ph[3]);
@@ -394,53 +686,63 @@ int bg_batch_upload(bg_ctx* ctx, int dev_index, const bg_batch* in, bg_dbatch** 
     int rc = check_batch(ctx, in);
     if (rc) return rc;
     Device& dv = ctx->devs[dev_index];
+    WorkSet& ws = dv.ws[0];
     CU_TRY(ctx, cudaSetDevice(dv.ordinal));
     bg_dbatch* B = new bg_dbatch();
     B->ctx = ctx; B->dev_index = dev_index; B->n_pairs = in->n_pairs;
+    for (DevBuf* b : {&B->residues, &B->desc_align, &B->desc_edit}) b->cache = dv.cache;
     const uint64_t base = in->n_pairs ? in->seq_off[0] : 0;
     B->seq_off.resize(2 * in->n_pairs + 1);
     for (uint64_t s = 0; s <= 2 * in->n_pairs; ++s) B->seq_off[s] = in->n_pairs ? in->seq_off[s] - base : 0;
     B->n_residues = B->seq_off.back();
-    cudaError_t e = B->residues.ensure(B->n_residues + 16);
-    if (e != cudaSuccess) { delete B; ctx->set_error("device allocation for residues failed"); return BG_ENOMEM; }
+    if (!B->residues.ensure(B->n_residues + 16)) { delete B; ctx->set_error("device allocation for residues failed"); return BG_ENOMEM; }
     if (B->n_residues) {
-        e = cudaMemcpyAsync(B->residues.p, in->residues + base, B->n_residues, cudaMemcpyHostToDevice, dv.stream);
+        cudaError_t e = cudaMemcpyAsync(B->residues.p, in->residues + base, B->n_residues, cudaMemcpyHostToDevice, ws.stream);
         if (e != cudaSuccess) { B->residues.release(); delete B; ctx->set_error(cudaGetErrorString(e)); return BG_ECUDA; }
     }
-    ctx->timing.h2d_bytes = B->n_residues;
+    ctx->h2d = B->n_residues;
     *out = B;
     return BG_OK;
 }
 
 void bg_dbatch_free(bg_dbatch* b) {
     if (!b) return;
-    cudaSetDevice(b->ctx->devs[b->dev_index].ordinal);
-    cudaStreamSynchronize(b->ctx->devs[b->dev_index].stream);
+    Device& dv = b->ctx->devs[b->dev_index];
+    cudaSetDevice(dv.ordinal);
+    cudaStreamSynchronize(dv.ws[0].stream);
     b->residues.release(); b->desc_align.release(); b->desc_edit.release();
     delete b;
 }
 
 void bg_dresult_free(bg_dresult* r) {
     if (!r) return;
-    cudaSetDevice(r->ctx->devs[r->dev_index].ordinal);
-    cudaStreamSynchronize(r->ctx->devs[r->dev_index].stream);
+    Device& dv = r->ctx->devs[r->dev_index];
+    cudaSetDevice(dv.ordinal);
+    cudaStreamSynchronize(dv.ws[0].stream);
     for (DevBuf* b : {&r->score, &r->flags, &r->lens2, &r->off, &r->arena, &r->out64}) b->release();
     delete r;
 }
 
 static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit) {
     Device& dv = ctx->devs[B->dev_index];
+    WorkSet& ws = dv.ws[0];
     Plan& P = edit ? B->plan_edit : B->plan_align;
     DevBuf& D = edit ? B->desc_edit : B->desc_align;
     if (P.built) return BG_OK;
-    int rc = build_plan(ctx, B->seq_off, B->n_pairs, !edit, P);
-    if (rc) return rc;
-    if (!P.desc.empty()) {
-        if (D.ensure(P.desc.size() * sizeof(PairDesc)) != cudaSuccess) { ctx->set_error("device allocation for descriptors failed"); return BG_ENOMEM; }
-        CU_TRY(ctx, cudaMemcpyAsync(D.p, P.desc.data(), P.desc.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, dv.stream));
-        CU_TRY(ctx, cudaStreamSynchronize(dv.stream));   // P.desc is pageable host memory
-        ctx->timing.h2d_bytes += P.desc.size() * sizeof(PairDesc);
-    }
+    // descriptors are built straight into cached pinned memory and copied once
+    const size_t cap = plan_desc_capacity(B->n_pairs);
+    PinBuf stage;
+    if (!stage.ensure(cap * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, ctx->trace_budget_words, P, stage.as<PairDesc>());
+    if (rc) { stage.release(); return rc; }
+    if (P.n_slots) {
+        if (!D.ensure(P.n_slots * sizeof(PairDesc))) { stage.release(); ctx->set_error("device allocation for descriptors failed"); return BG_ENOMEM; }
+        cudaError_t ce = cudaMemcpyAsync(D.p, stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, ws.stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ws.stream);
+        stage.release();
+        CU_TRY(ctx, ce);
+        ctx->h2d += P.n_slots * sizeof(PairDesc);
+    } else stage.release();
     return BG_OK;
 }
 
@@ -455,140 +757,39 @@ int bg_align_device(bg_ctx* ctx, const bg_dbatch* cin, const bg_params* p, bg_dr
     if (!ctx || !cin || !p || !out) return BG_EINVAL_ARG;
     *out = nullptr;
     bg_dbatch* B = const_cast<bg_dbatch*>(cin);
-    const int mode = p->mode;
-    if (mode < BG_GLOBAL || mode > BG_OVERLAP) { ctx->set_error("unknown mode"); return BG_EINVAL_ARG; }
-    // aligner.rs:87-89,153-155,219-221: sign check in global / local / fitting only
-    if ((mode == BG_GLOBAL || mode == BG_LOCAL || mode == BG_FITTING) && (p->gap_open > 0 || p->gap_extend > 0)) return BG_EINVAL_RANGE;
-    if (!p->table || !p->row_code || !p->col_code || p->n_rows <= 0 || p->n_cols <= 0 || p->n_rows > 255 || p->n_cols > 255) {
-        ctx->set_error("score table missing or malformed"); return BG_EINVAL_ARG;
-    }
     const uint64_t N = B->n_pairs;
-    if (mode == BG_FITTING)   // aligner.rs:223-225
-        for (uint64_t q = 0; q < N; ++q)
-            if (B->seq_off[2 * q + 1] - B->seq_off[2 * q] < B->seq_off[2 * q + 2] - B->seq_off[2 * q + 1]) return BG_EINVAL_SIZE;
-
+    Prepared pp;
+    int rc = prepare_params(ctx, p, B->seq_off.data(), N, pp);
+    if (rc) return rc;
     Device& dv = ctx->devs[B->dev_index];
+    WorkSet& ws = dv.ws[0];
     CU_TRY(ctx, cudaSetDevice(dv.ordinal));
-    int rc = ensure_plan(ctx, B, false);
+    rc = ensure_plan(ctx, B, false);
     if (rc) return rc;
     Plan& P = B->plan_align;
 
-    // 32-bit safety of the recurrence (bg_common.cuh NEG_INF)
-    int64_t maxabs = std::max<int64_t>(llabs((long long)p->gap_open), llabs((long long)p->gap_extend));
-    bool fits8 = true;
-    for (int i = 0; i < p->n_rows * p->n_cols; ++i) {
-        maxabs = std::max<int64_t>(maxabs, llabs((long long)p->table[i]));
-        if (p->table[i] < -128 || p->table[i] > 127) fits8 = false;
-    }
-    if (maxabs > (1 << 20) || (int64_t)((uint64_t)P.max_n + P.max_m + 2) * maxabs >= (1ll << 28)) {
-        ctx->set_error("scores * length exceed the 32-bit-safe range"); return BG_EUNSUPPORTED;
-    }
-    const size_t smem = 512 + (size_t)p->n_rows * (p->n_cols + 1) * 4;
-    if (smem > 48 * 1024) { ctx->set_error("score table too large for shared memory"); return BG_EUNSUPPORTED; }
-    const bool prof4 = fits8 && p->n_rows <= 4;
-    const bool local = (mode == BG_LOCAL);
-    const bool score_only = (p->flags & BG_F_SCORE_ONLY) != 0;
-
     bg_dresult* R = new bg_dresult();
-    R->ctx = ctx; R->dev_index = B->dev_index; R->n_pairs = N; R->kind = 0; R->mode = mode; R->score_only = score_only;
+    R->ctx = ctx; R->dev_index = B->dev_index; R->n_pairs = N; R->kind = 0; R->mode = pp.mode; R->score_only = pp.score_only;
+    for (DevBuf* b : {&R->score, &R->flags, &R->lens2, &R->off, &R->arena, &R->out64}) b->cache = dv.cache;
     R->n.resize(N); R->m.resize(N);
     for (uint64_t q = 0; q < N; ++q) {
         R->n[q] = (uint32_t)(B->seq_off[2 * q + 1] - B->seq_off[2 * q]);
         R->m[q] = (uint32_t)(B->seq_off[2 * q + 2] - B->seq_off[2 * q + 1]);
     }
-    auto fail = [&](int code, const char* what) { ctx->set_error(what); bg_dresult_free(R); return code; };
+    bool ok = R->score.ensure(std::max<uint64_t>(1, N) * 4) && R->flags.ensure(std::max<uint64_t>(1, N));
+    if (!pp.score_only)
+        ok = ok && R->lens2.ensure((2 * N + 1) * 8) && R->off.ensure((2 * N + 1) * 8) && R->arena.ensure(std::max<uint64_t>(1, P.pad_bytes));
+    if (!ok) { bg_dresult_free(R); ctx->set_error("device allocation failed (output buffers)"); return BG_ENOMEM; }
 
-    const size_t n_slots = P.desc.size();
-    bool ok = true;
-    ok &= dv.table.ensure((size_t)p->n_rows * p->n_cols * 4) == cudaSuccess;
-    ok &= dv.codes.ensure(512) == cudaSuccess;
-    ok &= dv.err.ensure(4) == cudaSuccess;
-    ok &= dv.end.ensure(std::max<size_t>(1, n_slots) * sizeof(EndCell)) == cudaSuccess;
-    ok &= dv.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2)) == cudaSuccess;
-    ok &= R->score.ensure(std::max<uint64_t>(1, N) * 4) == cudaSuccess;
-    ok &= R->flags.ensure(std::max<uint64_t>(1, N)) == cudaSuccess;
-    if (!score_only) {
-        ok &= dv.trace.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4) == cudaSuccess;
-        ok &= dv.pad.ensure(std::max<uint64_t>(1, P.pad_bytes)) == cudaSuccess;
-        ok &= R->lens2.ensure((2 * N + 1) * 8) == cudaSuccess;
-        ok &= R->off.ensure((2 * N + 1) * 8) == cudaSuccess;
-        ok &= R->arena.ensure(std::max<uint64_t>(1, P.pad_bytes)) == cudaSuccess;
-    }
-    if (!ok) return fail(BG_ENOMEM, "device allocation failed (trace / output buffers)");
-
-    cudaStream_t st = dv.stream;
-    dv.evs.clear(); dv.ev_used = 0;
-    ctx->timing.cells = P.cells; ctx->timing.launches = 0;
-    ctx->timing.trace_bytes = score_only ? 0 : P.total_trace_words * 4;
-
-    // small parameter uploads (pageable -> staged synchronously by the runtime)
-    uint8_t codes[512];
-    memcpy(codes, p->row_code, 256); memcpy(codes + 256, p->col_code, 256);
-    for (int i = 0; i < 256; ++i) {
-        if (codes[i] != 0xFF && codes[i] >= p->n_rows) return fail(BG_EINVAL_ARG, "row_code entry out of range");
-        if (codes[256 + i] != 0xFF && codes[256 + i] >= p->n_cols) return fail(BG_EINVAL_ARG, "col_code entry out of range");
-    }
-    CU_TRY(ctx, cudaMemcpyAsync(dv.table.p, p->table, (size_t)p->n_rows * p->n_cols * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemcpyAsync(dv.codes.p, codes, 512, cudaMemcpyHostToDevice, st));
-    CU_TRY(ctx, cudaMemsetAsync(dv.err.p, 0, 4, st));
-    if (!score_only) CU_TRY(ctx, cudaMemsetAsync(R->lens2.p, 0, (2 * N + 1) * 8, st));
-
-    FillArgs fa;
-    fa.desc = nullptr; fa.n_slots = 0;
-    fa.residues = B->residues.as<uint8_t>();
-    fa.table = dv.table.as<int32_t>(); fa.n_rows = p->n_rows; fa.n_cols = p->n_cols;
-    fa.row_code = dv.codes.as<uint8_t>(); fa.col_code = dv.codes.as<uint8_t>() + 256;
-    fa.a = p->gap_open; fa.b = p->gap_extend; fa.mode = mode; fa.want_trace = score_only ? 0 : 1;
-    fa.trace = dv.trace.as<uint32_t>(); fa.bnd = dv.bnd.as<int2>(); fa.end = nullptr; fa.err_flag = dv.err.as<uint32_t>();
-
-    for (const LaunchClass& lc : P.classes) {
-        const uint32_t G = 32 / lc.sh.L;
-        for (const Chunk& ch : lc.chunks) {
-            const uint32_t ns = ch.slot_end - ch.slot_begin;
-            if (!ns) continue;
-            fa.desc = B->desc_align.as<PairDesc>() + ch.slot_begin;
-            fa.end = dv.end.as<EndCell>() + ch.slot_begin;
-            fa.n_slots = ns;
-            const uint32_t nwarps = (ns + G - 1) / G;
-            {
-                Phase ph(dv, 1);
-                dispatch_k1(lc.sh, local, prof4, dim3((nwarps + 3) / 4), smem, st, fa);
-                ctx->timing.launches++;
-            }
-            CU_TRY(ctx, cudaGetLastError());
-            {
-                Phase ph(dv, 2);
-                if (score_only) {
-                    k_scores_only<<<(ns + 127) / 128, 128, 0, st>>>(fa.desc, fa.end, ns, R->score.as<int32_t>(), R->flags.as<uint8_t>());
-                } else {
-                    WalkArgs wa;
-                    wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
-                    wa.trace = fa.trace; wa.mode = mode; wa.L = lc.sh.L; wa.C = lc.sh.C;
-                    wa.pad = dv.pad.as<uint8_t>(); wa.score = R->score.as<int32_t>(); wa.walk_flags = R->flags.as<uint8_t>();
-                    wa.lens2 = R->lens2.as<uint64_t>();
-                    k3_walk<<<(ns + 127) / 128, 128, 0, st>>>(wa);
-                }
-                ctx->timing.launches++;
-            }
-            CU_TRY(ctx, cudaGetLastError());
-        }
-    }
-    if (!score_only) {
-        Phase ph(dv, 3);
-        size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, R->lens2.as<uint64_t>(), R->off.as<uint64_t>(), (int)(2 * N + 1), st);
-        if (dv.cubtmp.ensure(tmp + 16) != cudaSuccess) return fail(BG_ENOMEM, "device allocation failed (scan)");
-        cub::DeviceScan::ExclusiveSum(dv.cubtmp.p, tmp, R->lens2.as<uint64_t>(), R->off.as<uint64_t>(), (int)(2 * N + 1), st);
-        ctx->timing.launches += 2;
-        if (n_slots) {
-            GatherArgs ga;
-            ga.desc = B->desc_align.as<PairDesc>(); ga.n_slots = (uint32_t)n_slots; ga.pad = dv.pad.as<uint8_t>();
-            ga.off = R->off.as<uint64_t>(); ga.arena = R->arena.as<uint8_t>();
-            k_gather<<<(unsigned)((n_slots + 3) / 4), 128, 0, st>>>(ga);
-            ctx->timing.launches++;
-        }
-        CU_TRY(ctx, cudaGetLastError());
-    }
+    ws.reset_events();
+    ctx->launches = 0;
+    ctx->timing.cells = P.cells;
+    ctx->timing.trace_bytes = pp.score_only ? 0 : P.total_trace_words * 4;
+    rc = upload_params(ctx, ws, pp);
+    AlignIO io{B->residues.as<uint8_t>(), B->desc_align.as<PairDesc>(), &P, N,
+               R->score.as<int32_t>(), R->flags.as<uint8_t>(), R->lens2.as<uint64_t>(), R->off.as<uint64_t>(), R->arena.as<uint8_t>()};
+    if (!rc) rc = run_align(ctx, ws, io, pp);
+    if (rc) { bg_dresult_free(R); return rc; }
     *out = R;
     return BG_OK;
 }
@@ -598,6 +799,7 @@ int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* cin, bg_dresult** out)
     *out = nullptr;
     bg_dbatch* B = const_cast<bg_dbatch*>(cin);
     Device& dv = ctx->devs[B->dev_index];
+    WorkSet& ws = dv.ws[0];
     CU_TRY(ctx, cudaSetDevice(dv.ordinal));
     int rc = ensure_plan(ctx, B, true);
     if (rc) return rc;
@@ -605,26 +807,13 @@ int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* cin, bg_dresult** out)
     const uint64_t N = B->n_pairs;
     bg_dresult* R = new bg_dresult();
     R->ctx = ctx; R->dev_index = B->dev_index; R->n_pairs = N; R->kind = 1;
-    bool ok = R->out64.ensure(std::max<uint64_t>(1, N) * 8) == cudaSuccess;
-    ok &= dv.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2)) == cudaSuccess;
-    if (!ok) { ctx->set_error("device allocation failed"); bg_dresult_free(R); return BG_ENOMEM; }
-    dv.evs.clear(); dv.ev_used = 0;
-    ctx->timing.cells = P.cells; ctx->timing.launches = 0; ctx->timing.trace_bytes = 0;
-    EditArgs ea;
-    ea.residues = B->residues.as<uint8_t>(); ea.bnd = dv.bnd.as<int32_t>(); ea.out = R->out64.as<uint64_t>();
-    for (const LaunchClass& lc : P.classes) {
-        const uint32_t G = 32 / lc.sh.L;
-        for (const Chunk& ch : lc.chunks) {
-            const uint32_t ns = ch.slot_end - ch.slot_begin;
-            if (!ns) continue;
-            ea.desc = B->desc_edit.as<PairDesc>() + ch.slot_begin; ea.n_slots = ns;
-            const uint32_t nwarps = (ns + G - 1) / G;
-            Phase ph(dv, 1);
-            dispatch_k4(lc.sh, dim3((nwarps + 3) / 4), dv.stream, ea);
-            ctx->timing.launches++;
-        }
-    }
-    CU_TRY(ctx, cudaGetLastError());
+    for (DevBuf* b : {&R->score, &R->flags, &R->lens2, &R->off, &R->arena, &R->out64}) b->cache = dv.cache;
+    if (!R->out64.ensure(std::max<uint64_t>(1, N) * 8)) { bg_dresult_free(R); ctx->set_error("device allocation failed"); return BG_ENOMEM; }
+    ws.reset_events();
+    ctx->launches = 0;
+    ctx->timing.cells = P.cells; ctx->timing.trace_bytes = 0;
+    rc = run_edit(ctx, ws, B->residues.as<uint8_t>(), B->desc_edit.as<PairDesc>(), P, R->out64.as<uint64_t>());
+    if (rc) { bg_dresult_free(R); return rc; }
     *out = R;
     return BG_OK;
 }
@@ -651,37 +840,40 @@ int bg_dresult_download(bg_ctx* ctx, bg_dresult* r, bg_result* out) {
     if (!ctx || !r || !out || r->kind != 0) return BG_EINVAL_ARG;
     memset(out, 0, sizeof *out);
     Device& dv = ctx->devs[r->dev_index];
+    WorkSet& ws = dv.ws[0];
     CU_TRY(ctx, cudaSetDevice(dv.ordinal));
     const uint64_t N = r->n_pairs;
-    uint32_t err = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&err, dv.err.p, 4, cudaMemcpyDeviceToHost, dv.stream));
-    uint64_t total = 0;
+    if (!ws.scalars.ensure(16)) { ctx->set_error("pinned allocation failed"); return BG_ENOMEM; }
+    uint64_t* h_total = ws.scalars.as<uint64_t>();
+    uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
+    *h_total = 0; *h_err = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(h_err, ws.err.p, 4, cudaMemcpyDeviceToHost, ws.stream));
     if (!r->score_only)
-        CU_TRY(ctx, cudaMemcpyAsync(&total, r->off.as<uint64_t>() + 2 * N, 8, cudaMemcpyDeviceToHost, dv.stream));
-    CU_TRY(ctx, cudaStreamSynchronize(dv.stream));
-    if (err & 1u) { ctx->set_error("a residue byte has no row/column in the score table"); return BG_EINVAL_RESIDUE; }
+        CU_TRY(ctx, cudaMemcpyAsync(h_total, r->off.as<uint64_t>() + 2 * N, 8, cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+    if (*h_err & 1u) { ctx->set_error("a residue byte has no row/column in the score table"); return BG_EINVAL_RESIDUE; }
+    const uint64_t total = *h_total;
 
     HostResultOwner* own = new HostResultOwner();
-    auto grab = [&](size_t bytes) -> void* { void* q = nullptr; if (pinned_alloc(&q, bytes) == BG_OK) own->pinned.push_back(q); return q; };
     out->n_pairs = N;
-    out->score = (int32_t*)grab(N * 4);
-    out->status = (uint8_t*)grab(N);
-    out->off = (uint64_t*)grab((2 * N + 1) * 8);
-    out->arena = (uint8_t*)grab(total);
+    out->score = (int32_t*)own->grab(N * 4);
+    out->status = (uint8_t*)own->grab(N);
+    out->off = (uint64_t*)own->grab((2 * N + 1) * 8);
+    out->arena = (uint8_t*)own->grab(total);
     out->owner_ = own;
     if (!out->score || !out->status || !out->off || !out->arena) { bg_result_free(out); ctx->set_error("pinned host allocation failed"); return BG_ENOMEM; }
     if (N) {
-        CU_TRY(ctx, cudaMemcpyAsync(out->score, r->score.p, N * 4, cudaMemcpyDeviceToHost, dv.stream));
-        CU_TRY(ctx, cudaMemcpyAsync(out->status, r->flags.p, N, cudaMemcpyDeviceToHost, dv.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(out->score, r->score.p, N * 4, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(out->status, r->flags.p, N, cudaMemcpyDeviceToHost, ws.stream));
     }
     if (!r->score_only) {
-        CU_TRY(ctx, cudaMemcpyAsync(out->off, r->off.p, (2 * N + 1) * 8, cudaMemcpyDeviceToHost, dv.stream));
-        if (total) CU_TRY(ctx, cudaMemcpyAsync(out->arena, r->arena.p, total, cudaMemcpyDeviceToHost, dv.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(out->off, r->off.p, (2 * N + 1) * 8, cudaMemcpyDeviceToHost, ws.stream));
+        if (total) CU_TRY(ctx, cudaMemcpyAsync(out->arena, r->arena.p, total, cudaMemcpyDeviceToHost, ws.stream));
     } else {
         memset(out->off, 0, (2 * N + 1) * 8);
     }
-    CU_TRY(ctx, cudaStreamSynchronize(dv.stream));
-    ctx->timing.d2h_bytes = N * 5 + (r->score_only ? 0 : (2 * N + 1) * 8 + total);
+    CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+    ctx->d2h = N * 5 + (r->score_only ? 0 : (2 * N + 1) * 8 + total);
     for (uint64_t q = 0; q < N; ++q)
         out->status[q] = (uint8_t)bg_ref_status(r->mode, r->n[q], r->m[q], out->score[q], out->status[q]);
     return BG_OK;
@@ -690,10 +882,11 @@ int bg_dresult_download(bg_ctx* ctx, bg_dresult* r, bg_result* out) {
 int bg_dresult_download_u64(bg_ctx* ctx, bg_dresult* r, uint64_t* out) {
     if (!ctx || !r || r->kind != 1 || (!out && r->n_pairs)) return BG_EINVAL_ARG;
     Device& dv = ctx->devs[r->dev_index];
+    WorkSet& ws = dv.ws[0];
     CU_TRY(ctx, cudaSetDevice(dv.ordinal));
-    if (r->n_pairs) CU_TRY(ctx, cudaMemcpyAsync(out, r->out64.p, r->n_pairs * 8, cudaMemcpyDeviceToHost, dv.stream));
-    CU_TRY(ctx, cudaStreamSynchronize(dv.stream));
-    ctx->timing.d2h_bytes = r->n_pairs * 8;
+    if (r->n_pairs) CU_TRY(ctx, cudaMemcpyAsync(out, r->out64.p, r->n_pairs * 8, cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+    ctx->d2h = r->n_pairs * 8;
     return BG_OK;
 }
 
@@ -701,14 +894,17 @@ void bg_result_free(bg_result* r) {
     if (!r) return;
     if (r->owner_) {
         HostResultOwner* own = (HostResultOwner*)r->owner_;
-        for (void* q : own->pinned) cudaFreeHost(q);
+        for (auto& q : own->pinned) pinned_cache().put(q.first, q.second);
         delete own;
     }
     memset(r, 0, sizeof *r);
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------ host-buffer entry points
 namespace {
+
 // contiguous shards with ~equal cell counts
 std::vector<uint64_t> shard_bounds(const bg_batch* in, int nd) {
     std::vector<uint64_t> b(nd + 1, 0);
@@ -728,36 +924,227 @@ std::vector<uint64_t> shard_bounds(const bg_batch* in, int nd) {
     b[nd] = N;
     return b;
 }
+
+// Cuts pairs [lo, hi) into pipeline chunks of roughly equal cell counts.
+std::vector<uint64_t> chunk_bounds(const uint64_t* off, uint64_t lo, uint64_t hi) {
+    std::vector<uint64_t> b{lo};
+    if (hi == lo) { b.push_back(hi); return b; }
+    double total = 0;
+    for (uint64_t q = lo; q < hi; ++q)
+        total += (double)(off[2 * q + 1] - off[2 * q]) * (double)(off[2 * q + 2] - off[2 * q + 1]) + 64.0;
+    const double target = std::max(total / 8.0, 1.0e9);
+    const uint64_t max_pairs = 262144;
+    double acc = 0; uint64_t cnt = 0;
+    for (uint64_t q = lo; q < hi; ++q) {
+        acc += (double)(off[2 * q + 1] - off[2 * q]) * (double)(off[2 * q + 2] - off[2 * q + 1]) + 64.0;
+        if (++cnt >= max_pairs || acc >= target) { b.push_back(q + 1); acc = 0; cnt = 0; }
+    }
+    if (b.back() != hi) b.push_back(hi);
+    return b;
+}
+
+struct FinalOut {      // the caller-visible arrays of one device's pair range
+    int32_t* score; uint8_t* status; uint64_t* off; uint8_t* arena; uint64_t arena_cap;
+};
+
+// One device's share of bg_align_batch: chunks of pairs [lo, hi) flow through the work sets.
+int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const Prepared& pp,
+                   const FinalOut& fo, uint64_t* total_out) {
+    Device& dv = ctx->devs[d];
+    if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
+    const uint64_t* off = in->seq_off;
+    const std::vector<uint64_t> cb = chunk_bounds(off, lo, hi);
+    const int nchunks = (int)cb.size() - 1;
+    const uint64_t ws_budget = std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
+    struct Fly { bool active = false; uint64_t c_lo = 0, c_n = 0; Plan plan; };
+    Fly fly[PIPE_DEPTH];
+    uint64_t arena_base = 0;
+    int rc_all = BG_OK;
+
+    auto finish = [&](int s) -> int {
+        WorkSet& ws = dv.ws[s];
+        Fly& f = fly[s];
+        f.active = false;
+        uint64_t* h_total = ws.scalars.as<uint64_t>();
+        uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
+        CU_TRY(ctx, cudaEventSynchronize(ws.ev_scan));
+        if (*h_err & 1u) { ctx->set_error("a residue byte has no row/column in the score table"); return BG_EINVAL_RESIDUE; }
+        const uint64_t total = pp.score_only ? 0 : *h_total;
+        const uint64_t rel = f.c_lo - lo;
+        if (total) {
+            if (arena_base + total > fo.arena_cap) { ctx->set_error("internal: arena bound exceeded"); return BG_ECUDA; }
+            CU_TRY(ctx, cudaMemcpyAsync(fo.arena + arena_base, ws.arena.p, total, cudaMemcpyDeviceToHost, ws.stream));
+        }
+        CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+        ctx->d2h += f.c_n * 5 + (pp.score_only ? 0 : 2 * f.c_n * 8 + total);
+        // host post-processing of the chunk while later chunks keep the GPU busy
+        uint64_t* o = fo.off + 2 * rel;
+        if (pp.score_only) { for (uint64_t s2 = 0; s2 < 2 * f.c_n; ++s2) o[s2] = 0; }
+        else if (arena_base) { for (uint64_t s2 = 0; s2 < 2 * f.c_n; ++s2) o[s2] += arena_base; }
+        for (uint64_t q = 0; q < f.c_n; ++q) {
+            const uint64_t g = f.c_lo + q;
+            fo.status[rel + q] = (uint8_t)bg_ref_status(pp.mode, off[2 * g + 1] - off[2 * g], off[2 * g + 2] - off[2 * g + 1],
+                                                        fo.score[rel + q], fo.status[rel + q]);
+        }
+        arena_base += total;
+        return BG_OK;
+    };
+
+    auto issue = [&](int s, int c) -> int {
+        WorkSet& ws = dv.ws[s];
+        Fly& f = fly[s];
+        f.c_lo = cb[c]; f.c_n = cb[c + 1] - cb[c];
+        const uint64_t n = f.c_n, base = off[2 * f.c_lo], nres = off[2 * (f.c_lo + n)] - base;
+        const uint64_t rel = f.c_lo - lo;
+        // plan on the host, straight into pinned staging
+        if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+        int rc = build_plan(ctx, off + 2 * f.c_lo, base, n, !pp.score_only, ws_budget, f.plan, ws.stage.as<PairDesc>());
+        if (rc) return rc;
+        const Plan& P = f.plan;
+        bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
+                  ws.score.ensure(n * 4) && ws.flags.ensure(n);
+        if (!pp.score_only)
+            ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((2 * n + 1) * 8) && ws.arena.ensure(std::max<uint64_t>(1, P.pad_bytes));
+        if (!ok) { ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM; }
+        cudaStream_t st = ws.stream;
+        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st));
+        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, ws.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        rc = upload_params(ctx, ws, pp);
+        if (rc) return rc;
+        AlignIO io{ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), &P, n,
+                   ws.score.as<int32_t>(), ws.flags.as<uint8_t>(), ws.lens2.as<uint64_t>(), ws.off.as<uint64_t>(), ws.arena.as<uint8_t>()};
+        rc = run_align(ctx, ws, io, pp);
+        if (rc) return rc;
+        uint64_t* h_total = ws.scalars.as<uint64_t>();
+        uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
+        CU_TRY(ctx, cudaMemcpyAsync(h_err, ws.err.p, 4, cudaMemcpyDeviceToHost, st));
+        if (!pp.score_only) {
+            CU_TRY(ctx, cudaMemcpyAsync(h_total, ws.off.as<uint64_t>() + 2 * n, 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaMemcpyAsync(fo.off + 2 * rel, ws.off.p, 2 * n * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(fo.score + rel, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(fo.status + rel, ws.flags.p, n, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st));
+        ctx->timing.cells += P.cells;
+        ctx->timing.trace_bytes += pp.score_only ? 0 : P.total_trace_words * 4;
+        f.active = true;
+        return BG_OK;
+    };
+
+    for (WorkSet& ws : dv.ws) ws.reset_events();
+    for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
+        const int s = c % PIPE_DEPTH;
+        if (fly[s].active) rc_all = finish(s);
+        if (rc_all == BG_OK) rc_all = issue(s, c);
+    }
+    // drain in chunk order
+    for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
+        const int s = c % PIPE_DEPTH;
+        if (!fly[s].active) continue;
+        if (rc_all == BG_OK) rc_all = finish(s);
+        else { cudaStreamSynchronize(dv.ws[s].stream); fly[s].active = false; }
+    }
+    for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
+    *total_out = arena_base;
+    return rc_all;
+}
+
+int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, uint64_t* out) {
+    Device& dv = ctx->devs[d];
+    if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
+    const uint64_t* off = in->seq_off;
+    const std::vector<uint64_t> cb = chunk_bounds(off, lo, hi);
+    const int nchunks = (int)cb.size() - 1;
+    Plan plans[PIPE_DEPTH];
+    bool active[PIPE_DEPTH] = {false, false, false};
+    // `out` is caller memory of unknown kind: results are staged in pinned memory per work set
+    PinBuf host_out[PIPE_DEPTH];
+    uint64_t c_lo[PIPE_DEPTH] = {0}, c_n[PIPE_DEPTH] = {0};
+    int rc_all = BG_OK;
+    auto finish = [&](int s) -> int {
+        active[s] = false;
+        CU_TRY(ctx, cudaStreamSynchronize(dv.ws[s].stream));
+        memcpy(out + c_lo[s], host_out[s].p, c_n[s] * 8);
+        ctx->d2h += c_n[s] * 8;
+        return BG_OK;
+    };
+    for (WorkSet& ws : dv.ws) ws.reset_events();
+    for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
+        const int s = c % PIPE_DEPTH;
+        WorkSet& ws = dv.ws[s];
+        if (active[s]) rc_all = finish(s);
+        if (rc_all) break;
+        c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
+        const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
+        if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !host_out[s].ensure(n * 8)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
+        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, plans[s], ws.stage.as<PairDesc>());
+        if (rc_all) break;
+        const Plan& P = plans[s];
+        if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(n * 8)) {
+            ctx->set_error("device allocation failed (pipeline buffers)"); rc_all = BG_ENOMEM; break;
+        }
+        cudaStream_t st = ws.stream;
+        cudaError_t ce = cudaSuccess;
+        if (nres) ce = cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess && P.n_slots) ce = cudaMemcpyAsync(ws.desc.p, ws.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
+        ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        rc_all = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>());
+        if (rc_all) break;
+        ce = cudaMemcpyAsync(host_out[s].p, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
+        ctx->timing.cells += P.cells;
+        active[s] = true;
+    }
+    for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
+        const int s = c % PIPE_DEPTH;
+        if (!active[s]) continue;
+        if (rc_all == BG_OK) rc_all = finish(s);
+        else { cudaStreamSynchronize(dv.ws[s].stream); active[s] = false; }
+    }
+    for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
+    for (auto& h : host_out) h.release();
+    return rc_all;
+}
+
 }  // namespace
+
+extern "C" {
 
 int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_result* out) {
     if (!ctx || !in || !p || !out) return BG_EINVAL_ARG;
     memset(out, 0, sizeof *out);
     int rc = check_batch(ctx, in);
     if (rc) return rc;
+    const uint64_t N = in->n_pairs;
+    Prepared pp;
+    static const uint64_t zero_off[1] = {0};
+    rc = prepare_params(ctx, p, N ? in->seq_off : zero_off, N, pp);
+    if (rc) return rc;
     const int nd = (int)ctx->devs.size();
     const std::vector<uint64_t> bounds = shard_bounds(in, nd);
-    std::vector<bg_result> parts(nd);
+    ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
+
+    // upper bound of each device's share of the arena: 2*(n+m) per pair
+    std::vector<uint64_t> ub(nd + 1, 0);
+    for (int d = 0; d < nd; ++d) {
+        uint64_t s = 0;
+        if (!pp.score_only && bounds[d + 1] > bounds[d]) s = 2 * (in->seq_off[2 * bounds[d + 1]] - in->seq_off[2 * bounds[d]]);
+        ub[d + 1] = ub[d] + s;
+    }
+    HostResultOwner* own = new HostResultOwner();
+    out->n_pairs = N; out->owner_ = own;
+    out->score = (int32_t*)own->grab(N * 4); out->status = (uint8_t*)own->grab(N);
+    out->off = (uint64_t*)own->grab((2 * N + 1) * 8); out->arena = (uint8_t*)own->grab(ub[nd]);
+    if (!out->score || !out->status || !out->off || !out->arena) { bg_result_free(out); ctx->set_error("pinned host allocation failed"); return BG_ENOMEM; }
+
     std::vector<int> rcs(nd, BG_OK);
-    std::vector<std::string> errs(nd);
-    uint64_t h2d = 0, d2h = 0;
-    std::mutex mu;
+    std::vector<uint64_t> totals(nd, 0);
     auto work = [&](int d) {
-        bg_batch sub; sub.n_pairs = bounds[d + 1] - bounds[d]; sub.residues = in->residues; sub.seq_off = in->seq_off + 2 * bounds[d];
-        memset(&parts[d], 0, sizeof(bg_result));
-        bg_dbatch* B = nullptr; bg_dresult* R = nullptr;
-        int r = bg_batch_upload(ctx, d, &sub, &B);
-        if (!r) r = bg_align_device(ctx, B, p, &R);
-        if (!r) r = bg_dresult_download(ctx, R, &parts[d]);
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            if (r) errs[d] = ctx->last_error;
-            if (B) h2d += B->n_residues + B->plan_align.desc.size() * sizeof(PairDesc);
-            d2h += ctx->timing.d2h_bytes;
-        }
-        if (R) bg_dresult_free(R);
-        if (B) bg_dbatch_free(B);
-        rcs[d] = r;
+        FinalOut fo{out->score + bounds[d], out->status + bounds[d], out->off + 2 * bounds[d], out->arena + ub[d], ub[d + 1] - ub[d]};
+        rcs[d] = align_pipeline(ctx, d, in, bounds[d], bounds[d + 1], pp, fo, &totals[d]);
     };
     if (nd == 1) work(0);
     else {
@@ -766,38 +1153,17 @@ int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_resul
         for (auto& t : th) t.join();
     }
     for (int d = 0; d < nd; ++d)
-        if (rcs[d]) {
-            ctx->set_error(errs[d]);
-            for (auto& q : parts) bg_result_free(&q);
-            return rcs[d];
+        if (rcs[d]) { bg_result_free(out); return rcs[d]; }
+    // close the gaps between the devices' arena regions (device 0's region is already in place)
+    uint64_t base = totals[0];
+    for (int d = 1; d < nd; ++d) {
+        if (totals[d]) {
+            if (ub[d] != base) memmove(out->arena + base, out->arena + ub[d], totals[d]);
+            for (uint64_t s = 2 * bounds[d]; s < 2 * bounds[d + 1]; ++s) out->off[s] += base;
+        } else {
+            for (uint64_t s = 2 * bounds[d]; s < 2 * bounds[d + 1]; ++s) out->off[s] = base;
         }
-    ctx->timing.h2d_bytes = h2d; ctx->timing.d2h_bytes = d2h;
-    if (nd == 1) { *out = parts[0]; return BG_OK; }
-    // stitch the shards back into input order (pairs were dealt in contiguous ranges)
-    const uint64_t N = in->n_pairs;
-    uint64_t total = 0;
-    for (auto& q : parts) total += q.off ? q.off[2 * q.n_pairs] : 0;
-    HostResultOwner* own = new HostResultOwner();
-    auto grab = [&](size_t bytes) -> void* { void* q = nullptr; if (pinned_alloc(&q, bytes) == BG_OK) own->pinned.push_back(q); return q; };
-    out->n_pairs = N; out->owner_ = own;
-    out->score = (int32_t*)grab(N * 4); out->status = (uint8_t*)grab(N);
-    out->off = (uint64_t*)grab((2 * N + 1) * 8); out->arena = (uint8_t*)grab(total);
-    if (!out->score || !out->status || !out->off || !out->arena) {
-        bg_result_free(out); for (auto& q : parts) bg_result_free(&q);
-        ctx->set_error("pinned host allocation failed"); return BG_ENOMEM;
-    }
-    uint64_t base = 0;
-    for (int d = 0; d < nd; ++d) {
-        bg_result& q = parts[d];
-        const uint64_t lo = bounds[d], cnt = q.n_pairs;
-        if (cnt) {
-            memcpy(out->score + lo, q.score, cnt * 4);
-            memcpy(out->status + lo, q.status, cnt);
-            for (uint64_t s = 0; s < 2 * cnt; ++s) out->off[2 * lo + s] = base + q.off[s];
-            memcpy(out->arena + base, q.arena, q.off[2 * cnt]);
-            base += q.off[2 * cnt];
-        }
-        bg_result_free(&q);
+        base += totals[d];
     }
     out->off[2 * N] = base;
     return BG_OK;
@@ -809,17 +1175,10 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     if (rc) return rc;
     const int nd = (int)ctx->devs.size();
     const std::vector<uint64_t> bounds = shard_bounds(in, nd);
+    ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
     std::vector<int> rcs(nd, BG_OK);
-    auto work = [&](int d) {
-        bg_batch sub; sub.n_pairs = bounds[d + 1] - bounds[d]; sub.residues = in->residues; sub.seq_off = in->seq_off + 2 * bounds[d];
-        bg_dbatch* B = nullptr; bg_dresult* R = nullptr;
-        int r = bg_batch_upload(ctx, d, &sub, &B);
-        if (!r) r = bg_edit_distance_device(ctx, B, &R);
-        if (!r) r = bg_dresult_download_u64(ctx, R, out + bounds[d]);
-        if (R) bg_dresult_free(R);
-        if (B) bg_dbatch_free(B);
-        rcs[d] = r;
-    };
+    auto work = [&](int d) { rcs[d] = edit_pipeline(ctx, d, in, bounds[d], bounds[d + 1], out); };
     if (nd == 1) work(0);
     else {
         std::vector<std::thread> th;

@@ -26,7 +26,7 @@ struct __align__(16) PairDesc {
     uint64_t b_off;      // seq2 bytes
     uint64_t trace_off;  // uint32-word offset of the WARP's trace block
     uint64_t bnd_off;    // int2 offset of this pair's band-boundary column scratch (multi-band only)
-    uint64_t pad_off;    // byte offset of this pair's padded output slot (2 * (n + m) bytes)
+    uint64_t pad_off;    // byte offset (multiple of 4) of this pair's padded output slot, 2 * round_up(n + m, 4) bytes
     uint32_t n, m;       // len1, len2
     uint32_t steps;      // systolic steps per band for this warp = max n in the warp + L - 1
     uint32_t pair_id;    // index in the caller's batch; 0xFFFFFFFF = empty slot

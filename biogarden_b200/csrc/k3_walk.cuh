@@ -8,7 +8,7 @@
 //
 // One thread per pair: the walk is a serial chain of dependent 4-byte loads, so the way to
 // keep the machine busy is many independent walks per SM, not lanes cooperating on one.
-// Characters are produced back to front into a padded slot of 2*(n+m) bytes; k_gather then
+// Characters are produced back to front into a padded slot of 2*round_up(n+m,4) bytes; k_gather then
 // packs all strings densely (offsets from a device-side scan of the lengths).
 #pragma once
 #include "bg_common.cuh"
@@ -42,12 +42,37 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
     const uint32_t lane_base = (slot % (32u / L)) * L;
     const uint8_t* sa = A.residues + d.a_off;
     const uint8_t* sb = A.residues + d.b_off;
+    // Output slot: two regions of cap4 = round_up(n + m, 4) bytes (pad_off is 4-byte aligned), filled back
+    // to front.  Characters are collected in a register and leave as aligned 32-bit stores; residues
+    // are fetched as aligned 32-bit words and cached -- the walk is bound by memory requests, not math.
+    const uint32_t cap4 = (n + m + 3u) & ~3u;
     uint8_t* outA = A.pad + d.pad_off;
-    uint8_t* outB = outA + (n + m);
-    uint32_t pos = n + m;
+    uint8_t* outB = outA + cap4;
+    uint32_t pos = cap4;
+    uint32_t wa = 0, wb = 0;
     const int mode = A.mode;
 
-    auto push = [&](uint8_t x, uint8_t y) { --pos; outA[pos] = x; outB[pos] = y; };
+    auto push = [&](uint32_t x, uint32_t y) {
+        --pos;
+        const uint32_t sh = (pos & 3u) * 8u;
+        wa |= x << sh; wb |= y << sh;
+        if ((pos & 3u) == 0) {
+            *reinterpret_cast<uint32_t*>(outA + pos) = wa;
+            *reinterpret_cast<uint32_t*>(outB + pos) = wb;
+            wa = 0; wb = 0;
+        }
+    };
+    uintptr_t wpa = 0, wpb = 0; uint32_t cwa = 0, cwb = 0;
+    auto res_a = [&](uint32_t idx) -> uint32_t {
+        const uintptr_t q = reinterpret_cast<uintptr_t>(sa + idx), w = q & ~(uintptr_t)3;
+        if (w != wpa) { wpa = w; cwa = __ldg(reinterpret_cast<const uint32_t*>(w)); }
+        return (cwa >> ((q & 3u) * 8u)) & 0xffu;
+    };
+    auto res_b = [&](uint32_t idx) -> uint32_t {
+        const uintptr_t q = reinterpret_cast<uintptr_t>(sb + idx), w = q & ~(uintptr_t)3;
+        if (w != wpb) { wpb = w; cwb = __ldg(reinterpret_cast<const uint32_t*>(w)); }
+        return (cwb >> ((q & 3u) * 8u)) & 0xffu;
+    };
     auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
         const uint32_t j0 = j - 1;
         const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
@@ -60,8 +85,8 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
     uint32_t k = e.k, l = e.l, flags = 0;
     const bool colbr = (e.flags & 1u) != 0;
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
-        if (colbr) { for (uint32_t i = n; i > k; --i) push(sa[i - 1], '-'); }
-        else       { for (uint32_t i = m; i > l; --i) push('-', sb[i - 1]); }
+        if (colbr) { for (uint32_t i = n; i > k; --i) push(res_a(i - 1), '-'); }
+        else       { for (uint32_t i = m; i > l; --i) push('-', res_b(i - 1)); }
     }
     uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
     const uint64_t bound = 2ull * ((uint64_t)n + m) + 8;
@@ -82,24 +107,28 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
         if (cur == 0) {
             uint32_t t;   // m_trace borders: column 0 'X', then row 0 'Y' (aligner.rs:107-108)
             if (l == 0) t = TR_X; else if (k == 0) t = TR_Y; else t = nib & 3u;
-            if (t == TR_R) { push(sa[k - 1], sb[l - 1]); --k; --l; }
-            else if (t == TR_X) { push(sa[k - 1], '-'); --k; cur = 1; }
-            else { push('-', sb[l - 1]); --l; cur = 2; }
+            if (t == TR_R) { push(res_a(k - 1), res_b(l - 1)); --k; --l; }
+            else if (t == TR_X) { push(res_a(k - 1), '-'); --k; cur = 1; }
+            else { push('-', res_b(l - 1)); --l; cur = 2; }
         } else if (cur == 1) {
             if (interior && (nib & TR_XOPEN)) cur = 0;                 // x_trace borders stay 'I' (aligner.rs:52)
             else if (k == 0) { flags |= WALK_UNDERFLOW; break; }      // reference: seq1[usize::MAX] -> panic
-            else { push(sa[k - 1], '-'); --k; }
+            else { push(res_a(k - 1), '-'); --k; }
         } else {
             if (interior && (nib & TR_YOPEN)) cur = 0;
             else if (l == 0) { flags |= WALK_UNDERFLOW; break; }
-            else { push('-', sb[l - 1]); --l; }
+            else { push('-', res_b(l - 1)); --l; }
         }
     }
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
-        if (colbr) { for (uint32_t i = k; i > 0; --i) push(sa[i - 1], '-'); }
-        else       { for (uint32_t i = l; i > 0; --i) push('-', sb[i - 1]); }
+        if (colbr) { for (uint32_t i = k; i > 0; --i) push(res_a(i - 1), '-'); }
+        else       { for (uint32_t i = l; i > 0; --i) push('-', res_b(i - 1)); }
     }
-    const uint32_t len = n + m - pos;
+    if (pos & 3u) {   // flush the partial word (its low bytes lie below the string and are never read)
+        *reinterpret_cast<uint32_t*>(outA + (pos & ~3u)) = wa;
+        *reinterpret_cast<uint32_t*>(outB + (pos & ~3u)) = wb;
+    }
+    const uint32_t len = cap4 - pos;
     A.score[d.pair_id] = e.score;
     A.walk_flags[d.pair_id] = (uint8_t)flags;
     A.lens2[2ull * d.pair_id] = len;
@@ -134,9 +163,9 @@ __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
     if (d.pair_id == 0xFFFFFFFFu) return;
     const uint64_t o0 = A.off[2ull * d.pair_id], o1 = A.off[2ull * d.pair_id + 1];
     const uint32_t len = (uint32_t)(o1 - o0);
-    const uint32_t cap = d.n + d.m;
-    const uint8_t* srcA = A.pad + d.pad_off + (cap - len);
-    const uint8_t* srcB = srcA + cap;
+    const uint32_t cap4 = (d.n + d.m + 3u) & ~3u;
+    const uint8_t* srcA = A.pad + d.pad_off + (cap4 - len);
+    const uint8_t* srcB = srcA + cap4;
     for (uint32_t x = lane; x < len; x += 32) {
         A.arena[o0 + x] = srcA[x];
         A.arena[o1 + x] = srcB[x];

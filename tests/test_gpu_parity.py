@@ -17,7 +17,8 @@ from biogarden_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(32, 2), (32, 4), (32, 5), (32, 8), (32, 12), (32, 16), (16, 10), (8, 19)]
+SHAPES = [(8, 8), (8, 12), (8, 16), (8, 19), (8, 24), (16, 10), (16, 16), (32, 5), (32, 8), (32, 12), (32, 16), (32, 20),
+          (32, 24), (32, 32)]
 
 
 @pytest.fixture(scope="module")
@@ -185,7 +186,7 @@ def test_cfg2_sample_vs_oracle(aligner):
     """BASELINE config #2 shape (150 bp DNA, global, +1/-1, a=-2, b=-1): a 20k-pair prefix of the
     seeded stream against the oracle, digest compare of all strings + exact compare of a few."""
     batch = synth.make("cfg2_dna150_global", n_pairs=20000)
-    for shape in (None, (8, 19), (16, 10)):
+    for shape in (None, (32, 5), (16, 10)):
         if shape:
             aligner.context.set_shape(*shape)
         try:
@@ -197,6 +198,21 @@ def test_cfg2_sample_vs_oracle(aligner):
         assert np.array_equal(eng.score, ora["score"]), "shape %r" % (shape,)
         assert np.all(eng.status == 0)
         assert np.array_equal(_cmp.fnv_pairs(eng), ora["hash"]), "shape %r" % (shape,)
+        eng.close()
+
+
+def test_pipeline_mixed_lengths_multi_chunk(aligner):
+    """Host-buffer path with several pipeline chunks and several length classes per chunk
+    (100-300 bp): every score and every aligned string (digest) against the oracle."""
+    batch = synth.make("cfg3_edit_100_300", n_pairs=60000)
+    for mode, a, b in (("global", -2, -1), ("semiglobal", -1, -1)):
+        eng = _cmp.engine_align(aligner, batch, mode, "unit", a, b)
+        ora = _cmp.oracle_align(batch, mode, "unit", a, b, lean=True, want_strings=False)
+        ok = ora["status"] == orc.OK
+        assert ok.mean() > 0.95
+        assert np.array_equal(eng.score[ok], ora["score"][ok]), mode
+        assert np.array_equal(eng.status == 0, ok), mode
+        assert np.array_equal(_cmp.fnv_pairs(eng)[ok], ora["hash"][ok]), mode
         eng.close()
 
 
