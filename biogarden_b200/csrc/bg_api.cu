@@ -420,11 +420,13 @@ int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_
     pp.n_rows = p->n_rows; pp.n_cols = p->n_cols;
     pp.table.assign(p->table, p->table + (size_t)p->n_rows * p->n_cols);
     int64_t maxabs = std::max<int64_t>(llabs((long long)p->gap_open), llabs((long long)p->gap_extend));
-    bool fits8 = true;
+    bool fits8 = true;   // the packed byte profile holds s - a (k1_fill.cuh)
     for (int32_t v : pp.table) {
         maxabs = std::max<int64_t>(maxabs, llabs((long long)v));
-        if (v < -128 || v > 127) fits8 = false;
+        const int64_t biased = (int64_t)v - p->gap_open;
+        if (biased < -128 || biased > 127) fits8 = false;
     }
+    if (-(int64_t)p->gap_open < -128 || -(int64_t)p->gap_open > 127) fits8 = false;
     // 32-bit safety of the recurrence (bg_common.cuh NEG_INF)
     if (maxabs > (1 << 20) || (int64_t)(max_len_sum + 2) * maxabs >= (1ll << 28)) {
         ctx->set_error("scores * length exceed the 32-bit-safe range"); return BG_EUNSUPPORTED;
@@ -476,7 +478,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     fa.residues = io.residues;
     fa.table = ws.table.as<int32_t>(); fa.n_rows = pp.n_rows; fa.n_cols = pp.n_cols;
     fa.row_code = ws.codes.as<uint8_t>(); fa.col_code = ws.codes.as<uint8_t>() + 256;
-    fa.a = pp.a; fa.b = pp.b; fa.mode = pp.mode; fa.want_trace = pp.score_only ? 0 : 1;
+    fa.a = pp.a; fa.b = pp.b; fa.mode = pp.mode; fa.want_trace = pp.score_only ? 0 : 1; fa.one = 1;
     fa.trace = ws.trace.as<uint32_t>(); fa.bnd = ws.bnd.as<int2>(); fa.end = nullptr; fa.err_flag = ws.err.as<uint32_t>();
 
     for (const LaunchClass& lc : P.classes) {
@@ -714,11 +716,11 @@ void bg_dbatch_free(bg_dbatch* b) {
     delete b;
 }
 
+// Does not synchronise: the blocks go back to the device cache and are only ever handed out again to
+// work that is enqueued behind the current work on work set 0's stream (device-resident calls) or after
+// a full sync (the host-buffer entry points sync all streams first), so stream order protects them.
 void bg_dresult_free(bg_dresult* r) {
     if (!r) return;
-    Device& dv = r->ctx->devs[r->dev_index];
-    cudaSetDevice(dv.ordinal);
-    cudaStreamSynchronize(dv.ws[0].stream);
     for (DevBuf* b : {&r->score, &r->flags, &r->lens2, &r->off, &r->arena, &r->out64}) b->release();
     delete r;
 }
@@ -1124,6 +1126,8 @@ int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_resul
     if (rc) return rc;
     const int nd = (int)ctx->devs.size();
     const std::vector<uint64_t> bounds = shard_bounds(in, nd);
+    rc = bg_sync(ctx);   // cached blocks may still be in use by device-resident work (see bg_dresult_free)
+    if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
     ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
 
@@ -1175,6 +1179,8 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     if (rc) return rc;
     const int nd = (int)ctx->devs.size();
     const std::vector<uint64_t> bounds = shard_bounds(in, nd);
+    rc = bg_sync(ctx);
+    if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
     ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
     std::vector<int> rcs(nd, BG_OK);

@@ -11,11 +11,15 @@ namespace bg {
 // real score could come within 2^28 of it.
 constexpr int32_t NEG_INF = -(1 << 29);
 
-// Direction nibble, one per DP cell: everything backtrack() reads.
-//   bits 1:0  m_trace  0 = 'R', 1 = 'X', 2 = 'Y', 3 = STOP (local mode only: M == 0, which implies 'Y')
-//   bit  2    x_trace == 'M'  (gap in seq2 was opened here; aligner.rs:444)
-//   bit  3    y_trace == 'M'  (aligner.rs:448)
-constexpr uint32_t TR_R = 0, TR_X = 1, TR_Y = 2, TR_STOP = 3, TR_XOPEN = 4, TR_YOPEN = 8;
+// Direction nibble, one per DP cell: everything backtrack() reads, as four
+// independent tie bits so that the fill kernel never needs a select chain:
+//   bit 0  M == X   (aligner.rs:458)      decode of m_trace: bit 1 -> 'Y', else bit 0 -> 'X', else 'R'
+//   bit 1  M == Y   (aligner.rs:455)      (the reference tests Y first, so both bits set means 'Y')
+//   bit 2  x_trace == 'M'  (gap in seq2 was opened here; aligner.rs:444)
+//   bit 3  y_trace == 'M'  (aligner.rs:448)
+// Local mode only: bit 0 is overloaded when bit 1 is set -- it then says M == 0 (STOP), which is all
+// the walk's `m[k][l] > 0` test needs because M == 0 implies m_trace == 'Y' (A.3).
+constexpr uint32_t TR_XEQ = 1, TR_YEQ = 2, TR_XOPEN = 4, TR_YOPEN = 8;
 
 enum Mode : int { M_GLOBAL = 0, M_LOCAL = 1, M_SEMIGLOBAL = 2, M_FITTING = 3, M_OVERLAP = 4 };
 

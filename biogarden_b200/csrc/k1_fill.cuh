@@ -10,9 +10,14 @@
 //   * rows stream through the lanes systolically: at step t lane p computes row t-p, so the
 //     only cross-lane traffic is (M, Y, row residue) of the strip's last column, handed to
 //     lane p+1 with __shfl_up_sync -- no shared-memory round trip on the recurrence;
-//   * per cell the recurrence is the DPX forms VIADDMNMX / VIMNMX3 plus the tie tests that
-//     become the 4-bit direction code (bg_common.cuh); one 32-bit word of codes per lane-step
-//     is written to HBM with a fully coalesced 128-byte warp store (layout in bg_common.cuh);
+//   * per cell the recurrence is the DPX forms VIADDMNMX x2 / VIMNMX3 plus the four tie tests that
+//     become the 4-bit direction code (bg_common.cuh).  The kernel is bound by the SM's ALU pipe
+//     (ncu: 92 % ALU, 15 % FMA in the first version), so everything that can run on the FMA pipe
+//     does: registers hold M + a instead of M (the "+ a" of both gap-open terms disappears and the
+//     diagonal term uses a score table pre-biased by -a), the two remaining adds are IMADs, and every
+//     tie bit is folded into the trace word by a predicated IMAD instead of SEL / IADD3 chains.
+//     One 32-bit word of codes per lane-step and 8 columns is written to HBM with a fully coalesced
+//     128-byte warp store (layout in bg_common.cuh);
 //   * substitution scores: for <= 4-letter row alphabets with |s| <= 127 every column keeps a
 //     packed byte profile in a register and a single PRMT (byte select + sign extend) yields
 //     s(row residue, column residue); otherwise the dense table sits in shared memory.
@@ -38,12 +43,34 @@ struct FillArgs {
     int2* bnd;
     EndCell* end;
     uint32_t* err_flag;        // bit 0: residue without a table row/column
+    int32_t one;               // == 1 at run time; keeps the FMA-pipe adds below as IMADs (see k1_fill)
 };
 
 __device__ __forceinline__ int32_t prmt_sx(uint32_t packed, uint32_t sel) {
     int32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(packed), "r"(0u), "r"(sel));
     return d;
+}
+
+// x * one + y with one == 1 only known at run time: an integer add that ptxas has to issue as IMAD,
+// i.e. on the FMA pipe, which this kernel leaves idle otherwise.
+__device__ __forceinline__ int32_t fma_add(int32_t x, int32_t one, int32_t y) {
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(y));
+    return d;
+}
+// if (x == y) w += bit   -- compare on the ALU pipe, accumulate as a predicated IMAD (w = one*bit + w)
+__device__ __forceinline__ void acc_if_eq(uint32_t& w, int32_t x, int32_t y, int32_t one, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+        : "+r"(w) : "r"(x), "r"(y), "r"(one), "r"(bit));
+}
+// local mode, bit 0: (mx == Y) ? (mx == 0) : (mx == X)
+__device__ __forceinline__ void acc_local_bit0(uint32_t& w, int32_t mx, int32_t X, int32_t Y, int32_t one, uint32_t bit) {
+    asm("{\n\t.reg .pred px, py, pz, p;\n\t"
+        "setp.eq.s32 px, %1, %2;\n\tsetp.eq.s32 py, %1, %3;\n\tsetp.eq.s32 pz, %1, 0;\n\t"
+        "and.pred p, py, pz;\n\t{\n\t.reg .pred q, nq;\n\tnot.pred nq, py;\n\tand.pred q, nq, px;\n\tor.pred p, p, q;\n\t}\n\t"
+        "@p mad.lo.u32 %0, %4, %5, %0;\n\t}"
+        : "+r"(w) : "r"(mx), "r"(X), "r"(Y), "r"(one), "r"(bit));
 }
 
 // M[0][j] and M[i][0].
@@ -54,8 +81,10 @@ __device__ __forceinline__ int32_t border_col(bool col_gap, int32_t a, int32_t b
     return (col_gap && i > 0) ? a + (int32_t)(i - 1) * b : 0;
 }
 
+// Register budget: the recurrence is a dependent chain (Y -> M -> M+a -> next Y), so the kernel needs
+// >= 4 warps per scheduler to keep the ALU pipe fed (ncu: 3 warps/scheduler left it 29 % idle).
 template <int L, int C, bool IS_LOCAL, bool PROF4>
-__global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
+__global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs A) {
     constexpr int G = 32 / L;
     constexpr int K = (C + 7) / 8;
     constexpr unsigned FULL = 0xffffffffu;
@@ -64,11 +93,12 @@ __global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
     uint8_t* s_col = smem_raw + 256;      // [256]
     int32_t* s_tab = reinterpret_cast<int32_t*>(smem_raw + 512);   // n_rows x (n_cols + 1), last column = 0 (padding)
 
+    // The table is stored pre-biased by -a: registers carry M + a, so diag + (s - a) = M[i-1][j-1] + s.
     const int ncol1 = A.n_cols + 1;
     for (int x = threadIdx.x; x < 256; x += blockDim.x) { s_row[x] = A.row_code[x]; s_col[x] = A.col_code[x]; }
     for (int x = threadIdx.x; x < A.n_rows * ncol1; x += blockDim.x) {
         const int r = x / ncol1, c = x - r * ncol1;
-        s_tab[x] = (c < A.n_cols) ? A.table[r * A.n_cols + c] : 0;
+        s_tab[x] = ((c < A.n_cols) ? A.table[r * A.n_cols + c] : 0) - A.a;
     }
     __syncthreads();
 
@@ -87,7 +117,7 @@ __global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
     const uint32_t steps_w = __reduce_max_sync(FULL, has_pair ? d.steps : 0u);
     const uint32_t nbands_w = __reduce_max_sync(FULL, my_nbands);
 
-    const int32_t a = A.a, b = A.b;
+    const int32_t a = A.a, b = A.b, one = A.one;
     const int mode = A.mode;
     const bool row_gap = (mode == M_GLOBAL || mode == M_FITTING);
     const bool col_gap = (mode == M_GLOBAL);
@@ -118,9 +148,10 @@ __global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
         const bool lane_has_cols = band_on && jbase < m;
         const bool last_band_for_pair = (bd + 1 == my_nbands);
 
-        // per-column constants: packed score profile (PROF4) or byte offset of the table column
+        // per-column constants: packed (biased) score profile (PROF4) or byte offset of the table column;
+        // per-column state: MuA = M[i-1][j] + a, Xu = X[i-1][j]
         uint32_t cprof[C];
-        int32_t Mu[C], Xu[C];
+        int32_t MuA[C], Xu[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const uint32_t j0 = jbase + c;
@@ -133,18 +164,18 @@ __global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
                 uint32_t pk = 0;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const int32_t sv = (r < A.n_rows) ? s_tab[r * ncol1 + code] : 0;
+                    const int32_t sv = (r < A.n_rows) ? s_tab[r * ncol1 + code] : -a;
                     pk |= ((uint32_t)sv & 0xffu) << (8 * r);
                 }
                 cprof[c] = pk;
             } else {
                 cprof[c] = code * 4u;
             }
-            Mu[c] = border_row(row_gap, a, b, j0 + 1);
+            MuA[c] = border_row(row_gap, a, b, j0 + 1) + a;
             Xu[c] = NEG_INF;
         }
-        int32_t Mdiag = border_row(row_gap, a, b, jbase);
-        int32_t Mlast = 0, Ylast = NEG_INF;
+        int32_t MdiagA = border_row(row_gap, a, b, jbase) + a;
+        int32_t MlastA = a, Ylast = NEG_INF;
         uint32_t rcur = 0;
 
         // row residues: each lane of the group fetches one every L steps, lane 0 consumes one per step
@@ -158,28 +189,28 @@ __global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
             return cd;
         };
         uint32_t cur_blk = 0, next_blk = load_rows(0);
-        int2 bnd_in = make_int2(0, NEG_INF);
+        int2 bnd_in = make_int2(a, NEG_INF);
         if (bd > 0 && p == 0 && band_on && n > 0) bnd_in = __ldcg(A.bnd + d.bnd_off);
 
         for (uint32_t t = 0; t < steps_w; ++t) {
             if ((t & (L - 1)) == 0) { cur_blk = next_blk; next_blk = load_rows(t + L); }
             const uint32_t r0 = __shfl_sync(FULL, cur_blk, (int)(t & (L - 1)), L);
-            int32_t Ml = __shfl_up_sync(FULL, Mlast, 1, L);
+            int32_t MlA = __shfl_up_sync(FULL, MlastA, 1, L);
             int32_t Yl = __shfl_up_sync(FULL, Ylast, 1, L);
             uint32_t r = __shfl_up_sync(FULL, rcur, 1, L);
             const uint32_t i0 = t - (uint32_t)p;          // 0-based row; wraps (inactive) while t < p
             const bool active = band_on && i0 < n;
             if (p == 0) {
                 r = r0;
-                if (bd == 0) { Ml = border_col(col_gap, a, b, i0 + 1); Yl = NEG_INF; }
+                if (bd == 0) { MlA = border_col(col_gap, a, b, i0 + 1) + a; Yl = NEG_INF; }
                 else {
-                    Ml = bnd_in.x; Yl = bnd_in.y;
+                    MlA = bnd_in.x; Yl = bnd_in.y;
                     if (band_on && i0 + 1 < n) bnd_in = __ldcg(A.bnd + d.bnd_off + i0 + 1);
                 }
             }
             rcur = r;
             if (active) {
-                int32_t diag = Mdiag, left = Ml, Y = Yl;
+                int32_t diagA = MdiagA, leftA = MlA, Y = Yl;
                 uint32_t w[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) w[k] = 0;
@@ -188,54 +219,57 @@ __global__ void __launch_bounds__(128) k1_fill(const FillArgs A) {
                 else rowp = reinterpret_cast<const unsigned char*>(s_tab) + r * (uint32_t)(ncol1 * 4);
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const int32_t up = Mu[c];
-                    // aligner.rs:443-444 / 477-480
-                    const int32_t xo = up + a;
-                    int32_t X = __viaddmax_s32(Xu[c], b, xo);
-                    uint32_t nib = (X == xo) ? TR_XOPEN : 0u;
-                    // aligner.rs:447-448 / 483-486
-                    const int32_t yo = left + a;
-                    Y = __viaddmax_s32(Y, b, yo);
-                    nib |= (Y == yo) ? TR_YOPEN : 0u;
+                    uint32_t& wk = w[c >> 3];
+                    const uint32_t sh = 4u * (c & 7);
+                    const int32_t upA = MuA[c];
+                    // aligner.rs:443-444 / 477-480: xo = M[i-1][j] + a is the register itself
+                    int32_t X = __viaddmax_s32(Xu[c], b, upA);
+                    acc_if_eq(wk, X, upA, one, TR_XOPEN << sh);
+                    // aligner.rs:447-448 / 483-486: yo = M[i][j-1] + a likewise
+                    Y = __viaddmax_s32(Y, b, leftA);
+                    acc_if_eq(wk, Y, leftA, one, TR_YOPEN << sh);
                     if (IS_LOCAL) { X = max(X, 0); Y = max(Y, 0); }
                     // aligner.rs:451-466 / 489-506
-                    int32_t s;
-                    if (PROF4) s = prmt_sx(cprof[c], sel);
-                    else s = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
-                    const int32_t mx = __vimax3_s32(diag + s, X, Y);
-                    uint32_t code = (mx == Y) ? TR_Y : ((mx == X) ? TR_X : TR_R);
+                    int32_t sb_;   // s - a
+                    if (PROF4) sb_ = prmt_sx(cprof[c], sel);
+                    else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
+                    const int32_t mx = __vimax3_s32(fma_add(diagA, one, sb_), X, Y);
+                    acc_if_eq(wk, mx, Y, one, TR_YEQ << sh);
                     if (IS_LOCAL) {
-                        if (mx == 0) code = TR_STOP;      // mx >= 0 here; M == 0 implies m_trace == 'Y' (A.3)
+                        acc_local_bit0(wk, mx, X, Y, one, TR_XEQ << sh);   // STOP when M == 0 (A.3)
                         if (mx > best) { best = mx; bi = i0 + 1; bj = jbase + c + 1; }
+                    } else {
+                        acc_if_eq(wk, mx, X, one, TR_XEQ << sh);
                     }
-                    nib |= code;
-                    w[c >> 3] |= nib << (4 * (c & 7));
-                    diag = up; left = mx;
-                    Mu[c] = mx; Xu[c] = X;
+                    const int32_t mxA = fma_add(mx, one, a);
+                    diagA = upA; leftA = mxA;
+                    MuA[c] = mxA; Xu[c] = X;
                 }
-                Mlast = left; Ylast = Y; Mdiag = Ml;
+                MlastA = leftA; Ylast = Y; MdiagA = MlA;
                 if (A.want_trace && lane_has_cols) {
                     uint32_t* tp = A.trace + d.trace_off + ((uint64_t)(bd * d.steps + t) * K) * 32u + lane;
 #pragma unroll
                     for (int k = 0; k < K; ++k) tp[k * 32] = w[k];
                 }
                 if (track_col && bd == bd_m) {
-                    int32_t v = Mu[0];
+                    int32_t v = MuA[0];
 #pragma unroll
-                    for (int c = 1; c < C; ++c) v = (c_m == (uint32_t)c) ? Mu[c] : v;
+                    for (int c = 1; c < C; ++c) v = (c_m == (uint32_t)c) ? MuA[c] : v;
+                    v -= a;
                     if (col_lane && v > cbest) { cbest = v; ci = i0 + 1; }
                 }
-                if (p == L - 1 && !last_band_for_pair) A.bnd[d.bnd_off + i0] = make_int2(Mlast, Ylast);
+                if (p == L - 1 && !last_band_for_pair) A.bnd[d.bnd_off + i0] = make_int2(MlastA, Ylast);
             }
         }
-        // Mu[] now holds row n of this band (row 0 borders if n == 0)
+        // MuA[] now holds row n of this band, biased by a (row 0 borders if n == 0)
         if (band_on) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const uint32_t j = jbase + c + 1;
+                const int32_t v = MuA[c] - a;
                 if (j <= m) {
-                    if (track_row && Mu[c] >= rbest) { rbest = Mu[c]; rj = j; }
-                    if (j == m) corner = Mu[c];
+                    if (track_row && v >= rbest) { rbest = v; rj = j; }
+                    if (j == m) corner = v;
                 }
             }
         }

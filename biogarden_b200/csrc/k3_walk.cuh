@@ -99,16 +99,16 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
         bool valid;
         switch (mode) {
             case M_GLOBAL: valid = (k != 0 || l != 0); break;                                   // aligner.rs:117
-            case M_LOCAL: valid = interior && (nib & 3u) != TR_STOP; break;                     // aligner.rs:181 (borders are 0)
+            case M_LOCAL: valid = interior && (nib & 3u) != 3u; break;                          // aligner.rs:181 (borders are 0)
             case M_SEMIGLOBAL: valid = interior; break;                                         // aligner.rs:409
             default: valid = (l != 0); break;                                                 // aligner.rs:256,317
         }
         if (!valid) break;
         if (cur == 0) {
-            uint32_t t;   // m_trace borders: column 0 'X', then row 0 'Y' (aligner.rs:107-108)
-            if (l == 0) t = TR_X; else if (k == 0) t = TR_Y; else t = nib & 3u;
-            if (t == TR_R) { push(res_a(k - 1), res_b(l - 1)); --k; --l; }
-            else if (t == TR_X) { push(res_a(k - 1), '-'); --k; cur = 1; }
+            uint32_t t;   // 0 'R', 1 'X', 2 'Y'; m_trace borders: column 0 'X', then row 0 'Y' (aligner.rs:107-108)
+            if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib & TR_YEQ) ? 2u : (nib & TR_XEQ);
+            if (t == 0) { push(res_a(k - 1), res_b(l - 1)); --k; --l; }
+            else if (t == 1) { push(res_a(k - 1), '-'); --k; cur = 1; }
             else { push('-', res_b(l - 1)); --l; cur = 2; }
         } else if (cur == 1) {
             if (interior && (nib & TR_XOPEN)) cur = 0;                 // x_trace borders stay 'I' (aligner.rs:52)
