@@ -29,6 +29,7 @@
 
 #include "bg_common.cuh"
 #include "k1_fill.cuh"
+#include "k2_wave.cuh"
 #include "k3_walk.cuh"
 #include "k4_edit.cuh"
 
@@ -53,6 +54,9 @@ struct Shape { int L, C; };
     X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 5) X(32, 8) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
 constexpr int MAX_SHAPES = 16;
 constexpr int PIPE_DEPTH = 3;
+// Pairs wider than this run on K2 (one pair per thread-block cluster, bands of 32 * WAVE_C columns).
+constexpr uint32_t WAVE_MIN_COLS = 4096;
+constexpr int WAVE_C = 16;
 
 // Size-keyed free lists so that steady-state calls never hit cudaMalloc / cudaFree / cudaHostAlloc
 // (each of which synchronises the device or pins pages: milliseconds to 100s of milliseconds).
@@ -128,12 +132,14 @@ struct PinBuf {   // pinned host block from the global cache
 };
 
 struct Chunk { uint32_t slot_begin, slot_end; uint64_t trace_words; };
-struct LaunchClass { Shape sh; std::vector<Chunk> chunks; };
+struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; };
 
 struct Plan {
     std::vector<LaunchClass> classes;
     size_t n_slots = 0;
     uint64_t max_trace_words = 0, bnd_elems = 0, pad_bytes = 0, cells = 0, total_trace_words = 0;
+    uint64_t max_wave_slots = 0;      // largest K2 launch (slots), for the progress / candidate scratch
+    int max_Q = 1;
     uint32_t max_n = 0, max_m = 0;
     bool built = false;
 };
@@ -145,7 +151,7 @@ struct WorkSet {
     int ordinal = 0;
     cudaStream_t stream = nullptr;
     BlockCache* cache = nullptr;
-    DevBuf trace, end, bnd, pad, table, codes, err, cubtmp;             // scratch + parameters
+    DevBuf trace, end, bnd, pad, table, codes, err, cubtmp, progress, cand;   // scratch + parameters
     DevBuf residues, desc, score, flags, lens2, off, arena, out64;     // pipeline mode: chunk in / out
     PinBuf stage;                                                     // descriptor staging
     PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
@@ -159,7 +165,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64};
+        return {&trace, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64};
     }
 };
 
@@ -264,7 +270,7 @@ size_t plan_desc_capacity(uint64_t n_pairs) { return (size_t)n_pairs + 4 * MAX_S
 // `dst` (capacity plan_desc_capacity(n_pairs)).  with_trace: trace blocks are laid out and the
 // launches are cut into chunks that fit the trace budget.
 int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs, bool with_trace,
-               uint64_t budget_words, Plan& P, PairDesc* dst) {
+               uint64_t budget_words, uint64_t wave_budget_words, Plan& P, PairDesc* dst) {
     P = Plan();
     if (n_pairs >= 0xFFFFFFF0ull) { ctx->set_error("too many pairs in one device batch"); return BG_EINVAL_ARG; }
     Shape shapes[MAX_SHAPES];
@@ -272,6 +278,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
 #define X(L_, C_) shapes[nshape++] = Shape{L_, C_};
     BG_SHAPES(X)
 #undef X
+    const int wave_si = nshape;               // pseudo class: K2 wavefront (alignment only)
+    shapes[nshape++] = Shape{32, WAVE_C};
     // pass 1: class of every pair
     std::vector<uint8_t> cls(n_pairs);
     size_t count[MAX_SHAPES] = {0};
@@ -280,7 +288,9 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const uint64_t n = off[2 * p + 1] - off[2 * p], m = off[2 * p + 2] - off[2 * p + 1];
         if (n > 0x7FFFFFF0ull || m > 0x7FFFFFF0ull) { ctx->set_error("sequence longer than 2^31"); return BG_EUNSUPPORTED; }
         if ((uint32_t)m != last_m) {
-            last_m = (uint32_t)m; last_si = shape_index(pick_shape(ctx, last_m));
+            last_m = (uint32_t)m;
+            if (with_trace && m > WAVE_MIN_COLS && !ctx->force_L) last_si = wave_si;
+            else last_si = shape_index(pick_shape(ctx, last_m));
             if (last_si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
         }
         cls[p] = (uint8_t)last_si; count[last_si]++;
@@ -304,7 +314,9 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         uint32_t* cid = ids.data() + start[si];
         const size_t cn = count[si];
         const Shape sh = shapes[si];
+        const bool wave = (si == wave_si);
         const uint32_t G = 32 / sh.L, K = words_per_lane_step(sh.C), band_cols = sh.L * sh.C;
+        const uint64_t class_budget = wave ? wave_budget_words : budget_words;
         auto len_n = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 1] - off[2 * (uint64_t)id]); };
         auto len_m = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
         // longest first so that the lane groups of a warp and the warps of a wave carry similar work;
@@ -313,9 +325,28 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const uint32_t n0 = len_n(cid[0]);
         for (size_t k = 1; k < cn; ++k) if (len_n(cid[k]) != n0) { uniform = false; break; }
         if (!uniform) {
-            std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) { return len_n(x) > len_n(y); });
+            uint32_t nmin = n0, nmax = n0;
+            for (size_t k = 1; k < cn; ++k) { const uint32_t v = len_n(cid[k]); nmin = std::min(nmin, v); nmax = std::max(nmax, v); }
+            const uint64_t range = (uint64_t)nmax - nmin + 1;
+            if (range <= (1u << 22) && range <= 4 * cn + 1024) {
+                // stable counting sort, descending by row count (a comparison sort of 10^6 ids costs more
+                // than the GPU needs for the whole chunk)
+                std::vector<uint32_t> cnt(range + 1, 0), tmp(cid, cid + cn);
+                for (size_t k = 0; k < cn; ++k) cnt[nmax - len_n(tmp[k]) + 1]++;
+                for (uint64_t r = 0; r < range; ++r) cnt[r + 1] += cnt[r];
+                for (size_t k = 0; k < cn; ++k) cid[cnt[nmax - len_n(tmp[k])]++] = tmp[k];
+            } else {
+                std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) { return len_n(x) > len_n(y); });
+            }
         }
-        LaunchClass lc; lc.sh = sh;
+        LaunchClass lc; lc.sh = sh; lc.wave = wave;
+        if (wave) {   // CTAs per pair: enough workers (16 warps per CTA) for the widest pair's bands
+            uint32_t maxb = 0;
+            for (size_t k = 0; k < cn; ++k) maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
+            lc.Q = maxb > 64 ? 8 : maxb > 32 ? 4 : maxb > 16 ? 2 : 1;
+            P.max_Q = std::max(P.max_Q, lc.Q);
+        }
+        const uint64_t ring = wave ? (uint64_t)lc.Q * K2_WARPS + 1 : 1;
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
         const size_t nwarps = (cn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
@@ -328,10 +359,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             }
             const uint32_t steps = maxn + sh.L - 1;
             const uint64_t warp_words = with_trace ? (uint64_t)maxb * steps * K * 32ull : 0;
-            if (with_trace && ch.trace_words > 0 && ch.trace_words + warp_words > budget_words) {
+            if (with_trace && ch.trace_words > 0 && ch.trace_words + warp_words > class_budget) {
                 ch.slot_end = (uint32_t)nd;
                 lc.chunks.push_back(ch);
                 P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
+                if (wave) P.max_wave_slots = std::max<uint64_t>(P.max_wave_slots, ch.slot_end - ch.slot_begin);
                 ch.slot_begin = ch.slot_end; ch.trace_words = 0;
             }
             for (uint32_t gidx = 0; gidx < G; ++gidx) {
@@ -346,7 +378,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     d.nbands = (d.m + band_cols - 1) / band_cols;
                     d.pair_id = (uint32_t)id;
                     d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull);
-                    if (d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }
+                    if (wave) { d.bnd_off = bnd_off; bnd_off += ring * (((uint64_t)d.n + 31ull) & ~31ull); }
+                    else if (d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }
                 }
             }
             ch.trace_words += warp_words;
@@ -355,6 +388,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         ch.slot_end = (uint32_t)nd;
         lc.chunks.push_back(ch);
         P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
+        if (wave) P.max_wave_slots = std::max<uint64_t>(P.max_wave_slots, ch.slot_end - ch.slot_begin);
         P.classes.push_back(lc);
     }
     P.n_slots = nd;
@@ -378,6 +412,23 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
 #define X(L_, C_) if (sh.L == L_ && sh.C == C_) { launch_k1<L_, C_>(local, prof4, grid, smem, st, a); return; }
     BG_SHAPES(X)
 #undef X
+}
+cudaError_t launch_k2(bool local, bool prof4, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_slots * (unsigned)Q);
+    cfg.blockDim = dim3(K2_WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)Q; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (local) {
+        if (prof4) return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, true, true>, a);
+        return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, true, false>, a);
+    }
+    if (prof4) return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, false, true>, a);
+    return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, false, false>, a);
 }
 void dispatch_k4(Shape sh, dim3 grid, cudaStream_t st, const EditArgs& a) {
 #define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k4_edit<L_, C_><<<grid, 128, 0, st>>>(a); return; }
@@ -469,6 +520,10 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
         ok = ok && ws.trace.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4);
         ok = ok && ws.pad.ensure(std::max<uint64_t>(1, P.pad_bytes));
     }
+    if (P.max_wave_slots) {
+        const uint64_t nw = (uint64_t)P.max_Q * K2_WARPS;
+        ok = ok && ws.progress.ensure(P.max_wave_slots * (nw + 1) * 8) && ws.cand.ensure(P.max_wave_slots * nw * sizeof(WaveCand));
+    }
     if (!ok) { ctx->set_error("device allocation failed (trace / scratch buffers)"); return BG_ENOMEM; }
     cudaStream_t st = ws.stream;
     if (!pp.score_only) CU_TRY(ctx, cudaMemsetAsync(io.lens2, 0, (2 * N + 1) * 8, st));
@@ -490,7 +545,13 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             fa.end = ws.end.as<EndCell>() + ch.slot_begin;
             fa.n_slots = ns;
             const uint32_t nwarps = (ns + G - 1) / G;
-            {
+            if (lc.wave) {
+                const uint64_t nw = (uint64_t)lc.Q * K2_WARPS;
+                CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, (uint64_t)ns * (nw + 1) * 8, st));
+                WaveArgs wa; wa.f = fa; wa.progress = ws.progress.as<unsigned long long>(); wa.cand = ws.cand.as<WaveCand>(); wa.Q = lc.Q;
+                Phase ph(ws, 1);
+                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ns, lc.Q, pp.smem, st, wa));
+            } else {
                 Phase ph(ws, 1);
                 dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, st, fa);
             }
@@ -735,7 +796,9 @@ static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit) {
     const size_t cap = plan_desc_capacity(B->n_pairs);
     PinBuf stage;
     if (!stage.ensure(cap * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
-    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, ctx->trace_budget_words, P, stage.as<PairDesc>());
+    // long pairs (K2) need whole traces of several GB each: let them use most of the device
+    const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
+    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, ctx->trace_budget_words, wave_budget, P, stage.as<PairDesc>());
     if (rc) { stage.release(); return rc; }
     if (P.n_slots) {
         if (!D.ensure(P.n_slots * sizeof(PairDesc))) { stage.release(); ctx->set_error("device allocation for descriptors failed"); return BG_ENOMEM; }
@@ -955,9 +1018,15 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
     const uint64_t* off = in->seq_off;
-    const std::vector<uint64_t> cb = chunk_bounds(off, lo, hi);
+    // Batches with long pairs (K2 class) are not cut into pipeline chunks: their traces take GBs per
+    // pair, the copies are negligible next to the fill, and every launch should see as many pairs as
+    // memory allows.  Everything else flows through the 3-deep chunk pipeline.
+    bool long_mode = false;
+    for (uint64_t q = lo; q < hi && !long_mode; ++q) long_mode = (off[2 * q + 2] - off[2 * q + 1]) > WAVE_MIN_COLS;
+    std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds(off, lo, hi);
     const int nchunks = (int)cb.size() - 1;
-    const uint64_t ws_budget = std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
+    const uint64_t ws_budget = long_mode ? ctx->trace_budget_words : std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
+    const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
     struct Fly { bool active = false; uint64_t c_lo = 0, c_n = 0; Plan plan; };
     Fly fly[PIPE_DEPTH];
     uint64_t arena_base = 0;
@@ -1000,7 +1069,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         const uint64_t rel = f.c_lo - lo;
         // plan on the host, straight into pinned staging
         if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
-        int rc = build_plan(ctx, off + 2 * f.c_lo, base, n, !pp.score_only, ws_budget, f.plan, ws.stage.as<PairDesc>());
+        int rc = build_plan(ctx, off + 2 * f.c_lo, base, n, !pp.score_only, ws_budget, wave_budget, f.plan, ws.stage.as<PairDesc>());
         if (rc) return rc;
         const Plan& P = f.plan;
         bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
@@ -1080,7 +1149,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
         const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
         if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !host_out[s].ensure(n * 8)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
-        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, plans[s], ws.stage.as<PairDesc>());
+        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, 0, plans[s], ws.stage.as<PairDesc>());
         if (rc_all) break;
         const Plan& P = plans[s];
         if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(n * 8)) {

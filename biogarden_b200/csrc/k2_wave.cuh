@@ -1,0 +1,315 @@
+// k2_wave.cuh -- K2: intra-sequence wavefront fill for long pairs (>= several kbp) on sm_100a.
+//
+// Same recurrence, same cell code and same trace layout as K1 (k1_fill.cuh), but ONE pair is spread
+// over all warps of a thread-block CLUSTER instead of living in one warp:
+//   * the columns are cut into bands of 32*C; band b is owned by worker (b mod NW), a worker being one
+//     warp of one CTA of the cluster (NW = cluster size * warps per CTA, up to 8 x 16 = 128);
+//   * inside a band the 32 lanes run the K1 systolic schedule over all rows;
+//   * band b+1 consumes the last column (M + a, Y) of band b: the producer's lane 31 values are
+//     collected across 32 steps with shuffles and written as one coalesced 256-byte block to a ring
+//     of NW+1 boundary columns in global memory, then a per-boundary progress counter is bumped;
+//     the consumer waits on that counter once per 32 rows and fetches the block with one coalesced
+//     load.  Adjacent bands therefore run 64 rows apart: the anti-diagonal wavefront of the north
+//     star, at band granularity, with the diagonal tiles staged through registers / L2;
+//   * cluster launch guarantees all workers of a pair are co-resident, so the spin waits cannot
+//     deadlock; end-cell candidates of the workers are merged after a cluster barrier.
+// The walk (K3) reads the trace exactly as for K1 with L = 32.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "bg_common.cuh"
+#include "k1_fill.cuh"
+
+namespace bg {
+
+struct WaveCand {          // one worker's end-cell candidates (SURVEY A.5 tie rules applied when merged)
+    int32_t best; uint32_t bi, bj;        // local
+    int32_t rbest; uint32_t rj;           // last row, last max
+    int32_t cbest; uint32_t ci;           // last column, first max (valid iff has_col)
+    int32_t corner;                       // M[n][m] (valid iff has_col)
+    uint32_t has_col;
+    uint32_t pad_[7];
+};
+static_assert(sizeof(WaveCand) == 64, "WaveCand layout");
+
+struct WaveArgs {
+    FillArgs f;
+    unsigned long long* progress;   // [slot][NW + 1], zeroed before launch
+    WaveCand* cand;                 // [slot][NW]
+    int32_t Q;                      // CTAs per cluster (= per pair)
+};
+
+constexpr int K2_WARPS = 16;        // warps per CTA
+
+template <int C, bool IS_LOCAL, bool PROF4>
+__global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
+    namespace cg = cooperative_groups;
+    constexpr int L = 32;
+    constexpr int K = (C + 7) / 8;
+    constexpr unsigned FULL = 0xffffffffu;
+    const FillArgs& A = W.f;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t* s_row = smem_raw;
+    uint8_t* s_col = smem_raw + 256;
+    int32_t* s_tab = reinterpret_cast<int32_t*>(smem_raw + 512);
+    const int ncol1 = A.n_cols + 1;
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) { s_row[x] = A.row_code[x]; s_col[x] = A.col_code[x]; }
+    for (int x = threadIdx.x; x < A.n_rows * ncol1; x += blockDim.x) {
+        const int r = x / ncol1, c = x - r * ncol1;
+        s_tab[x] = ((c < A.n_cols) ? A.table[r * A.n_cols + c] : 0) - A.a;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, p = lane;
+    const uint32_t Q = (uint32_t)W.Q, NW = Q * K2_WARPS, R = NW + 1;
+    const uint32_t slot = blockIdx.x / Q, cta_rank = blockIdx.x % Q;
+    const uint32_t wk = cta_rank * K2_WARPS + (threadIdx.x >> 5);
+    const PairDesc d = A.desc[slot];
+    const uint32_t n = d.n, m = d.m, nbands = d.nbands, steps = d.steps;
+    const uint32_t n_pad = (n + 31u) & ~31u;
+    const int32_t a = A.a, b = A.b, one = A.one;
+    const int mode = A.mode;
+    const bool row_gap = (mode == M_GLOBAL || mode == M_FITTING);
+    const bool col_gap = (mode == M_GLOBAL);
+    const bool track_col = (mode == M_SEMIGLOBAL || mode == M_FITTING);
+    const bool track_row = (mode == M_SEMIGLOBAL || mode == M_OVERLAP);
+    const uint8_t* sa = A.residues + d.a_off;
+    const uint8_t* sb = A.residues + d.b_off;
+    bool bad_residue = false;
+
+    const uint32_t band_cols = (uint32_t)(L * C);
+    const uint32_t mcol0 = m ? m - 1 : 0;
+    const uint32_t bd_m = mcol0 / band_cols;
+    const uint32_t p_m = (mcol0 % band_cols) / C;
+    const uint32_t c_m = mcol0 % C;
+    const bool col_lane = (m > 0) && ((uint32_t)p == p_m);
+
+    int32_t best = 0; uint32_t bi = 0, bj = 0;
+    int32_t rbest = INT32_MIN; uint32_t rj = 0;
+    int32_t cbest = border_row(row_gap, a, b, m); uint32_t ci = 0;
+    int32_t corner = border_col(col_gap, a, b, n);
+    uint32_t has_col = 0;
+    if (wk == 0 && p == 0) { rbest = border_col(col_gap, a, b, n); rj = 0; }   // row n, column 0 candidate
+
+    int2* const ring = A.bnd + d.bnd_off;
+    volatile unsigned long long* const prog = W.progress + (uint64_t)slot * R;
+
+    for (uint32_t bd = wk; bd < nbands; bd += NW) {
+        const uint32_t jbase = bd * band_cols + (uint32_t)p * C;
+        const bool lane_has_cols = jbase < m;
+        const bool has_next = (bd + 1 < nbands);
+        const int2* bnd_rd = ring + (uint64_t)((bd + R - 1) % R) * n_pad;
+        int2* bnd_wr = ring + (uint64_t)(bd % R) * n_pad;
+        const unsigned long long rd_base = (unsigned long long)(bd - 1) * (n + 1ull);   // unused for bd == 0
+        const unsigned long long wr_base = (unsigned long long)bd * (n + 1ull);
+
+        uint32_t cprof[C];
+        int32_t MuA[C], Xu[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const uint32_t j0 = jbase + c;
+            uint32_t code = (uint32_t)A.n_cols;
+            if (j0 < m) {
+                code = s_col[sb[j0]];
+                if (code == 0xFFu) { bad_residue = true; code = 0; }
+            }
+            if (PROF4) {
+                uint32_t pk = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int32_t sv = (r < A.n_rows) ? s_tab[r * ncol1 + code] : -a;
+                    pk |= ((uint32_t)sv & 0xffu) << (8 * r);
+                }
+                cprof[c] = pk;
+            } else {
+                cprof[c] = code * 4u;
+            }
+            MuA[c] = border_row(row_gap, a, b, j0 + 1) + a;
+            Xu[c] = NEG_INF;
+        }
+        int32_t MdiagA = border_row(row_gap, a, b, jbase) + a;
+        int32_t MlastA = a, Ylast = NEG_INF;
+        uint32_t rcur = 0;
+        uint32_t cur_blk = 0;
+        int2 in_blk = make_int2(a, NEG_INF);    // boundary rows [t0, t0+32) of the band to the left
+        int2 out_blk = make_int2(0, 0);         // this band's last column, rows collected over 32 steps
+
+        for (uint32_t t = 0; t < steps; ++t) {
+            const uint32_t tq = t & 31u;
+            if (tq == 0) {
+                // row residues of the next 32 rows
+                {
+                    const uint32_t idx = t + (uint32_t)p;
+                    uint32_t cd = 0;
+                    if (idx < n) { cd = s_row[sa[idx]]; if (cd == 0xFFu) { bad_residue = true; cd = 0; } }
+                    cur_blk = cd;
+                }
+                if (bd > 0) {
+                    // wait until the left band has published rows [t, t+32)
+                    const unsigned long long need = rd_base + (unsigned long long)min(t + 32u, n);
+                    if (lane == 0 && t < n) {
+                        unsigned ns = 32;
+                        while (prog[(bd + R - 1) % R] < need) { __nanosleep(ns); if (ns < 1024) ns *= 2; }
+                    }
+                    __syncwarp();
+                    __threadfence();
+                    const uint32_t row = t + (uint32_t)lane;
+                    in_blk = (row < n) ? __ldcg(bnd_rd + row) : make_int2(a, NEG_INF);
+                }
+            }
+            const uint32_t r0 = __shfl_sync(FULL, cur_blk, (int)tq);
+            const int32_t inM = __shfl_sync(FULL, in_blk.x, (int)tq);
+            const int32_t inY = __shfl_sync(FULL, in_blk.y, (int)tq);
+            int32_t MlA = __shfl_up_sync(FULL, MlastA, 1);
+            int32_t Yl = __shfl_up_sync(FULL, Ylast, 1);
+            uint32_t r = __shfl_up_sync(FULL, rcur, 1);
+            const uint32_t i0 = t - (uint32_t)p;
+            const bool active = i0 < n;
+            if (p == 0) {
+                r = r0;
+                if (bd == 0) { MlA = border_col(col_gap, a, b, i0 + 1) + a; Yl = NEG_INF; }
+                else { MlA = inM; Yl = inY; }
+            }
+            rcur = r;
+            if (active) {
+                int32_t diagA = MdiagA, leftA = MlA, Y = Yl;
+                uint32_t w[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) w[k] = 0;
+                uint32_t sel; const unsigned char* rowp;
+                if (PROF4) sel = r * 0x1111u + 0x8880u;
+                else rowp = reinterpret_cast<const unsigned char*>(s_tab) + r * (uint32_t)(ncol1 * 4);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    uint32_t& wk_ = w[c >> 3];
+                    const uint32_t sh = 4u * (c & 7);
+                    const int32_t upA = MuA[c];
+                    int32_t X = __viaddmax_s32(Xu[c], b, upA);
+                    acc_if_eq(wk_, X, upA, one, TR_XOPEN << sh);
+                    Y = __viaddmax_s32(Y, b, leftA);
+                    acc_if_eq(wk_, Y, leftA, one, TR_YOPEN << sh);
+                    if (IS_LOCAL) { X = max(X, 0); Y = max(Y, 0); }
+                    int32_t sb_;
+                    if (PROF4) sb_ = prmt_sx(cprof[c], sel);
+                    else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
+                    const int32_t mx = __vimax3_s32(fma_add(diagA, one, sb_), X, Y);
+                    acc_if_eq(wk_, mx, Y, one, TR_YEQ << sh);
+                    if (IS_LOCAL) {
+                        acc_local_bit0(wk_, mx, X, Y, one, TR_XEQ << sh);
+                        if (mx > best) { best = mx; bi = i0 + 1; bj = jbase + c + 1; }
+                    } else {
+                        acc_if_eq(wk_, mx, X, one, TR_XEQ << sh);
+                    }
+                    const int32_t mxA = fma_add(mx, one, a);
+                    diagA = upA; leftA = mxA;
+                    MuA[c] = mxA; Xu[c] = X;
+                }
+                MlastA = leftA; Ylast = Y; MdiagA = MlA;
+                if (A.want_trace && lane_has_cols) {
+                    uint32_t* tp = A.trace + d.trace_off + ((uint64_t)bd * steps + t) * (uint64_t)(K * 32) + lane;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) tp[k * 32] = w[k];
+                }
+                if (track_col && bd == bd_m) {
+                    int32_t v = MuA[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c) v = (c_m == (uint32_t)c) ? MuA[c] : v;
+                    v -= a;
+                    if (col_lane && v > cbest) { cbest = v; ci = i0 + 1; }
+                }
+            }
+            if (has_next) {
+                // collect lane 31's (row t-31) boundary value in lane tq; flush every 32 steps
+                const int32_t oM = __shfl_sync(FULL, MlastA, 31);
+                const int32_t oY = __shfl_sync(FULL, Ylast, 31);
+                if (lane == (int)tq) out_blk = make_int2(oM, oY);
+                if (tq == 31u || t + 1 == steps) {
+                    const uint32_t t0 = t & ~31u;
+                    const int64_t row = (int64_t)t0 + lane - 31;       // lane q holds the value of step t0 + q
+                    if (row >= 0 && row < (int64_t)n && (uint32_t)lane <= tq) bnd_wr[row] = out_blk;
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) {
+                        long long done = (long long)t - 30;             // rows 0 .. t-31 are out
+                        if (done < 0) done = 0;
+                        if (done > (long long)n) done = (long long)n;
+                        prog[bd % R] = wr_base + (unsigned long long)done;
+                    }
+                }
+            }
+        }
+        // MuA[] holds row n of this band (biased by a)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const uint32_t j = jbase + c + 1;
+            const int32_t v = MuA[c] - a;
+            if (j <= m) {
+                if (track_row && v >= rbest) { rbest = v; rj = j; }
+                if (j == m) { corner = v; }
+            }
+        }
+        if (bd == bd_m && m > 0) has_col = 1;
+        __syncwarp();
+    }
+
+    if (bad_residue) atomicOr(A.err_flag, 1u);
+
+    // ---- merge inside the warp, then across the workers of the cluster --------------------
+    if (track_row) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int32_t ov = __shfl_xor_sync(FULL, rbest, o);
+            const uint32_t oj = __shfl_xor_sync(FULL, rj, o);
+            if (ov > rbest || (ov == rbest && oj > rj)) { rbest = ov; rj = oj; }
+        }
+    }
+    if (IS_LOCAL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int32_t ov = __shfl_xor_sync(FULL, best, o);
+            const uint32_t oi = __shfl_xor_sync(FULL, bi, o);
+            const uint32_t oj = __shfl_xor_sync(FULL, bj, o);
+            if (ov > best || (ov == best && (oi < bi || (oi == bi && oj < bj)))) { best = ov; bi = oi; bj = oj; }
+        }
+    }
+    const int32_t cbest0 = __shfl_sync(FULL, cbest, (int)p_m);
+    const uint32_t ci0 = __shfl_sync(FULL, ci, (int)p_m);
+    const int32_t corner0 = __shfl_sync(FULL, corner, (int)p_m);
+    if (lane == 0) {
+        WaveCand c;
+        c.best = best; c.bi = bi; c.bj = bj; c.rbest = rbest; c.rj = rj;
+        c.cbest = cbest0; c.ci = ci0; c.corner = corner0; c.has_col = has_col;
+        W.cand[(uint64_t)slot * NW + wk] = c;
+        __threadfence();
+    }
+    cg::this_cluster().sync();
+    if (wk == 0 && lane == 0) {
+        const WaveCand* cc = W.cand + (uint64_t)slot * NW;
+        int32_t fbest = 0; uint32_t fbi = 0, fbj = 0;
+        int32_t frb = INT32_MIN; uint32_t frj = 0;
+        int32_t fcb = border_row(row_gap, a, b, m); uint32_t fci = 0;
+        int32_t fcorner = border_col(col_gap, a, b, n);
+        for (uint32_t q = 0; q < NW; ++q) {
+            const volatile WaveCand* c = cc + q;
+            const int32_t vb = c->best; const uint32_t vbi = c->bi, vbj = c->bj;
+            if (vb > fbest || (vb == fbest && (vbi < fbi || (vbi == fbi && vbj < fbj)))) { fbest = vb; fbi = vbi; fbj = vbj; }
+            const int32_t vr = c->rbest; const uint32_t vrj = c->rj;
+            if (vr > frb || (vr == frb && vrj > frj)) { frb = vr; frj = vrj; }
+            if (c->has_col) { fcb = c->cbest; fci = c->ci; fcorner = c->corner; }
+        }
+        EndCell e; e.flags = 0;
+        switch (mode) {
+        case M_GLOBAL: e.score = fcorner; e.k = n; e.l = m; break;
+        case M_LOCAL: e.score = fbest; e.k = fbi; e.l = fbj; break;
+        case M_FITTING: e.score = fcb; e.k = fci; e.l = m; break;
+        case M_OVERLAP: e.score = frb; e.k = n; e.l = frj; break;
+        default:
+            if (fcb > frb) { e.score = fcb; e.k = fci; e.l = m; e.flags = 1; }
+            else { e.score = frb; e.k = n; e.l = frj; }
+            break;
+        }
+        A.end[slot] = e;
+    }
+}
+
+}  // namespace bg

@@ -251,6 +251,38 @@ def test_cfg5_small_long_pair(aligner):
     assert not problems, "\n".join(problems)
 
 
+def test_wavefront_kernel_long_pairs(aligner):
+    """K2 (pairs wider than 4096 columns: one pair per thread-block cluster, 1/2/4/8 CTAs per pair)
+    mixed with K1 classes in one batch; all modes against the lean oracle."""
+    rng = random.Random(99)
+    seqs = []
+    for n, m in [(5000, 4200), (3000, 9000), (9000, 17000), (7000, 33000), (300, 5000), (6000, 300), (4500, 4097)]:
+        s1 = bytes(rng.choice(b"ACGT") for _ in range(n))
+        s2 = bytearray()
+        for c in s1:
+            r = rng.random()
+            if r < 0.06:
+                s2.append(rng.choice(b"ACGT"))
+            elif r < 0.08:
+                continue
+            elif r < 0.10:
+                s2.append(c); s2.append(rng.choice(b"ACGT"))
+            else:
+                s2.append(c)
+        while len(s2) < m:
+            s2.append(rng.choice(b"ACGT"))
+        seqs += [s1, bytes(s2[:m])]
+    batch = native.Batch.from_sequences(seqs)
+    problems = []
+    for mode, scorer, a, b in [("semiglobal", "unit", -1, -1), ("local", "blosum62", -11, -1), ("global", "unit", -2, -1),
+                               ("overlap", "unit", -2, -2)]:
+        eng = _cmp.engine_align(aligner, batch, mode, scorer, a, b)
+        ora = _cmp.oracle_align(batch, mode, scorer, a, b, lean=True)
+        problems += _cmp.diff(batch, eng, ora, "K2 %s/%s" % (mode, scorer))
+        eng.close()
+    assert not problems, "\n".join(problems)
+
+
 def test_full_size_properties_cfg2(aligner):
     """Config #2 at full size (1M pairs): size-independent properties + a random sample vs the oracle.
       * global alignment strings, with '-' removed, are exactly the inputs; equal lengths; no column
