@@ -35,6 +35,7 @@ WORKLOADS = {
     "cfg2": ("cfg2_dna150_global", 1_000_000),
     "cfg4": ("cfg4_protein_local", 100_000),
     "cfg3": ("cfg3_edit_100_300", 1_250_000),
+    "cfg5": ("cfg5_long_semiglobal", 125),     # 1000 pairs over 8 GPUs
 }
 ALG_OPS_PER_CELL = {"global": 12, "semiglobal": 12, "local": 15, "edit": 4}
 
@@ -144,7 +145,13 @@ def run_reference(args, rank, world):
     cfg = synth.CONFIGS[cfg_name]
     cores = orc.hw_threads()
     sample = args.ref_pairs or (2500 * cores if args.workload == "cfg2" else 40 * cores)
-    batch = synth.make(cfg_name, n_pairs=sample)
+    if args.workload == "cfg5":
+        from biogarden_b200 import native
+        cores = min(cores, 8)
+        sample = cores
+        batch = native.synth_pairs(cfg["seed"], 0, sample, cfg["alphabet"], 10000, 10000, cfg["resize_b"])
+    else:
+        batch = synth.make(cfg_name, n_pairs=sample)
     cells = batch.cells()
 
     def step():
@@ -354,7 +361,14 @@ def cpu_baseline(args, cfg_name, cfg):
     cores = orc.hw_threads()
     per_core = {"cfg2": 1500, "cfg3": 300, "cfg4": 12}.get(args.workload, 100)
     sample = per_core * cores
-    batch = synth.make(cfg_name, n_pairs=sample)
+    if args.workload == "cfg5":
+        # the literal layout needs 15 B/cell: time 10 kbp pairs of the same generator
+        from biogarden_b200 import native
+        cores = min(cores, 8)
+        sample = cores
+        batch = native.synth_pairs(cfg["seed"], 0, sample, cfg["alphabet"], 10000, 10000, cfg["resize_b"])
+    else:
+        batch = synth.make(cfg_name, n_pairs=sample)
     t0 = time.perf_counter()
     if cfg["mode"] == "edit":
         _, secs = orc.edit_distance_batch(batch.residues, batch.seq_off, threads=cores, lean=False)

@@ -197,6 +197,7 @@ struct bg_ctx {
     std::atomic<uint64_t> h2d{0}, d2h{0}, launches{0};
     uint64_t trace_budget_words = 0;
     int force_L = 0, force_C = 0;
+    int num_sms = 148;
     void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu); last_error = s; }
 };
 
@@ -324,7 +325,12 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         bool uniform = true;
         const uint32_t n0 = len_n(cid[0]);
         for (size_t k = 1; k < cn; ++k) if (len_n(cid[k]) != n0) { uniform = false; break; }
-        if (!uniform) {
+        if (wave) {
+            // K2: largest pairs (cells) first; cluster c then owns pairs c, c + NC, ... of this list
+            std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) {
+                return (uint64_t)len_n(x) * len_m(x) > (uint64_t)len_n(y) * len_m(y);
+            });
+        } else if (!uniform) {
             uint32_t nmin = n0, nmax = n0;
             for (size_t k = 1; k < cn; ++k) { const uint32_t v = len_n(cid[k]); nmin = std::min(nmin, v); nmax = std::max(nmax, v); }
             const uint64_t range = (uint64_t)nmax - nmin + 1;
@@ -344,9 +350,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             uint32_t maxb = 0;
             for (size_t k = 0; k < cn; ++k) maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
             lc.Q = maxb > 64 ? 8 : maxb > 32 ? 4 : maxb > 16 ? 2 : 1;
+            if (lc.Q == 8 && cn > (size_t)ctx->num_sms / 8) lc.Q = 4;   // enough pairs to fill the machine: prefer the shorter wavefront ramp
             P.max_Q = std::max(P.max_Q, lc.Q);
         }
         const uint64_t ring = wave ? (uint64_t)lc.Q * K2_WARPS + 1 : 1;
+        const size_t wave_clusters = std::max<size_t>(1, (size_t)ctx->num_sms / (size_t)lc.Q);   // resident pair groups of a K2 launch
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
         const size_t nwarps = (cn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
@@ -359,7 +367,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             }
             const uint32_t steps = maxn + sh.L - 1;
             const uint64_t warp_words = with_trace ? (uint64_t)maxb * steps * K * 32ull : 0;
-            if (with_trace && ch.trace_words > 0 && ch.trace_words + warp_words > class_budget) {
+            // K2 launches run one pair per resident cluster at a time: close a chunk at a multiple of the
+            // cluster count once memory is nearly used up, so that the (length-sorted) pairs of a launch finish together
+            const bool wave_round = wave && ch.trace_words > 0 && ((nd - ch.slot_begin) % wave_clusters) == 0 &&
+                                    ch.trace_words + warp_words * wave_clusters > class_budget;
+            if (with_trace && ch.trace_words > 0 && (wave_round || ch.trace_words + warp_words > class_budget)) {
                 ch.slot_end = (uint32_t)nd;
                 lc.chunks.push_back(ch);
                 P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
@@ -413,22 +425,35 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
     BG_SHAPES(X)
 #undef X
 }
-cudaError_t launch_k2(bool local, bool prof4, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
+// K2 is launched COOPERATIVELY (all CTAs co-resident, which its spin waits need) as a persistent grid of
+// pair groups: Q consecutive CTAs work on one pair.  (Thread-block clusters would give the same
+// guarantee, but clusters of 4 must sit inside one GPC and strand 16 of the B200's 148 SMs:
+// 33 resident clusters instead of 37 groups -- measured, see profiles/.)
+template <class Kern>
+cudaError_t launch_k2_impl(Kern kern, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_WARPS * 32, smem) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+    const uint32_t groups = std::max<uint32_t>(1, std::min<uint32_t>(n_slots, (uint32_t)(sms * per_sm) / (uint32_t)Q));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_slots * (unsigned)Q);
+    cfg.gridDim = dim3(groups * (unsigned)Q);
     cfg.blockDim = dim3(K2_WARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)Q; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+cudaError_t launch_k2(bool local, bool prof4, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
     if (local) {
-        if (prof4) return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, true, true>, a);
-        return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, true, false>, a);
+        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_slots, Q, smem, st, a);
+        return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_slots, Q, smem, st, a);
     }
-    if (prof4) return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, false, true>, a);
-    return cudaLaunchKernelEx(&cfg, k2_wave<WAVE_C, false, false>, a);
+    if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_slots, Q, smem, st, a);
+    return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_slots, Q, smem, st, a);
 }
 void dispatch_k4(Shape sh, dim3 grid, cudaStream_t st, const EditArgs& a) {
 #define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k4_edit<L_, C_><<<grid, 128, 0, st>>>(a); return; }
@@ -522,7 +547,8 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     }
     if (P.max_wave_slots) {
         const uint64_t nw = (uint64_t)P.max_Q * K2_WARPS;
-        ok = ok && ws.progress.ensure(P.max_wave_slots * (nw + 1) * 8) && ws.cand.ensure(P.max_wave_slots * nw * sizeof(WaveCand));
+        // progress counters, then one "workers done" counter per pair
+        ok = ok && ws.progress.ensure(P.max_wave_slots * (nw + 1) * 8 + (P.max_wave_slots + 2) * 4) && ws.cand.ensure(P.max_wave_slots * nw * sizeof(WaveCand));
     }
     if (!ok) { ctx->set_error("device allocation failed (trace / scratch buffers)"); return BG_ENOMEM; }
     cudaStream_t st = ws.stream;
@@ -547,8 +573,10 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             const uint32_t nwarps = (ns + G - 1) / G;
             if (lc.wave) {
                 const uint64_t nw = (uint64_t)lc.Q * K2_WARPS;
-                CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, (uint64_t)ns * (nw + 1) * 8, st));
+                const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
+                CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + ((uint64_t)ns + 2) * 4, st));
                 WaveArgs wa; wa.f = fa; wa.progress = ws.progress.as<unsigned long long>(); wa.cand = ws.cand.as<WaveCand>(); wa.Q = lc.Q;
+                wa.done = reinterpret_cast<uint32_t*>(ws.progress.as<unsigned char>() + prog_bytes);
                 Phase ph(ws, 1);
                 CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ns, lc.Q, pp.smem, st, wa));
             } else {
@@ -565,7 +593,9 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
                     wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C;
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
-                    k3_walk<<<(ns + 127) / 128, 128, 0, st>>>(wa);
+                    // long pairs: one warp per pair looks 32 codes ahead; short pairs: one thread per pair
+                    if (lc.wave || (uint64_t)P.max_n + P.max_m > 16384) k3_walk_warp<<<(ns + 3) / 4, 128, 0, st>>>(wa);
+                    else k3_walk<<<(ns + 127) / 128, 128, 0, st>>>(wa);
                 }
             }
             CU_TRY(ctx, cudaGetLastError());
@@ -668,6 +698,7 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
         if (o < 0 || o >= count || cudaSetDevice(o) != cudaSuccess) { bg_destroy(ctx); return BG_ENODEVICE; }
         dv.ordinal = o;
         size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); dv.total_mem = tot;
+        { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, o) == cudaSuccess && sms > 0) ctx->num_sms = sms; }
         dv.cache = new BlockCache();
         for (WorkSet& ws : dv.ws) {
             ws.ordinal = o; ws.cache = dv.cache;

@@ -1,9 +1,9 @@
 // k2_wave.cuh -- K2: intra-sequence wavefront fill for long pairs (>= several kbp) on sm_100a.
 //
 // Same recurrence, same cell code and same trace layout as K1 (k1_fill.cuh), but ONE pair is spread
-// over all warps of a thread-block CLUSTER instead of living in one warp:
+// over all warps of a GROUP of Q co-resident CTAs instead of living in one warp:
 //   * the columns are cut into bands of 32*C; band b is owned by worker (b mod NW), a worker being one
-//     warp of one CTA of the cluster (NW = cluster size * warps per CTA, up to 8 x 16 = 128);
+//     warp of one CTA of the group (NW = Q * warps per CTA, up to 8 x 16 = 128);
 //   * inside a band the 32 lanes run the K1 systolic schedule over all rows;
 //   * band b+1 consumes the last column (M + a, Y) of band b: the producer's lane 31 values are
 //     collected across 32 steps with shuffles and written as one coalesced 256-byte block to a ring
@@ -11,8 +11,12 @@
 //     the consumer waits on that counter once per 32 rows and fetches the block with one coalesced
 //     load.  Adjacent bands therefore run 64 rows apart: the anti-diagonal wavefront of the north
 //     star, at band granularity, with the diagonal tiles staged through registers / L2;
-//   * cluster launch guarantees all workers of a pair are co-resident, so the spin waits cannot
-//     deadlock; end-cell candidates of the workers are merged after a cluster barrier.
+//   * the launch is cooperative, so all workers are co-resident and the spin waits cannot deadlock;
+//     the last worker to finish a pair merges the workers' end-cell candidates;
+//   * the grid is persistent: as many groups as fit on the machine; group c owns pairs c, c + NC,
+//     ... of the (largest-first) list and its workers move on to the next pair as soon as their own
+//     bands are done -- there is no barrier between pairs, so the partly filled last round of one
+//     pair's wavefront overlaps the first round of the next.
 // The walk (K3) reads the trace exactly as for K1 with L = 32.
 #pragma once
 #include <cooperative_groups.h>
@@ -36,10 +40,24 @@ struct WaveArgs {
     FillArgs f;
     unsigned long long* progress;   // [slot][NW + 1], zeroed before launch
     WaveCand* cand;                 // [slot][NW]
-    int32_t Q;                      // CTAs per cluster (= per pair)
+    uint32_t* done;                 // [slot] workers that have finished the pair (zeroed before launch)
+    int32_t Q;                      // CTAs per pair group
 };
 
 constexpr int K2_WARPS = 16;        // warps per CTA
+
+// Boundary hand-over flags: release / acquire at GPU scope on the counter itself.  The producer's 32
+// lanes write their block, __syncwarp() orders those writes before lane 0's release store; the consumer's
+// lane 0 acquires, __syncwarp() passes the ordering on to the other lanes.  (A full __threadfence() on
+// all lanes would also wait for every lane's outstanding trace stores.)
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int C, bool IS_LOCAL, bool PROF4>
 __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
@@ -62,8 +80,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
 
     const int lane = threadIdx.x & 31, p = lane;
     const uint32_t Q = (uint32_t)W.Q, NW = Q * K2_WARPS, R = NW + 1;
-    const uint32_t slot = blockIdx.x / Q, cta_rank = blockIdx.x % Q;
+    const uint32_t group_id = blockIdx.x / Q, cta_rank = blockIdx.x % Q;
     const uint32_t wk = cta_rank * K2_WARPS + (threadIdx.x >> 5);
+    bool bad_residue = false;
+
+    const uint32_t n_groups = gridDim.x / Q;
+  for (uint32_t slot = group_id; slot < A.n_slots; slot += n_groups) {
     const PairDesc d = A.desc[slot];
     const uint32_t n = d.n, m = d.m, nbands = d.nbands, steps = d.steps;
     const uint32_t n_pad = (n + 31u) & ~31u;
@@ -75,7 +97,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     const bool track_row = (mode == M_SEMIGLOBAL || mode == M_OVERLAP);
     const uint8_t* sa = A.residues + d.a_off;
     const uint8_t* sb = A.residues + d.b_off;
-    bool bad_residue = false;
 
     const uint32_t band_cols = (uint32_t)(L * C);
     const uint32_t mcol0 = m ? m - 1 : 0;
@@ -92,7 +113,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     if (wk == 0 && p == 0) { rbest = border_col(col_gap, a, b, n); rj = 0; }   // row n, column 0 candidate
 
     int2* const ring = A.bnd + d.bnd_off;
-    volatile unsigned long long* const prog = W.progress + (uint64_t)slot * R;
+    unsigned long long* const prog = W.progress + (uint64_t)slot * R;
 
     for (uint32_t bd = wk; bd < nbands; bd += NW) {
         const uint32_t jbase = bd * band_cols + (uint32_t)p * C;
@@ -149,10 +170,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
                     const unsigned long long need = rd_base + (unsigned long long)min(t + 32u, n);
                     if (lane == 0 && t < n) {
                         unsigned ns = 32;
-                        while (prog[(bd + R - 1) % R] < need) { __nanosleep(ns); if (ns < 1024) ns *= 2; }
+                        while (ld_acquire_gpu(prog + (bd + R - 1) % R) < need) { __nanosleep(ns); if (ns < 512) ns *= 2; }
                     }
                     __syncwarp();
-                    __threadfence();
                     const uint32_t row = t + (uint32_t)lane;
                     in_blk = (row < n) ? __ldcg(bnd_rd + row) : make_int2(a, NEG_INF);
                 }
@@ -227,13 +247,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
                     const uint32_t t0 = t & ~31u;
                     const int64_t row = (int64_t)t0 + lane - 31;       // lane q holds the value of step t0 + q
                     if (row >= 0 && row < (int64_t)n && (uint32_t)lane <= tq) bnd_wr[row] = out_blk;
-                    __threadfence();
                     __syncwarp();
                     if (lane == 0) {
                         long long done = (long long)t - 30;             // rows 0 .. t-31 are out
                         if (done < 0) done = 0;
                         if (done > (long long)n) done = (long long)n;
-                        prog[bd % R] = wr_base + (unsigned long long)done;
+                        st_release_gpu(prog + bd % R, wr_base + (unsigned long long)done);
                     }
                 }
             }
@@ -252,9 +271,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
         __syncwarp();
     }
 
-    if (bad_residue) atomicOr(A.err_flag, 1u);
-
-    // ---- merge inside the warp, then across the workers of the cluster --------------------
+    // ---- merge inside the warp, then across the workers of the group --------------------
     if (track_row) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -275,15 +292,17 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     const int32_t cbest0 = __shfl_sync(FULL, cbest, (int)p_m);
     const uint32_t ci0 = __shfl_sync(FULL, ci, (int)p_m);
     const int32_t corner0 = __shfl_sync(FULL, corner, (int)p_m);
+    bool merger = false;
     if (lane == 0) {
         WaveCand c;
         c.best = best; c.bi = bi; c.bj = bj; c.rbest = rbest; c.rj = rj;
         c.cbest = cbest0; c.ci = ci0; c.corner = corner0; c.has_col = has_col;
         W.cand[(uint64_t)slot * NW + wk] = c;
         __threadfence();
+        merger = (atomicAdd(W.done + slot, 1u) == NW - 1);   // last worker out merges
+        if (merger) __threadfence();
     }
-    cg::this_cluster().sync();
-    if (wk == 0 && lane == 0) {
+    if (merger) {
         const WaveCand* cc = W.cand + (uint64_t)slot * NW;
         int32_t fbest = 0; uint32_t fbi = 0, fbj = 0;
         int32_t frb = INT32_MIN; uint32_t frj = 0;
@@ -310,6 +329,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
         }
         A.end[slot] = e;
     }
+  }   // persistent loop
+    if (bad_residue) atomicOr(A.err_flag, 1u);
 }
 
 }  // namespace bg

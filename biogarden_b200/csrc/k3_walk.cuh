@@ -135,6 +135,122 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
     A.lens2[2ull * d.pair_id + 1] = len;
 }
 
+// K3, long-pair form: one WARP per pair.  A walk over a 100 kbp pair is ~150k dependent steps; one
+// thread pays a full memory round trip for each.  Here the 32 lanes fetch the direction codes of the
+// next 32 cells the walk would visit if it kept doing what it is doing -- along the diagonal in state
+// 'M', up the column in state 'X', along the row in state 'Y' -- and the whole run that really
+// continues is emitted at once with coalesced stores (the codes decide, exactly as in the scalar walk;
+// nothing is recomputed).  Whatever stops a run is handled by one iteration of the scalar state
+// machine, so the emitted path is the reference's path, character for character.
+__global__ void __launch_bounds__(128) k3_walk_warp(const WalkArgs A) {
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t q = threadIdx.x & 31;
+    constexpr unsigned FULL = 0xffffffffu;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const EndCell e = A.end[slot];
+    const uint32_t n = d.n, m = d.m;
+    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
+    const uint32_t K = (C + 7) / 8;
+    const uint32_t band_cols = L * C;
+    const uint32_t lane_base = (slot % (32u / L)) * L;
+    const uint8_t* sa = A.residues + d.a_off;
+    const uint8_t* sb = A.residues + d.b_off;
+    const uint32_t cap4 = (n + m + 3u) & ~3u;
+    uint8_t* outA = A.pad + d.pad_off;
+    uint8_t* outB = outA + cap4;
+    uint32_t pos = cap4;
+    const int mode = A.mode;
+
+    auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
+        const uint32_t j0 = j - 1;
+        const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
+        const uint32_t p = rr / C, c = rr - p * C;
+        const uint32_t t = (i - 1) + p;
+        const uint64_t idx = d.trace_off + ((uint64_t)bd * d.steps + t) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
+        return (__ldg(A.trace + idx) >> ((c & 7u) * 4u)) & 15u;
+    };
+    auto valid_at = [&](int64_t kk, int64_t ll, uint32_t nib) -> bool {
+        if (kk < 0 || ll < 0) return false;
+        const bool interior = (kk != 0 && ll != 0);
+        switch (mode) {
+            case M_GLOBAL: return (kk != 0 || ll != 0);
+            case M_LOCAL: return interior && (nib & 3u) != 3u;
+            case M_SEMIGLOBAL: return interior;
+            default: return ll != 0;
+        }
+    };
+
+    uint32_t k = e.k, l = e.l, flags = 0;
+    const bool colbr = (e.flags & 1u) != 0;
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404, emitted 32 characters at a time
+        if (colbr) { for (uint32_t i = n; i > k; ) { const uint32_t cnt = min(32u, i - k); if (q < cnt) { outA[pos - 1 - q] = sa[i - 1 - q]; outB[pos - 1 - q] = '-'; } pos -= cnt; i -= cnt; } }
+        else       { for (uint32_t i = m; i > l; ) { const uint32_t cnt = min(32u, i - l); if (q < cnt) { outA[pos - 1 - q] = '-'; outB[pos - 1 - q] = sb[i - 1 - q]; } pos -= cnt; i -= cnt; } }
+    }
+    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
+    const uint64_t bound = 2ull * ((uint64_t)n + m) + 8;
+    for (uint64_t it = 0;; ++it) {
+        if (it > bound) { flags |= WALK_HANG; break; }
+        // ---- vector phase: how far does the current kind of move continue? ----
+        const int64_t kq = (int64_t)k - ((cur == 2) ? 0 : (int64_t)q);
+        const int64_t lq = (int64_t)l - ((cur == 1) ? 0 : (int64_t)q);
+        const bool inb = (kq >= 1 && lq >= 1);
+        // the residues this lane would emit are fetched together with its direction code, so one memory
+        // round trip per iteration is on the critical path, not two
+        const uint8_t ra = (cur != 2 && kq >= 1) ? __ldg(sa + kq - 1) : (uint8_t)'-';
+        const uint8_t rb = (cur != 1 && lq >= 1) ? __ldg(sb + lq - 1) : (uint8_t)'-';
+        const uint32_t nib = inb ? nib_at((uint32_t)kq, (uint32_t)lq) : 0u;
+        const bool vq = valid_at(kq, lq, nib);
+        bool cont;
+        if (cur == 0) cont = vq && inb && (nib & 3u) == 0;                      // 'R'
+        else if (cur == 1) cont = vq && kq >= 1 && !(inb && (nib & TR_XOPEN));   // keep extending the gap in seq2
+        else cont = vq && lq >= 1 && !(inb && (nib & TR_YOPEN));
+        const uint32_t stopmask = ~__ballot_sync(FULL, cont);
+        const uint32_t run = stopmask ? (uint32_t)__ffs((int)stopmask) - 1u : 32u;   // leading lanes that continue (0..32)
+        if (run > 0) {
+            if (q < run) { outA[pos - 1 - q] = ra; outB[pos - 1 - q] = rb; }
+            pos -= run;
+            if (cur != 2) k -= run;
+            if (cur != 1) l -= run;
+            continue;
+        }
+        // ---- scalar phase: one iteration of backtrack() at (k, l); lane 0 holds its code ----
+        const uint32_t nib0 = __shfl_sync(FULL, nib, 0);
+        const bool interior = (k != 0 && l != 0);
+        if (!valid_at(k, l, nib0)) break;
+        uint8_t ea = 0, eb = 0; bool emit = false;
+        if (cur == 0) {
+            uint32_t t;
+            if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib0 & TR_YEQ) ? 2u : (nib0 & TR_XEQ);
+            emit = true;   // lane 0's ra / rb are the residues at (k, l) in state 'M'
+            if (t == 0) { ea = ra; eb = rb; --k; --l; }
+            else if (t == 1) { ea = ra; eb = '-'; --k; cur = 1; }
+            else { ea = '-'; eb = rb; --l; cur = 2; }
+        } else if (cur == 1) {
+            if (interior && (nib0 & TR_XOPEN)) cur = 0;
+            else if (k == 0) { flags |= WALK_UNDERFLOW; break; }
+            else { emit = true; ea = ra; eb = '-'; --k; }
+        } else {
+            if (interior && (nib0 & TR_YOPEN)) cur = 0;
+            else if (l == 0) { flags |= WALK_UNDERFLOW; break; }
+            else { emit = true; ea = '-'; eb = rb; --l; }
+        }
+        if (emit) { --pos; if (q == 0) { outA[pos] = ea; outB[pos] = eb; } }
+    }
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
+        if (colbr) { for (uint32_t i = k; i > 0; ) { const uint32_t cnt = min(32u, i); if (q < cnt) { outA[pos - 1 - q] = sa[i - 1 - q]; outB[pos - 1 - q] = '-'; } pos -= cnt; i -= cnt; } }
+        else       { for (uint32_t i = l; i > 0; ) { const uint32_t cnt = min(32u, i); if (q < cnt) { outA[pos - 1 - q] = '-'; outB[pos - 1 - q] = sb[i - 1 - q]; } pos -= cnt; i -= cnt; } }
+    }
+    if (q == 0) {
+        const uint32_t len = cap4 - pos;
+        A.score[d.pair_id] = e.score;
+        A.walk_flags[d.pair_id] = (uint8_t)flags;
+        A.lens2[2ull * d.pair_id] = len;
+        A.lens2[2ull * d.pair_id + 1] = len;
+    }
+}
+
 // Score-only epilogue when no traceback is requested.
 __global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t n_slots, int32_t* score,
                               uint8_t* walk_flags) {
