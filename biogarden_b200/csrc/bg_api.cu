@@ -594,7 +594,12 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C;
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
                     // long pairs: one warp per pair looks 32 codes ahead; short pairs: one thread per pair
-                    if (lc.wave || (uint64_t)P.max_n + P.max_m > 16384) k3_walk_warp<<<(ns + 3) / 4, 128, 0, st>>>(wa);
+                    if (lc.wave || (uint64_t)P.max_n + P.max_m > 16384) {
+                        static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return (e && !strcmp(e, "vec")) ? 1 : 0; }();
+                        // the window loader maps 8-column blocks onto trace words: needs C % 8 == 0 (true for K2)
+                        if (walk_kind == 1 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, st>>>(wa);
+                        else k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, st>>>(wa);
+                    }
                     else k3_walk<<<(ns + 127) / 128, 128, 0, st>>>(wa);
                 }
             }

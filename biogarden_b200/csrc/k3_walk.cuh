@@ -251,6 +251,153 @@ __global__ void __launch_bounds__(128) k3_walk_warp(const WalkArgs A) {
     }
 }
 
+// K3, tiled long-pair form: one warp per pair keeps a WINDOW of the trace in shared memory.
+// The walk only ever moves up and/or left, so the codes it will need next lie in the TILE_H x TILE_W
+// cell window whose bottom-right corner is the current cell.  The 32 lanes fetch that window with
+// independent loads (one memory latency for ~100 walk steps instead of one per step), then the
+// reference's scalar state machine runs against shared memory until it steps out of the window.
+// Unlike the run-lookahead form above this is insensitive to how gappy the path is (two unrelated
+// 75 kbp sequences change state every 2-3 cells).
+constexpr int TILE_H = 64;            // rows per window
+constexpr int TILE_WB = 9;            // 8-column blocks per window (covers >= 64 columns at any alignment)
+constexpr int WALK_TILE_WARPS = 4;
+
+__global__ void __launch_bounds__(WALK_TILE_WARPS * 32) k3_walk_tile(const WalkArgs A) {
+    __shared__ uint32_t s_tile[WALK_TILE_WARPS][TILE_H * TILE_WB];
+    __shared__ uint8_t s_outA[WALK_TILE_WARPS][2 * (TILE_H + 8 * TILE_WB) + 8];
+    __shared__ uint8_t s_outB[WALK_TILE_WARPS][2 * (TILE_H + 8 * TILE_WB) + 8];
+    __shared__ uint8_t s_resA[WALK_TILE_WARPS][TILE_H];             // seq1 residues of the window's rows
+    __shared__ uint8_t s_resB[WALK_TILE_WARPS][8 * TILE_WB];         // seq2 residues of the window's columns
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * WALK_TILE_WARPS + wib;
+    const uint32_t q = threadIdx.x & 31;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const EndCell e = A.end[slot];
+    const uint32_t n = d.n, m = d.m;
+    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
+    const uint32_t K = (C + 7) / 8;
+    const uint32_t band_cols = L * C;
+    const uint32_t lane_base = (slot % (32u / L)) * L;
+    const uint8_t* sa = A.residues + d.a_off;
+    const uint8_t* sb = A.residues + d.b_off;
+    const uint32_t cap4 = (n + m + 3u) & ~3u;
+    uint8_t* outA = A.pad + d.pad_off;
+    uint8_t* outB = outA + cap4;
+    uint32_t pos = cap4;
+    const int mode = A.mode;
+    uint32_t* tile = s_tile[wib];
+    uint8_t* bufA = s_outA[wib];
+    uint8_t* bufB = s_outB[wib];
+    uint8_t* resA = s_resA[wib];
+    uint8_t* resB = s_resB[wib];
+    constexpr uint32_t BUFCAP = 2 * (TILE_H + 8 * TILE_WB);
+
+    // coalesced block emission helper (semiglobal tail / prefix)
+    auto emit_run = [&](const uint8_t* src, uint32_t hi, uint32_t lo, bool into_a) {   // src[hi-1] .. src[lo] , descending
+        for (uint32_t i = hi; i > lo; ) {
+            const uint32_t cnt = min(32u, i - lo);
+            if (q < cnt) {
+                const uint8_t ch = src[i - 1 - q];
+                outA[pos - 1 - q] = into_a ? ch : (uint8_t)'-';
+                outB[pos - 1 - q] = into_a ? (uint8_t)'-' : ch;
+            }
+            pos -= cnt; i -= cnt;
+        }
+    };
+
+    uint32_t k = e.k, l = e.l, flags = 0;
+    const bool colbr = (e.flags & 1u) != 0;
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
+        if (colbr) emit_run(sa, n, k, true); else emit_run(sb, m, l, false);
+    }
+    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
+    const uint64_t bound = 3ull * ((uint64_t)n + m) + 64;   // emits + state switches + one probe per window
+    uint64_t it = 0;
+    bool done = false;
+    while (!done) {
+        // ---- load the window: rows (i_lo, k], 8-column blocks [cb_lo, cb_hi] ----
+        uint32_t i_lo = 0, cb_lo = 0;   // window covers rows i_lo+1 .. k, columns cb_lo*8+1 .. l
+        if (k >= 1 && l >= 1) {
+            i_lo = (k > (uint32_t)TILE_H) ? k - TILE_H : 0;
+            const uint32_t cb_hi = (l - 1) >> 3;
+            cb_lo = (cb_hi + 1 > (uint32_t)TILE_WB) ? cb_hi + 1 - TILE_WB : 0;
+            const uint32_t rows = k - i_lo, nb = cb_hi - cb_lo + 1;
+            for (uint32_t x = q; x < rows * nb; x += 32) {
+                const uint32_t rr = x / nb, cb = cb_lo + (x - rr * nb);
+                const uint32_t i = i_lo + 1 + rr;
+                const uint32_t j0 = cb << 3;
+                const uint32_t bd = j0 / band_cols, rem = j0 - bd * band_cols;
+                const uint32_t p = rem / C, c = rem - p * C;
+                const uint32_t t = (i - 1) + p;
+                const uint64_t idx = d.trace_off + ((uint64_t)bd * d.steps + t) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
+                tile[rr * TILE_WB + (cb - cb_lo)] = __ldg(A.trace + idx);
+            }
+            for (uint32_t x = q; x < rows; x += 32) resA[x] = sa[i_lo + x];                                   // row i_lo+1+x
+            for (uint32_t x = q; x < nb * 8; x += 32) { const uint32_t j0 = (cb_lo << 3) + x; resB[x] = (j0 < m) ? sb[j0] : 0; }
+        }
+        __syncwarp();
+        const uint32_t j_lo = cb_lo << 3;   // columns j_lo+1 .. l are cached
+        const uint32_t k_hi = k, l_hi = l;  // window anchor
+        auto ra_at = [&](uint32_t kk) -> uint8_t { return (kk > i_lo && kk <= k_hi && l_hi >= 1 && k_hi >= 1) ? resA[kk - i_lo - 1] : sa[kk - 1]; };
+        auto rb_at = [&](uint32_t ll) -> uint8_t { return (ll > j_lo && ll <= l_hi && l_hi >= 1 && k_hi >= 1) ? resB[ll - j_lo - 1] : sb[ll - 1]; };
+        // ---- scalar walk inside the window (all lanes execute it redundantly; lane 0 emits) ----
+        uint32_t nbuf = 0;
+        for (;;) {
+            if (++it > bound) { flags |= WALK_HANG; done = true; break; }
+            const bool interior = (k != 0 && l != 0);
+            if (interior && (k <= i_lo || l <= j_lo)) break;            // stepped out of the window: reload
+            uint32_t nib = 0;
+            if (interior) nib = (tile[(k - i_lo - 1) * TILE_WB + (((l - 1) >> 3) - cb_lo)] >> (((l - 1) & 7u) * 4u)) & 15u;
+            bool valid;
+            switch (mode) {
+                case M_GLOBAL: valid = (k != 0 || l != 0); break;
+                case M_LOCAL: valid = interior && (nib & 3u) != 3u; break;
+                case M_SEMIGLOBAL: valid = interior; break;
+                default: valid = (l != 0); break;
+            }
+            if (!valid) { done = true; break; }
+            uint8_t ea = 0, eb = 0; bool emit = false;
+            if (cur == 0) {
+                uint32_t t;
+                if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib & TR_YEQ) ? 2u : (nib & TR_XEQ);
+                emit = true;
+                if (t == 0) { ea = ra_at(k); eb = rb_at(l); --k; --l; }
+                else if (t == 1) { ea = ra_at(k); eb = '-'; --k; cur = 1; }
+                else { ea = '-'; eb = rb_at(l); --l; cur = 2; }
+            } else if (cur == 1) {
+                if (interior && (nib & TR_XOPEN)) cur = 0;
+                else if (k == 0) { flags |= WALK_UNDERFLOW; done = true; break; }
+                else { emit = true; ea = ra_at(k); eb = '-'; --k; }
+            } else {
+                if (interior && (nib & TR_YOPEN)) cur = 0;
+                else if (l == 0) { flags |= WALK_UNDERFLOW; done = true; break; }
+                else { emit = true; ea = '-'; eb = rb_at(l); --l; }
+            }
+            if (emit) {
+                if (q == 0) { bufA[nbuf] = ea; bufB[nbuf] = eb; }
+                if (++nbuf == BUFCAP) break;                           // flush (cannot happen inside one window, kept as a guard)
+            }
+        }
+        __syncwarp();
+        // ---- flush the characters of this window, coalesced ----
+        for (uint32_t x = q; x < nbuf; x += 32) { outA[pos - 1 - x] = bufA[x]; outB[pos - 1 - x] = bufB[x]; }
+        pos -= nbuf;
+        __syncwarp();
+    }
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
+        if (colbr) emit_run(sa, k, 0, true); else emit_run(sb, l, 0, false);
+    }
+    if (q == 0) {
+        const uint32_t len = cap4 - pos;
+        A.score[d.pair_id] = e.score;
+        A.walk_flags[d.pair_id] = (uint8_t)flags;
+        A.lens2[2ull * d.pair_id] = len;
+        A.lens2[2ull * d.pair_id + 1] = len;
+    }
+}
+
 // Score-only epilogue when no traceback is requested.
 __global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t n_slots, int32_t* score,
                               uint8_t* walk_flags) {
