@@ -47,6 +47,25 @@ def shard_range(n_total: int, rank: int, world: int):
     return lo, hi
 
 
+def reduce_over_ranks(dev_ms, e2e_ms, cells, world, device):
+    """Whole-job numbers: times are the MAX over ranks (the job is done when the slowest GPU is), cells the
+    SUM (every rank aligned its own slice of the stream).  Works on any torch.distributed backend."""
+    if world <= 1:
+        return dev_ms, e2e_ms, cells
+    import torch
+    import torch.distributed as dist
+    vals = torch.tensor([dev_ms, e2e_ms, cells], dtype=torch.float64, device=device)
+    mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return float(mx[0]), float(mx[1]), float(sm[2])
+
+
+def rank_batch(cfg_name, pairs_per_rank, rank):
+    """Weak scaling: rank r owns pairs [r * pairs, (r + 1) * pairs) of the workload's seeded stream."""
+    from biogarden_b200 import synth
+    return synth.make(cfg_name, n_pairs=pairs_per_rank, first_pair=rank * pairs_per_rank)
+
+
 def int32_peak():
     """(Top/s, source): measured VIADDMNMX-class issue rate x SMs x clock from profiles/, else nominal."""
     p = os.path.join(ROOT, "profiles", "int32_peak_r01.json")
@@ -232,7 +251,7 @@ def main():
     cfg = synth.CONFIGS[cfg_name]
     pairs = args.pairs or full_pairs
     # weak scaling: rank r owns pairs [r*pairs, (r+1)*pairs) of the seeded stream
-    batch = pinned_batch(synth.make(cfg_name, n_pairs=pairs, first_pair=rank * pairs))
+    batch = pinned_batch(rank_batch(cfg_name, pairs, rank))
     cells = batch.cells()
     is_edit = cfg["mode"] == "edit"
 
@@ -308,13 +327,7 @@ def main():
     barrier()
 
     # ---------------- reduce over ranks ----------------
-    vals = torch.tensor([dev_ms, e2e_s * 1e3, float(cells)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, e2e_ms_max, cells_total = float(mx[0]), float(mx[1]), float(sm[2])
-    else:
-        dev_ms_max, e2e_ms_max, cells_total = dev_ms, e2e_s * 1e3, float(cells)
+    dev_ms_max, e2e_ms_max, cells_total = reduce_over_ranks(dev_ms, e2e_s * 1e3, float(cells), world, "cuda")
 
     if rank == 0:
         ms_per_step = dev_ms_max / args.steps

@@ -337,3 +337,22 @@ def test_full_size_properties_cfg2(aligner):
     assert np.array_equal(eng2.score, score_full)
     assert (int(np.sum(a2.astype(np.uint64) * (np.arange(len(a2), dtype=np.uint64) % 1000003))), len(a2)) == digest_full
     eng2.close()
+
+
+def test_in_process_multi_gpu_sharding_is_result_invariant():
+    """bg_create with several devices: contiguous cell-balanced shards, results stitched in input order.
+    Output must be byte-identical to the single-device result (pairs are independent)."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    batch = synth.make("cfg3_edit_100_300", n_pairs=30000)
+    one = SequenceAligner([0])
+    many = SequenceAligner(list(range(min(n_dev, 8))))
+    r1 = _cmp.engine_align(one, batch, "global", "unit", -2, -1)
+    r2 = _cmp.engine_align(many, batch, "global", "unit", -2, -1)
+    assert np.array_equal(r1.score, r2.score) and np.array_equal(r1.status, r2.status)
+    assert np.array_equal(r1.off, r2.off) and np.array_equal(r1.arena, r2.arena)
+    e1 = one.context.edit_distance_batch(batch); e2 = many.context.edit_distance_batch(batch)
+    assert np.array_equal(e1, e2)
+    r1.close(); r2.close()
