@@ -29,6 +29,7 @@
 
 #include "bg_common.cuh"
 #include "k1_fill.cuh"
+#include "k1h_fill.cuh"
 #include "k2_wave.cuh"
 #include "k3_walk.cuh"
 #include "k4_edit.cuh"
@@ -132,7 +133,7 @@ struct PinBuf {   // pinned host block from the global cache
 };
 
 struct Chunk { uint32_t slot_begin, slot_end; uint64_t trace_words; };
-struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; };
+struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; bool half = false; };
 
 struct Plan {
     std::vector<LaunchClass> classes;
@@ -141,6 +142,7 @@ struct Plan {
     uint64_t max_wave_slots = 0;      // largest K2 launch (slots), for the progress / candidate scratch
     int max_Q = 1;
     uint32_t max_n = 0, max_m = 0;
+    int32_t half_maxabs = 0;          // > 0: short classes were laid out for K1h (packed 16 x 2) with this max |score|
     bool built = false;
 };
 
@@ -185,6 +187,7 @@ struct Prepared {
     std::vector<int32_t> table;
     uint8_t codes[512];
     int64_t maxabs = 0;
+    int32_t half_maxabs = 0;   // > 0: K1h (packed 16 x 2) may be used for short classes
 };
 
 }  // namespace
@@ -271,8 +274,9 @@ size_t plan_desc_capacity(uint64_t n_pairs) { return (size_t)n_pairs + 4 * MAX_S
 // `dst` (capacity plan_desc_capacity(n_pairs)).  with_trace: trace blocks are laid out and the
 // launches are cut into chunks that fit the trace budget.
 int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs, bool with_trace,
-               uint64_t budget_words, uint64_t wave_budget_words, Plan& P, PairDesc* dst) {
+               uint64_t budget_words, uint64_t wave_budget_words, int32_t half_maxabs, Plan& P, PairDesc* dst) {
     P = Plan();
+    P.half_maxabs = half_maxabs;
     if (n_pairs >= 0xFFFFFFF0ull) { ctx->set_error("too many pairs in one device batch"); return BG_EINVAL_ARG; }
     Shape shapes[MAX_SHAPES];
     int nshape = 0;
@@ -316,7 +320,17 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const size_t cn = count[si];
         const Shape sh = shapes[si];
         const bool wave = (si == wave_si);
-        const uint32_t G = 32 / sh.L, K = words_per_lane_step(sh.C), band_cols = sh.L * sh.C;
+        const uint32_t K = words_per_lane_step(sh.C), band_cols = sh.L * sh.C;
+        auto len_n0 = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 1] - off[2 * (uint64_t)id]); };
+        auto len_m0 = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
+        // K1h (two pairs per lane group, 16-bit halves): short single-band classes whose scores provably fit
+        bool half = false;
+        if (with_trace && half_maxabs > 0 && !wave && sh.L == 8 && !ctx->force_L) {
+            uint32_t cmn = 0, cmm = 0;
+            for (size_t k = 0; k < count[si]; ++k) { cmn = std::max(cmn, len_n0(ids[start[si] + k])); cmm = std::max(cmm, len_m0(ids[start[si] + k])); }
+            half = cmm <= band_cols && ((int64_t)cmn + cmm + 2) * half_maxabs <= HB_RANGE;
+        }
+        const uint32_t G = (half ? 2u : 1u) * (32 / sh.L);
         const uint64_t class_budget = wave ? wave_budget_words : budget_words;
         auto len_n = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 1] - off[2 * (uint64_t)id]); };
         auto len_m = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
@@ -345,7 +359,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) { return len_n(x) > len_n(y); });
             }
         }
-        LaunchClass lc; lc.sh = sh; lc.wave = wave;
+        LaunchClass lc; lc.sh = sh; lc.wave = wave; lc.half = half;
         if (wave) {   // CTAs per pair: enough workers (16 warps per CTA) for the widest pair's bands
             uint32_t maxb = 0;
             for (size_t k = 0; k < cn; ++k) maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
@@ -366,7 +380,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
             }
             const uint32_t steps = maxn + sh.L - 1;
-            const uint64_t warp_words = with_trace ? (uint64_t)maxb * steps * K * 32ull : 0;
+            const uint64_t warp_words = with_trace ? (uint64_t)maxb * steps * K * 32ull * (half ? 2 : 1) : 0;
             // K2 launches run one pair per resident cluster at a time: close a chunk at a multiple of the
             // cluster count once memory is nearly used up, so that the (length-sorted) pairs of a launch finish together
             const bool wave_round = wave && ch.trace_words > 0 && ((nd - ch.slot_begin) % wave_clusters) == 0 &&
@@ -429,6 +443,14 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
 // pair groups: Q consecutive CTAs work on one pair.  (Thread-block clusters would give the same
 // guarantee, but clusters of 4 must sit inside one GPC and strand 16 of the B200's 148 SMs:
 // 33 resident clusters instead of 37 groups -- measured, see profiles/.)
+#define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24)
+bool dispatch_k1h(Shape sh, dim3 grid, cudaStream_t st, const FillArgs& a) {
+#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k1h_fill<L_, C_><<<grid, 128, 0, st>>>(a); return true; }
+    BG_HALF_SHAPES(X)
+#undef X
+    return false;
+}
+
 template <class Kern>
 cudaError_t launch_k2_impl(Kern kern, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -511,6 +533,8 @@ int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_
     pp.smem = 512 + (size_t)p->n_rows * (p->n_cols + 1) * 4;
     if (pp.smem > 48 * 1024) { ctx->set_error("score table too large for shared memory"); return BG_EUNSUPPORTED; }
     pp.prof4 = fits8 && p->n_rows <= 4;
+    if (mode != BG_LOCAL && p->n_rows <= 4 && p->n_cols <= 4 && maxabs <= HB_MAXABS && !pp.score_only && !getenv("BG_NO_HALF"))
+        pp.half_maxabs = (int32_t)std::max<int64_t>(1, maxabs);
     memcpy(pp.codes, p->row_code, 256); memcpy(pp.codes + 256, p->col_code, 256);
     for (int i = 0; i < 256; ++i) {
         if (pp.codes[i] != 0xFF && pp.codes[i] >= p->n_rows) { ctx->set_error("row_code entry out of range"); return BG_EINVAL_ARG; }
@@ -579,6 +603,10 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 wa.done = reinterpret_cast<uint32_t*>(ws.progress.as<unsigned char>() + prog_bytes);
                 Phase ph(ws, 1);
                 CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ns, lc.Q, pp.smem, st, wa));
+            } else if (lc.half) {
+                Phase ph(ws, 1);
+                const uint32_t nw2 = (ns + 2 * G - 1) / (2 * G);
+                if (!dispatch_k1h(lc.sh, dim3((nw2 + 3) / 4), st, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
             } else {
                 Phase ph(ws, 1);
                 dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, st, fa);
@@ -591,10 +619,10 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 } else {
                     WalkArgs wa;
                     wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
-                    wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C;
+                    wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C; wa.H = lc.half ? 2 : 1;
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
                     // long pairs: one warp per pair looks 32 codes ahead; short pairs: one thread per pair
-                    if (lc.wave || (uint64_t)P.max_n + P.max_m > 16384) {
+                    if (!lc.half && (lc.wave || (uint64_t)P.max_n + P.max_m > 16384)) {
                         static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return (e && !strcmp(e, "vec")) ? 1 : 0; }();
                         // the window loader maps 8-column blocks onto trace words: needs C % 8 == 0 (true for K2)
                         if (walk_kind == 1 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, st>>>(wa);
@@ -822,19 +850,19 @@ void bg_dresult_free(bg_dresult* r) {
     delete r;
 }
 
-static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit) {
+static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit, int32_t half_maxabs = 0) {
     Device& dv = ctx->devs[B->dev_index];
     WorkSet& ws = dv.ws[0];
     Plan& P = edit ? B->plan_edit : B->plan_align;
     DevBuf& D = edit ? B->desc_edit : B->desc_align;
-    if (P.built) return BG_OK;
+    if (P.built && (edit || P.half_maxabs == half_maxabs)) return BG_OK;
     // descriptors are built straight into cached pinned memory and copied once
     const size_t cap = plan_desc_capacity(B->n_pairs);
     PinBuf stage;
     if (!stage.ensure(cap * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
     // long pairs (K2) need whole traces of several GB each: let them use most of the device
     const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
-    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, ctx->trace_budget_words, wave_budget, P, stage.as<PairDesc>());
+    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, ctx->trace_budget_words, wave_budget, edit ? 0 : half_maxabs, P, stage.as<PairDesc>());
     if (rc) { stage.release(); return rc; }
     if (P.n_slots) {
         if (!D.ensure(P.n_slots * sizeof(PairDesc))) { stage.release(); ctx->set_error("device allocation for descriptors failed"); return BG_ENOMEM; }
@@ -865,7 +893,7 @@ int bg_align_device(bg_ctx* ctx, const bg_dbatch* cin, const bg_params* p, bg_dr
     Device& dv = ctx->devs[B->dev_index];
     WorkSet& ws = dv.ws[0];
     CU_TRY(ctx, cudaSetDevice(dv.ordinal));
-    rc = ensure_plan(ctx, B, false);
+    rc = ensure_plan(ctx, B, false, pp.half_maxabs);
     if (rc) return rc;
     Plan& P = B->plan_align;
 
@@ -1105,7 +1133,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         const uint64_t rel = f.c_lo - lo;
         // plan on the host, straight into pinned staging
         if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
-        int rc = build_plan(ctx, off + 2 * f.c_lo, base, n, !pp.score_only, ws_budget, wave_budget, f.plan, ws.stage.as<PairDesc>());
+        int rc = build_plan(ctx, off + 2 * f.c_lo, base, n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs, f.plan, ws.stage.as<PairDesc>());
         if (rc) return rc;
         const Plan& P = f.plan;
         bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
@@ -1185,7 +1213,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
         const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
         if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !host_out[s].ensure(n * 8)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
-        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, 0, plans[s], ws.stage.as<PairDesc>());
+        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, 0, 0, plans[s], ws.stage.as<PairDesc>());
         if (rc_all) break;
         const Plan& P = plans[s];
         if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(n * 8)) {

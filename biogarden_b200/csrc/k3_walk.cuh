@@ -23,6 +23,7 @@ struct WalkArgs {
     const uint32_t* trace;
     int32_t mode;
     int32_t L, C;           // geometry K1 used for this launch
+    int32_t H;              // pairs per lane group: 1 (K1 / K2) or 2 (K1h, packed 16 x 2)
     uint8_t* pad;           // padded output slots
     int32_t* score;         // [pair]
     uint8_t* walk_flags;    // [pair]
@@ -39,7 +40,9 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
     const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
     const uint32_t K = (C + 7) / 8;
     const uint32_t band_cols = L * C;
-    const uint32_t lane_base = (slot % (32u / L)) * L;
+    const uint32_t H = (uint32_t)A.H;
+    const uint32_t lane_base = ((slot % (H * (32u / L))) / H) * L;
+    const uint32_t half = slot % H;
     const uint8_t* sa = A.residues + d.a_off;
     const uint8_t* sb = A.residues + d.b_off;
     // Output slot: two regions of cap4 = round_up(n + m, 4) bytes (pad_off is 4-byte aligned), filled back
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
         const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
         const uint32_t p = rr / C, c = rr - p * C;
         const uint32_t t = (i - 1) + p;
-        const uint64_t idx = d.trace_off + ((uint64_t)(bd * d.steps + t) * K + (c >> 3)) * 32u + lane_base + p;
+        const uint64_t idx = d.trace_off + (((uint64_t)(bd * d.steps + t) * K + (c >> 3)) * H + half) * 32u + lane_base + p;
         return (__ldg(A.trace + idx) >> ((c & 7u) * 4u)) & 15u;
     };
 
