@@ -53,7 +53,7 @@ struct Shape { int L, C; };
 // Kernel shapes compiled in: (lanes per pair, columns per lane).  A band is L*C columns.
 #define BG_SHAPES(X) \
     X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 5) X(32, 8) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
-constexpr int MAX_SHAPES = 16;
+constexpr int MAX_SHAPES = 20;
 constexpr int PIPE_DEPTH = 3;
 // Pairs wider than this run on K2 (one pair per thread-block cluster, bands of 32 * WAVE_C columns).
 constexpr uint32_t WAVE_MIN_COLS = 4096;
@@ -133,7 +133,7 @@ struct PinBuf {   // pinned host block from the global cache
 };
 
 struct Chunk { uint32_t slot_begin, slot_end; uint64_t trace_words; };
-struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; bool half = false; };
+struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; bool half = false; int myers_W = 0; };
 
 struct Plan {
     std::vector<LaunchClass> classes;
@@ -143,6 +143,7 @@ struct Plan {
     int max_Q = 1;
     uint32_t max_n = 0, max_m = 0;
     int32_t half_maxabs = 0;          // > 0: short classes were laid out for K1h (packed 16 x 2) with this max |score|
+    bool myers = false;               // edit distance: pairs with len2 <= 320 laid out one per thread for K4b
     bool built = false;
 };
 
@@ -212,6 +213,8 @@ struct bg_dbatch {
     DevBuf residues, desc_align, desc_edit;
     std::vector<uint64_t> seq_off;   // host copy, rebased to 0
     Plan plan_align, plan_edit;
+    bool edit_lut_ok = false;
+    uint8_t edit_lut[256];
 };
 
 struct bg_dresult {
@@ -276,9 +279,10 @@ size_t plan_desc_capacity(uint64_t n_pairs) { return (size_t)n_pairs + 4 * MAX_S
 // `dst` (capacity plan_desc_capacity(n_pairs)).  with_trace: trace blocks are laid out and the
 // launches are cut into chunks that fit the trace budget.
 int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs, bool with_trace,
-               uint64_t budget_words, uint64_t wave_budget_words, int32_t half_maxabs, Plan& P, PairDesc* dst) {
+               uint64_t budget_words, uint64_t wave_budget_words, int32_t half_maxabs, Plan& P, PairDesc* dst, bool myers = false) {
     P = Plan();
     P.half_maxabs = half_maxabs;
+    P.myers = myers;
     if (n_pairs >= 0xFFFFFFF0ull) { ctx->set_error("too many pairs in one device batch"); return BG_EINVAL_ARG; }
     Shape shapes[MAX_SHAPES];
     int nshape = 0;
@@ -287,6 +291,10 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
 #undef X
     const int wave_si = nshape;               // pseudo class: K2 wavefront (alignment only)
     shapes[nshape++] = Shape{32, WAVE_C};
+    // pseudo classes: K4b bit-parallel edit distance, one thread per pair, W = 4 / 8 / 10 blocks of 32 columns
+    static_assert(MAX_SHAPES >= 15 + 1 + 3, "room for the pseudo classes");
+    const int myers_si = nshape;
+    shapes[nshape++] = Shape{32, 4}; shapes[nshape++] = Shape{32, 8}; shapes[nshape++] = Shape{32, 10};
     // pass 1: class of every pair
     std::vector<uint8_t> cls(n_pairs);
     size_t count[MAX_SHAPES] = {0};
@@ -297,6 +305,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         if ((uint32_t)m != last_m) {
             last_m = (uint32_t)m;
             if (with_trace && m > WAVE_MIN_COLS && !ctx->force_L) last_si = wave_si;
+            else if (myers && m <= 320) last_si = myers_si + (m <= 128 ? 0 : m <= 256 ? 1 : 2);
             else last_si = shape_index(pick_shape(ctx, last_m));
             if (last_si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
         }
@@ -362,6 +371,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             }
         }
         LaunchClass lc; lc.sh = sh; lc.wave = wave; lc.half = half;
+        if (si >= myers_si) lc.myers_W = sh.C;
         if (wave) {   // CTAs per pair: enough workers (16 warps per CTA) for the widest pair's bands
             uint32_t maxb = 0;
             for (size_t k = 0; k < cn; ++k) maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
@@ -691,8 +701,17 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     return BG_OK;
 }
 
-int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* desc, const Plan& P, uint64_t* out) {
-    if (!ws.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2))) { ctx->set_error("device allocation failed"); return BG_ENOMEM; }
+template <int W>
+void launch_myers(uint32_t ns, cudaStream_t st, const MyersArgs& a) { k4_myers<W><<<(ns + 127) / 128, 128, 0, st>>>(a); }
+
+// lut: host [256] byte -> code 0..3 / 0xFF, only needed when the plan has K4b classes.
+int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* desc, const Plan& P, uint64_t* out,
+             const uint8_t* lut) {
+    if (!ws.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2)) || !ws.err.ensure(4) || !ws.codes.ensure(512)) {
+        ctx->set_error("device allocation failed"); return BG_ENOMEM;
+    }
+    CU_TRY(ctx, cudaMemsetAsync(ws.err.p, 0, 4, ws.stream));
+    if (P.myers && lut) CU_TRY(ctx, cudaMemcpyAsync(ws.codes.p, lut, 256, cudaMemcpyHostToDevice, ws.stream));
     EditArgs ea;
     ea.residues = residues; ea.bnd = ws.bnd.as<int32_t>(); ea.out = out;
     for (const LaunchClass& lc : P.classes) {
@@ -700,15 +719,33 @@ int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* 
         for (const Chunk& ch : lc.chunks) {
             const uint32_t ns = ch.slot_end - ch.slot_begin;
             if (!ns) continue;
-            ea.desc = desc + ch.slot_begin; ea.n_slots = ns;
-            const uint32_t nwarps = (ns + G - 1) / G;
             Phase ph(ws, 1);
-            dispatch_k4(lc.sh, dim3((nwarps + 3) / 4), ws.stream, ea);
+            if (lc.myers_W) {
+                MyersArgs ma;
+                ma.desc = desc + ch.slot_begin; ma.n_slots = ns; ma.residues = residues; ma.lut = ws.codes.as<uint8_t>();
+                ma.out = out; ma.err_flag = ws.err.as<uint32_t>();
+                if (lc.myers_W == 4) launch_myers<4>(ns, ws.stream, ma);
+                else if (lc.myers_W == 8) launch_myers<8>(ns, ws.stream, ma);
+                else launch_myers<10>(ns, ws.stream, ma);
+            } else {
+                ea.desc = desc + ch.slot_begin; ea.n_slots = ns;
+                const uint32_t nwarps = (ns + G - 1) / G;
+                dispatch_k4(lc.sh, dim3((nwarps + 3) / 4), ws.stream, ea);
+            }
             ctx->launches++;
         }
     }
     CU_TRY(ctx, cudaGetLastError());
     return BG_OK;
+}
+
+// <= 4 distinct byte values -> lut (byte -> 0..3, 0xFF elsewhere); false if the alphabet is richer
+bool make_edit_lut(const uint64_t* hist, uint8_t* lut) {
+    int k = 0;
+    for (int x = 0; x < 256; ++x) lut[x] = 0xFF;
+    for (int x = 0; x < 256; ++x)
+        if (hist[x]) { if (k == 4) return false; lut[x] = (uint8_t)k++; }
+    return true;
 }
 
 }  // namespace
@@ -901,9 +938,23 @@ static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit, int32_t half_maxabs
     if (!stage.ensure(cap * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
     // long pairs (K2) need whole traces of several GB each: let them use most of the device
     const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
-    // short-pair classes: chunks of <= 2 GiB of trace so that walk(c) overlaps fill(c+1) (run_align)
-    const uint64_t chunk_budget = std::min<uint64_t>(ctx->trace_budget_words, (2ull << 30) / 4);
-    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, chunk_budget, wave_budget, edit ? 0 : half_maxabs, P, stage.as<PairDesc>());
+    // with BG_OVERLAP: chunks of <= 2 GiB of trace so that walk(c) overlaps fill(c+1) (run_align); otherwise large
+    // chunks -- the walk is latency-bound and wants as many pairs per launch as possible
+    static const bool want_overlap = [] { const char* e = getenv("BG_OVERLAP"); return e && atoi(e) != 0; }();
+    const uint64_t chunk_budget = want_overlap ? std::min<uint64_t>(ctx->trace_budget_words, (2ull << 30) / 4) : ctx->trace_budget_words;
+    bool myers = false;
+    if (edit && B->n_residues && !getenv("BG_NO_MYERS")) {
+        // which byte values occur at all?  (<= 4 -> bit-parallel K4b)
+        if (!ws.cubtmp.ensure(1024) || !ws.scalars.ensure(1024)) { stage.release(); ctx->set_error("allocation failed"); return BG_ENOMEM; }
+        CU_TRY(ctx, cudaMemsetAsync(ws.cubtmp.p, 0, 1024, ws.stream));
+        k_byte_hist<<<ctx->num_sms * 4, 256, 0, ws.stream>>>(B->residues.as<uint8_t>(), B->n_residues, ws.cubtmp.as<unsigned int>());
+        CU_TRY(ctx, cudaMemcpyAsync(ws.scalars.p, ws.cubtmp.p, 1024, cudaMemcpyDeviceToHost, ws.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+        uint64_t hist[256];
+        for (int x = 0; x < 256; ++x) hist[x] = ws.scalars.as<unsigned int>()[x];
+        myers = B->edit_lut_ok = make_edit_lut(hist, B->edit_lut);
+    }
+    int rc = build_plan(ctx, B->seq_off.data(), 0, B->n_pairs, !edit, chunk_budget, wave_budget, edit ? 0 : half_maxabs, P, stage.as<PairDesc>(), myers);
     if (rc) { stage.release(); return rc; }
     if (P.n_slots) {
         if (!D.ensure(P.n_slots * sizeof(PairDesc))) { stage.release(); ctx->set_error("device allocation for descriptors failed"); return BG_ENOMEM; }
@@ -982,7 +1033,7 @@ int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* cin, bg_dresult** out)
     ws.reset_events();
     ctx->launches = 0;
     ctx->timing.cells = P.cells; ctx->timing.trace_bytes = 0;
-    rc = run_edit(ctx, ws, B->residues.as<uint8_t>(), B->desc_edit.as<PairDesc>(), P, R->out64.as<uint64_t>());
+    rc = run_edit(ctx, ws, B->residues.as<uint8_t>(), B->desc_edit.as<PairDesc>(), P, R->out64.as<uint64_t>(), B->edit_lut_ok ? B->edit_lut : nullptr);
     if (rc) { bg_dresult_free(R); return rc; }
     *out = R;
     return BG_OK;
@@ -1226,7 +1277,9 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     return rc_all;
 }
 
-int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, uint64_t* out) {
+constexpr int EDIT_RETRY_GENERAL = -77;   // internal: a byte outside the sampled 4-symbol alphabet turned up
+
+int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, uint64_t* out, const uint8_t* lut) {
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
     const uint64_t* off = in->seq_off;
@@ -1241,6 +1294,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     auto finish = [&](int s) -> int {
         active[s] = false;
         CU_TRY(ctx, cudaStreamSynchronize(dv.ws[s].stream));
+        if (lut && (*reinterpret_cast<uint32_t*>(dv.ws[s].scalars.as<uint64_t>() + 1) & 2u)) return EDIT_RETRY_GENERAL;
         memcpy(out + c_lo[s], host_out[s].p, c_n[s] * 8);
         ctx->d2h += c_n[s] * 8;
         return BG_OK;
@@ -1253,8 +1307,8 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         if (rc_all) break;
         c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
         const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
-        if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !host_out[s].ensure(n * 8)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
-        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, 0, 0, plans[s], ws.stage.as<PairDesc>());
+        if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !host_out[s].ensure(n * 8) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
+        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, 0, 0, plans[s], ws.stage.as<PairDesc>(), lut != nullptr);
         if (rc_all) break;
         const Plan& P = plans[s];
         if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(n * 8)) {
@@ -1266,9 +1320,10 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         if (ce == cudaSuccess && P.n_slots) ce = cudaMemcpyAsync(ws.desc.p, ws.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st);
         if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
-        rc_all = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>());
+        rc_all = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);
         if (rc_all) break;
         ce = cudaMemcpyAsync(host_out[s].p, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(ws.scalars.as<uint64_t>() + 1, ws.err.p, 4, cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
         ctx->timing.cells += P.cells;
         active[s] = true;
@@ -1357,16 +1412,38 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
     ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
-    std::vector<int> rcs(nd, BG_OK);
-    auto work = [&](int d) { rcs[d] = edit_pipeline(ctx, d, in, bounds[d], bounds[d + 1], out); };
-    if (nd == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
-        for (auto& t : th) t.join();
+    // Alphabet from a sample of the batch: <= 4 byte values -> bit-parallel K4b.  The kernel flags any
+    // byte outside the sampled alphabet, in which case the batch is redone with the general kernel.
+    uint8_t lut[256];
+    bool use_lut = false;
+    if (in->n_pairs && !getenv("BG_NO_MYERS")) {
+        const uint64_t b0 = in->seq_off[0], b1 = in->seq_off[2 * in->n_pairs];
+        uint64_t hist[256] = {0};
+        const uint64_t span = b1 - b0, take = std::min<uint64_t>(span, 1u << 20);
+        for (uint64_t x = 0; x < take; ++x) hist[in->residues[b0 + x]]++;
+        for (uint64_t x = 0; x < take; ++x) hist[in->residues[b1 - 1 - x]]++;
+        use_lut = span > 0 && make_edit_lut(hist, lut);
     }
-    for (int r : rcs) if (r) return r;
-    return BG_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        std::vector<int> rcs(nd, BG_OK);
+        auto work = [&](int d) { rcs[d] = edit_pipeline(ctx, d, in, bounds[d], bounds[d + 1], out, use_lut ? lut : nullptr); };
+        if (nd == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
+            for (auto& t : th) t.join();
+        }
+        bool retry = false;
+        for (int r : rcs) {
+            if (r == EDIT_RETRY_GENERAL) retry = true;
+            else if (r) return r;
+        }
+        if (!retry) return BG_OK;
+        use_lut = false;
+        rc = bg_sync(ctx);
+        if (rc) return rc;
+    }
+    return BG_ECUDA;
 }
 
 const int8_t* bg_score_table26(const char* name) {

@@ -107,3 +107,116 @@ __global__ void __launch_bounds__(128) k4_edit(const EditArgs A) {
 }
 
 }  // namespace bg
+
+// ---------------------------------------------------------------------------------------------
+// K4b: bit-parallel Levenshtein distance (Myers 1999, block formulation as in Hyyro / Edlib) for
+// batches whose residues take at most 4 distinct byte values (DNA reads).  One thread per pair; the
+// pattern (seq2) lives in W 32-bit blocks of vertical delta vectors Pv / Mv plus 4 match masks per
+// block, all in registers; every text residue costs ~20 integer ops per BLOCK OF 32 CELLS instead of
+// ~7 per cell.  Exact: the same D[n][m] as the reference's table (seq.rs:105-130).  Pairs with
+// len2 > 32 * W or richer alphabets take the systolic kernel above.
+namespace bg {
+
+struct MyersArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* residues;
+    const uint8_t* lut;      // [256] byte -> code 0..3, 0xFF = not in the 4-symbol alphabet (device)
+    uint64_t* out;           // [pair]
+    uint32_t* err_flag;      // bit 1: a byte outside the alphabet was met (the caller then reruns with K4)
+};
+
+template <int W>
+__global__ void __launch_bounds__(128) k4_myers(const MyersArgs A) {
+    __shared__ uint8_t s_lut[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_lut[x] = A.lut[x];
+    __syncthreads();
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const uint32_t n = d.n, m = d.m;
+    if (m == 0 || n == 0) { A.out[d.pair_id] = (uint64_t)(m == 0 ? n : m); return; }
+    const uint8_t* text = A.residues + d.a_off;
+    const uint8_t* pat = A.residues + d.b_off;
+
+    // aligned 32-bit fetches of the byte streams
+    auto byte_at = [&](const uint8_t* base, uint32_t idx, uintptr_t& wp, uint32_t& cw) -> uint32_t {
+        const uintptr_t q = reinterpret_cast<uintptr_t>(base + idx), w = q & ~(uintptr_t)3;
+        if (w != wp) { wp = w; cw = __ldg(reinterpret_cast<const uint32_t*>(w)); }
+        return (cw >> ((q & 3u) * 8u)) & 0xffu;
+    };
+
+    uint32_t peq0[W], peq1[W], peq2[W], peq3[W], Pv[W], Mv[W];
+    uintptr_t wp = 0; uint32_t cw = 0;
+    bool bad = false;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        if ((uint32_t)w * 32u < m) {
+            const uint32_t cnt = min(32u, m - (uint32_t)w * 32u);
+            for (uint32_t bpos = 0; bpos < cnt; ++bpos) {
+                const uint32_t c = s_lut[byte_at(pat, (uint32_t)w * 32u + bpos, wp, cw)];
+                bad |= (c > 3u);
+                const uint32_t bit = 1u << bpos;
+                e0 |= (c == 0) ? bit : 0u; e1 |= (c == 1) ? bit : 0u; e2 |= (c == 2) ? bit : 0u; e3 |= (c == 3) ? bit : 0u;
+            }
+        }
+        peq0[w] = e0; peq1[w] = e1; peq2[w] = e2; peq3[w] = e3;
+        Pv[w] = 0xffffffffu; Mv[w] = 0u;
+    }
+    const uint32_t wl = (m - 1) >> 5, lastbit = (m - 1) & 31u;
+    int32_t score = (int32_t)m;
+    wp = 0; cw = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t c = s_lut[byte_at(text, i, wp, cw)];
+        bad |= (c > 3u);
+        const bool is0 = (c == 0), is1 = (c == 1), is2 = (c == 2);
+        uint32_t hp = 1u, hm = 0u;           // horizontal delta entering block 0: D[i][0] - D[i-1][0] = +1
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            if ((uint32_t)w <= wl) {
+                uint32_t Eq = is0 ? peq0[w] : (is1 ? peq1[w] : (is2 ? peq2[w] : peq3[w]));
+                const uint32_t pv = Pv[w], mv = Mv[w];
+                const uint32_t Xv = Eq | mv;
+                Eq |= hm;
+                const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                uint32_t Ph = mv | ~(Xh | pv);
+                uint32_t Mh = pv & Xh;
+                if ((uint32_t)w == wl) score += (int32_t)((Ph >> lastbit) & 1u) - (int32_t)((Mh >> lastbit) & 1u);
+                const uint32_t hp_out = Ph >> 31, hm_out = Mh >> 31;
+                Ph = (Ph << 1) | hp;
+                Mh = (Mh << 1) | hm;
+                Pv[w] = Mh | ~(Xv | Ph);
+                Mv[w] = Ph & Xv;
+                hp = hp_out; hm = hm_out;
+            }
+        }
+    }
+    A.out[d.pair_id] = (uint64_t)(uint32_t)score;
+    if (bad) atomicOr(A.err_flag, 2u);
+}
+
+// 256-bin byte histogram of a residue arena (which symbols occur at all)
+__global__ void k_byte_hist(const uint8_t* data, uint64_t n, unsigned int* hist) {
+    __shared__ unsigned int s[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s[x] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 16ull;
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16ull; base < n; base += stride) {
+        if (base + 16 <= n && ((reinterpret_cast<uintptr_t>(data) + base) & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(data + base);
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) atomicAdd(&s[(ws[k] >> (8 * b)) & 0xffu], 1u);
+        } else {
+            for (uint64_t x = base; x < n && x < base + 16; ++x) atomicAdd(&s[data[x]], 1u);
+        }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) if (s[x]) atomicAdd(&hist[x], 1u);
+}
+
+}  // namespace bg

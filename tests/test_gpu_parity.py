@@ -356,3 +356,37 @@ def test_in_process_multi_gpu_sharding_is_result_invariant():
     e1 = one.context.edit_distance_batch(batch); e2 = many.context.edit_distance_batch(batch)
     assert np.array_equal(e1, e2)
     r1.close(); r2.close()
+
+
+def test_edit_distance_bit_parallel_and_fallback():
+    """K4b (Myers bit-vectors, <= 4 byte values) against the oracle on mixed lengths (also > 320 columns,
+    which stay on the systolic kernel), through both the host-buffer and the device-resident entry points;
+    plus the fallback: a fifth symbol hidden in the middle of a large batch (the alphabet is sampled from
+    the ends) must be caught on the device and the batch redone with the general kernel."""
+    rng = random.Random(31)
+    seqs = []
+    for _ in range(3000):
+        n = rng.choice([0, 1, 31, 32, 33, 64, 100, 128, 129, 200, 256, 257, 300, 320, 321, 400, 700])
+        m = rng.choice([0, 1, 31, 32, 33, 64, 100, 128, 129, 200, 256, 257, 300, 320, 321, 400, 700])
+        s1 = bytes(rng.choice(b"ACGT") for _ in range(n))
+        s2 = bytearray(s1[:m]) + bytes(rng.choice(b"ACGT") for _ in range(max(0, m - n)))
+        for k in range(0, len(s2), 7):
+            s2[k] = rng.choice(b"ACGT")
+        seqs += [s1, bytes(s2)]
+    batch = native.Batch.from_sequences(seqs)
+    want, _ = orc.edit_distance_batch(batch.residues, batch.seq_off, threads=orc.hw_threads(), lean=True)
+    ctx = native.Context()
+    assert np.array_equal(ctx.edit_distance_batch(batch), want)
+    db = ctx.upload(batch, 0, prepare="edit")
+    r = ctx.edit_distance_device(db)
+    assert np.array_equal(ctx.download_u64(r, batch.n_pairs), want)
+    ctx.free_result(r); ctx.free_batch(db)
+    # fallback
+    big = synth.make("cfg3_edit_100_300", n_pairs=30000)
+    res = big.residues.copy()
+    mid = int(big.seq_off[30001])
+    res[mid + 5] = ord("N")
+    big2 = native.Batch(res, big.seq_off)
+    want2, _ = orc.edit_distance_batch(big2.residues, big2.seq_off, threads=orc.hw_threads(), lean=True)
+    assert np.array_equal(ctx.edit_distance_batch(big2), want2)
+    ctx.close()
