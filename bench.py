@@ -37,7 +37,7 @@ WORKLOADS = {
     "cfg3": ("cfg3_edit_100_300", 1_250_000),
     "cfg5": ("cfg5_long_semiglobal", 125),     # 1000 pairs over 8 GPUs
 }
-ALG_OPS_PER_CELL = {"global": 12, "semiglobal": 12, "local": 15, "edit": 4}
+ALG_OPS_PER_CELL = {"global": 12, "semiglobal": 12, "local": 15, "edit": 0.5}   # SURVEY 8d (edit: bit-parallel Myers, 16 ops per 32-cell word column)
 
 
 def shard_range(n_total: int, rank: int, world: int):

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -501,6 +502,75 @@ struct Phase {
     ~Phase() { cudaEvent_t b = ws.get_event(); cudaEventRecord(b, ws.stream); ws.evs.push_back(PhaseEv{a, b, phase}); }
 };
 
+// One multi-threaded pass over the offsets of a host batch: validity, length statistics and the cost
+// (cells) of every block of SCAN_BLOCK pairs -- everything the host-buffer entry points need before
+// they can start cutting chunks.  (Three separate serial passes cost ~8 ms per million pairs.)
+constexpr uint64_t SCAN_BLOCK = 4096;
+struct BatchScan {
+    bool monotone = true, fitting_violation = false, has_wide = false;
+    uint64_t max_len_sum = 0;
+    std::vector<double> block_cost;   // per SCAN_BLOCK pairs
+};
+void scan_batch(const bg_batch* in, BatchScan& S) {
+    const uint64_t N = in->n_pairs;
+    const uint64_t nblocks = (N + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    S.block_cost.assign(nblocks, 0.0);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(nt ? nt : 1, 8), nblocks / 8));
+    std::vector<BatchScan> part(nt);
+    auto work = [&](unsigned t) {
+        BatchScan& P = part[t];
+        const uint64_t b_lo = nblocks * t / nt, b_hi = nblocks * (t + 1) / nt;
+        const uint64_t* off = in->seq_off;
+        for (uint64_t blk = b_lo; blk < b_hi; ++blk) {
+            const uint64_t q_hi = std::min(N, (blk + 1) * SCAN_BLOCK);
+            double cost = 0;
+            for (uint64_t q = blk * SCAN_BLOCK; q < q_hi; ++q) {
+                const uint64_t o0 = off[2 * q], o1 = off[2 * q + 1], o2 = off[2 * q + 2];
+                if (o1 < o0 || o2 < o1) { P.monotone = false; continue; }
+                const uint64_t n = o1 - o0, m = o2 - o1;
+                if (n < m) P.fitting_violation = true;
+                if (m > WAVE_MIN_COLS) P.has_wide = true;
+                P.max_len_sum = std::max(P.max_len_sum, n + m);
+                cost += (double)n * (double)m + 64.0;
+            }
+            S.block_cost[blk] = cost;
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    for (auto& P : part) {
+        S.monotone = S.monotone && P.monotone;
+        S.fitting_violation = S.fitting_violation || P.fitting_violation;
+        S.has_wide = S.has_wide || P.has_wide;
+        S.max_len_sum = std::max(S.max_len_sum, P.max_len_sum);
+    }
+}
+
+// Pipeline chunks for pairs [lo, hi) at SCAN_BLOCK granularity, roughly equal cell counts.
+std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi) {
+    std::vector<uint64_t> b{lo};
+    if (hi == lo) { b.push_back(hi); return b; }
+    const uint64_t blk_lo = lo / SCAN_BLOCK, blk_hi = (hi + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    double total = 0;
+    for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
+    const double target = std::max(total / 8.0, 1.0e9);
+    const uint64_t max_pairs = 262144;
+    double acc = 0; uint64_t start = lo;
+    for (uint64_t k = blk_lo; k < blk_hi; ++k) {
+        acc += S.block_cost[k];
+        const uint64_t end = std::min(hi, (k + 1) * SCAN_BLOCK);
+        if (end <= start) continue;
+        if (acc >= target || end - start >= max_pairs) { b.push_back(end); start = end; acc = 0; }
+    }
+    if (b.back() != hi) b.push_back(hi);
+    return b;
+}
+
 int check_batch(bg_ctx* ctx, const bg_batch* in) {
     if (!in || (in->n_pairs && (!in->seq_off || (!in->residues && in->seq_off[2 * in->n_pairs] != in->seq_off[0])))) {
         ctx->set_error("null batch pointers"); return BG_EINVAL_ARG;
@@ -511,7 +581,7 @@ int check_batch(bg_ctx* ctx, const bg_batch* in) {
 }
 
 // Validates bg_params against the reference's rules and the engine's numeric range.
-int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_t N, Prepared& pp) {
+int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_t N, Prepared& pp, const BatchScan* scan = nullptr) {
     const int mode = p->mode;
     if (mode < BG_GLOBAL || mode > BG_OVERLAP) { ctx->set_error("unknown mode"); return BG_EINVAL_ARG; }
     // aligner.rs:87-89,153-155,219-221: sign check in global / local / fitting only
@@ -520,10 +590,15 @@ int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_
         ctx->set_error("score table missing or malformed"); return BG_EINVAL_ARG;
     }
     uint64_t max_len_sum = 0;
-    for (uint64_t q = 0; q < N; ++q) {
-        const uint64_t n = off[2 * q + 1] - off[2 * q], m = off[2 * q + 2] - off[2 * q + 1];
-        if (mode == BG_FITTING && n < m) return BG_EINVAL_SIZE;   // aligner.rs:223-225
-        max_len_sum = std::max(max_len_sum, n + m);
+    if (scan) {
+        if (mode == BG_FITTING && scan->fitting_violation) return BG_EINVAL_SIZE;   // aligner.rs:223-225
+        max_len_sum = scan->max_len_sum;
+    } else {
+        for (uint64_t q = 0; q < N; ++q) {
+            const uint64_t n = off[2 * q + 1] - off[2 * q], m = off[2 * q + 2] - off[2 * q + 1];
+            if (mode == BG_FITTING && n < m) return BG_EINVAL_SIZE;   // aligner.rs:223-225
+            max_len_sum = std::max(max_len_sum, n + m);
+        }
     }
     pp.mode = mode; pp.a = p->gap_open; pp.b = p->gap_extend;
     pp.local = (mode == BG_LOCAL); pp.score_only = (p->flags & BG_F_SCORE_ONLY) != 0;
@@ -1183,10 +1258,28 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     const int nchunks = (int)cb.size() - 1;
     const uint64_t ws_budget = long_mode ? ctx->trace_budget_words : std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
     const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
-    struct Fly { bool active = false; uint64_t c_lo = 0, c_n = 0; Plan plan; };
+    struct Fly { bool active = false; uint64_t c_lo = 0, c_n = 0; const Plan* plan = nullptr; };
     Fly fly[PIPE_DEPTH];
     uint64_t arena_base = 0;
     int rc_all = BG_OK;
+
+    // Launch plans of all chunks are built up front by one host thread per chunk, straight into pinned
+    // staging (planning a 125k-pair chunk takes longer than the GPU needs to align it).
+    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; };
+    std::vector<Prebuilt> pre(nchunks);
+    {
+        std::vector<std::thread> th;
+        for (int c = 0; c < nchunks; ++c)
+            th.emplace_back([&, c] {
+                const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
+                if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+                pre[c].rc = build_plan(ctx, off + 2 * c_lo, off[2 * c_lo], n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs,
+                                       pre[c].plan, pre[c].stage.as<PairDesc>());
+            });
+        for (auto& t : th) t.join();
+        for (int c = 0; c < nchunks; ++c) if (pre[c].rc) rc_all = pre[c].rc;
+    }
+    std::vector<std::thread> posts;   // status rules + offset rebasing of finished chunks, off the critical path
 
     auto finish = [&](int s) -> int {
         WorkSet& ws = dv.ws[s];
@@ -1204,14 +1297,19 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         }
         CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
         ctx->d2h += f.c_n * 5 + (pp.score_only ? 0 : 2 * f.c_n * 8 + total);
-        // host post-processing of the chunk while later chunks keep the GPU busy
-        uint64_t* o = fo.off + 2 * rel;
-        if (pp.score_only) { for (uint64_t s2 = 0; s2 < 2 * f.c_n; ++s2) o[s2] = 0; }
-        else if (arena_base) { for (uint64_t s2 = 0; s2 < 2 * f.c_n; ++s2) o[s2] += arena_base; }
-        for (uint64_t q = 0; q < f.c_n; ++q) {
-            const uint64_t g = f.c_lo + q;
-            fo.status[rel + q] = (uint8_t)bg_ref_status(pp.mode, off[2 * g + 1] - off[2 * g], off[2 * g + 2] - off[2 * g + 1],
-                                                        fo.score[rel + q], fo.status[rel + q]);
+        // host post-processing of the chunk on a helper thread while later chunks keep the GPU busy
+        {
+            const uint64_t base_now = arena_base, c_lo2 = f.c_lo, c_n2 = f.c_n;
+            posts.emplace_back([=, &pp] {
+                uint64_t* o = fo.off + 2 * rel;
+                if (pp.score_only) { for (uint64_t s2 = 0; s2 < 2 * c_n2; ++s2) o[s2] = 0; }
+                else if (base_now) { for (uint64_t s2 = 0; s2 < 2 * c_n2; ++s2) o[s2] += base_now; }
+                for (uint64_t q = 0; q < c_n2; ++q) {
+                    const uint64_t g = c_lo2 + q;
+                    fo.status[rel + q] = (uint8_t)bg_ref_status(pp.mode, off[2 * g + 1] - off[2 * g], off[2 * g + 2] - off[2 * g + 1],
+                                                                fo.score[rel + q], fo.status[rel + q]);
+                }
+            });
         }
         arena_base += total;
         return BG_OK;
@@ -1223,11 +1321,10 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         f.c_lo = cb[c]; f.c_n = cb[c + 1] - cb[c];
         const uint64_t n = f.c_n, base = off[2 * f.c_lo], nres = off[2 * (f.c_lo + n)] - base;
         const uint64_t rel = f.c_lo - lo;
-        // plan on the host, straight into pinned staging
-        if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
-        int rc = build_plan(ctx, off + 2 * f.c_lo, base, n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs, f.plan, ws.stage.as<PairDesc>());
-        if (rc) return rc;
-        const Plan& P = f.plan;
+        if (!ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+        int rc = BG_OK;
+        f.plan = &pre[c].plan;
+        const Plan& P = pre[c].plan;
         bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
                   ws.score.ensure(n * 4) && ws.flags.ensure(n);
         if (!pp.score_only)
@@ -1235,7 +1332,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         if (!ok) { ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM; }
         cudaStream_t st = ws.stream;
         if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st));
-        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, ws.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
         rc = upload_params(ctx, ws, pp);
         if (rc) return rc;
@@ -1260,11 +1357,19 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     };
 
     for (WorkSet& ws : dv.ws) ws.reset_events();
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    double t_issue = 0, t_finish = 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
         const int s = c % PIPE_DEPTH;
+        double t0 = now();
         if (fly[s].active) rc_all = finish(s);
+        double t1 = now();
         if (rc_all == BG_OK) rc_all = issue(s, c);
+        double t2 = now();
+        t_finish += t1 - t0; t_issue += t2 - t1;
     }
+    if (prof) fprintf(stderr, "[bgalign] pipeline: %d chunks, issue %.2f ms, finish(wait+post) %.2f ms\n", nchunks, t_issue, t_finish);
     // drain in chunk order
     for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
         const int s = c % PIPE_DEPTH;
@@ -1273,6 +1378,8 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         else { cudaStreamSynchronize(dv.ws[s].stream); fly[s].active = false; }
     }
     for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
+    for (auto& t : posts) t.join();
+    for (auto& pb : pre) pb.stage.release();
     *total_out = arena_base;
     return rc_all;
 }
@@ -1285,7 +1392,18 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     const uint64_t* off = in->seq_off;
     const std::vector<uint64_t> cb = chunk_bounds(off, lo, hi);
     const int nchunks = (int)cb.size() - 1;
-    Plan plans[PIPE_DEPTH];
+    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; };
+    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, built by one host thread per chunk (see align_pipeline)
+    {
+        std::vector<std::thread> th;
+        for (int c = 0; c < nchunks; ++c)
+            th.emplace_back([&, c] {
+                const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
+                if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+                pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
+            });
+        for (auto& t : th) t.join();
+    }
     bool active[PIPE_DEPTH] = {false, false, false};
     // `out` is caller memory of unknown kind: results are staged in pinned memory per work set
     PinBuf host_out[PIPE_DEPTH];
@@ -1307,17 +1425,17 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         if (rc_all) break;
         c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
         const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
-        if (!ws.stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc)) || !host_out[s].ensure(n * 8) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
-        rc_all = build_plan(ctx, off + 2 * c_lo[s], base, n, false, 0, 0, 0, plans[s], ws.stage.as<PairDesc>(), lut != nullptr);
+        if (!host_out[s].ensure(n * 8) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
+        rc_all = pre[c].rc;
         if (rc_all) break;
-        const Plan& P = plans[s];
+        const Plan& P = pre[c].plan;
         if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(n * 8)) {
             ctx->set_error("device allocation failed (pipeline buffers)"); rc_all = BG_ENOMEM; break;
         }
         cudaStream_t st = ws.stream;
         cudaError_t ce = cudaSuccess;
         if (nres) ce = cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess && P.n_slots) ce = cudaMemcpyAsync(ws.desc.p, ws.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess && P.n_slots) ce = cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st);
         if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
         rc_all = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);
@@ -1336,6 +1454,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     }
     for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
     for (auto& h : host_out) h.release();
+    for (auto& pb : pre) pb.stage.release();
     return rc_all;
 }
 

@@ -1,0 +1,15 @@
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from biogarden_b200 import native, score, synth
+from biogarden_b200.aligner import SequenceAligner
+batch = bench.pinned_batch(synth.make("cfg2_dna150_global", n_pairs=1000000))
+al = SequenceAligner([0]); ctx = al.context
+params = al.make_params(batch, "global", score.unit, -2, -1)
+for i in range(4):
+    t0 = time.perf_counter(); r = ctx.align_batch(batch, params); t1 = time.perf_counter(); r.close()
+    print("align_batch %.2f ms" % (1e3 * (t1 - t0)), flush=True)
+b3 = bench.pinned_batch(synth.make("cfg3_edit_100_300", n_pairs=1250000))
+for i in range(3):
+    t0 = time.perf_counter(); ctx.edit_distance_batch(b3); t1 = time.perf_counter()
+    print("edit_distance_batch %.2f ms" % (1e3 * (t1 - t0)), flush=True)
