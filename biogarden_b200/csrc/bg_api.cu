@@ -273,7 +273,9 @@ int shape_index(Shape s) {
     return -1;
 }
 
-size_t plan_desc_capacity(uint64_t n_pairs) { return (size_t)n_pairs + 4 * MAX_SHAPES; }
+// K1h leaves the second slot of a lane group empty when the next pair has a different row count, so a
+// plan can hold up to two slots per pair.
+size_t plan_desc_capacity(uint64_t n_pairs) { return 2 * (size_t)n_pairs + 8 * MAX_SHAPES; }
 
 // Builds launch classes for pairs [0, n_pairs) whose sequence offsets are off[0 .. 2n] (absolute;
 // `base` is subtracted, i.e. the residues of this batch start at device offset 0).  Descriptors go to
@@ -337,7 +339,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         auto len_m0 = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
         // K1h (two pairs per lane group, 16-bit halves): short single-band classes whose scores provably fit
         bool half = false;
-        if (with_trace && half_maxabs > 0 && !wave && sh.L == 8 && !ctx->force_L) {
+        if (with_trace && half_maxabs > 0 && !wave && (sh.L == 8 || (sh.L == 16 && sh.C == 10))) {
             uint32_t cmn = 0, cmm = 0;
             for (size_t k = 0; k < count[si]; ++k) { cmn = std::max(cmn, len_n0(ids[start[si] + k])); cmm = std::max(cmm, len_m0(ids[start[si] + k])); }
             half = cmm <= band_cols && ((int64_t)cmn + cmm + 2) * half_maxabs <= HB_RANGE;
@@ -371,6 +373,19 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) { return len_n(x) > len_n(y); });
             }
         }
+        // launch slots of the class in order; K1h: the two pairs of a lane group must have the same row
+        // count (k1h_fill.cuh), so a hole (HOLE) follows a pair whose successor differs
+        constexpr uint32_t HOLE = 0xFFFFFFFFu;
+        std::vector<uint32_t> slots_h;
+        if (half && !uniform) {
+            slots_h.reserve(cn + cn / 8 + 16);
+            for (size_t k = 0; k < cn; ++k) {
+                slots_h.push_back(cid[k]);
+                if ((slots_h.size() & 1) && (k + 1 == cn || len_n(cid[k + 1]) != len_n(cid[k]))) slots_h.push_back(HOLE);
+            }
+        }
+        const uint32_t* sl = slots_h.empty() ? cid : slots_h.data();
+        const size_t sn = slots_h.empty() ? cn : slots_h.size();
         LaunchClass lc; lc.sh = sh; lc.wave = wave; lc.half = half;
         if (si >= myers_si) lc.myers_W = sh.C;
         if (wave) {   // CTAs per pair: enough workers (16 warps per CTA) for the widest pair's bands
@@ -383,17 +398,20 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const uint64_t ring = wave ? (uint64_t)lc.Q * K2_WARPS + 1 : 1;
         const size_t wave_clusters = std::max<size_t>(1, (size_t)ctx->num_sms / (size_t)lc.Q);   // resident pair groups of a K2 launch
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
-        const size_t nwarps = (cn + G - 1) / G;
+        const size_t nwarps = (sn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
             uint32_t maxn = 0, maxb = 0;
             for (uint32_t gidx = 0; gidx < G; ++gidx) {
                 const size_t k = w * G + gidx;
-                if (k >= cn) break;
-                maxn = std::max(maxn, len_n(cid[k]));
-                maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
+                if (k >= sn) break;
+                if (sl[k] == HOLE) continue;
+                maxn = std::max(maxn, len_n(sl[k]));
+                maxb = std::max(maxb, (len_m(sl[k]) + band_cols - 1) / band_cols);
             }
-            const uint32_t steps = maxn + sh.L - 1;
-            const uint64_t warp_words = with_trace ? (uint64_t)maxb * steps * K * 32ull * (half ? 2 : 1) : 0;
+            // K1h: row-block trace layout, HB_TB steps per block, CW words per lane and block
+            const uint32_t steps = half ? ((maxn + sh.L - 1 + HB_TB - 1) / HB_TB) * HB_TB : maxn + sh.L - 1;
+            const uint64_t warp_words = !with_trace ? 0 :
+                half ? (uint64_t)(steps / HB_TB) * 32ull * hb_words_per_lane_block(sh.C) : (uint64_t)maxb * steps * K * 32ull;
             // K2 launches run one pair per resident cluster at a time: close a chunk at a multiple of the
             // cluster count once memory is nearly used up, so that the (length-sorted) pairs of a launch finish together
             const bool wave_round = wave && ch.trace_words > 0 && ((nd - ch.slot_begin) % wave_clusters) == 0 &&
@@ -410,8 +428,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 PairDesc& d = dst[nd++];
                 memset(&d, 0, sizeof d);
                 d.pair_id = 0xFFFFFFFFu; d.steps = steps; d.trace_off = ch.trace_words;
-                if (k < cn) {
-                    const uint64_t id = cid[k];
+                if (k < sn && sl[k] != HOLE) {
+                    const uint64_t id = sl[k];
                     d.a_off = off[2 * id] - base; d.b_off = off[2 * id + 1] - base;
                     d.n = (uint32_t)(off[2 * id + 1] - off[2 * id]); d.m = (uint32_t)(off[2 * id + 2] - off[2 * id + 1]);
                     d.nbands = (d.m + band_cols - 1) / band_cols;
@@ -456,9 +474,11 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
 // pair groups: Q consecutive CTAs work on one pair.  (Thread-block clusters would give the same
 // guarantee, but clusters of 4 must sit inside one GPC and strand 16 of the B200's 148 SMs:
 // 33 resident clusters instead of 37 groups -- measured, see profiles/.)
-#define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24)
-bool dispatch_k1h(Shape sh, dim3 grid, cudaStream_t st, const FillArgs& a) {
-#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k1h_fill<L_, C_><<<grid, 128, 0, st>>>(a); return true; }
+#define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10)
+bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a) {
+#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { \
+        if (track) k1h_fill<L_, C_, true><<<grid, 128, 0, st>>>(a); else k1h_fill<L_, C_, false><<<grid, 128, 0, st>>>(a); \
+        return true; }
     BG_HALF_SHAPES(X)
 #undef X
     return false;
@@ -715,7 +735,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             } else if (lc.half) {
                 Phase ph(ws, 1);
                 const uint32_t nw2 = (ns + 2 * G - 1) / (2 * G);
-                if (!dispatch_k1h(lc.sh, dim3((nw2 + 3) / 4), st, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
+                if (!dispatch_k1h(lc.sh, pp.mode != BG_GLOBAL, dim3((nw2 + 3) / 4), st, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
             } else {
                 Phase ph(ws, 1);
                 dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, st, fa);
@@ -735,6 +755,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     WalkArgs wa;
                     wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
                     wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C; wa.H = lc.half ? 2 : 1;
+                    wa.CW = lc.half ? (int32_t)hb_words_per_lane_block(lc.sh.C) : 0;
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
                     // long pairs: one warp per pair with a trace window in shared memory; short pairs: one thread per pair
                     if (!lc.half && (lc.wave || (uint64_t)P.max_n + P.max_m > 16384)) {

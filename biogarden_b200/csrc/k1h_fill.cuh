@@ -3,19 +3,42 @@
 // For short reads the scores fit 16 bits, so one 32-bit register carries the same DP cell of two
 // different pairs (pair A in the low half, pair B in the high half) and every instruction of the
 // recurrence does two cell updates:
-//   * values are stored unsigned with a bias of 2^14 (HB_BIAS); "minus infinity" is HB_NEG.  No half
-//     ever leaves [0, 65535], so a plain 32-bit IMAD adds a packed constant (b, a, the substitution
-//     score pair) to both halves at once -- on the FMA pipe;
+//   * values are stored unsigned with a bias of 2^15 (HB_BIAS); "minus infinity" is HB_NEG.  No half
+//     ever leaves [0, 65535], so a plain 32-bit IMAD adds a packed constant to both halves at once
+//     -- on the FMA pipe;
+//   * every value lives in an ANTI-DIAGONAL frame: cell (i, j) stores H(i, j) - (i + j) * b.  A gap
+//     extension moves one anti-diagonal on, so "X_up + b" and "Y_left + b" need no instruction at all:
+//         X^(i,j) = max(S(i-1,j), X^(i-1,j))      S = M^ + (a - b)   (the state the registers carry)
+//         Y^(i,j) = max(S(i,j-1), Y^(i,j-1))
+//         M^(i,j) = max(Y^, X^, S(i-1,j-1) + (s - a - b))
+//     which leaves two adds per cell pair (diagonal + score, M^ + (a - b)); ties are frame-independent
+//     because all operands of one max belong to the same cell.  "Minus infinity" is never added to,
+//     so it cannot drift.  The end-cell captures take the frame out again;
 //   * the four maxima of the cell are VIMNMX.U16x2 with its two predicate outputs, and those
 //     predicates ARE the reference's tie tests:
 //         X  = max(xo, xe)   p = (xo >= xe)  <=>  x_trace == 'M'      (aligner.rs:444, open wins ties)
 //         Y  = max(yo, ye)   p = (yo >= ye)  <=>  y_trace == 'M'      (aligner.rs:448)
 //         m1 = max(X, d)     p = (X  >= d)   <=>  M == X when M != Y  (aligner.rs:458)
 //         M  = max(Y, m1)    p = (Y  >= m1)  <=>  M == Y              (aligner.rs:455, Y tested first)
-//     each predicate adds its bit to the trace word of its pair with a predicated IMAD / LEA;
+//     each predicate adds its bit to the trace word of its column with one predicated instruction; the 8
+//     accumulations per cell pair are split between the ALU pipe (VIADD) and the FMA pipe (IMAD) by
+//     HB_PIPES so that both pipes carry ~8 instructions per cell pair (ncu of the first version, all
+//     on the FMA pipe: fmaheavy 78 % busy, ALU 41 %);
 //   * the substitution score pair comes from one LDS into a 256-entry table indexed by
-//     (row residue A, row residue B, column residue A, column residue B), pre-biased by -a.
-// 4 ALU-pipe + ~9 FMA/ALU instructions per TWO cells instead of 8 + 6 per cell in K1.
+//     (row residue A, row residue B, column residue A, column residue B), pre-biased by -(a + b).
+// 16 instructions per TWO cells (4 VIMNMX.U16x2, 8 accumulations, 2 adds, 1 address, 1 LDS).
+//
+// Trace layout ("row blocks"): a lane keeps one accumulator per COLUMN and collects HB_TB = 4
+// systolic steps in it -- pair A's nibbles in bits 0..15, pair B's in bits 16..31 -- then writes its
+// CW = round_up(C, 4) words with 128-bit stores:
+//     word (block tb, lane, column c) at trace_off + (tb * 32 + lane) * CW + c
+//     nibble of step t = 4 * tb + r: bits [4r, 4r + 4) (+16 for pair B).
+// The traceback walk moves along a diagonal, i.e. to column c - 1 and step t - 1: consecutive cells of
+// a path sit in adjacent words of one 32-byte sector instead of one 128-byte line per step (the
+// first layout cost the walk a 64-byte DRAM access per step: 20 KB per 150 bp pair, ncu).
+//
+// The two pairs of a lane group always have the same number of rows (the host leaves the second slot
+// empty otherwise), so row n of both halves is complete exactly when the lane's last active step is.
 // Restrictions (the host falls back to K1 otherwise -- still GPU, never CPU): not local mode,
 // <= 4 distinct residues per side, single band, (len1 + len2 + 2) * max|score| <= HB_RANGE.
 #pragma once
@@ -24,23 +47,53 @@
 
 namespace bg {
 
-constexpr int32_t HB_BIAS = 1 << 14;
-constexpr int32_t HB_NEG = 1 << 10;      // biased "minus infinity": true value -(2^14 - 2^10)
-constexpr int32_t HB_RANGE = 12000;      // max |true score| the host admits for this kernel
+constexpr int32_t HB_BIAS = 1 << 15;
+constexpr int32_t HB_NEG = 1 << 8;       // biased "minus infinity": below every value a cell can take (>= 2^15 - 2*HB_RANGE - 3*HB_MAXABS)
+constexpr int32_t HB_RANGE = 15000;      // max (len1 + len2 + 2) * max|score| the host admits: |H| and the frame shift each stay below it
 constexpr int32_t HB_MAXABS = 512;       // max |a|, |b|, |s|
+constexpr int HB_TB = 4;                 // systolic steps per trace row block
+constexpr int HB_PIPES = 0x15;           // two bits per max (X, Y, m1, M): low / high half accumulates on the ALU pipe
+
+__host__ __device__ inline uint32_t hb_words_per_lane_block(int C) { return (uint32_t)((C + 3) & ~3); }
 
 __device__ __forceinline__ uint32_t hb_pack(int32_t v) { return (uint32_t)v * 65537u; }   // same value in both halves
 __device__ __forceinline__ int32_t hb_half(uint32_t v, int h) { return (int32_t)((v >> (16 * h)) & 0xffffu); }
 
-// v = max.u16x2(x, y); per half: if (x >= y) w += bit   (w_lo for pair A, w_hi for pair B)
-__device__ __forceinline__ uint32_t hb_max_acc(uint32_t x, uint32_t y, uint32_t& w_lo, uint32_t& w_hi, uint32_t one, uint32_t bit) {
+// v = max.u16x2(x, y); per half: if (x >= y) w |= bit (pair A) / bit << 16 (pair B).  PIPES bit 0 / bit 1:
+// the low / high half's bit is added on the ALU pipe instead of the FMA pipe (predicated IMAD
+// w = one * bit + w; the bits of one word never collide, so add == or).
+template <int PIPES>
+__device__ __forceinline__ uint32_t hb_max_acc(uint32_t x, uint32_t y, uint32_t& w, uint32_t one, uint32_t bit) {
     uint32_t v;
-    asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, r2, r3;\n\t"
-        "max.u16x2 %0, %3, %4;\n\t"
-        "mov.b32 {r0, r1}, %0;\n\tmov.b32 {r2, r3}, %3;\n\t"
-        "setp.eq.u16 pl, r0, r2;\n\tsetp.eq.u16 ph, r1, r3;\n\t"
-        "@pl mad.lo.u32 %1, %5, %6, %1;\n\t@ph mad.lo.u32 %2, %5, %6, %2;\n\t}"
-        : "=r"(v), "+r"(w_lo), "+r"(w_hi) : "r"(x), "r"(y), "r"(one), "r"(bit));
+    const uint32_t lo = bit, hi = bit << 16;
+    if (PIPES == 0)
+        asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, r2, r3;\n\t"
+            "max.u16x2 %0, %2, %3;\n\t"
+            "mov.b32 {r0, r1}, %0;\n\tmov.b32 {r2, r3}, %2;\n\t"
+            "setp.eq.u16 pl, r0, r2;\n\tsetp.eq.u16 ph, r1, r3;\n\t"
+            "@pl mad.lo.u32 %1, %4, %5, %1;\n\t@ph mad.lo.u32 %1, %4, %6, %1;\n\t}"
+            : "=r"(v), "+r"(w) : "r"(x), "r"(y), "r"(one), "r"(lo), "r"(hi));
+    else if (PIPES == 1)
+        asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, r2, r3;\n\t"
+            "max.u16x2 %0, %2, %3;\n\t"
+            "mov.b32 {r0, r1}, %0;\n\tmov.b32 {r2, r3}, %2;\n\t"
+            "setp.eq.u16 pl, r0, r2;\n\tsetp.eq.u16 ph, r1, r3;\n\t"
+            "@pl or.b32 %1, %1, %5;\n\t@ph mad.lo.u32 %1, %4, %6, %1;\n\t}"
+            : "=r"(v), "+r"(w) : "r"(x), "r"(y), "r"(one), "r"(lo), "r"(hi));
+    else if (PIPES == 2)
+        asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, r2, r3;\n\t"
+            "max.u16x2 %0, %2, %3;\n\t"
+            "mov.b32 {r0, r1}, %0;\n\tmov.b32 {r2, r3}, %2;\n\t"
+            "setp.eq.u16 pl, r0, r2;\n\tsetp.eq.u16 ph, r1, r3;\n\t"
+            "@pl mad.lo.u32 %1, %4, %5, %1;\n\t@ph or.b32 %1, %1, %6;\n\t}"
+            : "=r"(v), "+r"(w) : "r"(x), "r"(y), "r"(one), "r"(lo), "r"(hi));
+    else
+        asm("{\n\t.reg .pred ph, pl;\n\t.reg .u16 r0, r1, r2, r3;\n\t"
+            "max.u16x2 %0, %2, %3;\n\t"
+            "mov.b32 {r0, r1}, %0;\n\tmov.b32 {r2, r3}, %2;\n\t"
+            "setp.eq.u16 pl, r0, r2;\n\tsetp.eq.u16 ph, r1, r3;\n\t"
+            "@pl or.b32 %1, %1, %5;\n\t@ph or.b32 %1, %1, %6;\n\t}"
+            : "=r"(v), "+r"(w) : "r"(x), "r"(y), "r"(one), "r"(lo), "r"(hi));
     return v;
 }
 __device__ __forceinline__ uint32_t hb_add(uint32_t x, uint32_t one, uint32_t y) {
@@ -50,22 +103,22 @@ __device__ __forceinline__ uint32_t hb_add(uint32_t x, uint32_t one, uint32_t y)
 }
 
 // Launch geometry: a warp holds 32/L lane groups, each with two pairs: slots (2g, 2g+1) of the warp's
-// 2*(32/L) consecutive slots.  Trace word (t, k, half h, lane) at
-//   trace_off + (((t * K) + k) * 2 + h) * 32 + lane          (single band).
-template <int L, int C>
-__global__ void __launch_bounds__(128, (C <= 19 ? 4 : 3)) k1h_fill(const FillArgs A) {
+// 2*(32/L) consecutive slots.  TRACK: the last-column / last-row end-cell scans of semiglobal, fitting
+// and overlap are compiled in (global only needs the corner cell).
+template <int L, int C, bool TRACK>
+__global__ void __launch_bounds__(128, (C <= 10 ? 5 : 3)) k1h_fill(const FillArgs A) {
     constexpr int GP = 32 / L;
-    constexpr int K = (C + 7) / 8;
+    constexpr int CW = (C + 3) & ~3;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint8_t s_row[256];
     __shared__ uint8_t s_col[256];
-    __shared__ uint32_t s_pack[256];   // [(rA*4 + rB) * 16 + (cA*4 + cB)] = (sA - a) + (sB - a) * 65536
+    __shared__ uint32_t s_pack[256];   // [(rA*4 + rB) * 16 + (cA*4 + cB)] = (sA - a - b) + (sB - a - b) * 65536
 
     for (int x = threadIdx.x; x < 256; x += blockDim.x) {
         s_row[x] = A.row_code[x]; s_col[x] = A.col_code[x];
         const int rA = (x >> 6) & 3, rB = (x >> 4) & 3, cA = (x >> 2) & 3, cB = x & 3;
-        const int32_t sA = ((rA < A.n_rows && cA < A.n_cols) ? A.table[rA * A.n_cols + cA] : 0) - A.a;
-        const int32_t sB = ((rB < A.n_rows && cB < A.n_cols) ? A.table[rB * A.n_cols + cB] : 0) - A.a;
+        const int32_t sA = ((rA < A.n_rows && cA < A.n_cols) ? A.table[rA * A.n_cols + cA] : 0) - A.a - A.b;
+        const int32_t sB = ((rB < A.n_rows && cB < A.n_cols) ? A.table[rB * A.n_cols + cB] : 0) - A.a - A.b;
         s_pack[x] = (uint32_t)(sA + sB * 65536);
     }
     __syncthreads();
@@ -75,48 +128,46 @@ __global__ void __launch_bounds__(128, (C <= 19 ? 4 : 3)) k1h_fill(const FillArg
     const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t slot0 = (warp_global * GP + g) * 2;
 
-    PairDesc d[2];
+    // descriptors: only what the loop needs stays live (lengths, sequence pointers)
+    uint32_t n[2], m[2], steps_mine = 0;
+    const uint8_t* sa[2]; const uint8_t* sb[2];
+    uint64_t trace_off = 0;
+    bool has[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        d[h].n = 0; d[h].m = 0; d[h].steps = 0; d[h].nbands = 0; d[h].pair_id = 0xFFFFFFFFu;
-        d[h].a_off = d[h].b_off = d[h].trace_off = d[h].bnd_off = d[h].pad_off = 0;
-        if (slot0 + h < A.n_slots) d[h] = A.desc[slot0 + h];
+        n[h] = 0; m[h] = 0; has[h] = false; sa[h] = A.residues; sb[h] = A.residues;
+        if (slot0 + h < A.n_slots) {
+            const PairDesc& d = A.desc[slot0 + h];
+            if (d.pair_id != 0xFFFFFFFFu) {
+                has[h] = true; n[h] = d.n; m[h] = d.m;
+                sa[h] = A.residues + d.a_off; sb[h] = A.residues + d.b_off;
+                steps_mine = d.steps; trace_off = d.trace_off;
+            }
+        }
     }
-    bool has[2]; uint32_t n[2], m[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) { has[h] = d[h].pair_id != 0xFFFFFFFFu; n[h] = has[h] ? d[h].n : 0; m[h] = has[h] ? d[h].m : 0; }
-    const uint32_t n_max = max(n[0], n[1]), m_max = max(m[0], m[1]);
-    const uint32_t steps_mine = has[0] ? d[0].steps : (has[1] ? d[1].steps : 0u);
-    const uint32_t steps_w = __reduce_max_sync(FULL, steps_mine);
-    const uint64_t trace_off = has[0] ? d[0].trace_off : d[1].trace_off;
+    const uint32_t n_max = max(n[0], n[1]), m_max = max(m[0], m[1]);   // host: n[0] == n[1] when both slots are used
+    const uint32_t steps_w = __reduce_max_sync(FULL, steps_mine);       // multiple of HB_TB
 
     const int32_t a = A.a, b = A.b;
     const uint32_t one = (uint32_t)A.one;
-    const uint32_t a2 = (uint32_t)(a * 65537), b2 = (uint32_t)(b * 65537);
+    const uint32_t amb2 = (uint32_t)((a - b) * 65537);
     const int mode = A.mode;
     const bool row_gap = (mode == M_GLOBAL || mode == M_FITTING);
     const bool col_gap = (mode == M_GLOBAL);
-    const bool track_col = (mode == M_SEMIGLOBAL || mode == M_FITTING);
-    const bool track_row = (mode == M_SEMIGLOBAL || mode == M_OVERLAP);
-    const uint8_t* sa[2] = {A.residues + d[0].a_off, A.residues + d[1].a_off};
-    const uint8_t* sb[2] = {A.residues + d[0].b_off, A.residues + d[1].b_off};
-    bool bad_residue = false;
-
-    uint32_t p_m[2], c_m[2]; bool col_lane[2];
-    int32_t rbest[2], cbest[2], corner[2]; uint32_t rj[2], ci[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t mcol0 = m[h] ? m[h] - 1 : 0;
-        p_m[h] = mcol0 / C; c_m[h] = mcol0 % C;
-        col_lane[h] = (m[h] > 0) && ((uint32_t)p == p_m[h]);
-        rbest[h] = INT32_MIN; rj[h] = 0;
-        cbest[h] = border_row(row_gap, a, b, m[h]); ci[h] = 0;
-        corner[h] = border_col(col_gap, a, b, n[h]);
-        if (p == 0) { rbest[h] = border_col(col_gap, a, b, n[h]); rj[h] = 0; }
-    }
+    // state of cell (i, j) in the registers: S = M(i, j) - (i + j) * b + (a - b) + HB_BIAS
+    auto to_state = [&](int32_t mval, uint32_t i, uint32_t j) -> uint32_t {
+        return hb_pack(mval - (int32_t)(i + j) * b + (a - b) + HB_BIAS);
+    };
+    auto from_state = [&](uint32_t packed, int h, uint32_t i, uint32_t j) -> int32_t {
+        return hb_half(packed, h) - HB_BIAS - (a - b) + (int32_t)(i + j) * b;
+    };
+    // column border as a packed linear function of the row: S(i, 0) = colS0 + i * colS1 for i >= 1
+    // (global: a + (i-1) b - i b + (a - b) = 2 (a - b), constant; otherwise -i b + (a - b))
+    const uint32_t colS1 = (uint32_t)(((col_gap ? b : 0) - b) * 65537);
+    const uint32_t colS0 = hb_pack((col_gap ? a - b : 0) + (a - b) + HB_BIAS);
+    uint32_t bad_residue = 0;
 
     const uint32_t jbase = (uint32_t)p * C;
-    const bool lane_has_cols = jbase < m_max;
     uint32_t cc[C], MuA[C], Xu[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -125,123 +176,142 @@ __global__ void __launch_bounds__(128, (C <= 19 ? 4 : 3)) k1h_fill(const FillArg
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             code[h] = 0;
-            if (has[h] && j0 < m[h]) {
+            if (j0 < m[h]) {
                 code[h] = s_col[sb[h][j0]];
-                if (code[h] > 3u) { bad_residue = true; code[h] = 0; }
+                if (code[h] > 3u) { bad_residue = 1; code[h] = 0; }
             }
         }
         cc[c] = (code[0] * 4u + code[1]) * 4u;
-        MuA[c] = hb_pack(border_row(row_gap, a, b, j0 + 1) + a + HB_BIAS);
+        MuA[c] = to_state(border_row(row_gap, a, b, j0 + 1), 0, j0 + 1);
         Xu[c] = hb_pack(HB_NEG);
     }
-    // row-n capture for a half: this lane's columns of row n_h are in MuA (biased by a + HB_BIAS)
-    auto capture_row = [&](int h) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const uint32_t j = jbase + c + 1;
-            const int32_t v = hb_half(MuA[c], h) - HB_BIAS - a;
-            if (j <= m[h]) {
-                if (track_row && v >= rbest[h]) { rbest[h] = v; rj[h] = j; }
-                if (j == m[h]) corner[h] = v;
-            }
-        }
-    };
-    if (has[0] && n[0] == 0) capture_row(0);
-    if (has[1] && n[1] == 0) capture_row(1);
 
-    uint32_t MdiagA = hb_pack(border_row(row_gap, a, b, jbase) + a + HB_BIAS);
-    uint32_t MlastA = hb_pack(a + HB_BIAS), Ylast = hb_pack(HB_NEG);
+    // last-column scan state (TRACK): first max over the rows of column m (aligner.rs:376-380, 247-251)
+    uint32_t c_m[2]; bool col_lane[2]; int32_t cbest[2]; uint32_t ci[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t mcol0 = m[h] ? m[h] - 1 : 0;
+        c_m[h] = mcol0 % C;
+        col_lane[h] = (m[h] > 0) && ((uint32_t)p == mcol0 / C);
+        cbest[h] = border_row(row_gap, a, b, m[h]); ci[h] = 0;
+    }
+
+    uint32_t MdiagA = to_state(border_row(row_gap, a, b, jbase), 0, jbase);
+    uint32_t MlastA = hb_pack(HB_BIAS), Ylast = hb_pack(HB_NEG);
     uint32_t rcur = 0;
     auto load_rows = [&](uint32_t base) -> uint32_t {   // combined row code rA*4 + rB of row base + p
         const uint32_t idx = base + (uint32_t)p;
         uint32_t cd[2] = {0, 0};
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-            if (has[h] && idx < n[h]) { cd[h] = s_row[sa[h][idx]]; if (cd[h] > 3u) { bad_residue = true; cd[h] = 0; } }
+            if (idx < n[h]) { cd[h] = s_row[sa[h][idx]]; if (cd[h] > 3u) { bad_residue = 1; cd[h] = 0; } }
         return cd[0] * 4u + cd[1];
     };
     uint32_t cur_blk = 0, next_blk = load_rows(0);
+    const uint32_t first_lane = (p == 0) ? 0xffffffffu : 0u;   // integer mask instead of a live predicate
+    uint32_t* tp = A.trace + trace_off + (uint64_t)lane * CW;
 
-    for (uint32_t t = 0; t < steps_w; ++t) {
-        if ((t & (L - 1)) == 0) { cur_blk = next_blk; next_blk = load_rows(t + L); }
-        const uint32_t r0 = __shfl_sync(FULL, cur_blk, (int)(t & (L - 1)), L);
-        uint32_t MlA = __shfl_up_sync(FULL, MlastA, 1, L);
-        uint32_t Yl = __shfl_up_sync(FULL, Ylast, 1, L);
-        uint32_t r = __shfl_up_sync(FULL, rcur, 1, L);
-        const uint32_t i0 = t - (uint32_t)p;
-        const bool active = i0 < n_max;
-        if (p == 0) {
-            r = r0;
-            MlA = hb_pack(border_col(col_gap, a, b, i0 + 1) + a + HB_BIAS);
-            Yl = hb_pack(HB_NEG);
-        }
-        rcur = r;
-        if (active) {
-            uint32_t diagA = MdiagA, leftA = MlA, Y = Yl;
-            uint32_t wA[K], wB[K];
+    for (uint32_t t0 = 0; t0 < steps_w; t0 += HB_TB) {
+        uint32_t w[C];
 #pragma unroll
-            for (int k = 0; k < K; ++k) { wA[k] = 0; wB[k] = 0; }
-            const unsigned char* rowp = reinterpret_cast<const unsigned char*>(s_pack) + r * 64u;
+        for (int c = 0; c < C; ++c) w[c] = 0;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                uint32_t& wa_ = wA[c >> 3];
-                uint32_t& wb_ = wB[c >> 3];
-                const uint32_t sh = 4u * (c & 7);
-                const uint32_t upA = MuA[c];
-                const uint32_t X = hb_max_acc(upA, hb_add(Xu[c], one, b2), wa_, wb_, one, TR_XOPEN << sh);
-                Y = hb_max_acc(leftA, hb_add(Y, one, b2), wa_, wb_, one, TR_YOPEN << sh);
-                const uint32_t s2 = *reinterpret_cast<const uint32_t*>(rowp + cc[c]);
-                const uint32_t m1 = hb_max_acc(X, hb_add(diagA, one, s2), wa_, wb_, one, TR_XEQ << sh);
-                const uint32_t mx = hb_max_acc(Y, m1, wa_, wb_, one, TR_YEQ << sh);
-                const uint32_t mxA = hb_add(mx, one, a2);
-                diagA = upA; leftA = mxA;
-                MuA[c] = mxA; Xu[c] = X;
-            }
-            MlastA = leftA; Ylast = Y; MdiagA = MlA;
-            if (A.want_trace && lane_has_cols) {
-                uint32_t* tp = A.trace + trace_off + (uint64_t)t * (uint64_t)(K * 64) + lane;
+        for (int rr = 0; rr < HB_TB; ++rr) {
+            const uint32_t t = t0 + rr;
+            if (rr == 0 && (t0 & (L - 1)) == 0) { cur_blk = next_blk; next_blk = load_rows(t0 + L); }
+            const uint32_t r0 = __shfl_sync(FULL, cur_blk, (int)(t & (L - 1)), L);
+            uint32_t MlA = __shfl_up_sync(FULL, MlastA, 1, L);
+            uint32_t Yl = __shfl_up_sync(FULL, Ylast, 1, L);
+            uint32_t r = __shfl_up_sync(FULL, rcur, 1, L);
+            const uint32_t i0 = t - (uint32_t)p;
+            // lane 0 of the group: row residue from the block, column border instead of a left neighbour
+            r = (r & ~first_lane) | (r0 & first_lane);
+            MlA = (MlA & ~first_lane) | ((colS0 + (i0 + 1) * colS1) & first_lane);
+            Yl = (Yl & ~first_lane) | (hb_pack(HB_NEG) & first_lane);
+            rcur = r;
+            if (i0 < n_max) {
+                uint32_t diagA = MdiagA, leftA = MlA, Y = Yl;
+                const unsigned char* rowp = reinterpret_cast<const unsigned char*>(s_pack) + r * 64u;
 #pragma unroll
-                for (int k = 0; k < K; ++k) { tp[k * 64] = wA[k]; tp[k * 64 + 32] = wB[k]; }
-            }
-            if (track_col) {
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t sh = 4u * rr;   // this step's nibble inside the column word (compile-time after unrolling)
+                    const uint32_t upA = MuA[c];
+                    const uint32_t X = hb_max_acc<HB_PIPES & 3>(upA, Xu[c], w[c], one, TR_XOPEN << sh);
+                    Y = hb_max_acc<(HB_PIPES >> 2) & 3>(leftA, Y, w[c], one, TR_YOPEN << sh);
+                    const uint32_t s2 = *reinterpret_cast<const uint32_t*>(rowp + cc[c]);
+                    const uint32_t m1 = hb_max_acc<(HB_PIPES >> 4) & 3>(X, hb_add(diagA, one, s2), w[c], one, TR_XEQ << sh);
+                    const uint32_t mx = hb_max_acc<(HB_PIPES >> 6) & 3>(Y, m1, w[c], one, TR_YEQ << sh);
+                    const uint32_t mxA = hb_add(mx, one, amb2);
+                    diagA = upA; leftA = mxA;
+                    MuA[c] = mxA; Xu[c] = X;
+                }
+                MlastA = leftA; Ylast = Y; MdiagA = MlA;
+                if (TRACK) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v = MuA[0];
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v = MuA[0];
 #pragma unroll
-                    for (int c = 1; c < C; ++c) v = (c_m[h] == (uint32_t)c) ? MuA[c] : v;
-                    const int32_t vv = hb_half(v, h) - HB_BIAS - a;
-                    if (col_lane[h] && i0 < n[h] && vv > cbest[h]) { cbest[h] = vv; ci[h] = i0 + 1; }
+                        for (int c = 1; c < C; ++c) v = (c_m[h] == (uint32_t)c) ? MuA[c] : v;
+                        const int32_t vv = from_state(v, h, i0 + 1, m[h]);
+                        if (col_lane[h] && i0 < n[h] && vv > cbest[h]) { cbest[h] = vv; ci[h] = i0 + 1; }
+                    }
                 }
             }
-            if (i0 + 1 == n[0]) capture_row(0);
-            if (i0 + 1 == n[1]) capture_row(1);
         }
+        if (jbase < m_max) {
+            uint4* q = reinterpret_cast<uint4*>(tp);
+#pragma unroll
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
+                uint4 v;
+                v.x = w[4 * c4];
+                v.y = (4 * c4 + 1 < C) ? w[(4 * c4 + 1 < C) ? 4 * c4 + 1 : 0] : 0u;
+                v.z = (4 * c4 + 2 < C) ? w[(4 * c4 + 2 < C) ? 4 * c4 + 2 : 0] : 0u;
+                v.w = (4 * c4 + 3 < C) ? w[(4 * c4 + 3 < C) ? 4 * c4 + 3 : 0] : 0u;
+                q[c4] = v;
+            }
+        }
+        tp += 32 * CW;
     }
     if (bad_residue) atomicOr(A.err_flag, 1u);
 
+    // ---- end cells: MuA[] holds row n of both halves (row 0 borders if n == 0) ------------------
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        if (track_row) {
+        const uint32_t mcol0 = m[h] ? m[h] - 1 : 0;
+        const uint32_t p_m = mcol0 / C;
+        int32_t rbest = INT32_MIN; uint32_t rj = 0;
+        int32_t corner = border_col(col_gap, a, b, n[h]);
+        if (p == 0) { rbest = border_col(col_gap, a, b, n[h]); rj = 0; }   // row n, column 0 candidate
 #pragma unroll
-            for (int o = L / 2; o > 0; o >>= 1) {
-                const int32_t ov = __shfl_xor_sync(FULL, rbest[h], o, L);
-                const uint32_t oj = __shfl_xor_sync(FULL, rj[h], o, L);
-                if (ov > rbest[h] || (ov == rbest[h] && oj > rj[h])) { rbest[h] = ov; rj[h] = oj; }
+        for (int c = 0; c < C; ++c) {
+            const uint32_t j = jbase + c + 1;
+            const int32_t v = from_state(MuA[c], h, n[h], j);
+            if (j <= m[h]) {
+                if (TRACK && v >= rbest) { rbest = v; rj = j; }   // last row, last max (aligner.rs:369-373)
+                if (j == m[h]) corner = v;
             }
         }
-        const int src = g * L + (int)p_m[h];
+        if (TRACK) {
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) {
+                const int32_t ov = __shfl_xor_sync(FULL, rbest, o, L);
+                const uint32_t oj = __shfl_xor_sync(FULL, rj, o, L);
+                if (ov > rbest || (ov == rbest && oj > rj)) { rbest = ov; rj = oj; }
+            }
+        }
+        const int src = g * L + (int)p_m;
         const int32_t cbest0 = __shfl_sync(FULL, cbest[h], src);
         const uint32_t ci0 = __shfl_sync(FULL, ci[h], src);
-        const int32_t corner0 = __shfl_sync(FULL, corner[h], src);
+        const int32_t corner0 = __shfl_sync(FULL, corner, src);
         if (p == 0 && has[h]) {
             EndCell e; e.flags = 0;
             switch (mode) {
             case M_GLOBAL: e.score = corner0; e.k = n[h]; e.l = m[h]; break;
             case M_FITTING: e.score = cbest0; e.k = ci0; e.l = m[h]; break;
-            case M_OVERLAP: e.score = rbest[h]; e.k = n[h]; e.l = rj[h]; break;
+            case M_OVERLAP: e.score = rbest; e.k = n[h]; e.l = rj; break;
             default:
-                if (cbest0 > rbest[h]) { e.score = cbest0; e.k = ci0; e.l = m[h]; e.flags = 1; }
-                else { e.score = rbest[h]; e.k = n[h]; e.l = rj[h]; }
+                if (cbest0 > rbest) { e.score = cbest0; e.k = ci0; e.l = m[h]; e.flags = 1; }
+                else { e.score = rbest; e.k = n[h]; e.l = rj; }
                 break;
             }
             A.end[slot0 + h] = e;

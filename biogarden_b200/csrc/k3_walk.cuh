@@ -24,6 +24,7 @@ struct WalkArgs {
     int32_t mode;
     int32_t L, C;           // geometry K1 used for this launch
     int32_t H;              // pairs per lane group: 1 (K1 / K2) or 2 (K1h, packed 16 x 2)
+    int32_t CW;             // 0: step-major trace words (bg_common.cuh); > 0: K1h row blocks, CW words per lane and block (k1h_fill.cuh)
     uint8_t* pad;           // padded output slots
     int32_t* score;         // [pair]
     uint8_t* walk_flags;    // [pair]
@@ -76,8 +77,15 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
         if (w != wpb) { wpb = w; cwb = __ldg(reinterpret_cast<const uint32_t*>(w)); }
         return (cwb >> ((q & 3u) * 8u)) & 0xffu;
     };
+    const uint32_t CW = (uint32_t)A.CW;
     auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
         const uint32_t j0 = j - 1;
+        if (CW) {   // K1h row blocks: a diagonal move goes to the previous word of the same 32-byte sector
+            const uint32_t p = j0 / C, c = j0 - p * C;
+            const uint32_t t = (i - 1) + p;
+            const uint64_t idx = d.trace_off + ((uint64_t)(t >> 2) * 32u + lane_base + p) * CW + c;
+            return (__ldg(A.trace + idx) >> ((t & 3u) * 4u + half * 16u)) & 15u;
+        }
         const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
         const uint32_t p = rr / C, c = rr - p * C;
         const uint32_t t = (i - 1) + p;
