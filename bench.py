@@ -37,7 +37,32 @@ WORKLOADS = {
     "cfg3": ("cfg3_edit_100_300", 1_250_000),
     "cfg5": ("cfg5_long_semiglobal", 125),     # 1000 pairs over 8 GPUs
 }
-ALG_OPS_PER_CELL = {"global": 12, "semiglobal": 12, "local": 15, "edit": 0.5}   # SURVEY 8d (edit: bit-parallel Myers, 16 ops per 32-cell word column)
+# Algorithmic int32 lane-instructions per cell: affine + traceback 12, local 15, edit distance 4.
+# Cells that ran through the packed 16 x 2 kernel (K1h) cost half -- one lane instruction updates the same
+# cell of two pairs -- and bit-parallel edit distance (K4b) costs 16 per 32-cell word column = 0.5.
+ALG_OPS_PER_CELL = {"global": 12, "semiglobal": 12, "local": 15, "edit": 4}
+PACKED_DIVISOR = 2
+BITPARALLEL_OPS_PER_CELL = 0.5
+
+
+def algorithmic_ops(mode, cells, cells_packed16, cells_bitparallel):
+    per = ALG_OPS_PER_CELL.get(mode, 12)
+    plain = cells - cells_packed16 - cells_bitparallel
+    return per * plain + per / PACKED_DIVISOR * cells_packed16 + BITPARALLEL_OPS_PER_CELL * cells_bitparallel
+
+
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per cell of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/ncu_traffic_r01.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch and the
+    cells that launch processed); None when no capture of that kernel is on file."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    try:
+        for e in json.load(open(p))["kernels"]:
+            if e["kernel"].startswith(kernel_prefix):
+                return (e["dram_bytes_read"] + e["dram_bytes_write"]) / e["cells"], e
+    except Exception:
+        pass
+    return None, None
 
 
 def shard_range(n_total: int, rank: int, world: int):
@@ -163,11 +188,11 @@ def run_reference(args, rank, world):
     cfg_name, _ = WORKLOADS[args.workload]
     cfg = synth.CONFIGS[cfg_name]
     cores = orc.hw_threads()
-    sample = args.ref_pairs or (2500 * cores if args.workload == "cfg2" else 40 * cores)
+    sample = args.ref_pairs or {"cfg2": 15000, "cfg3": 3000, "cfg4": 120}.get(args.workload, 40) * cores   # ~5 s per step
     if args.workload == "cfg5":
         from biogarden_b200 import native
         cores = min(cores, 8)
-        sample = cores
+        sample = 4 * cores
         batch = native.synth_pairs(cfg["seed"], 0, sample, cfg["alphabet"], 10000, 10000, cfg["resize_b"])
     else:
         batch = synth.make(cfg_name, n_pairs=sample)
@@ -301,6 +326,7 @@ def main():
     t = ctx.timing()                       # phases of the last step (events on the same stream)
     fill_ms, walk_ms, compact_ms, launches = t["fill_ms"], t["walk_ms"], t["compact_ms"], int(t["launches"])
     trace_bytes = int(t["trace_bytes"])
+    cells_packed, cells_bitpar, fill_launches = int(t["cells_packed16"]), int(t["cells_bitparallel"]), max(1, int(t["fill_launches"]))
     ctx.free_result(prev)
     ctx.free_batch(dbatch)
 
@@ -333,10 +359,15 @@ def main():
         ms_per_step = dev_ms_max / args.steps
         value = cells_total * args.steps / (dev_ms_max * 1e-3) / 1e9
         e2e_value = cells_total * args.steps / (e2e_ms_max * 1e-3) / 1e9
-        ops = ALG_OPS_PER_CELL.get(cfg["mode"], 12)
+        alg_ops = algorithmic_ops(cfg["mode"], cells, cells_packed, cells_bitpar)
+        ops = alg_ops / cells if cells else 0
         peak, peak_src = int32_peak()
-        achieved = ops * cells / (fill_ms * 1e-3) / 1e12 if fill_ms > 0 else None
+        achieved = alg_ops / (fill_ms * 1e-3) / 1e12 if fill_ms > 0 else None
         hbm, hbm_src = hbm_peak()
+        kern = ("k4_myers (bit-parallel edit distance)" if cells_bitpar * 2 > cells else "k4_edit") if is_edit else \
+               ("k1h_fill (packed 16x2 DP fill + direction codes)" if cells_packed * 2 > cells else
+                "k2_wave (wavefront DP fill + direction codes)" if args.workload == "cfg5" else "k1_fill (DP fill + direction codes)")
+        bytes_per_cell, cap = ncu_traffic(kern.split(" ")[0])
         line = {
             "metric": "GCUPS (cell updates/s, with traceback)" if not is_edit else "GCUPS (cell updates/s, score only)",
             "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -349,11 +380,16 @@ def main():
             "clocks": clocks,
             "phases_ms_last_step": {"fill": fill_ms, "walk": walk_ms, "compact": compact_ms},
             "roofline": {
-                "bound": "int32", "kernel": "k1_fill (DP fill + direction codes)",
+                "bound": "int32", "kernel": kern,
                 "achieved": achieved, "peak": peak, "unit": "Tops/s (int32 lane-ops)",
                 "frac": (achieved / peak) if achieved else None,
                 "ops_per_cell": ops, "gcups_fill_only": cells / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None,
-                "peak_source": peak_src, "traffic": None,
+                "launches_per_step": fill_launches, "avg_launch_ms": fill_ms / fill_launches,
+                "algorithmic_ops_per_launch": alg_ops / fill_launches,
+                "peak_source": peak_src,
+                "traffic": (bytes_per_cell * cells / fill_launches) if bytes_per_cell else None,
+                "traffic_source": ("profiles/ncu_traffic_r01.json: %s, %.3f B/cell DRAM read+write in one ncu --set full launch, scaled to this "
+                                   "run's cells per launch" % (cap["kernel"], bytes_per_cell)) if bytes_per_cell else None,
                 "hbm": {"trace_bytes_per_launch_set": trace_bytes,
                         "achieved_gbs": trace_bytes / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None,
                         "peak_gbs": hbm, "peak_source": hbm_src},
@@ -372,13 +408,13 @@ def cpu_baseline(args, cfg_name, cfg):
     import _oracle as orc
     from biogarden_b200 import synth
     cores = orc.hw_threads()
-    per_core = {"cfg2": 1500, "cfg3": 300, "cfg4": 12}.get(args.workload, 100)
+    per_core = {"cfg2": 30000, "cfg3": 6000, "cfg4": 250}.get(args.workload, 100)   # ~10 s on the box's cores
     sample = per_core * cores
     if args.workload == "cfg5":
         # the literal layout needs 15 B/cell: time 10 kbp pairs of the same generator
         from biogarden_b200 import native
         cores = min(cores, 8)
-        sample = cores
+        sample = 8 * cores
         batch = native.synth_pairs(cfg["seed"], 0, sample, cfg["alphabet"], 10000, 10000, cfg["resize_b"])
     else:
         batch = synth.make(cfg_name, n_pairs=sample)

@@ -134,12 +134,13 @@ struct PinBuf {   // pinned host block from the global cache
 };
 
 struct Chunk { uint32_t slot_begin, slot_end; uint64_t trace_words; };
-struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; bool half = false; int myers_W = 0; };
+struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; bool half = false; int myers_W = 0; bool ops_fmt = false; };
 
 struct Plan {
     std::vector<LaunchClass> classes;
     size_t n_slots = 0;
     uint64_t max_trace_words = 0, bnd_elems = 0, pad_bytes = 0, cells = 0, total_trace_words = 0;
+    uint64_t cells_half = 0, cells_myers = 0;   // of `cells`: in K1h / K4b classes
     uint64_t max_wave_slots = 0;      // largest K2 launch (slots), for the progress / candidate scratch
     int max_Q = 1;
     uint32_t max_n = 0, max_m = 0;
@@ -243,8 +244,9 @@ struct HostResultOwner {
 // Length class -> kernel shape.  Short pairs use few lanes per pair (the systolic pipeline costs
 // L-1 fill/drain steps per pair) and many columns per lane; wide pairs use a full warp, and pairs
 // wider than 1024 columns loop over bands of the L=32 shape that wastes the fewest padded columns.
-Shape pick_shape(const bg_ctx* ctx, uint32_t m) {
+Shape pick_shape(const bg_ctx* ctx, uint32_t m, bool half_ok = false) {
     if (ctx->force_L) return Shape{ctx->force_L, ctx->force_C};
+    if (half_ok && m > 128 && m <= 160) return Shape{16, 10};   // K1h: more resident warps beat the longer pipeline ramp
     if (m <= 64) return Shape{8, 8};
     if (m <= 96) return Shape{8, 12};
     if (m <= 128) return Shape{8, 16};
@@ -309,7 +311,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             last_m = (uint32_t)m;
             if (with_trace && m > WAVE_MIN_COLS && !ctx->force_L) last_si = wave_si;
             else if (myers && m <= 320) last_si = myers_si + (m <= 128 ? 0 : m <= 256 ? 1 : 2);
-            else last_si = shape_index(pick_shape(ctx, last_m));
+            else last_si = shape_index(pick_shape(ctx, last_m, with_trace && half_maxabs > 0));
             if (last_si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
         }
         cls[p] = (uint8_t)last_si; count[last_si]++;
@@ -388,6 +390,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const size_t sn = slots_h.empty() ? cn : slots_h.size();
         LaunchClass lc; lc.sh = sh; lc.wave = wave; lc.half = half;
         if (si >= myers_si) lc.myers_W = sh.C;
+        if (half || si >= myers_si) {
+            uint64_t cc = 0;
+            for (size_t k = 0; k < cn; ++k) cc += (uint64_t)len_n(cid[k]) * len_m(cid[k]);
+            (half ? P.cells_half : P.cells_myers) += cc;
+        }
         if (wave) {   // CTAs per pair: enough workers (16 warps per CTA) for the widest pair's bands
             uint32_t maxb = 0;
             for (size_t k = 0; k < cn; ++k) maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
@@ -411,7 +418,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             // K1h: row-block trace layout, HB_TB steps per block, CW words per lane and block
             const uint32_t steps = half ? ((maxn + sh.L - 1 + HB_TB - 1) / HB_TB) * HB_TB : maxn + sh.L - 1;
             const uint64_t warp_words = !with_trace ? 0 :
-                half ? (uint64_t)(steps / HB_TB) * 32ull * hb_words_per_lane_block(sh.C) : (uint64_t)maxb * steps * K * 32ull;
+                half ? (uint64_t)((steps / HB_TB + HB_TG_MAX - 1) / HB_TG_MAX) * HB_TG_MAX * 32ull * hb_words_per_lane_block(sh.C) : (uint64_t)maxb * steps * K * 32ull;
             // K2 launches run one pair per resident cluster at a time: close a chunk at a multiple of the
             // cluster count once memory is nearly used up, so that the (length-sorted) pairs of a launch finish together
             const bool wave_round = wave && ch.trace_words > 0 && ((nd - ch.slot_begin) % wave_clusters) == 0 &&
@@ -434,7 +441,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     d.n = (uint32_t)(off[2 * id + 1] - off[2 * id]); d.m = (uint32_t)(off[2 * id + 2] - off[2 * id + 1]);
                     d.nbands = (d.m + band_cols - 1) / band_cols;
                     d.pair_id = (uint32_t)id;
-                    d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull);
+                    d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull) + 16ull;   // + header of an op slot (k3_walk.cuh)
                     if (wave) { d.bnd_off = bnd_off; bnd_off += ring * (((uint64_t)d.n + 31ull) & ~31ull); }
                     else if (d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }
                 }
@@ -450,6 +457,13 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     }
     P.n_slots = nd;
     P.pad_bytes = pad_off; P.bnd_elems = bnd_off;
+    // which walker a class gets (run_align): k3_walk leaves 2-bit ops in the slot, the long-pair walkers characters
+    for (LaunchClass& lc : P.classes) {
+        lc.ops_fmt = lc.half || !(lc.wave || (uint64_t)P.max_n + P.max_m > 16384);
+        if (lc.ops_fmt)
+            for (const Chunk& ch : lc.chunks)
+                for (uint32_t sidx = ch.slot_begin; sidx < ch.slot_end; ++sidx) dst[sidx].pad_ = 1u;
+    }
     P.built = true;
     return BG_OK;
 }
@@ -475,9 +489,13 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
 // guarantee, but clusters of 4 must sit inside one GPC and strand 16 of the B200's 148 SMs:
 // 33 resident clusters instead of 37 groups -- measured, see profiles/.)
 #define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10)
+// Blocks per SM by columns per lane (registers ~ 4 C + 60; measured on cfg2: (16,10) with 6 blocks/SM and
+// 4 of the 8 accumulations on the ALU pipe fills 11 % faster than (8,19) with 3 blocks/SM).
+constexpr int k1h_minb(int C) { return C <= 10 ? 6 : C <= 12 ? 4 : 3; }
 bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a) {
 #define X(L_, C_) if (sh.L == L_ && sh.C == C_) { \
-        if (track) k1h_fill<L_, C_, true><<<grid, 128, 0, st>>>(a); else k1h_fill<L_, C_, false><<<grid, 128, 0, st>>>(a); \
+        if (track) k1h_fill<L_, C_, true, 0x55, k1h_minb(C_)><<<grid, 128, 0, st>>>(a); \
+        else k1h_fill<L_, C_, false, 0x55, k1h_minb(C_)><<<grid, 128, 0, st>>>(a); \
         return true; }
     BG_HALF_SHAPES(X)
 #undef X
@@ -585,15 +603,24 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
         acc += S.block_cost[k];
         const uint64_t end = std::min(hi, (k + 1) * SCAN_BLOCK);
         if (end <= start) continue;
-        if (acc >= target || end - start >= max_pairs) { b.push_back(end); start = end; acc = 0; }
+        // ramp: the first two chunks are a quarter / a half of the rest, so planning + H2D of chunk 0 is short
+        const size_t nb = b.size();
+        const double scale = nb == 1 ? 0.25 : nb == 2 ? 0.5 : 1.0;
+        if (acc >= target * scale || (double)(end - start) >= (double)max_pairs * scale) { b.push_back(end); start = end; acc = 0; }
     }
     if (b.back() != hi) b.push_back(hi);
     return b;
 }
 
-int check_batch(bg_ctx* ctx, const bg_batch* in) {
+// scan != nullptr: the host-buffer entry points validate and measure the batch in one multi-threaded pass.
+int check_batch(bg_ctx* ctx, const bg_batch* in, BatchScan* scan = nullptr) {
     if (!in || (in->n_pairs && (!in->seq_off || (!in->residues && in->seq_off[2 * in->n_pairs] != in->seq_off[0])))) {
         ctx->set_error("null batch pointers"); return BG_EINVAL_ARG;
+    }
+    if (scan) {
+        scan_batch(in, *scan);
+        if (!scan->monotone) { ctx->set_error("seq_off not monotone"); return BG_EINVAL_ARG; }
+        return BG_OK;
     }
     for (uint64_t s = 0; s < 2 * in->n_pairs; ++s)
         if (in->seq_off[s + 1] < in->seq_off[s]) { ctx->set_error("seq_off not monotone"); return BG_EINVAL_ARG; }
@@ -691,6 +718,8 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     fa.table = ws.table.as<int32_t>(); fa.n_rows = pp.n_rows; fa.n_cols = pp.n_cols;
     fa.row_code = ws.codes.as<uint8_t>(); fa.col_code = ws.codes.as<uint8_t>() + 256;
     fa.a = pp.a; fa.b = pp.b; fa.mode = pp.mode; fa.want_trace = pp.score_only ? 0 : 1; fa.one = 1;
+    static const int tg_shift = [] { const char* e = getenv("BG_K1H_TG"); const int v = e ? atoi(e) : 1; return v < 0 ? 0 : v > 2 ? 2 : v; }();   // measured on cfg2: 1 (pairs of row blocks) is best
+    fa.tg_shift = tg_shift;
     fa.trace = ws.trace.as<uint32_t>(); fa.bnd = ws.bnd.as<int2>(); fa.end = nullptr; fa.err_flag = ws.err.as<uint32_t>();
 
     // Chunks alternate between two trace buffers; the walk of chunk c runs on its own stream next to the
@@ -755,10 +784,11 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     WalkArgs wa;
                     wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
                     wa.trace = fa.trace; wa.mode = pp.mode; wa.L = lc.sh.L; wa.C = lc.sh.C; wa.H = lc.half ? 2 : 1;
+                    wa.tg_shift = fa.tg_shift;
                     wa.CW = lc.half ? (int32_t)hb_words_per_lane_block(lc.sh.C) : 0;
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
                     // long pairs: one warp per pair with a trace window in shared memory; short pairs: one thread per pair
-                    if (!lc.half && (lc.wave || (uint64_t)P.max_n + P.max_m > 16384)) {
+                    if (!lc.ops_fmt) {
                         static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return (e && !strcmp(e, "vec")) ? 1 : 0; }();
                         // the window loader maps 8-column blocks onto trace words: needs C % 8 == 0 (true for K2)
                         if (walk_kind == 1 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
@@ -788,7 +818,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
         if (P.n_slots) {
             GatherArgs ga;
             ga.desc = io.desc; ga.n_slots = (uint32_t)P.n_slots; ga.pad = ws.pad.as<uint8_t>();
-            ga.off = io.off; ga.arena = io.arena;
+            ga.off = io.off; ga.arena = io.arena; ga.residues = io.residues;
             k_gather<<<(unsigned)((P.n_slots + 3) / 4), 128, 0, st>>>(ga);
             ctx->launches++;
         }
@@ -957,7 +987,7 @@ int bg_last_timing(const bg_ctx* cctx, bg_timing* out) {
     if (!ctx || !out) return BG_EINVAL_ARG;
     bg_timing t = ctx->timing;
     t.encode_ms = t.fill_ms = t.walk_ms = t.compact_ms = t.total_ms = 0;
-    t.h2d_bytes = ctx->h2d; t.d2h_bytes = ctx->d2h; t.launches = ctx->launches;
+    t.h2d_bytes = ctx->h2d; t.d2h_bytes = ctx->d2h; t.launches = ctx->launches; t.fill_launches = 0;
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.ordinal);
         double ph[4] = {0, 0, 0, 0}, tot = 0;
@@ -966,6 +996,7 @@ int bg_last_timing(const bg_ctx* cctx, bg_timing* out) {
             for (auto& ev : ws.evs) {
                 float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
                 ph[ev.phase] += ms;
+                if (ev.phase == 1) t.fill_launches++;
             }
             if (!ws.evs.empty()) { float ms = 0; cudaEventElapsedTime(&ms, ws.evs.front().a, ws.evs.back().b); tot = std::max<double>(tot, ms); }
         }
@@ -1100,7 +1131,7 @@ int bg_align_device(bg_ctx* ctx, const bg_dbatch* cin, const bg_params* p, bg_dr
 
     ws.reset_events();
     ctx->launches = 0;
-    ctx->timing.cells = P.cells;
+    ctx->timing.cells = P.cells; ctx->timing.cells_packed16 = P.cells_half; ctx->timing.cells_bitparallel = 0;
     ctx->timing.trace_bytes = pp.score_only ? 0 : P.total_trace_words * 4;
     rc = upload_params(ctx, ws, pp);
     AlignIO io{B->residues.as<uint8_t>(), B->desc_align.as<PairDesc>(), &P, N,
@@ -1128,7 +1159,7 @@ int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* cin, bg_dresult** out)
     if (!R->out64.ensure(std::max<uint64_t>(1, N) * 8)) { bg_dresult_free(R); ctx->set_error("device allocation failed"); return BG_ENOMEM; }
     ws.reset_events();
     ctx->launches = 0;
-    ctx->timing.cells = P.cells; ctx->timing.trace_bytes = 0;
+    ctx->timing.cells = P.cells; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = P.cells_myers;
     rc = run_edit(ctx, ws, B->residues.as<uint8_t>(), B->desc_edit.as<PairDesc>(), P, R->out64.as<uint64_t>(), B->edit_lut_ok ? B->edit_lut : nullptr);
     if (rc) { bg_dresult_free(R); return rc; }
     *out = R;
@@ -1242,21 +1273,20 @@ std::vector<uint64_t> shard_bounds(const bg_batch* in, int nd) {
     return b;
 }
 
-// Cuts pairs [lo, hi) into pipeline chunks of roughly equal cell counts.
-std::vector<uint64_t> chunk_bounds(const uint64_t* off, uint64_t lo, uint64_t hi) {
-    std::vector<uint64_t> b{lo};
-    if (hi == lo) { b.push_back(hi); return b; }
+// contiguous shards with ~equal cell counts at SCAN_BLOCK granularity
+std::vector<uint64_t> shard_bounds_from_scan(const BatchScan& S, uint64_t N, int nd) {
+    std::vector<uint64_t> b(nd + 1, 0);
+    b[nd] = N;
+    if (nd == 1) return b;
     double total = 0;
-    for (uint64_t q = lo; q < hi; ++q)
-        total += (double)(off[2 * q + 1] - off[2 * q]) * (double)(off[2 * q + 2] - off[2 * q + 1]) + 64.0;
-    const double target = std::max(total / 8.0, 1.0e9);
-    const uint64_t max_pairs = 262144;
-    double acc = 0; uint64_t cnt = 0;
-    for (uint64_t q = lo; q < hi; ++q) {
-        acc += (double)(off[2 * q + 1] - off[2 * q]) * (double)(off[2 * q + 2] - off[2 * q + 1]) + 64.0;
-        if (++cnt >= max_pairs || acc >= target) { b.push_back(q + 1); acc = 0; cnt = 0; }
+    for (double c : S.block_cost) total += c;
+    double acc = 0; int d = 1;
+    for (size_t k = 0; k < S.block_cost.size() && d < nd; ++k) {
+        acc += S.block_cost[k];
+        while (d < nd && acc >= total * d / nd) { b[d] = std::min<uint64_t>(N, (k + 1) * SCAN_BLOCK); ++d; }
     }
-    if (b.back() != hi) b.push_back(hi);
+    for (; d < nd; ++d) b[d] = N;
+    for (int q = 1; q <= nd; ++q) if (b[q] < b[q - 1]) b[q] = b[q - 1];
     return b;
 }
 
@@ -1266,7 +1296,7 @@ struct FinalOut {      // the caller-visible arrays of one device's pair range
 
 // One device's share of bg_align_batch: chunks of pairs [lo, hi) flow through the work sets.
 int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const Prepared& pp,
-                   const FinalOut& fo, uint64_t* total_out) {
+                   const BatchScan& scan, const FinalOut& fo, uint64_t* total_out) {
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
     const uint64_t* off = in->seq_off;
@@ -1274,8 +1304,9 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     // pair, the copies are negligible next to the fill, and every launch should see as many pairs as
     // memory allows.  Everything else flows through the 3-deep chunk pipeline.
     bool long_mode = false;
-    for (uint64_t q = lo; q < hi && !long_mode; ++q) long_mode = (off[2 * q + 2] - off[2 * q + 1]) > WAVE_MIN_COLS;
-    std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds(off, lo, hi);
+    if (scan.has_wide)
+        for (uint64_t q = lo; q < hi && !long_mode; ++q) long_mode = (off[2 * q + 2] - off[2 * q + 1]) > WAVE_MIN_COLS;
+    std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds_from_scan(scan, lo, hi);
     const int nchunks = (int)cb.size() - 1;
     const uint64_t ws_budget = long_mode ? ctx->trace_budget_words : std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
     const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
@@ -1284,22 +1315,18 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     uint64_t arena_base = 0;
     int rc_all = BG_OK;
 
-    // Launch plans of all chunks are built up front by one host thread per chunk, straight into pinned
-    // staging (planning a 125k-pair chunk takes longer than the GPU needs to align it).
-    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; };
+    // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
+    // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon
+    // as ITS plan is ready, so the GPU starts after the (small) first chunk's plan.
+    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; std::thread th; };
     std::vector<Prebuilt> pre(nchunks);
-    {
-        std::vector<std::thread> th;
-        for (int c = 0; c < nchunks; ++c)
-            th.emplace_back([&, c] {
-                const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
-                if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
-                pre[c].rc = build_plan(ctx, off + 2 * c_lo, off[2 * c_lo], n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs,
-                                       pre[c].plan, pre[c].stage.as<PairDesc>());
-            });
-        for (auto& t : th) t.join();
-        for (int c = 0; c < nchunks; ++c) if (pre[c].rc) rc_all = pre[c].rc;
-    }
+    for (int c = 0; c < nchunks; ++c)
+        pre[c].th = std::thread([&, c] {
+            const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
+            if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+            pre[c].rc = build_plan(ctx, off + 2 * c_lo, off[2 * c_lo], n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs,
+                                   pre[c].plan, pre[c].stage.as<PairDesc>());
+        });
     std::vector<std::thread> posts;   // status rules + offset rebasing of finished chunks, off the critical path
 
     auto finish = [&](int s) -> int {
@@ -1343,7 +1370,9 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         const uint64_t n = f.c_n, base = off[2 * f.c_lo], nres = off[2 * (f.c_lo + n)] - base;
         const uint64_t rel = f.c_lo - lo;
         if (!ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
-        int rc = BG_OK;
+        if (pre[c].th.joinable()) pre[c].th.join();
+        int rc = pre[c].rc;
+        if (rc) return rc;
         f.plan = &pre[c].plan;
         const Plan& P = pre[c].plan;
         bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
@@ -1371,7 +1400,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         CU_TRY(ctx, cudaMemcpyAsync(fo.score + rel, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaMemcpyAsync(fo.status + rel, ws.flags.p, n, cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st));
-        ctx->timing.cells += P.cells;
+        ctx->timing.cells += P.cells; ctx->timing.cells_packed16 += P.cells_half;
         ctx->timing.trace_bytes += pp.score_only ? 0 : P.total_trace_words * 4;
         f.active = true;
         return BG_OK;
@@ -1381,6 +1410,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
     double t_issue = 0, t_finish = 0;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
         const int s = c % PIPE_DEPTH;
         double t0 = now();
@@ -1389,8 +1419,10 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         if (rc_all == BG_OK) rc_all = issue(s, c);
         double t2 = now();
         t_finish += t1 - t0; t_issue += t2 - t1;
+        if (prof) fprintf(stderr, "[bgalign]   chunk %d (%llu pairs): finish-prev %.2f ms, issue %.2f ms, at %.2f ms\n", c,
+                          (unsigned long long)(cb[c + 1] - cb[c]), t1 - t0, t2 - t1, t2 - t_begin);
     }
-    if (prof) fprintf(stderr, "[bgalign] pipeline: %d chunks, issue %.2f ms, finish(wait+post) %.2f ms\n", nchunks, t_issue, t_finish);
+    if (prof) fprintf(stderr, "[bgalign] pipeline: %d chunks, issue %.2f ms, finish(wait+post) %.2f ms, loop %.2f ms\n", nchunks, t_issue, t_finish, now() - t_begin);
     // drain in chunk order
     for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
         const int s = c % PIPE_DEPTH;
@@ -1399,32 +1431,29 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         else { cudaStreamSynchronize(dv.ws[s].stream); fly[s].active = false; }
     }
     for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
+    if (prof) fprintf(stderr, "[bgalign] drained at %.2f ms\n", now() - t_begin);
     for (auto& t : posts) t.join();
-    for (auto& pb : pre) pb.stage.release();
+    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
     *total_out = arena_base;
     return rc_all;
 }
 
 constexpr int EDIT_RETRY_GENERAL = -77;   // internal: a byte outside the sampled 4-symbol alphabet turned up
 
-int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, uint64_t* out, const uint8_t* lut) {
+int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const BatchScan& scan, uint64_t* out, const uint8_t* lut) {
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
     const uint64_t* off = in->seq_off;
-    const std::vector<uint64_t> cb = chunk_bounds(off, lo, hi);
+    const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi);
     const int nchunks = (int)cb.size() - 1;
-    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; };
-    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, built by one host thread per chunk (see align_pipeline)
-    {
-        std::vector<std::thread> th;
-        for (int c = 0; c < nchunks; ++c)
-            th.emplace_back([&, c] {
-                const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
-                if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
-                pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
-            });
-        for (auto& t : th) t.join();
-    }
+    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; std::thread th; };
+    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one host thread per chunk, consumed as they finish (see align_pipeline)
+    for (int c = 0; c < nchunks; ++c)
+        pre[c].th = std::thread([&, c] {
+            const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
+            if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+            pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
+        });
     bool active[PIPE_DEPTH] = {false, false, false};
     // `out` is caller memory of unknown kind: results are staged in pinned memory per work set
     PinBuf host_out[PIPE_DEPTH];
@@ -1447,6 +1476,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
         const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
         if (!host_out[s].ensure(n * 8) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
+        if (pre[c].th.joinable()) pre[c].th.join();
         rc_all = pre[c].rc;
         if (rc_all) break;
         const Plan& P = pre[c].plan;
@@ -1464,7 +1494,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         ce = cudaMemcpyAsync(host_out[s].p, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(ws.scalars.as<uint64_t>() + 1, ws.err.p, 4, cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
-        ctx->timing.cells += P.cells;
+        ctx->timing.cells += P.cells; ctx->timing.cells_bitparallel += P.cells_myers;
         active[s] = true;
     }
     for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
@@ -1475,7 +1505,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     }
     for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
     for (auto& h : host_out) h.release();
-    for (auto& pb : pre) pb.stage.release();
+    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
     return rc_all;
 }
 
@@ -1486,19 +1516,24 @@ extern "C" {
 int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_result* out) {
     if (!ctx || !in || !p || !out) return BG_EINVAL_ARG;
     memset(out, 0, sizeof *out);
-    int rc = check_batch(ctx, in);
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count(); };
+    BatchScan scan;
+    int rc = check_batch(ctx, in, &scan);
     if (rc) return rc;
+    if (prof) fprintf(stderr, "[bgalign] scan done at %.2f ms\n", since());
     const uint64_t N = in->n_pairs;
     Prepared pp;
     static const uint64_t zero_off[1] = {0};
-    rc = prepare_params(ctx, p, N ? in->seq_off : zero_off, N, pp);
+    rc = prepare_params(ctx, p, N ? in->seq_off : zero_off, N, pp, &scan);
     if (rc) return rc;
     const int nd = (int)ctx->devs.size();
-    const std::vector<uint64_t> bounds = shard_bounds(in, nd);
+    const std::vector<uint64_t> bounds = (N < 8ull * SCAN_BLOCK * nd) ? shard_bounds(in, nd) : shard_bounds_from_scan(scan, N, nd);
     rc = bg_sync(ctx);   // cached blocks may still be in use by device-resident work (see bg_dresult_free)
     if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
-    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0;
 
     // upper bound of each device's share of the arena: 2*(n+m) per pair
     std::vector<uint64_t> ub(nd + 1, 0);
@@ -1513,11 +1548,12 @@ int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_resul
     out->off = (uint64_t*)own->grab((2 * N + 1) * 8); out->arena = (uint8_t*)own->grab(ub[nd]);
     if (!out->score || !out->status || !out->off || !out->arena) { bg_result_free(out); ctx->set_error("pinned host allocation failed"); return BG_ENOMEM; }
 
+    if (prof) fprintf(stderr, "[bgalign] pipelines start at %.2f ms\n", since());
     std::vector<int> rcs(nd, BG_OK);
     std::vector<uint64_t> totals(nd, 0);
     auto work = [&](int d) {
         FinalOut fo{out->score + bounds[d], out->status + bounds[d], out->off + 2 * bounds[d], out->arena + ub[d], ub[d + 1] - ub[d]};
-        rcs[d] = align_pipeline(ctx, d, in, bounds[d], bounds[d + 1], pp, fo, &totals[d]);
+        rcs[d] = align_pipeline(ctx, d, in, bounds[d], bounds[d + 1], pp, scan, fo, &totals[d]);
     };
     if (nd == 1) work(0);
     else {
@@ -1539,19 +1575,21 @@ int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_resul
         base += totals[d];
     }
     out->off[2 * N] = base;
+    if (prof) fprintf(stderr, "[bgalign] bg_align_batch returns at %.2f ms\n", since());
     return BG_OK;
 }
 
 int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     if (!ctx || !in || (!out && in->n_pairs)) return BG_EINVAL_ARG;
-    int rc = check_batch(ctx, in);
+    BatchScan scan;
+    int rc = check_batch(ctx, in, &scan);
     if (rc) return rc;
     const int nd = (int)ctx->devs.size();
-    const std::vector<uint64_t> bounds = shard_bounds(in, nd);
+    const std::vector<uint64_t> bounds = (in->n_pairs < 8ull * SCAN_BLOCK * nd) ? shard_bounds(in, nd) : shard_bounds_from_scan(scan, in->n_pairs, nd);
     rc = bg_sync(ctx);
     if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
-    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0;
     // Alphabet from a sample of the batch: <= 4 byte values -> bit-parallel K4b.  The kernel flags any
     // byte outside the sampled alphabet, in which case the batch is redone with the general kernel.
     uint8_t lut[256];
@@ -1566,7 +1604,7 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         std::vector<int> rcs(nd, BG_OK);
-        auto work = [&](int d) { rcs[d] = edit_pipeline(ctx, d, in, bounds[d], bounds[d + 1], out, use_lut ? lut : nullptr); };
+        auto work = [&](int d) { rcs[d] = edit_pipeline(ctx, d, in, bounds[d], bounds[d + 1], scan, out, use_lut ? lut : nullptr); };
         if (nd == 1) work(0);
         else {
             std::vector<std::thread> th;

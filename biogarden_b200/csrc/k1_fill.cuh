@@ -44,6 +44,7 @@ struct FillArgs {
     EndCell* end;
     uint32_t* err_flag;        // bit 0: residue without a table row/column
     int32_t one;               // == 1 at run time; keeps the FMA-pipe adds below as IMADs (see k1_fill)
+    int32_t tg_shift;          // K1h trace tiling (k1h_fill.cuh)
 };
 
 __device__ __forceinline__ int32_t prmt_sx(uint32_t packed, uint32_t sel) {

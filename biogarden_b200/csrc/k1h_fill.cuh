@@ -31,11 +31,13 @@
 // Trace layout ("row blocks"): a lane keeps one accumulator per COLUMN and collects HB_TB = 4
 // systolic steps in it -- pair A's nibbles in bits 0..15, pair B's in bits 16..31 -- then writes its
 // CW = round_up(C, 4) words with 128-bit stores:
-//     word (block tb, lane, column c) at trace_off + (tb * 32 + lane) * CW + c
+//     word (block tb, lane, column c) at trace_off + ((tb / 4) * 32 + lane) * 4 CW + (tb % 4) * CW + c
 //     nibble of step t = 4 * tb + r: bits [4r, 4r + 4) (+16 for pair B).
-// The traceback walk moves along a diagonal, i.e. to column c - 1 and step t - 1: consecutive cells of
-// a path sit in adjacent words of one 32-byte sector instead of one 128-byte line per step (the
-// first layout cost the walk a 64-byte DRAM access per step: 20 KB per 150 bp pair, ncu).
+// HB_TG = 4 consecutive row blocks of a lane are contiguous, so 16 steps x C columns of a lane group's
+// pair form one 4 CW-word tile (192 B for C = 10) next to the tiles of the neighbouring lanes.  The
+// traceback walk moves along a diagonal, i.e. to column c - 1 and step t - 1: consecutive cells of a
+// path sit in adjacent words and a path stays ~10 steps inside one or two 128-byte lines (the first,
+// step-major layout cost the walk a DRAM access per step: 20 KB per 150 bp pair, ncu).
 //
 // The two pairs of a lane group always have the same number of rows (the host leaves the second slot
 // empty otherwise), so row n of both halves is complete exactly when the lane's last active step is.
@@ -52,7 +54,8 @@ constexpr int32_t HB_NEG = 1 << 8;       // biased "minus infinity": below every
 constexpr int32_t HB_RANGE = 15000;      // max (len1 + len2 + 2) * max|score| the host admits: |H| and the frame shift each stay below it
 constexpr int32_t HB_MAXABS = 512;       // max |a|, |b|, |s|
 constexpr int HB_TB = 4;                 // systolic steps per trace row block
-constexpr int HB_PIPES = 0x15;           // two bits per max (X, Y, m1, M): low / high half accumulates on the ALU pipe
+constexpr int HB_TG_MAX = 4;             // FillArgs::tg_shift <= 2: 2^tg_shift row blocks of one lane are stored back to back
+// HB_PIPES (template argument below): two bits per max (X, Y, m1, M): low / high half accumulates on the ALU pipe
 
 __host__ __device__ inline uint32_t hb_words_per_lane_block(int C) { return (uint32_t)((C + 3) & ~3); }
 
@@ -105,8 +108,8 @@ __device__ __forceinline__ uint32_t hb_add(uint32_t x, uint32_t one, uint32_t y)
 // Launch geometry: a warp holds 32/L lane groups, each with two pairs: slots (2g, 2g+1) of the warp's
 // 2*(32/L) consecutive slots.  TRACK: the last-column / last-row end-cell scans of semiglobal, fitting
 // and overlap are compiled in (global only needs the corner cell).
-template <int L, int C, bool TRACK>
-__global__ void __launch_bounds__(128, (C <= 10 ? 5 : 3)) k1h_fill(const FillArgs A) {
+template <int L, int C, bool TRACK, int HB_PIPES, int MINB>
+__global__ void __launch_bounds__(128, MINB) k1h_fill(const FillArgs A) {
     constexpr int GP = 32 / L;
     constexpr int CW = (C + 3) & ~3;
     constexpr unsigned FULL = 0xffffffffu;
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(128, (C <= 10 ? 5 : 3)) k1h_fill(const FillArg
     };
     uint32_t cur_blk = 0, next_blk = load_rows(0);
     const uint32_t first_lane = (p == 0) ? 0xffffffffu : 0u;   // integer mask instead of a live predicate
-    uint32_t* tp = A.trace + trace_off + (uint64_t)lane * CW;
+    const uint32_t tgs = (uint32_t)A.tg_shift;
+    uint32_t* const tbase = A.trace + trace_off + (((uint64_t)lane * CW) << tgs);
 
     for (uint32_t t0 = 0; t0 < steps_w; t0 += HB_TB) {
         uint32_t w[C];
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(128, (C <= 10 ? 5 : 3)) k1h_fill(const FillArg
             }
         }
         if (jbase < m_max) {
-            uint4* q = reinterpret_cast<uint4*>(tp);
+            const uint32_t tb = t0 / HB_TB;
+            uint4* q = reinterpret_cast<uint4*>(tbase + (((uint64_t)(tb >> tgs) * (32u * CW)) << tgs) + (tb & ((1u << tgs) - 1u)) * CW);
 #pragma unroll
             for (int c4 = 0; c4 < CW / 4; ++c4) {
                 uint4 v;
@@ -270,7 +275,6 @@ __global__ void __launch_bounds__(128, (C <= 10 ? 5 : 3)) k1h_fill(const FillArg
                 q[c4] = v;
             }
         }
-        tp += 32 * CW;
     }
     if (bad_residue) atomicOr(A.err_flag, 1u);
 

@@ -15,6 +15,10 @@
 
 namespace bg {
 
+#ifndef K3_MINB
+#define K3_MINB 16
+#endif
+
 struct WalkArgs {
     const PairDesc* desc;
     const EndCell* end;
@@ -24,6 +28,7 @@ struct WalkArgs {
     int32_t mode;
     int32_t L, C;           // geometry K1 used for this launch
     int32_t H;              // pairs per lane group: 1 (K1 / K2) or 2 (K1h, packed 16 x 2)
+    int32_t tg_shift;       // K1h trace tiling
     int32_t CW;             // 0: step-major trace words (bg_common.cuh); > 0: K1h row blocks, CW words per lane and block (k1h_fill.cuh)
     uint8_t* pad;           // padded output slots
     int32_t* score;         // [pair]
@@ -31,7 +36,7 @@ struct WalkArgs {
     uint64_t* lens2;        // [2*pairs + 1]: lens2[2p] = lens2[2p+1] = aligned length
 };
 
-__global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
+__global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= A.n_slots) return;
     const PairDesc d = A.desc[slot];
@@ -44,47 +49,36 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
     const uint32_t H = (uint32_t)A.H;
     const uint32_t lane_base = ((slot % (H * (32u / L))) / H) * L;
     const uint32_t half = slot % H;
-    const uint8_t* sa = A.residues + d.a_off;
-    const uint8_t* sb = A.residues + d.b_off;
-    // Output slot: two regions of cap4 = round_up(n + m, 4) bytes (pad_off is 4-byte aligned), filled back
-    // to front.  Characters are collected in a register and leave as aligned 32-bit stores; residues
-    // are fetched as aligned 32-bit words and cached -- the walk is bound by memory requests, not math.
-    const uint32_t cap4 = (n + m + 3u) & ~3u;
-    uint8_t* outA = A.pad + d.pad_off;
-    uint8_t* outB = outA + cap4;
-    uint32_t pos = cap4;
-    uint32_t wa = 0, wb = 0;
+    // Output: the walk only records WHAT it did -- one 2-bit op per step (0 both residues, 1 seq1 residue
+    // over a gap, 2 gap over seq2 residue), 16 per word, back to front -- plus where it ended.  k_gather turns
+    // ops into the two aligned strings with coalesced residue reads; the walk itself is then a single chain
+    // of dependent trace loads (fetching residues here cost two more memory round trips per step, ncu).
+    // Slot: [first_a][first_b][ops words ...], capacity n + m ops (every op consumes a residue).
+    uint32_t* slotw = reinterpret_cast<uint32_t*>(A.pad + d.pad_off);
+    uint32_t* ops = slotw + 2;
+    uint32_t pos = n + m;
+    uint32_t wops = 0;
     const int mode = A.mode;
-
-    auto push = [&](uint32_t x, uint32_t y) {
+    auto push = [&](uint32_t op) {
         --pos;
-        const uint32_t sh = (pos & 3u) * 8u;
-        wa |= x << sh; wb |= y << sh;
-        if ((pos & 3u) == 0) {
-            *reinterpret_cast<uint32_t*>(outA + pos) = wa;
-            *reinterpret_cast<uint32_t*>(outB + pos) = wb;
-            wa = 0; wb = 0;
-        }
-    };
-    uintptr_t wpa = 0, wpb = 0; uint32_t cwa = 0, cwb = 0;
-    auto res_a = [&](uint32_t idx) -> uint32_t {
-        const uintptr_t q = reinterpret_cast<uintptr_t>(sa + idx), w = q & ~(uintptr_t)3;
-        if (w != wpa) { wpa = w; cwa = __ldg(reinterpret_cast<const uint32_t*>(w)); }
-        return (cwa >> ((q & 3u) * 8u)) & 0xffu;
-    };
-    auto res_b = [&](uint32_t idx) -> uint32_t {
-        const uintptr_t q = reinterpret_cast<uintptr_t>(sb + idx), w = q & ~(uintptr_t)3;
-        if (w != wpb) { wpb = w; cwb = __ldg(reinterpret_cast<const uint32_t*>(w)); }
-        return (cwb >> ((q & 3u) * 8u)) & 0xffu;
+        wops |= op << ((pos & 15u) * 2u);
+        if ((pos & 15u) == 0) { ops[pos >> 4] = wops; wops = 0; }
     };
     const uint32_t CW = (uint32_t)A.CW;
+    uint64_t quad_idx = ~0ull; uint4 quad = make_uint4(0, 0, 0, 0);
     auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
         const uint32_t j0 = j - 1;
-        if (CW) {   // K1h row blocks: a diagonal move goes to the previous word of the same 32-byte sector
+        if (CW) {   // K1h row blocks: a diagonal move goes to the previous word of the same 16-byte quad, which
+                    // is kept in registers (2048 walks per SM touch 5 lines each: L1 cannot hold them, ncu 13 % hits)
             const uint32_t p = j0 / C, c = j0 - p * C;
             const uint32_t t = (i - 1) + p;
-            const uint64_t idx = d.trace_off + ((uint64_t)(t >> 2) * 32u + lane_base + p) * CW + c;
-            return (__ldg(A.trace + idx) >> ((t & 3u) * 4u + half * 16u)) & 15u;
+            const uint32_t tb = t >> 2;
+            const uint32_t tgs = (uint32_t)A.tg_shift;
+            const uint64_t idx = d.trace_off + ((((uint64_t)(tb >> tgs) * 32u + lane_base + p) * CW) << tgs) + (tb & ((1u << tgs) - 1u)) * CW + c;
+            const uint64_t q = idx >> 2;
+            if (q != quad_idx) { quad_idx = q; quad = __ldg(reinterpret_cast<const uint4*>(A.trace) + q); }
+            const uint32_t lo2 = (idx & 1u) ? quad.y : quad.x, hi2 = (idx & 1u) ? quad.w : quad.z;
+            return (((idx & 2u) ? hi2 : lo2) >> ((t & 3u) * 4u + half * 16u)) & 15u;
         }
         const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
         const uint32_t p = rr / C, c = rr - p * C;
@@ -96,12 +90,12 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
     uint32_t k = e.k, l = e.l, flags = 0;
     const bool colbr = (e.flags & 1u) != 0;
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
-        if (colbr) { for (uint32_t i = n; i > k; --i) push(res_a(i - 1), '-'); }
-        else       { for (uint32_t i = m; i > l; --i) push('-', res_b(i - 1)); }
+        if (colbr) { for (uint32_t i = n; i > k; --i) push(1u); }
+        else       { for (uint32_t i = m; i > l; --i) push(2u); }
     }
     uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
-    const uint64_t bound = 2ull * ((uint64_t)n + m) + 8;
-    uint64_t it = 0;
+    const uint32_t bound = 2u * (n + m) + 8u;
+    uint32_t it = 0;
     for (;; ++it) {
         if (it > bound) { flags |= WALK_HANG; break; }
         const bool interior = (k != 0 && l != 0);
@@ -118,28 +112,27 @@ __global__ void __launch_bounds__(128) k3_walk(const WalkArgs A) {
         if (cur == 0) {
             uint32_t t;   // 0 'R', 1 'X', 2 'Y'; m_trace borders: column 0 'X', then row 0 'Y' (aligner.rs:107-108)
             if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib & TR_YEQ) ? 2u : (nib & TR_XEQ);
-            if (t == 0) { push(res_a(k - 1), res_b(l - 1)); --k; --l; }
-            else if (t == 1) { push(res_a(k - 1), '-'); --k; cur = 1; }
-            else { push('-', res_b(l - 1)); --l; cur = 2; }
+            push(t);
+            if (t == 0) { --k; --l; }
+            else if (t == 1) { --k; cur = 1; }
+            else { --l; cur = 2; }
         } else if (cur == 1) {
             if (interior && (nib & TR_XOPEN)) cur = 0;                 // x_trace borders stay 'I' (aligner.rs:52)
             else if (k == 0) { flags |= WALK_UNDERFLOW; break; }      // reference: seq1[usize::MAX] -> panic
-            else { push(res_a(k - 1), '-'); --k; }
+            else { push(1u); --k; }
         } else {
             if (interior && (nib & TR_YOPEN)) cur = 0;
             else if (l == 0) { flags |= WALK_UNDERFLOW; break; }
-            else { push('-', res_b(l - 1)); --l; }
+            else { push(2u); --l; }
         }
     }
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
-        if (colbr) { for (uint32_t i = k; i > 0; --i) push(res_a(i - 1), '-'); }
-        else       { for (uint32_t i = l; i > 0; --i) push('-', res_b(i - 1)); }
+        if (colbr) { for (uint32_t i = k; i > 0; --i) push(1u); k = 0; }
+        else       { for (uint32_t i = l; i > 0; --i) push(2u); l = 0; }
     }
-    if (pos & 3u) {   // flush the partial word (its low bytes lie below the string and are never read)
-        *reinterpret_cast<uint32_t*>(outA + (pos & ~3u)) = wa;
-        *reinterpret_cast<uint32_t*>(outB + (pos & ~3u)) = wb;
-    }
-    const uint32_t len = cap4 - pos;
+    if (pos & 15u) ops[pos >> 4] = wops;   // partial word (its low ops lie below the string and are never read)
+    slotw[0] = k; slotw[1] = l;            // the strings start at seq1[k], seq2[l]
+    const uint32_t len = n + m - pos;
     A.score[d.pair_id] = e.score;
     A.walk_flags[d.pair_id] = (uint8_t)flags;
     A.lens2[2ull * d.pair_id] = len;
@@ -420,13 +413,17 @@ __global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t
     walk_flags[id] = 0;
 }
 
-// Dense packing: one warp per slot copies a_align then b_align to arena[off[2p]..], arena[off[2p+1]..].
+// Dense packing: one warp per slot writes a_align then b_align to arena[off[2p]..], arena[off[2p+1]..]:
+// a copy for the long-pair walkers (character slots), and for k3_walk's op slots (PairDesc::pad_ == 1) the
+// materialisation -- op q reads seq1[first_a + #(ops before q that consume seq1)] resp. seq2 likewise, the
+// counts coming from warp ballots.
 struct GatherArgs {
     const PairDesc* desc;
     uint32_t n_slots;
     const uint8_t* pad;
     const uint64_t* off;   // exclusive scan of lens2
     uint8_t* arena;
+    const uint8_t* residues;
 };
 
 __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
@@ -437,6 +434,29 @@ __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
     if (d.pair_id == 0xFFFFFFFFu) return;
     const uint64_t o0 = A.off[2ull * d.pair_id], o1 = A.off[2ull * d.pair_id + 1];
     const uint32_t len = (uint32_t)(o1 - o0);
+    if (d.pad_ == 1u) {
+        const uint32_t* slotw = reinterpret_cast<const uint32_t*>(A.pad + d.pad_off);
+        const uint32_t* ops = slotw + 2;
+        const uint8_t* sa = A.residues + d.a_off;
+        const uint8_t* sb = A.residues + d.b_off;
+        uint32_t ia = slotw[0], ib = slotw[1];
+        const uint32_t pos0 = d.n + d.m - len;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (uint32_t base = 0; base < len; base += 32) {
+            const uint32_t x = base + lane;
+            const bool valid = x < len;
+            uint32_t op = 3u;
+            if (valid) { const uint32_t q = pos0 + x; op = (ops[q >> 4] >> ((q & 15u) * 2u)) & 3u; }
+            const bool useA = valid && op != 2u, useB = valid && op != 1u;
+            const uint32_t bA = __ballot_sync(0xffffffffu, useA), bB = __ballot_sync(0xffffffffu, useB);
+            if (valid) {
+                A.arena[o0 + x] = useA ? sa[ia + __popc(bA & lt)] : (uint8_t)'-';
+                A.arena[o1 + x] = useB ? sb[ib + __popc(bB & lt)] : (uint8_t)'-';
+            }
+            ia += __popc(bA); ib += __popc(bB);
+        }
+        return;
+    }
     const uint32_t cap4 = (d.n + d.m + 3u) & ~3u;
     const uint8_t* srcA = A.pad + d.pad_off + (cap4 - len);
     const uint8_t* srcB = srcA + cap4;

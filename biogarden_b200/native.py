@@ -39,7 +39,8 @@ class bg_timing(C.Structure):
     _fields_ = [("encode_ms", C.c_double), ("fill_ms", C.c_double), ("walk_ms", C.c_double),
                 ("compact_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_uint64),
                 ("launches", C.c_uint64), ("trace_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("cells_packed16", C.c_uint64), ("cells_bitparallel", C.c_uint64),
+                ("fill_launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

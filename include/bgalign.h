@@ -114,6 +114,9 @@ typedef struct {
     uint64_t launches;  /* kernels launched */
     uint64_t trace_bytes; /* bytes of packed direction codes written */
     uint64_t h2d_bytes, d2h_bytes; /* of the last host-buffer call */
+    uint64_t cells_packed16;    /* of `cells`: filled by the packed 16 x 2 kernel (two cells per lane instruction) */
+    uint64_t cells_bitparallel; /* of `cells`: edit distance by the bit-parallel kernel (32 cells per word column) */
+    uint64_t fill_launches;     /* DP fill kernel launches behind fill_ms */
 } bg_timing;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
