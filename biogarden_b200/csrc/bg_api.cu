@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -156,10 +157,12 @@ struct WorkSet {
     int ordinal = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t walk_stream = nullptr;   // traceback walks of chunk c run here, next to the fill of chunk c+1
+    cudaStream_t post_stream = nullptr;   // host-buffer pipeline: walk + scan + gather of this set's chunk go here (next to the next chunk's fill)
     BlockCache* cache = nullptr;
     DevBuf trace2;                        // second trace buffer (chunks alternate)
     DevBuf trace, end, bnd, pad, table, codes, err, cubtmp, progress, cand;   // scratch + parameters
     DevBuf residues, desc, score, flags, lens2, off, arena, out64;     // pipeline mode: chunk in / out
+    DevBuf run;                                                        // pipeline mode: [0] this chunk's string bytes, [1] (work set 0) running arena base
     PinBuf stage;                                                     // descriptor staging
     PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
     cudaEvent_t ev_scan = nullptr;
@@ -172,7 +175,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64};
+        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run};
     }
 };
 
@@ -225,7 +228,6 @@ struct bg_dresult {
     int kind = 0;             // 0 align, 1 edit distance
     int mode = 0; bool score_only = false;
     DevBuf score, flags, lens2, off, arena, out64;
-    std::vector<uint32_t> n, m;   // for status rules
 };
 
 namespace {
@@ -303,6 +305,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     // pass 1: class of every pair
     std::vector<uint8_t> cls(n_pairs);
     size_t count[MAX_SHAPES] = {0};
+    uint32_t cls_min_n[MAX_SHAPES], cls_max_n[MAX_SHAPES] = {0}, cls_max_m[MAX_SHAPES] = {0};
+    for (int s = 0; s < MAX_SHAPES; ++s) cls_min_n[s] = 0xFFFFFFFFu;
     uint32_t last_m = 0xFFFFFFFFu; int last_si = -1;
     for (uint64_t p = 0; p < n_pairs; ++p) {
         const uint64_t n = off[2 * p + 1] - off[2 * p], m = off[2 * p + 2] - off[2 * p + 1];
@@ -316,9 +320,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         }
         cls[p] = (uint8_t)last_si; count[last_si]++;
         P.cells += n * m;
-        P.max_n = std::max<uint32_t>(P.max_n, (uint32_t)n);
-        P.max_m = std::max<uint32_t>(P.max_m, (uint32_t)m);
+        cls_min_n[last_si] = std::min<uint32_t>(cls_min_n[last_si], (uint32_t)n);
+        cls_max_n[last_si] = std::max<uint32_t>(cls_max_n[last_si], (uint32_t)n);
+        cls_max_m[last_si] = std::max<uint32_t>(cls_max_m[last_si], (uint32_t)m);
     }
+    for (int s = 0; s < nshape; ++s) { P.max_n = std::max(P.max_n, cls_max_n[s]); P.max_m = std::max(P.max_m, cls_max_m[s]); }
     // pass 2: bucket pair ids per class
     std::vector<uint32_t> ids(n_pairs);
     size_t start[MAX_SHAPES + 1]; start[0] = 0;
@@ -337,13 +343,10 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const Shape sh = shapes[si];
         const bool wave = (si == wave_si);
         const uint32_t K = words_per_lane_step(sh.C), band_cols = sh.L * sh.C;
-        auto len_n0 = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 1] - off[2 * (uint64_t)id]); };
-        auto len_m0 = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
         // K1h (two pairs per lane group, 16-bit halves): short single-band classes whose scores provably fit
         bool half = false;
         if (with_trace && half_maxabs > 0 && !wave && (sh.L == 8 || (sh.L == 16 && sh.C == 10))) {
-            uint32_t cmn = 0, cmm = 0;
-            for (size_t k = 0; k < count[si]; ++k) { cmn = std::max(cmn, len_n0(ids[start[si] + k])); cmm = std::max(cmm, len_m0(ids[start[si] + k])); }
+            const uint32_t cmn = cls_max_n[si], cmm = cls_max_m[si];
             half = cmm <= band_cols && ((int64_t)cmn + cmm + 2) * half_maxabs <= HB_RANGE;
         }
         const uint32_t G = (half ? 2u : 1u) * (32 / sh.L);
@@ -352,17 +355,15 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         auto len_m = [&](uint32_t id) { return (uint32_t)(off[2 * (uint64_t)id + 2] - off[2 * (uint64_t)id + 1]); };
         // longest first so that the lane groups of a warp and the warps of a wave carry similar work;
         // skipped when the class is uniform.
-        bool uniform = true;
-        const uint32_t n0 = len_n(cid[0]);
-        for (size_t k = 1; k < cn; ++k) if (len_n(cid[k]) != n0) { uniform = false; break; }
+        const bool uniform = cls_min_n[si] == cls_max_n[si];
+        const uint32_t n0 = cls_min_n[si];
         if (wave) {
             // K2: largest pairs (cells) first; cluster c then owns pairs c, c + NC, ... of this list
             std::stable_sort(cid, cid + cn, [&](uint32_t x, uint32_t y) {
                 return (uint64_t)len_n(x) * len_m(x) > (uint64_t)len_n(y) * len_m(y);
             });
         } else if (!uniform) {
-            uint32_t nmin = n0, nmax = n0;
-            for (size_t k = 1; k < cn; ++k) { const uint32_t v = len_n(cid[k]); nmin = std::min(nmin, v); nmax = std::max(nmax, v); }
+            const uint32_t nmin = n0, nmax = cls_max_n[si];
             const uint64_t range = (uint64_t)nmax - nmin + 1;
             if (range <= (1u << 22) && range <= 4 * cn + 1024) {
                 // stable counting sort, descending by row count (a comparison sort of 10^6 ids costs more
@@ -433,8 +434,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             for (uint32_t gidx = 0; gidx < G; ++gidx) {
                 const size_t k = w * G + gidx;
                 PairDesc& d = dst[nd++];
-                memset(&d, 0, sizeof d);
                 d.pair_id = 0xFFFFFFFFu; d.steps = steps; d.trace_off = ch.trace_words;
+                d.a_off = d.b_off = d.bnd_off = d.pad_off = 0; d.n = d.m = d.nbands = d.pad_ = 0;
                 if (k < sn && sl[k] != HOLE) {
                     const uint64_t id = sl[k];
                     d.a_off = off[2 * id] - base; d.b_off = off[2 * id + 1] - base;
@@ -536,8 +537,9 @@ void dispatch_k4(Shape sh, dim3 grid, cudaStream_t st, const EditArgs& a) {
 
 struct Phase {
     WorkSet& ws; int phase; cudaEvent_t a;
-    Phase(WorkSet& w, int ph) : ws(w), phase(ph) { a = ws.get_event(); cudaEventRecord(a, ws.stream); }
-    ~Phase() { cudaEvent_t b = ws.get_event(); cudaEventRecord(b, ws.stream); ws.evs.push_back(PhaseEv{a, b, phase}); }
+    cudaStream_t st;
+    Phase(WorkSet& w, int ph, cudaStream_t s = nullptr) : ws(w), phase(ph), st(s ? s : w.stream) { a = ws.get_event(); cudaEventRecord(a, st); }
+    ~Phase() { cudaEvent_t b = ws.get_event(); cudaEventRecord(b, st); ws.evs.push_back(PhaseEv{a, b, phase}); }
 };
 
 // One multi-threaded pass over the offsets of a host batch: validity, length statistics and the cost
@@ -598,15 +600,19 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
     for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
     const double target = std::max(total / 8.0, 1.0e9);
     const uint64_t max_pairs = 262144;
-    double acc = 0; uint64_t start = lo;
+    double acc = 0, done_cost = 0; uint64_t start = lo;
     for (uint64_t k = blk_lo; k < blk_hi; ++k) {
         acc += S.block_cost[k];
         const uint64_t end = std::min(hi, (k + 1) * SCAN_BLOCK);
         if (end <= start) continue;
         // ramp: the first two chunks are a quarter / a half of the rest, so planning + H2D of chunk 0 is short
+        // ... and ramp down: the last chunk's strings travel D2H after the GPU has gone idle, so the chunks
+        // shrink towards the end (half of what is left, but not below a quarter of the regular size)
         const size_t nb = b.size();
-        const double scale = nb == 1 ? 0.25 : nb == 2 ? 0.5 : 1.0;
-        if (acc >= target * scale || (double)(end - start) >= (double)max_pairs * scale) { b.push_back(end); start = end; acc = 0; }
+        const double scale = nb == 1 ? 0.25 : (nb == 2 || nb == 3) ? 0.5 : 1.0;
+        const double left = total - done_cost;
+        const double want = std::min(target * scale, std::max(left * 0.5, target * 0.25));
+        if (acc >= want || (double)(end - start) >= (double)max_pairs * scale) { b.push_back(end); start = end; done_cost += acc; acc = 0; }
     }
     if (b.back() != hi) b.push_back(hi);
     return b;
@@ -732,7 +738,11 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     static const bool want_overlap = [] { const char* e = getenv("BG_OVERLAP"); return e && atoi(e) != 0; }();
     const bool overlap = want_overlap && !pp.score_only && n_chunks >= 2 && P.max_wave_slots == 0;   // K2 traces need the memory of both buffers
     if (overlap && !ws.trace2.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4)) { ctx->set_error("device allocation failed (second trace buffer)"); return BG_ENOMEM; }
-    cudaStream_t wst = overlap ? ws.walk_stream : st;
+    // host-buffer pipeline: everything after the fill runs on the work set's post stream, so that the next
+    // chunk's fill (integer-pipe bound) overlaps this chunk's walk / scan / gather (latency bound, small grids)
+    const bool split = ws.post_stream != nullptr && !overlap && !pp.score_only && n_chunks == 1;
+    cudaStream_t wst = overlap ? ws.walk_stream : split ? ws.post_stream : st;
+    cudaStream_t pst = split ? ws.post_stream : st;
     cudaEvent_t ev_walk_done[2] = {nullptr, nullptr};
     if (overlap) {
         cudaEvent_t ev0 = ws.get_event();
@@ -770,7 +780,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, st, fa);
             }
             CU_TRY(ctx, cudaGetLastError());
-            if (overlap) {
+            if (overlap || split) {
                 cudaEvent_t evf = ws.get_event();
                 CU_TRY(ctx, cudaEventRecord(evf, st));
                 CU_TRY(ctx, cudaStreamWaitEvent(wst, evf, 0));
@@ -779,7 +789,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 cudaEvent_t pa = ws.get_event();
                 cudaEventRecord(pa, wst);
                 if (pp.score_only) {
-                    k_scores_only<<<(ns + 127) / 128, 128, 0, wst>>>(fa.desc, fa.end, ns, io.score, io.flags);
+                    k_scores_only<<<(ns + 127) / 128, 128, 0, wst>>>(fa.desc, fa.end, ns, io.score, io.flags, pp.mode);
                 } else {
                     WalkArgs wa;
                     wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
@@ -809,17 +819,17 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
         for (int b2 = 0; b2 < 2; ++b2)
             if (ev_walk_done[b2]) CU_TRY(ctx, cudaStreamWaitEvent(st, ev_walk_done[b2], 0));   // scan / gather need every walk
     if (!pp.score_only) {
-        Phase ph(ws, 3);
+        Phase ph(ws, 3, pst);
         size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, io.lens2, io.off, (int)(2 * N + 1), st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
         if (!ws.cubtmp.ensure(tmp + 16)) { ctx->set_error("device allocation failed (scan)"); return BG_ENOMEM; }
-        cub::DeviceScan::ExclusiveSum(ws.cubtmp.p, tmp, io.lens2, io.off, (int)(2 * N + 1), st);
+        cub::DeviceScan::ExclusiveSum(ws.cubtmp.p, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
         ctx->launches += 2;
         if (P.n_slots) {
             GatherArgs ga;
             ga.desc = io.desc; ga.n_slots = (uint32_t)P.n_slots; ga.pad = ws.pad.as<uint8_t>();
             ga.off = io.off; ga.arena = io.arena; ga.residues = io.residues;
-            k_gather<<<(unsigned)((P.n_slots + 3) / 4), 128, 0, st>>>(ga);
+            k_gather<<<(unsigned)((P.n_slots + 3) / 4), 128, 0, pst>>>(ga);
             ctx->launches++;
         }
         CU_TRY(ctx, cudaGetLastError());
@@ -934,11 +944,15 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
         size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); dv.total_mem = tot;
         { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, o) == cudaSuccess && sms > 0) ctx->num_sms = sms; }
         dv.cache = new BlockCache();
+        // the walk / post streams get the highest priority: their small, latency-bound grids must slip in
+        // between the blocks of a concurrently running fill instead of queueing behind all of them
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
         for (WorkSet& ws : dv.ws) {
             ws.ordinal = o; ws.cache = dv.cache;
             for (DevBuf* b : ws.all_bufs()) b->cache = dv.cache;
             if (cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaStreamCreateWithFlags(&ws.walk_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithPriority(&ws.walk_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
                 cudaEventCreateWithFlags(&ws.ev_scan, cudaEventDisableTiming) != cudaSuccess) { bg_destroy(ctx); return BG_ECUDA; }
         }
     }
@@ -1119,11 +1133,6 @@ int bg_align_device(bg_ctx* ctx, const bg_dbatch* cin, const bg_params* p, bg_dr
     bg_dresult* R = new bg_dresult();
     R->ctx = ctx; R->dev_index = B->dev_index; R->n_pairs = N; R->kind = 0; R->mode = pp.mode; R->score_only = pp.score_only;
     for (DevBuf* b : {&R->score, &R->flags, &R->lens2, &R->off, &R->arena, &R->out64}) b->cache = dv.cache;
-    R->n.resize(N); R->m.resize(N);
-    for (uint64_t q = 0; q < N; ++q) {
-        R->n[q] = (uint32_t)(B->seq_off[2 * q + 1] - B->seq_off[2 * q]);
-        R->m[q] = (uint32_t)(B->seq_off[2 * q + 2] - B->seq_off[2 * q + 1]);
-    }
     bool ok = R->score.ensure(std::max<uint64_t>(1, N) * 4) && R->flags.ensure(std::max<uint64_t>(1, N));
     if (!pp.score_only)
         ok = ok && R->lens2.ensure((2 * N + 1) * 8) && R->off.ensure((2 * N + 1) * 8) && R->arena.ensure(std::max<uint64_t>(1, P.pad_bytes));
@@ -1167,21 +1176,7 @@ int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* cin, bg_dresult** out)
 }
 
 int bg_ref_status(int mode, uint64_t n, uint64_t m, int32_t score, int walk_flags) {
-    // Fresh-aligner buffer dims (aligner.rs:45, 92-94, 594-595)
-    uint64_t R, C;
-    if (n > 1024 || m > 1024) { R = n + 1; C = m + 1; } else { R = 1024; C = 1024; }
-    if (walk_flags & (WALK_UNDERFLOW | WALK_HANG)) return BG_ST_REF_UNDEFINED;
-    const bool row_border = (mode == BG_GLOBAL || mode == BG_FITTING);   // writes row0[1..=m]
-    const bool col_border = (mode == BG_GLOBAL);                          // writes col0[1..=n]
-    if (row_border && (C < 2 || m >= C)) return BG_ST_REF_UNDEFINED;
-    if (col_border && (R < 2 || n >= R)) return BG_ST_REF_UNDEFINED;
-    if (n >= 1 && m >= 1 && (n >= R || m >= C)) return BG_ST_REF_UNDEFINED;   // fill indexes [n][m]
-    if ((mode == BG_OVERLAP || mode == BG_SEMIGLOBAL) && n >= R) return BG_ST_REF_UNDEFINED;   // .row(len1)
-    if ((mode == BG_FITTING || mode == BG_SEMIGLOBAL) && m >= C) return BG_ST_REF_UNDEFINED;   // .column(len2)
-    // whole-buffer scans see the zeroed cells outside the rectangle (aligner.rs:247,308,369,376)
-    if ((mode == BG_SEMIGLOBAL || mode == BG_OVERLAP) && score == 0 && C > m + 1) return BG_ST_REF_UNDEFINED;
-    if (mode == BG_FITTING && score < 0 && R > n + 1) return BG_ST_REF_UNDEFINED;
-    return BG_ST_OK;
+    return ref_status(mode, n, m, score, (uint32_t)walk_flags) ? BG_ST_REF_UNDEFINED : BG_ST_OK;
 }
 
 int bg_dresult_download(bg_ctx* ctx, bg_dresult* r, bg_result* out) {
@@ -1222,9 +1217,7 @@ int bg_dresult_download(bg_ctx* ctx, bg_dresult* r, bg_result* out) {
     }
     CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
     ctx->d2h = N * 5 + (r->score_only ? 0 : (2 * N + 1) * 8 + total);
-    for (uint64_t q = 0; q < N; ++q)
-        out->status[q] = (uint8_t)bg_ref_status(r->mode, r->n[q], r->m[q], out->score[q], out->status[q]);
-    return BG_OK;
+    return BG_OK;   // status: evaluated by the walk kernels (bg_common.cuh ref_status)
 }
 
 int bg_dresult_download_u64(bg_ctx* ctx, bg_dresult* r, uint64_t* out) {
@@ -1294,7 +1287,15 @@ struct FinalOut {      // the caller-visible arrays of one device's pair range
     int32_t* score; uint8_t* status; uint64_t* off; uint8_t* arena; uint64_t arena_cap;
 };
 
-// One device's share of bg_align_batch: chunks of pairs [lo, hi) flow through the work sets.
+// One device's share of bg_align_batch: chunks of pairs [lo, hi) flow through the three work sets as a
+// classic three-stage pipeline on dedicated streams --
+//     H2D stream:      residues + launch descriptors of chunk c
+//     compute stream:  all kernels, strictly chunk after chunk (each chunk gets the whole GPU; with one
+//                      stream per chunk the kernels of three chunks time-share the SMs, all three finish
+//                      together and the copy engines then sit idle: measured 17 ms instead of 11 for cfg2)
+//     D2H streams:     scores / status / offsets, then the dense strings once their size is known
+// driven by two host threads: the caller's thread issues chunks as work sets become free, a finisher
+// thread waits for each chunk's results, issues the string copy and post-processes (status rules).
 int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const Prepared& pp,
                    const BatchScan& scan, const FinalOut& fo, uint64_t* total_out) {
     Device& dv = ctx->devs[d];
@@ -1302,7 +1303,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     const uint64_t* off = in->seq_off;
     // Batches with long pairs (K2 class) are not cut into pipeline chunks: their traces take GBs per
     // pair, the copies are negligible next to the fill, and every launch should see as many pairs as
-    // memory allows.  Everything else flows through the 3-deep chunk pipeline.
+    // memory allows.  Everything else flows through the chunk pipeline.
     bool long_mode = false;
     if (scan.has_wide)
         for (uint64_t q = lo; q < hi && !long_mode; ++q) long_mode = (off[2 * q + 2] - off[2 * q + 1]) > WAVE_MIN_COLS;
@@ -1310,10 +1311,6 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     const int nchunks = (int)cb.size() - 1;
     const uint64_t ws_budget = long_mode ? ctx->trace_budget_words : std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
     const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
-    struct Fly { bool active = false; uint64_t c_lo = 0, c_n = 0; const Plan* plan = nullptr; };
-    Fly fly[PIPE_DEPTH];
-    uint64_t arena_base = 0;
-    int rc_all = BG_OK;
 
     // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
     // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon
@@ -1324,116 +1321,183 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         pre[c].th = std::thread([&, c] {
             const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+            const auto t0 = std::chrono::steady_clock::now();
             pre[c].rc = build_plan(ctx, off + 2 * c_lo, off[2 * c_lo], n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs,
                                    pre[c].plan, pre[c].stage.as<PairDesc>());
+            if (getenv("BG_PROFILE_HOST"))
+                fprintf(stderr, "[bgalign]   plan of chunk %d (%llu pairs): %.2f ms\n", c, (unsigned long long)n,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         });
-    std::vector<std::thread> posts;   // status rules + offset rebasing of finished chunks, off the critical path
 
-    auto finish = [&](int s) -> int {
-        WorkSet& ws = dv.ws[s];
-        Fly& f = fly[s];
-        f.active = false;
-        uint64_t* h_total = ws.scalars.as<uint64_t>();
-        uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
-        CU_TRY(ctx, cudaEventSynchronize(ws.ev_scan));
-        if (*h_err & 1u) { ctx->set_error("a residue byte has no row/column in the score table"); return BG_EINVAL_RESIDUE; }
-        const uint64_t total = pp.score_only ? 0 : *h_total;
-        const uint64_t rel = f.c_lo - lo;
-        if (total) {
-            if (arena_base + total > fo.arena_cap) { ctx->set_error("internal: arena bound exceeded"); return BG_ECUDA; }
-            CU_TRY(ctx, cudaMemcpyAsync(fo.arena + arena_base, ws.arena.p, total, cudaMemcpyDeviceToHost, ws.stream));
-        }
-        CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
-        ctx->d2h += f.c_n * 5 + (pp.score_only ? 0 : 2 * f.c_n * 8 + total);
-        // host post-processing of the chunk on a helper thread while later chunks keep the GPU busy
-        {
-            const uint64_t base_now = arena_base, c_lo2 = f.c_lo, c_n2 = f.c_n;
-            posts.emplace_back([=, &pp] {
-                uint64_t* o = fo.off + 2 * rel;
-                if (pp.score_only) { for (uint64_t s2 = 0; s2 < 2 * c_n2; ++s2) o[s2] = 0; }
-                else if (base_now) { for (uint64_t s2 = 0; s2 < 2 * c_n2; ++s2) o[s2] += base_now; }
-                for (uint64_t q = 0; q < c_n2; ++q) {
-                    const uint64_t g = c_lo2 + q;
-                    fo.status[rel + q] = (uint8_t)bg_ref_status(pp.mode, off[2 * g + 1] - off[2 * g], off[2 * g + 2] - off[2 * g + 1],
-                                                                fo.score[rel + q], fo.status[rel + q]);
+    // streams: the work sets' own streams are borrowed for the stages; kernels of every work set go to st_comp
+    cudaStream_t st_comp = dv.ws[0].stream, st_h2d = dv.ws[1].stream, st_small = dv.ws[2].stream, st_arena = dv.ws[0].walk_stream;
+    static const bool no_split = getenv("BG_NO_SPLIT") != nullptr;
+    cudaStream_t st_post = (long_mode || no_split) ? st_comp : dv.ws[1].walk_stream;
+    cudaStream_t saved[PIPE_DEPTH];
+    for (int s = 0; s < PIPE_DEPTH; ++s) {
+        saved[s] = dv.ws[s].stream; dv.ws[s].stream = st_comp; dv.ws[s].reset_events();
+        dv.ws[s].post_stream = (st_post == st_comp) ? nullptr : st_post;
+    }
+    cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH], ev_arena[PIPE_DEPTH];
+    for (int s = 0; s < PIPE_DEPTH; ++s) {
+        cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_comp[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_arena[s], cudaEventDisableTiming);
+    }
+
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    // running arena base of this call (device scalar next to work set 0's chunk total)
+    uint64_t* d_base = nullptr;
+    if (dv.ws[0].run.ensure(16)) { d_base = dv.ws[0].run.as<uint64_t>() + 1; cudaMemsetAsync(d_base, 0, 8, st_comp); }
+
+    // issuer -> finisher hand-over
+    std::mutex mu; std::condition_variable cv;
+    int issued = 0;                       // chunks handed to the finisher
+    int finished = 0;                     // chunks whose work set is free again
+    bool issuer_done = false;
+    std::atomic<int> rc_shared{BG_OK};
+    uint64_t arena_base = 0;              // finisher only
+
+    std::thread finisher([&] {
+        cudaSetDevice(dv.ordinal);
+        for (int c = 0;; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return issued > c || issuer_done; });
+                if (issued <= c) break;
+            }
+            const int s = c % PIPE_DEPTH;
+            WorkSet& ws = dv.ws[s];
+            const uint64_t c_n = cb[c + 1] - cb[c];
+            uint64_t* h_total = ws.scalars.as<uint64_t>();
+            uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
+            int rc = BG_OK;
+            if (cudaEventSynchronize(ws.ev_scan) != cudaSuccess) { ctx->set_error("cudaEventSynchronize failed"); rc = BG_ECUDA; }
+            uint64_t total = 0;
+            if (!rc && (*h_err & 1u)) { ctx->set_error("a residue byte has no row/column in the score table"); rc = BG_EINVAL_RESIDUE; }
+            if (!rc) {
+                total = pp.score_only ? 0 : *h_total;
+                if (total) {
+                    if (arena_base + total > fo.arena_cap) { ctx->set_error("internal: arena bound exceeded"); rc = BG_ECUDA; }
+                    else if (cudaMemcpyAsync(fo.arena + arena_base, ws.arena.p, total, cudaMemcpyDeviceToHost, st_arena) != cudaSuccess ||
+                             cudaEventRecord(ev_arena[s], st_arena) != cudaSuccess || cudaEventSynchronize(ev_arena[s]) != cudaSuccess) {
+                        ctx->set_error("string copy failed"); rc = BG_ECUDA;
+                    }
                 }
-            });
+            }
+            if (prof) fprintf(stderr, "[bgalign]   chunk %d results on the host at %.2f ms\n", c, since());
+            if (!rc) {
+                ctx->d2h += c_n * 5 + (pp.score_only ? 0 : 2 * c_n * 8 + total);
+                arena_base += total;   // offsets were rebased and the status rules applied on the device
+            } else {
+                int expect = BG_OK; rc_shared.compare_exchange_strong(expect, rc);
+            }
+            { std::lock_guard<std::mutex> lk(mu); finished = c + 1; }
+            cv.notify_all();
         }
-        arena_base += total;
-        return BG_OK;
-    };
+    });
 
     auto issue = [&](int s, int c) -> int {
         WorkSet& ws = dv.ws[s];
-        Fly& f = fly[s];
-        f.c_lo = cb[c]; f.c_n = cb[c + 1] - cb[c];
-        const uint64_t n = f.c_n, base = off[2 * f.c_lo], nres = off[2 * (f.c_lo + n)] - base;
-        const uint64_t rel = f.c_lo - lo;
+        const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
+        const uint64_t base = off[2 * c_lo], nres = off[2 * (c_lo + n)] - base, rel = c_lo - lo;
         if (!ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
         if (pre[c].th.joinable()) pre[c].th.join();
         int rc = pre[c].rc;
         if (rc) return rc;
-        f.plan = &pre[c].plan;
         const Plan& P = pre[c].plan;
-        bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
+        bool ok = ws.run.ensure(16) && ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
                   ws.score.ensure(n * 4) && ws.flags.ensure(n);
         if (!pp.score_only)
             ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((2 * n + 1) * 8) && ws.arena.ensure(std::max<uint64_t>(1, P.pad_bytes));
         if (!ok) { ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM; }
-        cudaStream_t st = ws.stream;
-        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st));
-        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
+        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
+        CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         rc = upload_params(ctx, ws, pp);
         if (rc) return rc;
         AlignIO io{ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), &P, n,
                    ws.score.as<int32_t>(), ws.flags.as<uint8_t>(), ws.lens2.as<uint64_t>(), ws.off.as<uint64_t>(), ws.arena.as<uint8_t>()};
         rc = run_align(ctx, ws, io, pp);
         if (rc) return rc;
+        // which stream the chunk's last kernels went to (run_align: post stream unless the plan has several launches)
+        size_t n_launch = 0;
+        for (const LaunchClass& lc : P.classes) n_launch += lc.chunks.size();
+        cudaStream_t st_last = (ws.post_stream && !pp.score_only && n_launch == 1) ? ws.post_stream : st_comp;
+        if (!pp.score_only) {   // chunk-relative offsets -> offsets into the caller's arena, on the device
+            if (st_last != st_post && st_post != st_comp) {   // keep the running base stream-ordered on st_post
+                CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_last));
+                CU_TRY(ctx, cudaStreamWaitEvent(st_post, ev_comp[s], 0));
+                st_last = st_post;
+            }
+            k_rebase<<<(unsigned)((2 * n + 1 + 255) / 256), 256, 0, st_last>>>(ws.off.as<uint64_t>(), 2 * n + 1, d_base);
+            k_bump<<<1, 1, 0, st_last>>>(d_base, ws.off.as<uint64_t>() + 2 * n, ws.run.as<uint64_t>());
+            CU_TRY(ctx, cudaGetLastError());
+            ctx->launches += 2;
+        } else {
+            memset(fo.off + 2 * rel, 0, 2 * n * 8);
+        }
+        CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_last));
+        CU_TRY(ctx, cudaStreamWaitEvent(st_small, ev_comp[s], 0));
         uint64_t* h_total = ws.scalars.as<uint64_t>();
         uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
-        CU_TRY(ctx, cudaMemcpyAsync(h_err, ws.err.p, 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(h_err, ws.err.p, 4, cudaMemcpyDeviceToHost, st_small));
         if (!pp.score_only) {
-            CU_TRY(ctx, cudaMemcpyAsync(h_total, ws.off.as<uint64_t>() + 2 * n, 8, cudaMemcpyDeviceToHost, st));
-            CU_TRY(ctx, cudaMemcpyAsync(fo.off + 2 * rel, ws.off.p, 2 * n * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaMemcpyAsync(h_total, ws.run.p, 8, cudaMemcpyDeviceToHost, st_small));
+            CU_TRY(ctx, cudaMemcpyAsync(fo.off + 2 * rel, ws.off.p, 2 * n * 8, cudaMemcpyDeviceToHost, st_small));
         }
-        CU_TRY(ctx, cudaMemcpyAsync(fo.score + rel, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaMemcpyAsync(fo.status + rel, ws.flags.p, n, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st));
+        CU_TRY(ctx, cudaMemcpyAsync(fo.score + rel, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st_small));
+        CU_TRY(ctx, cudaMemcpyAsync(fo.status + rel, ws.flags.p, n, cudaMemcpyDeviceToHost, st_small));
+        CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st_small));
         ctx->timing.cells += P.cells; ctx->timing.cells_packed16 += P.cells_half;
         ctx->timing.trace_bytes += pp.score_only ? 0 : P.total_trace_words * 4;
-        f.active = true;
         return BG_OK;
     };
 
-    for (WorkSet& ws : dv.ws) ws.reset_events();
-    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
-    double t_issue = 0, t_finish = 0;
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_begin = now();
+    int rc_all = BG_OK;
     for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
         const int s = c % PIPE_DEPTH;
-        double t0 = now();
-        if (fly[s].active) rc_all = finish(s);
-        double t1 = now();
-        if (rc_all == BG_OK) rc_all = issue(s, c);
-        double t2 = now();
-        t_finish += t1 - t0; t_issue += t2 - t1;
-        if (prof) fprintf(stderr, "[bgalign]   chunk %d (%llu pairs): finish-prev %.2f ms, issue %.2f ms, at %.2f ms\n", c,
-                          (unsigned long long)(cb[c + 1] - cb[c]), t1 - t0, t2 - t1, t2 - t_begin);
+        {   // work set s is free once chunk c - PIPE_DEPTH has left it
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return finished >= c - PIPE_DEPTH + 1; });
+        }
+        rc_all = rc_shared.load();
+        if (rc_all) break;
+        const double t0 = prof ? since() : 0;
+        rc_all = issue(s, c);
+        if (prof) fprintf(stderr, "[bgalign]   chunk %d (%llu pairs) issued %.2f .. %.2f ms\n", c, (unsigned long long)(cb[c + 1] - cb[c]), t0, since());
+        if (rc_all) break;
+        { std::lock_guard<std::mutex> lk(mu); issued = c + 1; }
+        cv.notify_all();
     }
-    if (prof) fprintf(stderr, "[bgalign] pipeline: %d chunks, issue %.2f ms, finish(wait+post) %.2f ms, loop %.2f ms\n", nchunks, t_issue, t_finish, now() - t_begin);
-    // drain in chunk order
-    for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
-        const int s = c % PIPE_DEPTH;
-        if (!fly[s].active) continue;
-        if (rc_all == BG_OK) rc_all = finish(s);
-        else { cudaStreamSynchronize(dv.ws[s].stream); fly[s].active = false; }
+    { std::lock_guard<std::mutex> lk(mu); issuer_done = true; }
+    cv.notify_all();
+    finisher.join();
+    if (rc_all == BG_OK) rc_all = rc_shared.load();
+    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_comp); cudaStreamSynchronize(st_small); cudaStreamSynchronize(st_arena);
+    if (prof) {
+        fprintf(stderr, "[bgalign] drained at %.2f ms\n", since());
+        // GPU-side timeline of the kernels (events on the compute stream), relative to the first one
+        cudaEvent_t e0 = nullptr;
+        for (int s = 0; s < PIPE_DEPTH && !e0; ++s) if (!dv.ws[s].evs.empty()) e0 = dv.ws[s].evs.front().a;
+        if (!dv.ws[0].evs.empty()) e0 = dv.ws[0].evs.front().a;
+        for (int s = 0; s < PIPE_DEPTH; ++s)
+            for (auto& ev : dv.ws[s].evs) {
+                float t_a = 0, dur = 0;
+                cudaEventElapsedTime(&t_a, e0, ev.a); cudaEventElapsedTime(&dur, ev.a, ev.b);
+                fprintf(stderr, "[bgalign]   gpu ws%d phase %d: start %.3f ms, %.3f ms\n", s, ev.phase, t_a, dur);
+            }
     }
-    for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
-    if (prof) fprintf(stderr, "[bgalign] drained at %.2f ms\n", now() - t_begin);
-    for (auto& t : posts) t.join();
     for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
+    cudaStreamSynchronize(st_post);
+    for (int s = 0; s < PIPE_DEPTH; ++s) {
+        dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr;
+        cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); cudaEventDestroy(ev_arena[s]);
+    }
     *total_out = arena_base;
     return rc_all;
 }
@@ -1441,71 +1505,109 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
 constexpr int EDIT_RETRY_GENERAL = -77;   // internal: a byte outside the sampled 4-symbol alphabet turned up
 
 int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const BatchScan& scan, uint64_t* out, const uint8_t* lut) {
+    // Same three-stage structure as align_pipeline (H2D stream | compute stream | D2H stream, issuer + finisher
+    // threads); the path is bound by the H2D copy of the residues (4 B of input per ~45 cells).
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
     const uint64_t* off = in->seq_off;
     const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi);
     const int nchunks = (int)cb.size() - 1;
     struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; std::thread th; };
-    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one host thread per chunk, consumed as they finish (see align_pipeline)
+    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one host thread per chunk, consumed as they finish
     for (int c = 0; c < nchunks; ++c)
         pre[c].th = std::thread([&, c] {
             const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
             pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
         });
-    bool active[PIPE_DEPTH] = {false, false, false};
+    cudaStream_t st_comp = dv.ws[0].stream, st_h2d = dv.ws[1].stream, st_d2h = dv.ws[2].stream;
+    cudaStream_t saved[PIPE_DEPTH];
+    for (int s = 0; s < PIPE_DEPTH; ++s) { saved[s] = dv.ws[s].stream; dv.ws[s].stream = st_comp; dv.ws[s].reset_events(); }
+    cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH];
+    for (int s = 0; s < PIPE_DEPTH; ++s) {
+        cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_comp[s], cudaEventDisableTiming);
+    }
     // `out` is caller memory of unknown kind: results are staged in pinned memory per work set
     PinBuf host_out[PIPE_DEPTH];
-    uint64_t c_lo[PIPE_DEPTH] = {0}, c_n[PIPE_DEPTH] = {0};
-    int rc_all = BG_OK;
-    auto finish = [&](int s) -> int {
-        active[s] = false;
-        CU_TRY(ctx, cudaStreamSynchronize(dv.ws[s].stream));
-        if (lut && (*reinterpret_cast<uint32_t*>(dv.ws[s].scalars.as<uint64_t>() + 1) & 2u)) return EDIT_RETRY_GENERAL;
-        memcpy(out + c_lo[s], host_out[s].p, c_n[s] * 8);
-        ctx->d2h += c_n[s] * 8;
+
+    std::mutex mu; std::condition_variable cv;
+    int issued = 0, finished = 0; bool issuer_done = false;
+    std::atomic<int> rc_shared{BG_OK};
+    std::thread finisher([&] {
+        cudaSetDevice(dv.ordinal);
+        for (int c = 0;; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return issued > c || issuer_done; });
+                if (issued <= c) break;
+            }
+            const int s = c % PIPE_DEPTH;
+            WorkSet& ws = dv.ws[s];
+            int rc = BG_OK;
+            if (cudaEventSynchronize(ws.ev_scan) != cudaSuccess) { ctx->set_error("cudaEventSynchronize failed"); rc = BG_ECUDA; }
+            if (!rc && lut && (*reinterpret_cast<uint32_t*>(ws.scalars.as<uint64_t>() + 1) & 2u)) rc = EDIT_RETRY_GENERAL;
+            if (!rc) {
+                const uint64_t c_lo = cb[c], c_n = cb[c + 1] - cb[c];
+                memcpy(out + c_lo, host_out[s].p, c_n * 8);
+                ctx->d2h += c_n * 8;
+            } else {
+                int expect = BG_OK; rc_shared.compare_exchange_strong(expect, rc);
+            }
+            { std::lock_guard<std::mutex> lk(mu); finished = c + 1; }
+            cv.notify_all();
+        }
+    });
+
+    auto issue = [&](int s, int c) -> int {
+        WorkSet& ws = dv.ws[s];
+        const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
+        const uint64_t base = off[2 * c_lo], nres = off[2 * (c_lo + n)] - base;
+        if (!host_out[s].ensure(std::max<uint64_t>(1, n) * 8) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+        if (pre[c].th.joinable()) pre[c].th.join();
+        if (pre[c].rc) return pre[c].rc;
+        const Plan& P = pre[c].plan;
+        if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(std::max<uint64_t>(1, n) * 8)) {
+            ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM;
+        }
+        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
+        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
+        CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
+        ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
+        int rc = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_comp));
+        CU_TRY(ctx, cudaStreamWaitEvent(st_d2h, ev_comp[s], 0));
+        if (n) CU_TRY(ctx, cudaMemcpyAsync(host_out[s].p, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st_d2h));
+        CU_TRY(ctx, cudaMemcpyAsync(ws.scalars.as<uint64_t>() + 1, ws.err.p, 4, cudaMemcpyDeviceToHost, st_d2h));
+        CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st_d2h));
+        ctx->timing.cells += P.cells; ctx->timing.cells_bitparallel += P.cells_myers;
         return BG_OK;
     };
-    for (WorkSet& ws : dv.ws) ws.reset_events();
+
+    int rc_all = BG_OK;
     for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
         const int s = c % PIPE_DEPTH;
-        WorkSet& ws = dv.ws[s];
-        if (active[s]) rc_all = finish(s);
-        if (rc_all) break;
-        c_lo[s] = cb[c]; c_n[s] = cb[c + 1] - cb[c];
-        const uint64_t n = c_n[s], base = off[2 * c_lo[s]], nres = off[2 * (c_lo[s] + n)] - base;
-        if (!host_out[s].ensure(n * 8) || !ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); rc_all = BG_ENOMEM; break; }
-        if (pre[c].th.joinable()) pre[c].th.join();
-        rc_all = pre[c].rc;
-        if (rc_all) break;
-        const Plan& P = pre[c].plan;
-        if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(n * 8)) {
-            ctx->set_error("device allocation failed (pipeline buffers)"); rc_all = BG_ENOMEM; break;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return finished >= c - PIPE_DEPTH + 1; });
         }
-        cudaStream_t st = ws.stream;
-        cudaError_t ce = cudaSuccess;
-        if (nres) ce = cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess && P.n_slots) ce = cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st);
-        if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
-        ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
-        rc_all = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);
+        rc_all = rc_shared.load();
         if (rc_all) break;
-        ce = cudaMemcpyAsync(host_out[s].p, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(ws.scalars.as<uint64_t>() + 1, ws.err.p, 4, cudaMemcpyDeviceToHost, st);
-        if (ce != cudaSuccess) { ctx->set_error(cudaGetErrorString(ce)); rc_all = BG_ECUDA; break; }
-        ctx->timing.cells += P.cells; ctx->timing.cells_bitparallel += P.cells_myers;
-        active[s] = true;
+        rc_all = issue(s, c);
+        if (rc_all) break;
+        { std::lock_guard<std::mutex> lk(mu); issued = c + 1; }
+        cv.notify_all();
     }
-    for (int c = std::max(0, nchunks - PIPE_DEPTH); c < nchunks; ++c) {
-        const int s = c % PIPE_DEPTH;
-        if (!active[s]) continue;
-        if (rc_all == BG_OK) rc_all = finish(s);
-        else { cudaStreamSynchronize(dv.ws[s].stream); active[s] = false; }
-    }
-    for (WorkSet& ws : dv.ws) cudaStreamSynchronize(ws.stream);
+    { std::lock_guard<std::mutex> lk(mu); issuer_done = true; }
+    cv.notify_all();
+    finisher.join();
+    if (rc_all == BG_OK) rc_all = rc_shared.load();
+    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_comp); cudaStreamSynchronize(st_d2h);
     for (auto& h : host_out) h.release();
     for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
+    for (int s = 0; s < PIPE_DEPTH; ++s) { dv.ws[s].stream = saved[s]; cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); }
     return rc_all;
 }
 

@@ -49,6 +49,27 @@ struct __align__(16) EndCell {
 constexpr uint32_t WALK_UNDERFLOW = 1;  // reference would index seq[usize::MAX] (A.6)
 constexpr uint32_t WALK_HANG = 2;       // step bound exceeded (cannot happen with well-formed traces)
 
+// Does the REFERENCE define a result for this pair?  (restated for a fresh aligner whose
+// buffers are 1024 x 1024 unless a length exceeds 1024: aligner.rs:45, 92-94, 594-595.)  0 = yes,
+// 1 = the reference panics / hangs / reads outside the rectangle (BG_ST_REF_UNDEFINED); the engine's
+// result is then its documented extension.  Evaluated on the device by the walk kernels.
+__host__ __device__ inline int ref_status(int mode, uint64_t n, uint64_t m, int32_t score, uint32_t walk_flags) {
+    uint64_t R, C;
+    if (n > 1024 || m > 1024) { R = n + 1; C = m + 1; } else { R = 1024; C = 1024; }
+    if (walk_flags & (WALK_UNDERFLOW | WALK_HANG)) return 1;
+    const bool row_border = (mode == M_GLOBAL || mode == M_FITTING);   // writes row0[1..=m]
+    const bool col_border = (mode == M_GLOBAL);                          // writes col0[1..=n]
+    if (row_border && (C < 2 || m >= C)) return 1;
+    if (col_border && (R < 2 || n >= R)) return 1;
+    if (n >= 1 && m >= 1 && (n >= R || m >= C)) return 1;                          // fill indexes [n][m]
+    if ((mode == M_OVERLAP || mode == M_SEMIGLOBAL) && n >= R) return 1;            // .row(len1)
+    if ((mode == M_FITTING || mode == M_SEMIGLOBAL) && m >= C) return 1;            // .column(len2)
+    // whole-buffer scans see the zeroed cells outside the rectangle (aligner.rs:247,308,369,376)
+    if ((mode == M_SEMIGLOBAL || mode == M_OVERLAP) && score == 0 && C > m + 1) return 1;
+    if (mode == M_FITTING && score < 0 && R > n + 1) return 1;
+    return 0;
+}
+
 // Geometry of the trace block of a warp: word (t, k, lane) of band bd lives at
 //   trace_off + ((bd * steps + t) * K + k) * 32 + lane,   K = ceil(C / 8) words per lane-step.
 // Every warp-wide store of one k is a fully coalesced 128-byte line.

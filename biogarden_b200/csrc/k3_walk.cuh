@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     slotw[0] = k; slotw[1] = l;            // the strings start at seq1[k], seq2[l]
     const uint32_t len = n + m - pos;
     A.score[d.pair_id] = e.score;
-    A.walk_flags[d.pair_id] = (uint8_t)flags;
+    A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
     A.lens2[2ull * d.pair_id] = len;
     A.lens2[2ull * d.pair_id + 1] = len;
 }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128) k3_walk_warp(const WalkArgs A) {
     if (q == 0) {
         const uint32_t len = cap4 - pos;
         A.score[d.pair_id] = e.score;
-        A.walk_flags[d.pair_id] = (uint8_t)flags;
+        A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
         A.lens2[2ull * d.pair_id] = len;
         A.lens2[2ull * d.pair_id + 1] = len;
     }
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(WALK_TILE_WARPS * 32) k3_walk_tile(const WalkA
     if (q == 0) {
         const uint32_t len = cap4 - pos;
         A.score[d.pair_id] = e.score;
-        A.walk_flags[d.pair_id] = (uint8_t)flags;
+        A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
         A.lens2[2ull * d.pair_id] = len;
         A.lens2[2ull * d.pair_id + 1] = len;
     }
@@ -404,13 +404,26 @@ __global__ void __launch_bounds__(WALK_TILE_WARPS * 32) k3_walk_tile(const WalkA
 
 // Score-only epilogue when no traceback is requested.
 __global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t n_slots, int32_t* score,
-                              uint8_t* walk_flags) {
+                              uint8_t* walk_flags, int mode) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const uint32_t id = desc[slot].pair_id;
     if (id == 0xFFFFFFFFu) return;
     score[id] = end[slot].score;
-    walk_flags[id] = 0;
+    walk_flags[id] = (uint8_t)ref_status(mode, desc[slot].n, desc[slot].m, end[slot].score, 0u);
+}
+
+// Host-buffer pipeline: chunk-relative string offsets -> offsets into the caller's arena.  `base` is a
+// device scalar that runs along the chunks of one bg_align_batch call (the chunks' kernels are
+// stream-ordered); k_bump publishes this chunk's byte count and advances it.
+__global__ void k_rebase(uint64_t* off, uint64_t count, const uint64_t* base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) off[i] += *base;
+}
+__global__ void k_bump(uint64_t* base, const uint64_t* chunk_total_entry, uint64_t* chunk_total_out) {
+    const uint64_t t = *chunk_total_entry - *base;   // the entry was rebased as well
+    *chunk_total_out = t;
+    *base += t;
 }
 
 // Dense packing: one warp per slot writes a_align then b_align to arena[off[2p]..], arena[off[2p+1]..]:
