@@ -131,7 +131,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.idx),
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -140,23 +140,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (host clock around the timed region); the sampler itself runs from
+        process start because nvidia-smi needs up to a second before its first line."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        window = "timed region"
+        if not rows and t0 is not None:   # region shorter than the sampling period: nearest samples around it
+            rows = [r for t, r in self.rows if t0 - 0.5 <= t <= t1 + 0.5]
+            window = "within 0.5 s of the timed region"
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def pinned_batch(batch):
@@ -237,7 +244,7 @@ def workload_config(args, cfg, pairs_per_gpu, note=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -272,6 +279,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)   # runs from here on; only the samples inside the timed region are reported
+    sampler.start()
     cfg_name, full_pairs = WORKLOADS[args.workload]
     cfg = synth.CONFIGS[cfg_name]
     pairs = args.pairs or full_pairs
@@ -305,12 +314,11 @@ def main():
         prev = r
     ctx.sync()
     ctx.free_result(prev)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fill_ms = walk_ms = compact_ms = 0.0
     launches = 0
+    t_timed0 = time.perf_counter()
     e0.record(stream)
     prev = None
     for _ in range(args.steps):
@@ -321,7 +329,7 @@ def main():
     e1.record(stream)
     ctx.sync()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_timed0, time.perf_counter())
     dev_ms = e0.elapsed_time(e1)
     t = ctx.timing()                       # phases of the last step (events on the same stream)
     fill_ms, walk_ms, compact_ms, launches = t["fill_ms"], t["walk_ms"], t["compact_ms"], int(t["launches"])

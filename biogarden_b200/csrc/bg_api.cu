@@ -548,6 +548,7 @@ struct Phase {
 constexpr uint64_t SCAN_BLOCK = 4096;
 struct BatchScan {
     bool monotone = true, fitting_violation = false, has_wide = false;
+    uint32_t class_mask = 0;          // length classes present (by len2)
     uint64_t max_len_sum = 0;
     std::vector<double> block_cost;   // per SCAN_BLOCK pairs
 };
@@ -571,6 +572,8 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                 const uint64_t n = o1 - o0, m = o2 - o1;
                 if (n < m) P.fitting_violation = true;
                 if (m > WAVE_MIN_COLS) P.has_wide = true;
+                P.class_mask |= 1u << (m <= 64 ? 0 : m <= 96 ? 1 : m <= 128 ? 2 : m <= 160 ? 3 : m <= 192 ? 4 : m <= 256 ? 5 : m <= 384 ? 6 :
+                                       m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
                 P.max_len_sum = std::max(P.max_len_sum, n + m);
                 cost += (double)n * (double)m + 64.0;
             }
@@ -587,6 +590,7 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
         S.monotone = S.monotone && P.monotone;
         S.fitting_violation = S.fitting_violation || P.fitting_violation;
         S.has_wide = S.has_wide || P.has_wide;
+        S.class_mask |= P.class_mask;
         S.max_len_sum = std::max(S.max_len_sum, P.max_len_sum);
     }
 }
@@ -600,6 +604,8 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
     for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
     const double target = std::max(total / 8.0, 1.0e9);
     const uint64_t max_pairs = 262144;
+    // every length class of a chunk becomes its own launch: keep >= ~4 waves of warps per launch
+    const uint64_t min_pairs = 8192ull * (uint64_t)__builtin_popcount(S.class_mask ? S.class_mask : 1u);
     double acc = 0, done_cost = 0; uint64_t start = lo;
     for (uint64_t k = blk_lo; k < blk_hi; ++k) {
         acc += S.block_cost[k];
@@ -612,7 +618,9 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
         const double scale = nb == 1 ? 0.25 : (nb == 2 || nb == 3) ? 0.5 : 1.0;
         const double left = total - done_cost;
         const double want = std::min(target * scale, std::max(left * 0.5, target * 0.25));
-        if (acc >= want || (double)(end - start) >= (double)max_pairs * scale) { b.push_back(end); start = end; done_cost += acc; acc = 0; }
+        if ((acc >= want && (double)(end - start) >= (double)min_pairs * scale) || (double)(end - start) >= (double)max_pairs * scale) {
+            b.push_back(end); start = end; done_cost += acc; acc = 0;
+        }
     }
     if (b.back() != hi) b.push_back(hi);
     return b;
@@ -705,8 +713,15 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     const uint64_t N = io.N;
     bool ok = ws.end.ensure(std::max<size_t>(1, P.n_slots) * sizeof(EndCell));
     ok = ok && ws.bnd.ensure(std::max<uint64_t>(1, P.bnd_elems) * sizeof(int2));
+    size_t n_chunks = 0;
+    for (const LaunchClass& lc : P.classes) n_chunks += lc.chunks.size();
+    // Host-buffer pipeline: everything after a fill runs on the work set's post stream, so that the next fill
+    // (integer-pipe bound) overlaps the walk / scan / gather of the previous launch (latency bound, small
+    // grids).  Every launch then needs its own trace region, which pipeline chunks can afford.
+    const bool split = ws.post_stream != nullptr && !pp.score_only && P.max_wave_slots == 0 &&
+                       (n_chunks == 1 || P.total_trace_words <= (6ull << 30) / 4);
     if (!pp.score_only) {
-        ok = ok && ws.trace.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4);
+        ok = ok && ws.trace.ensure(std::max<uint64_t>(1, split ? P.total_trace_words : P.max_trace_words) * 4);
         ok = ok && ws.pad.ensure(std::max<uint64_t>(1, P.pad_bytes));
     }
     if (P.max_wave_slots) {
@@ -731,16 +746,11 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     // Chunks alternate between two trace buffers; the walk of chunk c runs on its own stream next to the
     // fill of chunk c+1 (the fill is bound by the integer pipes, the walk by memory requests, so they
     // overlap well on the same SMs).  Events order: fill(c) -> walk(c) -> fill(c+2) (buffer reuse).
-    size_t n_chunks = 0;
-    for (const LaunchClass& lc : P.classes) n_chunks += lc.chunks.size();
     // Measured on B200 (cfg2): overlapping buys 2 % (17.9 vs 18.3 ms/step) -- both kernels just time-share the
     // SMs -- and it blurs the per-kernel event timings the roofline is computed from, so it is opt-in.
     static const bool want_overlap = [] { const char* e = getenv("BG_OVERLAP"); return e && atoi(e) != 0; }();
-    const bool overlap = want_overlap && !pp.score_only && n_chunks >= 2 && P.max_wave_slots == 0;   // K2 traces need the memory of both buffers
+    const bool overlap = want_overlap && !split && !pp.score_only && n_chunks >= 2 && P.max_wave_slots == 0;   // K2 traces need the memory of both buffers
     if (overlap && !ws.trace2.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4)) { ctx->set_error("device allocation failed (second trace buffer)"); return BG_ENOMEM; }
-    // host-buffer pipeline: everything after the fill runs on the work set's post stream, so that the next
-    // chunk's fill (integer-pipe bound) overlaps this chunk's walk / scan / gather (latency bound, small grids)
-    const bool split = ws.post_stream != nullptr && !overlap && !pp.score_only && n_chunks == 1;
     cudaStream_t wst = overlap ? ws.walk_stream : split ? ws.post_stream : st;
     cudaStream_t pst = split ? ws.post_stream : st;
     cudaEvent_t ev_walk_done[2] = {nullptr, nullptr};
@@ -750,6 +760,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
         CU_TRY(ctx, cudaStreamWaitEvent(wst, ev0, 0));     // parameters / memsets issued on the main stream so far
     }
     size_t chunk_no = 0;
+    uint64_t trace_base = 0;   // split: launches do not share trace memory
     for (const LaunchClass& lc : P.classes) {
         const uint32_t G = 32 / lc.sh.L;
         for (const Chunk& ch : lc.chunks) {
@@ -757,7 +768,8 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             if (!ns) continue;
             const int buf = overlap ? (int)(chunk_no & 1) : 0;
             ++chunk_no;
-            fa.trace = (buf ? ws.trace2 : ws.trace).as<uint32_t>();
+            fa.trace = (buf ? ws.trace2 : ws.trace).as<uint32_t>() + (split ? trace_base : 0);
+            trace_base += ch.trace_words;
             if (overlap && ev_walk_done[buf]) CU_TRY(ctx, cudaStreamWaitEvent(st, ev_walk_done[buf], 0));
             fa.desc = io.desc + ch.slot_begin;
             fa.end = ws.end.as<EndCell>() + ch.slot_begin;
@@ -1309,7 +1321,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         for (uint64_t q = lo; q < hi && !long_mode; ++q) long_mode = (off[2 * q + 2] - off[2 * q + 1]) > WAVE_MIN_COLS;
     std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds_from_scan(scan, lo, hi);
     const int nchunks = (int)cb.size() - 1;
-    const uint64_t ws_budget = long_mode ? ctx->trace_budget_words : std::min<uint64_t>(ctx->trace_budget_words, (3ull << 30) / 4);
+    const uint64_t ws_budget = ctx->trace_budget_words;   // per work set; three of them fit the B200's 180 GB many times over
     const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
 
     // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
@@ -1427,7 +1439,8 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         // which stream the chunk's last kernels went to (run_align: post stream unless the plan has several launches)
         size_t n_launch = 0;
         for (const LaunchClass& lc : P.classes) n_launch += lc.chunks.size();
-        cudaStream_t st_last = (ws.post_stream && !pp.score_only && n_launch == 1) ? ws.post_stream : st_comp;
+        cudaStream_t st_last = (ws.post_stream && !pp.score_only && P.max_wave_slots == 0 &&
+                                (n_launch == 1 || P.total_trace_words <= (6ull << 30) / 4)) ? ws.post_stream : st_comp;
         if (!pp.score_only) {   // chunk-relative offsets -> offsets into the caller's arena, on the device
             if (st_last != st_post && st_post != st_comp) {   // keep the running base stream-ordered on st_post
                 CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_last));
