@@ -134,8 +134,11 @@ struct PinBuf {   // pinned host block from the global cache
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Chunk { uint32_t slot_begin, slot_end; uint64_t trace_words; };
-struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; int Q = 1; bool half = false; int myers_W = 0; bool ops_fmt = false; };
+struct Chunk {
+    uint32_t slot_begin, slot_end; uint64_t trace_words;
+    std::vector<WaveAssign> assign; uint32_t n_rounds = 0, max_Q = 1;   // K2 launches only
+};
+struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; bool half = false; int myers_W = 0; bool ops_fmt = false, long_walk = false; };
 
 struct Plan {
     std::vector<LaunchClass> classes;
@@ -162,6 +165,7 @@ struct WorkSet {
     DevBuf trace2;                        // second trace buffer (chunks alternate)
     DevBuf trace, end, bnd, pad, table, codes, err, cubtmp, progress, cand;   // scratch + parameters
     DevBuf residues, desc, score, flags, lens2, off, arena, out64;     // pipeline mode: chunk in / out
+    DevBuf assign;                                                     // K2: CTA assignment table of the launch
     DevBuf run;                                                        // pipeline mode: [0] this chunk's string bytes, [1] (work set 0) running arena base
     PinBuf stage;                                                     // descriptor staging
     PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
@@ -175,7 +179,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run};
+        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign};
     }
 };
 
@@ -396,15 +400,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             for (size_t k = 0; k < cn; ++k) cc += (uint64_t)len_n(cid[k]) * len_m(cid[k]);
             (half ? P.cells_half : P.cells_myers) += cc;
         }
-        if (wave) {   // CTAs per pair: enough workers (16 warps per CTA) for the widest pair's bands
-            uint32_t maxb = 0;
-            for (size_t k = 0; k < cn; ++k) maxb = std::max(maxb, (len_m(cid[k]) + band_cols - 1) / band_cols);
-            lc.Q = maxb > 64 ? 8 : maxb > 32 ? 4 : maxb > 16 ? 2 : 1;
-            if (lc.Q == 8 && cn > (size_t)ctx->num_sms / 8) lc.Q = 4;   // enough pairs to fill the machine: prefer the shorter wavefront ramp
-            P.max_Q = std::max(P.max_Q, lc.Q);
-        }
-        const uint64_t ring = wave ? (uint64_t)lc.Q * K2_WARPS + 1 : 1;
-        const size_t wave_clusters = std::max<size_t>(1, (size_t)ctx->num_sms / (size_t)lc.Q);   // resident pair groups of a K2 launch
+        const size_t wave_clusters = std::max<size_t>(1, (size_t)ctx->num_sms / 4);   // pairs a K2 launch keeps busy at once
+        const uint64_t bnd_off_class = bnd_off;
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
         const size_t nwarps = (sn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
@@ -443,8 +440,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     d.nbands = (d.m + band_cols - 1) / band_cols;
                     d.pair_id = (uint32_t)id;
                     d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull) + 16ull;   // + header of an op slot (k3_walk.cuh)
-                    if (wave) { d.bnd_off = bnd_off; bnd_off += ring * (((uint64_t)d.n + 31ull) & ~31ull); }
-                    else if (d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }
+                    if (!wave && d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }   // K2: assigned below, once the group sizes are known
                 }
             }
             ch.trace_words += warp_words;
@@ -454,13 +450,56 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         lc.chunks.push_back(ch);
         P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
         if (wave) P.max_wave_slots = std::max<uint64_t>(P.max_wave_slots, ch.slot_end - ch.slot_begin);
+        if (wave) {
+            // CTA groups of every K2 launch: sizes proportional to the pairs' cell counts (bounded by the number
+            // of bands a pair has), CTAs handed out to the pairs -- largest first -- by earliest availability
+            bnd_off = bnd_off_class;
+            const uint32_t n_cta = (uint32_t)std::max(1, ctx->num_sms);
+            for (Chunk& wc : lc.chunks) {
+                const uint32_t ns = wc.slot_end - wc.slot_begin;
+                double total = 0;
+                for (uint32_t x = 0; x < ns; ++x) total += (double)dst[wc.slot_begin + x].n * (double)dst[wc.slot_begin + x].m;
+                const double ideal = std::max(1.0, total / n_cta);                 // cells per CTA if the launch were perfectly balanced
+                std::vector<double> avail(n_cta, 0.0);
+                std::vector<std::vector<WaveAssign>> lists(n_cta);
+                std::vector<uint32_t> order(n_cta);
+                for (uint32_t x = 0; x < ns; ++x) {                                  // slots are in largest-first order
+                    PairDesc& d = dst[wc.slot_begin + x];
+                    const double cells = (double)d.n * (double)d.m;
+                    uint32_t q = (uint32_t)std::max(1.0, std::floor(cells / ideal + 0.5));
+                    q = std::min<uint32_t>(q, std::max<uint32_t>(1, (d.nbands + K2_WARPS - 1) / K2_WARPS));
+                    q = std::min<uint32_t>(std::min<uint32_t>(q, K2_MAX_Q), n_cta);
+                    if (const char* e = getenv("BG_K2_Q")) q = std::min<uint32_t>(std::max(1, atoi(e)), std::min<uint32_t>(K2_MAX_Q, n_cta));
+                    for (uint32_t c = 0; c < n_cta; ++c) order[c] = c;
+                    std::partial_sort(order.begin(), order.begin() + q, order.end(),
+                                      [&](uint32_t u, uint32_t v) { return avail[u] < avail[v] || (avail[u] == avail[v] && u < v); });
+                    double start = 0;
+                    for (uint32_t r = 0; r < q; ++r) start = std::max(start, avail[order[r]]);
+                    for (uint32_t r = 0; r < q; ++r) {
+                        lists[order[r]].push_back(WaveAssign{x, (uint16_t)r, (uint16_t)q});
+                        avail[order[r]] = start + cells / q;
+                    }
+                    wc.max_Q = std::max(wc.max_Q, q);
+                    d.bnd_off = bnd_off; bnd_off += ((uint64_t)q * K2_WARPS + 1) * (((uint64_t)d.n + 31ull) & ~31ull);
+                }
+                wc.n_rounds = 0;
+                for (auto& l : lists) wc.n_rounds = std::max<uint32_t>(wc.n_rounds, (uint32_t)l.size());
+                wc.assign.assign((size_t)wc.n_rounds * n_cta, WaveAssign{0, 0, 0});
+                for (uint32_t c = 0; c < n_cta; ++c)
+                    for (size_t r = 0; r < lists[c].size(); ++r) wc.assign[r * n_cta + c] = lists[c][r];
+                P.max_Q = std::max<int>(P.max_Q, (int)wc.max_Q);
+            }
+        }
         P.classes.push_back(lc);
     }
     P.n_slots = nd;
     P.pad_bytes = pad_off; P.bnd_elems = bnd_off;
-    // which walker a class gets (run_align): k3_walk leaves 2-bit ops in the slot, the long-pair walkers characters
+    // which walker a class gets (run_align): k3_walk (one thread per pair) or, for long pairs, k3_walk_diag (one
+    // warp per pair) -- both leave 2-bit ops in the slot; the older long-pair walkers (BG_LONG_WALK) characters
+    static const int long_walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
     for (LaunchClass& lc : P.classes) {
-        lc.ops_fmt = lc.half || !(lc.wave || (uint64_t)P.max_n + P.max_m > 16384);
+        lc.long_walk = !lc.half && (lc.wave || (uint64_t)P.max_n + P.max_m > 16384);
+        lc.ops_fmt = !lc.long_walk || (long_walk_kind == 0 && (lc.sh.C & 7) == 0);
         if (lc.ops_fmt)
             for (const Chunk& ch : lc.chunks)
                 for (uint32_t sidx = ch.slot_begin; sidx < ch.slot_end; ++sidx) dst[sidx].pad_ = 1u;
@@ -504,14 +543,9 @@ bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillAr
 }
 
 template <class Kern>
-cudaError_t launch_k2_impl(Kern kern, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_WARPS * 32, smem) != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
-    const uint32_t groups = std::max<uint32_t>(1, std::min<uint32_t>(n_slots, (uint32_t)(sms * per_sm) / (uint32_t)Q));
+cudaError_t launch_k2_impl(Kern kern, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(groups * (unsigned)Q);
+    cfg.gridDim = dim3((unsigned)n_cta);          // one CTA per SM (launch bounds: 1 block of 16 warps per SM)
     cfg.blockDim = dim3(K2_WARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -521,13 +555,13 @@ cudaError_t launch_k2_impl(Kern kern, uint32_t n_slots, int Q, size_t smem, cuda
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
-cudaError_t launch_k2(bool local, bool prof4, uint32_t n_slots, int Q, size_t smem, cudaStream_t st, const WaveArgs& a) {
+cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a) {
     if (local) {
-        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_slots, Q, smem, st, a);
-        return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_slots, Q, smem, st, a);
+        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_cta, smem, st, a);
+        return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_cta, smem, st, a);
     }
-    if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_slots, Q, smem, st, a);
-    return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_slots, Q, smem, st, a);
+    if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_cta, smem, st, a);
+    return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_cta, smem, st, a);
 }
 void dispatch_k4(Shape sh, dim3 grid, cudaStream_t st, const EditArgs& a) {
 #define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k4_edit<L_, C_><<<grid, 128, 0, st>>>(a); return; }
@@ -727,7 +761,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     if (P.max_wave_slots) {
         const uint64_t nw = (uint64_t)P.max_Q * K2_WARPS;
         // progress counters, then one "workers done" counter per pair
-        ok = ok && ws.progress.ensure(P.max_wave_slots * (nw + 1) * 8 + (P.max_wave_slots + 2) * 4) && ws.cand.ensure(P.max_wave_slots * nw * sizeof(WaveCand));
+        ok = ok && ws.progress.ensure(P.max_wave_slots * (nw + 1) * 8 + (2 * P.max_wave_slots + 4) * 4) && ws.cand.ensure(P.max_wave_slots * nw * sizeof(WaveCand));
     }
     if (!ok) { ctx->set_error("device allocation failed (trace / scratch buffers)"); return BG_ENOMEM; }
     cudaStream_t st = ws.stream;
@@ -776,13 +810,18 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             fa.n_slots = ns;
             const uint32_t nwarps = (ns + G - 1) / G;
             if (lc.wave) {
-                const uint64_t nw = (uint64_t)lc.Q * K2_WARPS;
+                const uint64_t nw = (uint64_t)ch.max_Q * K2_WARPS;
                 const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
-                CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + ((uint64_t)ns + 2) * 4, st));
-                WaveArgs wa; wa.f = fa; wa.progress = ws.progress.as<unsigned long long>(); wa.cand = ws.cand.as<WaveCand>(); wa.Q = lc.Q;
+                CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + (2 * (uint64_t)ns + 4) * 4, st));
+                if (!ws.assign.ensure(std::max<size_t>(1, ch.assign.size()) * sizeof(WaveAssign))) { ctx->set_error("device allocation failed (K2 assignment)"); return BG_ENOMEM; }
+                CU_TRY(ctx, cudaMemcpyAsync(ws.assign.p, ch.assign.data(), ch.assign.size() * sizeof(WaveAssign), cudaMemcpyHostToDevice, st));
+                WaveArgs wa; wa.f = fa; wa.progress = ws.progress.as<unsigned long long>(); wa.cand = ws.cand.as<WaveCand>();
+                wa.assign = ws.assign.as<WaveAssign>(); wa.n_rounds = ch.n_rounds;
+                wa.prog_stride = (uint32_t)(nw + 1); wa.cand_stride = (uint32_t)nw;
                 wa.done = reinterpret_cast<uint32_t*>(ws.progress.as<unsigned char>() + prog_bytes);
+                wa.next_band = wa.done + ns + 2;
                 Phase ph(ws, 1);
-                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ns, lc.Q, pp.smem, st, wa));
+                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, pp.smem, st, wa));
             } else if (lc.half) {
                 Phase ph(ws, 1);
                 const uint32_t nw2 = (ns + 2 * G - 1) / (2 * G);
@@ -810,10 +849,11 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     wa.CW = lc.half ? (int32_t)hb_words_per_lane_block(lc.sh.C) : 0;
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
                     // long pairs: one warp per pair with a trace window in shared memory; short pairs: one thread per pair
-                    if (!lc.ops_fmt) {
-                        static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return (e && !strcmp(e, "vec")) ? 1 : 0; }();
-                        // the window loader maps 8-column blocks onto trace words: needs C % 8 == 0 (true for K2)
-                        if (walk_kind == 1 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
+                    if (lc.long_walk) {
+                        static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
+                        // the window loaders map 8-column blocks onto trace words: need C % 8 == 0 (true for K2)
+                        if (lc.ops_fmt) k3_walk_diag<<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
+                        else if (walk_kind == 2 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
                         else k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, wst>>>(wa);
                     }
                     else k3_walk<<<(ns + 127) / 128, 128, 0, wst>>>(wa);

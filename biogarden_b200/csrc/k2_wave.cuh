@@ -2,8 +2,8 @@
 //
 // Same recurrence, same cell code and same trace layout as K1 (k1_fill.cuh), but ONE pair is spread
 // over all warps of a GROUP of Q co-resident CTAs instead of living in one warp:
-//   * the columns are cut into bands of 32*C; band b is owned by worker (b mod NW), a worker being one
-//     warp of one CTA of the group (NW = Q * warps per CTA, up to 8 x 16 = 128);
+//   * the columns are cut into bands of 32*C; the group's workers -- a worker being one warp of one CTA
+//     of the group, NW = Q * 16 of them -- claim bands in order from a per-pair counter;
 //   * inside a band the 32 lanes run the K1 systolic schedule over all rows;
 //   * band b+1 consumes the last column (M + a, Y) of band b: the producer's lane 31 values are
 //     collected across 32 steps with shuffles and written as one coalesced 256-byte block to a ring
@@ -13,10 +13,10 @@
 //     star, at band granularity, with the diagonal tiles staged through registers / L2;
 //   * the launch is cooperative, so all workers are co-resident and the spin waits cannot deadlock;
 //     the last worker to finish a pair merges the workers' end-cell candidates;
-//   * the grid is persistent: as many groups as fit on the machine; group c owns pairs c, c + NC,
-//     ... of the (largest-first) list and its workers move on to the next pair as soon as their own
-//     bands are done -- there is no barrier between pairs, so the partly filled last round of one
-//     pair's wavefront overlaps the first round of the next.
+//   * the grid is persistent (one CTA per SM) and every CTA walks its own list of (pair, group rank,
+//     group size) assignments built by the host (WaveAssign): groups are sized in proportion to the
+//     pairs' cell counts so that the pairs of a launch finish together, and a CTA moves on to its next
+//     pair as soon as its own bands are done -- there is no barrier between pairs.
 // The walk (K3) reads the trace exactly as for K1 with L = 32.
 #pragma once
 #include <cooperative_groups.h>
@@ -36,13 +36,25 @@ struct WaveCand {          // one worker's end-cell candidates (SURVEY A.5 tie r
 };
 static_assert(sizeof(WaveCand) == 64, "WaveCand layout");
 
+// Which pair a CTA works on in round r of a launch, as which member of the pair's CTA group.  The host
+// sizes the groups in proportion to the pairs' cell counts (a launch holds only as many pairs as their
+// traces fit in memory -- about as many as the machine has SMs / 4 -- so equal groups would leave the SMs
+// of the small pairs idle until the largest pair is done) and hands every CTA its list.
+struct WaveAssign { uint32_t slot; uint16_t rank; uint16_t Q; };   // Q == 0: idle in this round
+
 struct WaveArgs {
     FillArgs f;
-    unsigned long long* progress;   // [slot][NW + 1], zeroed before launch
-    WaveCand* cand;                 // [slot][NW]
+    unsigned long long* progress;   // [slot][prog_stride], zeroed before launch
+    WaveCand* cand;                 // [slot][cand_stride]
     uint32_t* done;                 // [slot] workers that have finished the pair (zeroed before launch)
-    int32_t Q;                      // CTAs per pair group
+    uint32_t* next_band;            // [slot] next unclaimed band of the pair (zeroed before launch)
+    const WaveAssign* assign;       // [n_rounds][gridDim.x]
+    uint32_t n_rounds;
+    uint32_t prog_stride;           // >= max(Q) * K2_WARPS + 1
+    uint32_t cand_stride;           // >= max(Q) * K2_WARPS
 };
+
+constexpr int K2_MAX_Q = 12;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
 
 constexpr int K2_WARPS = 16;        // warps per CTA
 
@@ -79,13 +91,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     __syncthreads();
 
     const int lane = threadIdx.x & 31, p = lane;
-    const uint32_t Q = (uint32_t)W.Q, NW = Q * K2_WARPS, R = NW + 1;
-    const uint32_t group_id = blockIdx.x / Q, cta_rank = blockIdx.x % Q;
-    const uint32_t wk = cta_rank * K2_WARPS + (threadIdx.x >> 5);
     bool bad_residue = false;
 
-    const uint32_t n_groups = gridDim.x / Q;
-  for (uint32_t slot = group_id; slot < A.n_slots; slot += n_groups) {
+  for (uint32_t rd = 0; rd < W.n_rounds; ++rd) {
+    const WaveAssign as = W.assign[(uint64_t)rd * gridDim.x + blockIdx.x];
+    if (as.Q == 0) continue;
+    const uint32_t slot = as.slot;
+    const uint32_t Q = as.Q, NW = Q * K2_WARPS, R = NW + 1;
+    const uint32_t wk = (uint32_t)as.rank * K2_WARPS + (threadIdx.x >> 5);
     const PairDesc d = A.desc[slot];
     const uint32_t n = d.n, m = d.m, nbands = d.nbands, steps = d.steps;
     const uint32_t n_pad = (n + 31u) & ~31u;
@@ -113,9 +126,16 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     if (wk == 0 && p == 0) { rbest = border_col(col_gap, a, b, n); rj = 0; }   // row n, column 0 candidate
 
     int2* const ring = A.bnd + d.bnd_off;
-    unsigned long long* const prog = W.progress + (uint64_t)slot * R;
+    unsigned long long* const prog = W.progress + (uint64_t)slot * W.prog_stride;
 
-    for (uint32_t bd = wk; bd < nbands; bd += NW) {
+    // Bands are claimed dynamically (band b is always claimed before band b + 1, by a resident warp, and
+    // depends on band b - 1 only): a static round-robin leaves most workers idle in a pair's last,
+    // partly filled round (196 bands on 64 workers: 4 rounds for 3.06 rounds of work).
+    for (;;) {
+        uint32_t bd = 0;
+        if (lane == 0) bd = atomicAdd(W.next_band + slot, 1u);
+        bd = __shfl_sync(FULL, bd, 0);
+        if (bd >= nbands) break;
         const uint32_t jbase = bd * band_cols + (uint32_t)p * C;
         const bool lane_has_cols = jbase < m;
         const bool has_next = (bd + 1 < nbands);
@@ -297,13 +317,13 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
         WaveCand c;
         c.best = best; c.bi = bi; c.bj = bj; c.rbest = rbest; c.rj = rj;
         c.cbest = cbest0; c.ci = ci0; c.corner = corner0; c.has_col = has_col;
-        W.cand[(uint64_t)slot * NW + wk] = c;
+        W.cand[(uint64_t)slot * W.cand_stride + wk] = c;
         __threadfence();
         merger = (atomicAdd(W.done + slot, 1u) == NW - 1);   // last worker out merges
         if (merger) __threadfence();
     }
     if (merger) {
-        const WaveCand* cc = W.cand + (uint64_t)slot * NW;
+        const WaveCand* cc = W.cand + (uint64_t)slot * W.cand_stride;
         int32_t fbest = 0; uint32_t fbi = 0, fbj = 0;
         int32_t frb = INT32_MIN; uint32_t frj = 0;
         int32_t fcb = border_row(row_gap, a, b, m); uint32_t fci = 0;

@@ -402,6 +402,174 @@ __global__ void __launch_bounds__(WALK_TILE_WARPS * 32) k3_walk_tile(const WalkA
     }
 }
 
+// K3, diagonal-window long-pair form: one warp per pair, 2-bit op output.
+// A walk over a long pair is ~(n + m) dependent steps; what limits it is how many steps it gets out of one
+// round of memory latency.  The path of two related sequences hugs a diagonal, so the window follows the
+// diagonal: DIAG_ROWS rows tall, and in row k - r the 9 eight-column blocks around column l - r (+-32
+// columns of drift).  The 32 lanes fetch the window with independent loads (one latency for up to
+// DIAG_ROWS steps; the square window of k3_walk_tile gave 64), then the reference's scalar state machine
+// runs against shared memory until the path leaves the window (long gap runs, drift) and the window is
+// re-anchored at the current cell.  Like k3_walk the walk only records 2-bit ops; k_gather turns them into
+// strings.  Needs C % 8 == 0 (an eight-column block is one trace word), true for K2 and the wide K1 shapes.
+constexpr int DIAG_ROWS = 256;
+constexpr int DIAG_WB = 9;
+constexpr int DIAG_HALF = 4;          // blocks left of the diagonal's block
+constexpr int WALK_DIAG_WARPS = 4;
+
+__global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkArgs A) {
+    __shared__ uint32_t s_tile[WALK_DIAG_WARPS][DIAG_ROWS * DIAG_WB];
+    // interior-cell state machine as a table: [state * 16 + code] -> bit 0 emit, bits 1-2 op, bit 3 k--, bit 4 l--,
+    // bits 5-6 next state (borders and the local stop test are handled outside the table)
+    __shared__ uint8_t s_lut[48];
+    if (threadIdx.x < 48) {
+        const uint32_t st = threadIdx.x >> 4, nb = threadIdx.x & 15u;
+        uint32_t ent;
+        if (st == 0) {
+            const uint32_t t = (nb & TR_YEQ) ? 2u : (nb & TR_XEQ);
+            ent = 1u | (t << 1) | ((t != 2u) << 3) | ((t != 1u) << 4) | (t << 5);
+        } else if (st == 1) {
+            ent = (nb & TR_XOPEN) ? 0u : (1u | (1u << 1) | (1u << 3) | (1u << 5));
+        } else {
+            ent = (nb & TR_YOPEN) ? 0u : (1u | (2u << 1) | (1u << 4) | (2u << 5));
+        }
+        s_lut[threadIdx.x] = (uint8_t)ent;
+    }
+    __syncthreads();
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * WALK_DIAG_WARPS + wib;
+    const uint32_t q = threadIdx.x & 31;
+    constexpr unsigned FULL = 0xffffffffu;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const EndCell e = A.end[slot];
+    const uint32_t n = d.n, m = d.m;
+    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
+    const uint32_t K = (C + 7) / 8;
+    const uint32_t band_cols = L * C;
+    const uint32_t lane_base = (slot % (32u / L)) * L;
+    const int mode = A.mode;
+    uint32_t* tile = s_tile[wib];
+    uint32_t* slotw = reinterpret_cast<uint32_t*>(A.pad + d.pad_off);
+    uint32_t* ops = slotw + 2;
+    uint32_t pos = n + m;
+    uint32_t wops = 0;
+    auto push = [&](uint32_t op) {     // every lane tracks pos / wops, lane 0 stores
+        --pos;
+        wops |= op << ((pos & 15u) * 2u);
+        if ((pos & 15u) == 0) { if (q == 0) ops[pos >> 4] = wops; wops = 0; }
+    };
+    auto push_run = [&](uint32_t op, uint32_t count) {   // `count` equal ops, up to a word per iteration
+        const uint32_t pattern = op * 0x55555555u;
+        while (count) {
+            const uint32_t hi = (pos & 15u) ? (pos & 15u) : 16u;      // free fields of the current word: [0, hi)
+            const uint32_t take = min(count, hi), lo = hi - take;
+            const uint32_t mask = (take == 16u) ? 0xffffffffu : (((1u << (2u * take)) - 1u) << (2u * lo));
+            wops |= pattern & mask;
+            pos -= take; count -= take;
+            if ((pos & 15u) == 0) { if (q == 0) ops[pos >> 4] = wops; wops = 0; }
+        }
+    };
+
+    uint32_t k = e.k, l = e.l, flags = 0;
+    const bool colbr = (e.flags & 1u) != 0;
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
+        if (colbr) push_run(1u, n - k); else push_run(2u, m - l);
+    }
+    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
+    const uint64_t bound = 3ull * ((uint64_t)n + m) + 64;   // emits + state switches + one probe per window
+    uint64_t it = 0;
+    uint32_t probe_skip = 0;
+    bool done = false;
+    while (!done) {
+        // ---- load the window anchored at (k, l): row r is DP row k - r, blocks cb_c(r) - 4 .. cb_c(r) + 4 ----
+        const uint32_t k_hi = k, l_hi = l;
+        if (k >= 1 && l >= 1) {
+            const uint32_t rows = min(k, (uint32_t)DIAG_ROWS);
+            for (uint32_t x = q; x < rows * DIAG_WB; x += 32) {
+                const uint32_t rr = x / DIAG_WB, bx = x - rr * DIAG_WB;
+                const int32_t cb = (((int32_t)l_hi - (int32_t)rr - 1) >> 3) - DIAG_HALF + (int32_t)bx;
+                uint32_t wv = 0;
+                if (cb >= 0 && ((uint32_t)cb << 3) < m) {
+                    const uint32_t i = k_hi - rr;
+                    const uint32_t j0 = (uint32_t)cb << 3;
+                    const uint32_t bd = j0 / band_cols, rem = j0 - bd * band_cols;
+                    const uint32_t p = rem / C, c = rem - p * C;
+                    const uint32_t t = (i - 1) + p;
+                    const uint64_t idx = d.trace_off + ((uint64_t)bd * d.steps + t) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
+                    wv = __ldg(A.trace + idx);
+                }
+                tile[x] = wv;
+            }
+        }
+        __syncwarp();
+        // ---- walk inside the window (all lanes execute it redundantly; lane 0 stores) ----
+        for (;;) {
+            if (++it > bound) { flags |= WALK_HANG; done = true; break; }
+            if (k != 0 && l != 0) {
+                const uint32_t rr = k_hi - k;
+                const int32_t bx = (int32_t)((l - 1) >> 3) - ((((int32_t)l_hi - (int32_t)rr - 1) >> 3) - DIAG_HALF);
+                if (rr >= (uint32_t)DIAG_ROWS || bx < 0 || bx >= DIAG_WB) break;     // left the window: re-anchor
+                if (cur == 0 && probe_skip == 0) {
+                    // vector probe: lane q looks at cell (k - q, l - q); a run of plain diagonal moves (neither tie
+                    // bit set: 'R', and in local mode not the stop code) is emitted at once.  After a short run the
+                    // next few steps go through the scalar path (unrelated sequences change state every 2-3 cells)
+                    const uint32_t rq = rr + q;
+                    bool good = (q < k) && (q < l) && rq < (uint32_t)DIAG_ROWS;
+                    if (good) {
+                        const uint32_t lq = l - q;
+                        const int32_t bq = (int32_t)((lq - 1) >> 3) - ((((int32_t)l_hi - (int32_t)rq - 1) >> 3) - DIAG_HALF);
+                        good = bq >= 0 && bq < DIAG_WB;
+                        if (good) good = ((tile[rq * DIAG_WB + (uint32_t)bq] >> (((lq - 1) & 7u) * 4u)) & 3u) == 0u;
+                    }
+                    const uint32_t mask = __ballot_sync(FULL, good);
+                    const uint32_t run = (mask == FULL) ? 32u : (uint32_t)(__ffs((int)~mask) - 1);
+                    if (run < 4u) probe_skip = 8u;
+                    if (run) { push_run(0u, run); k -= run; l -= run; continue; }
+                } else if (probe_skip) --probe_skip;
+                const uint32_t nib = (tile[rr * DIAG_WB + (uint32_t)bx] >> (((l - 1) & 7u) * 4u)) & 15u;
+                if (mode == M_LOCAL && (nib & 3u) == 3u) { done = true; break; }     // aligner.rs:181
+                const uint32_t ent = s_lut[cur * 16u + nib];
+                if (ent & 1u) push((ent >> 1) & 3u);
+                k -= (ent >> 3) & 1u; l -= (ent >> 4) & 1u; cur = (ent >> 5) & 3u;
+                continue;
+            }
+            // border cells (k == 0 or l == 0): the reference's border trace values (aligner.rs:107-108, 52)
+            bool valid;
+            switch (mode) {
+                case M_GLOBAL: valid = (k != 0 || l != 0); break;
+                case M_LOCAL: valid = false; break;
+                case M_SEMIGLOBAL: valid = false; break;
+                default: valid = (l != 0); break;
+            }
+            if (!valid) { done = true; break; }
+            if (cur == 0) {
+                if (l == 0) { push(1u); --k; cur = 1; }
+                else { push(2u); --l; cur = 2; }
+            } else if (cur == 1) {
+                if (k == 0) { flags |= WALK_UNDERFLOW; done = true; break; }
+                push(1u); --k;
+            } else {
+                if (l == 0) { flags |= WALK_UNDERFLOW; done = true; break; }
+                push(2u); --l;
+            }
+        }
+        __syncwarp();
+    }
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
+        if (colbr) { push_run(1u, k); k = 0; } else { push_run(2u, l); l = 0; }
+    }
+    if (q == 0) {
+        if (pos & 15u) ops[pos >> 4] = wops;
+        slotw[0] = k; slotw[1] = l;
+        const uint32_t len = n + m - pos;
+        A.score[d.pair_id] = e.score;
+        A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
+        A.lens2[2ull * d.pair_id] = len;
+        A.lens2[2ull * d.pair_id + 1] = len;
+    }
+}
+
 // Score-only epilogue when no traceback is requested.
 __global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t n_slots, int32_t* score,
                               uint8_t* walk_flags, int mode) {
