@@ -137,6 +137,11 @@ struct PinBuf {   // pinned host block from the global cache
 struct Chunk {
     uint32_t slot_begin, slot_end; uint64_t trace_words;
     std::vector<WaveAssign> assign; uint32_t n_rounds = 0, max_Q = 1;   // K2 launches only
+    // bounded-memory traceback (k2_wave.cuh): pairs whose whole traces do not fit the budget; trace_words then
+    // covers one row block of every pair
+    uint32_t ckpt_nb = 0;                 // > 0: bounded-memory chunk, every pair cut into this many row blocks
+    std::vector<CkptSlot> ck_table;       // [ckpt_nb + 1][slots]: pass 1, then the blocks bottom-up
+    uint64_t ckpt_elems = 0;
 };
 struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; bool half = false; int myers_W = 0; bool ops_fmt = false, long_walk = false; };
 
@@ -145,7 +150,9 @@ struct Plan {
     size_t n_slots = 0;
     uint64_t max_trace_words = 0, bnd_elems = 0, pad_bytes = 0, cells = 0, total_trace_words = 0;
     uint64_t cells_half = 0, cells_myers = 0;   // of `cells`: in K1h / K4b classes
+    uint64_t cells_ckpt = 0;                    // of `cells`: pairs on the bounded-memory path (filled twice)
     uint64_t max_wave_slots = 0;      // largest K2 launch (slots), for the progress / candidate scratch
+    uint64_t ckpt_elems = 0;          // bounded-memory traceback: int2 elements of the largest checkpoint array
     int max_Q = 1;
     uint32_t max_n = 0, max_m = 0;
     int32_t half_maxabs = 0;          // > 0: short classes were laid out for K1h (packed 16 x 2) with this max |score|
@@ -166,6 +173,7 @@ struct WorkSet {
     DevBuf trace, end, bnd, pad, table, codes, err, cubtmp, progress, cand;   // scratch + parameters
     DevBuf residues, desc, score, flags, lens2, off, arena, out64;     // pipeline mode: chunk in / out
     DevBuf assign;                                                     // K2: CTA assignment table of the launch
+    DevBuf ckpt, wstate, ckslots;                                      // K2 bounded-memory traceback: row checkpoints, suspended walks, launch table
     DevBuf run;                                                        // pipeline mode: [0] this chunk's string bytes, [1] (work set 0) running arena base
     PinBuf stage;                                                     // descriptor staging
     PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
@@ -179,7 +187,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign};
+        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots};
     }
 };
 
@@ -211,6 +219,7 @@ struct bg_ctx {
     bg_timing timing{};
     std::atomic<uint64_t> h2d{0}, d2h{0}, launches{0};
     uint64_t trace_budget_words = 0;
+    uint64_t long_budget_words = 0;   // K2 pairs; 0 = automatic (most of the device)
     int force_L = 0, force_C = 0;
     int num_sms = 148;
     void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu); last_error = s; }
@@ -402,6 +411,53 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         }
         const size_t wave_clusters = std::max<size_t>(1, (size_t)ctx->num_sms / 4);   // pairs a K2 launch keeps busy at once
         const uint64_t bnd_off_class = bnd_off;
+        // K2, bounded-memory traceback: when the whole traces of the next pairs do not fit the budget -- one pair
+        // alone, or so few together that most SMs would idle (a pair keeps at most 12 CTAs busy) -- a group of up
+        // to `wave_clusters` pairs is cut into nb row blocks each (same nb for all, so they stay in step) such
+        // that one block of every pair fits.  ck_group[k] != 0 marks the members (k = position in the sorted list).
+        std::vector<uint32_t> ck_group, ck_rb, ck_nb;
+        if (wave && with_trace) {
+            auto full_words = [&](size_t k) {
+                const uint64_t nb_ = (len_m(cid[k]) + band_cols - 1) / band_cols;
+                return nb_ * ((uint64_t)len_n(cid[k]) + sh.L - 1) * K * 32ull;
+            };
+            static const size_t min_fit = [] { const char* e = getenv("BG_CKPT_MIN_FIT"); return e ? (size_t)std::max(1, atoi(e)) : (size_t)6; }();
+            uint32_t gid = 0;
+            auto fits_from = [&](size_t k) {       // how many pairs from position k on fit together, whole traces
+                size_t fit = 0; uint64_t words = 0;
+                while (k + fit < cn && fit < min_fit && words + full_words(k + fit) <= class_budget) { words += full_words(k + fit); ++fit; }
+                return fit;
+            };
+            for (size_t k = 0; k < cn;) {
+                if (fits_from(k) >= std::min(min_fit, cn - k)) break;    // the list is sorted: the rest fits as well
+                if (ck_group.empty()) { ck_group.assign(cn, 0); ck_rb.assign(cn, 0); ck_nb.assign(cn, 0); }
+                size_t S = 1;
+                while (k + S < cn && S < wave_clusters && fits_from(k + S) < std::min(min_fit, cn - k - S)) ++S;
+                uint32_t nb = 0;
+                for (;; S = (S + 1) / 2) {
+                    uint32_t maxn_g = 0;
+                    for (size_t x = k; x < k + S; ++x) maxn_g = std::max(maxn_g, len_n(cid[x]));
+                    const uint32_t t_max = std::max(2u, (maxn_g + 63u) / 64u);      // blocks are at least 64 rows
+                    for (uint32_t t = 2;; t = std::min(t_max, t < 16 ? t + 1 : t + t / 8)) {
+                        uint64_t w2 = 0;
+                        for (size_t x = k; x < k + S; ++x) {
+                            const uint32_t rb = std::max(64u, ((len_n(cid[x]) + t - 1) / t + 31u) & ~31u);
+                            w2 += (uint64_t)((len_m(cid[x]) + band_cols - 1) / band_cols) * ((uint64_t)rb + sh.L - 1) * K * 32ull;
+                        }
+                        if (w2 <= class_budget) { nb = t; break; }
+                        if (t == t_max) break;
+                    }
+                    if (nb || S == 1) break;
+                }
+                if (!nb) { ctx->set_error("trace budget too small for 64-row blocks of the longest pair"); return BG_ENOMEM; }
+                ++gid;
+                for (size_t x = k; x < k + S; ++x) {
+                    ck_group[x] = gid; ck_nb[x] = nb;
+                    ck_rb[x] = std::max(64u, ((len_n(cid[x]) + nb - 1) / nb + 31u) & ~31u);
+                }
+                k += S;
+            }
+        }
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
         const size_t nwarps = (sn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
@@ -415,12 +471,25 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             }
             // K1h: row-block trace layout, HB_TB steps per block, CW words per lane and block
             const uint32_t steps = half ? ((maxn + sh.L - 1 + HB_TB - 1) / HB_TB) * HB_TB : maxn + sh.L - 1;
-            const uint64_t warp_words = !with_trace ? 0 :
+            uint64_t warp_words = !with_trace ? 0 :
                 half ? (uint64_t)((steps / HB_TB + HB_TG_MAX - 1) / HB_TG_MAX) * HB_TG_MAX * 32ull * hb_words_per_lane_block(sh.C) : (uint64_t)maxb * steps * K * 32ull;
             // K2 launches run one pair per resident cluster at a time: close a chunk at a multiple of the
             // cluster count once memory is nearly used up, so that the (length-sorted) pairs of a launch finish together
             const bool wave_round = wave && ch.trace_words > 0 && ((nd - ch.slot_begin) % wave_clusters) == 0 &&
                                     ch.trace_words + warp_words * wave_clusters > class_budget;
+            // bounded-memory groups (decided above): a chunk of their own, block-sized traces
+            const uint32_t grp = (wave && !ck_group.empty()) ? ck_group[w] : 0u;
+            const bool grp_first = grp && (w == 0 || ck_group[w - 1] != grp);
+            const bool grp_last = grp && (w + 1 == nwarps || ck_group[w + 1] != grp);
+            if (grp) warp_words = (uint64_t)maxb * (ck_rb[w] + sh.L - 1) * K * 32ull;
+            if (grp_first && nd > ch.slot_begin) {
+                ch.slot_end = (uint32_t)nd;
+                lc.chunks.push_back(ch);
+                P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
+                P.max_wave_slots = std::max<uint64_t>(P.max_wave_slots, ch.slot_end - ch.slot_begin);
+                ch = Chunk(); ch.slot_begin = ch.slot_end = (uint32_t)nd; ch.trace_words = 0;
+            }
+            if (!grp)
             if (with_trace && ch.trace_words > 0 && (wave_round || ch.trace_words + warp_words > class_budget)) {
                 ch.slot_end = (uint32_t)nd;
                 lc.chunks.push_back(ch);
@@ -442,6 +511,43 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull) + 16ull;   // + header of an op slot (k3_walk.cuh)
                     if (!wave && d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }   // K2: assigned below, once the group sizes are known
                 }
+            }
+            if (grp) {
+                PairDesc& d = dst[nd - 1];
+                d.steps = ck_rb[w] + sh.L - 1;
+                P.cells_ckpt += (uint64_t)d.n * d.m;
+                ch.trace_words += warp_words;
+                P.total_trace_words += warp_words;
+                if (grp_last) {
+                    // the launch table: entry [0] = pass 1 (whole pair), [1 + x] = row block nb - 1 - x
+                    const uint32_t nb = ck_nb[w], nsl = (uint32_t)nd - ch.slot_begin;
+                    ch.ckpt_nb = nb;
+                    ch.ck_table.assign((size_t)(nb + 1) * nsl, CkptSlot{});
+                    uint64_t ck_off = 0;
+                    for (uint32_t x = 0; x < nsl; ++x) {
+                        const PairDesc& dx = dst[ch.slot_begin + x];
+                        const uint32_t rb = dx.steps - (sh.L - 1), stride = (dx.m + 31u) & ~31u;
+                        for (uint32_t l = 0; l <= nb; ++l) {
+                            CkptSlot& e = ch.ck_table[(size_t)l * nsl + x];
+                            e.ck_off = ck_off; e.ck_stride = stride; e.every = rb;
+                            if (l == 0) { e.row0 = 0; e.nrows = dx.n; }
+                            else {
+                                const uint64_t r0 = (uint64_t)(nb - l) * rb;
+                                e.row0 = (uint32_t)std::min<uint64_t>(r0, dx.n);
+                                e.nrows = r0 < dx.n ? (uint32_t)std::min<uint64_t>(rb, dx.n - r0) : 0u;
+                            }
+                        }
+                        ck_off += (uint64_t)(nb - 1) * stride;
+                    }
+                    ch.ckpt_elems = ck_off;
+                    P.ckpt_elems = std::max<uint64_t>(P.ckpt_elems, ck_off);
+                    ch.slot_end = (uint32_t)nd;
+                    lc.chunks.push_back(ch);
+                    P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
+                    P.max_wave_slots = std::max<uint64_t>(P.max_wave_slots, nsl);
+                    ch = Chunk(); ch.slot_begin = ch.slot_end = (uint32_t)nd; ch.trace_words = 0;
+                }
+                continue;
             }
             ch.trace_words += warp_words;
             P.total_trace_words += warp_words;
@@ -468,8 +574,13 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     const double cells = (double)d.n * (double)d.m;
                     uint32_t q = (uint32_t)std::max(1.0, std::floor(cells / ideal + 0.5));
                     q = std::min<uint32_t>(q, std::max<uint32_t>(1, (d.nbands + K2_WARPS - 1) / K2_WARPS));
-                    q = std::min<uint32_t>(std::min<uint32_t>(q, K2_MAX_Q), n_cta);
-                    if (const char* e = getenv("BG_K2_Q")) q = std::min<uint32_t>(std::max(1, atoi(e)), std::min<uint32_t>(K2_MAX_Q, n_cta));
+                    uint32_t q_cap = K2_MAX_Q;
+                    if (wc.ckpt_nb && ns == 1) {   // a single huge pair may own the machine; its boundary ring (q * 16 + 1 columns of n rows) is kept below 2 GiB
+                        const uint64_t ring_q = ((2ull << 30) / sizeof(int2)) / ((((uint64_t)d.n + 31ull) & ~31ull) * K2_WARPS);
+                        q_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_cta, ring_q));
+                    }
+                    q = std::min<uint32_t>(std::min<uint32_t>(q, q_cap), n_cta);
+                    if (const char* e = getenv("BG_K2_Q")) q = std::min<uint32_t>(std::max(1, atoi(e)), std::min<uint32_t>(q_cap, n_cta));
                     for (uint32_t c = 0; c < n_cta; ++c) order[c] = c;
                     std::partial_sort(order.begin(), order.begin() + q, order.end(),
                                       [&](uint32_t u, uint32_t v) { return avail[u] < avail[v] || (avail[u] == avail[v] && u < v); });
@@ -555,7 +666,15 @@ cudaError_t launch_k2_impl(Kern kern, int n_cta, size_t smem, cudaStream_t st, c
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
-cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a) {
+cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false) {
+    if (ckpt) {
+        if (local) {
+            if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true, true>, n_cta, smem, st, a);
+            return launch_k2_impl(k2_wave<WAVE_C, true, false, true>, n_cta, smem, st, a);
+        }
+        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true, true>, n_cta, smem, st, a);
+        return launch_k2_impl(k2_wave<WAVE_C, false, false, true>, n_cta, smem, st, a);
+    }
     if (local) {
         if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_cta, smem, st, a);
         return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_cta, smem, st, a);
@@ -809,6 +928,51 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             fa.end = ws.end.as<EndCell>() + ch.slot_begin;
             fa.n_slots = ns;
             const uint32_t nwarps = (ns + G - 1) / G;
+            if (lc.wave && ch.ckpt_nb) {
+                // ---- bounded-memory traceback: pass 1 (checkpoints + end cells), then row block by row block,
+                //      bottom-up, re-fill with direction codes + resume the walks (k2_wave.cuh) ----
+                if (!lc.ops_fmt) { ctx->set_error("bounded-memory traceback needs the default long-pair walker"); return BG_EUNSUPPORTED; }
+                const uint32_t NB = ch.ckpt_nb;
+                if (!ws.ckpt.ensure(std::max<uint64_t>(1, ch.ckpt_elems) * sizeof(int2)) || !ws.wstate.ensure(ns * sizeof(WalkState)) ||
+                    !ws.ckslots.ensure(ch.ck_table.size() * sizeof(CkptSlot)) ||
+                    !ws.assign.ensure(std::max<size_t>(1, ch.assign.size()) * sizeof(WaveAssign))) {
+                    ctx->set_error("device allocation failed (row checkpoints)"); return BG_ENOMEM;
+                }
+                CU_TRY(ctx, cudaMemsetAsync(ws.wstate.p, 0, ns * sizeof(WalkState), st));
+                CU_TRY(ctx, cudaMemcpyAsync(ws.assign.p, ch.assign.data(), ch.assign.size() * sizeof(WaveAssign), cudaMemcpyHostToDevice, st));
+                CU_TRY(ctx, cudaMemcpyAsync(ws.ckslots.p, ch.ck_table.data(), ch.ck_table.size() * sizeof(CkptSlot), cudaMemcpyHostToDevice, st));
+                const uint64_t nw = (uint64_t)ch.max_Q * K2_WARPS;
+                const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
+                WaveArgs wa; wa.f = fa; wa.progress = ws.progress.as<unsigned long long>(); wa.cand = ws.cand.as<WaveCand>();
+                wa.assign = ws.assign.as<WaveAssign>(); wa.n_rounds = ch.n_rounds;
+                wa.prog_stride = (uint32_t)(nw + 1); wa.cand_stride = (uint32_t)nw;
+                wa.done = reinterpret_cast<uint32_t*>(ws.progress.as<unsigned char>() + prog_bytes);
+                wa.next_band = wa.done + ns + 2;
+                wa.ckpt = ws.ckpt.as<int2>();
+                wa.wstate = ws.wstate.as<WalkState>();
+                WalkArgs wk;
+                wk.desc = fa.desc; wk.end = fa.end; wk.n_slots = ns; wk.residues = fa.residues;
+                wk.trace = fa.trace; wk.mode = pp.mode; wk.L = lc.sh.L; wk.C = lc.sh.C; wk.H = 1; wk.tg_shift = fa.tg_shift; wk.CW = 0;
+                wk.pad = ws.pad.as<uint8_t>(); wk.score = io.score; wk.walk_flags = io.flags; wk.lens2 = io.lens2;
+                wk.wstate = ws.wstate.as<WalkState>();
+                for (uint32_t l = 0; l <= NB; ++l) {
+                    {
+                        Phase ph(ws, 1);
+                        CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + (2 * (uint64_t)ns + 4) * 4, st));
+                        wa.cks = ws.ckslots.as<CkptSlot>() + (size_t)l * ns;
+                        wa.f.want_trace = l ? 1 : 0; wa.ckpt_write = l ? 0 : 1; wa.write_end = l ? 0 : 1;
+                        CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, pp.smem, st, wa, true));
+                    }
+                    if (l) {
+                        Phase ph(ws, 2);
+                        wk.cks = wa.cks; wk.last_launch = (l == NB) ? 1u : 0u;
+                        k3_walk_diag<<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(wk);
+                    }
+                    CU_TRY(ctx, cudaGetLastError());
+                }
+                ctx->launches += 1 + 2 * (uint64_t)NB;
+                continue;
+            }
             if (lc.wave) {
                 const uint64_t nw = (uint64_t)ch.max_Q * K2_WARPS;
                 const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
@@ -1011,6 +1175,7 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
     uint64_t budget_mb = 8192;
     if (const char* e = getenv("BG_TRACE_BUDGET_MB")) budget_mb = strtoull(e, nullptr, 10);
     ctx->trace_budget_words = budget_mb * (1024ull * 1024ull / 4ull);
+    if (const char* e = getenv("BG_LONG_TRACE_BUDGET_MB")) ctx->long_budget_words = strtoull(e, nullptr, 10) * (1024ull * 1024ull / 4ull);
     if (const char* e = getenv("BG_FORCE_SHAPE")) {   // "L,C" -- experiments / tests
         int l = 0, c = 0;
         if (sscanf(e, "%d,%d", &l, &c) == 2) { ctx->force_L = l; ctx->force_C = c; }
@@ -1036,6 +1201,12 @@ int bg_set_shape(bg_ctx* ctx, int L, int C) {   // 0,0 = automatic
 int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes) {
     if (!ctx || bytes < 4096) return BG_EINVAL_ARG;
     ctx->trace_budget_words = bytes / 4;
+    return BG_OK;
+}
+
+int bg_set_long_trace_budget(bg_ctx* ctx, uint64_t bytes) {   // 0 = automatic
+    if (!ctx || (bytes && bytes < 4096)) return BG_EINVAL_ARG;
+    ctx->long_budget_words = bytes / 4;
     return BG_OK;
 }
 
@@ -1130,7 +1301,7 @@ static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit, int32_t half_maxabs
     PinBuf stage;
     if (!stage.ensure(cap * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
     // long pairs (K2) need whole traces of several GB each: let them use most of the device
-    const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
+    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
     // with BG_OVERLAP: chunks of <= 2 GiB of trace so that walk(c) overlaps fill(c+1) (run_align); otherwise large
     // chunks -- the walk is latency-bound and wants as many pairs per launch as possible
     static const bool want_overlap = [] { const char* e = getenv("BG_OVERLAP"); return e && atoi(e) != 0; }();
@@ -1192,7 +1363,7 @@ int bg_align_device(bg_ctx* ctx, const bg_dbatch* cin, const bg_params* p, bg_dr
 
     ws.reset_events();
     ctx->launches = 0;
-    ctx->timing.cells = P.cells; ctx->timing.cells_packed16 = P.cells_half; ctx->timing.cells_bitparallel = 0;
+    ctx->timing.cells = P.cells; ctx->timing.cells_packed16 = P.cells_half; ctx->timing.cells_bitparallel = 0; ctx->timing.cells_refilled = P.cells_ckpt;
     ctx->timing.trace_bytes = pp.score_only ? 0 : P.total_trace_words * 4;
     rc = upload_params(ctx, ws, pp);
     AlignIO io{B->residues.as<uint8_t>(), B->desc_align.as<PairDesc>(), &P, N,
@@ -1220,7 +1391,7 @@ int bg_edit_distance_device(bg_ctx* ctx, const bg_dbatch* cin, bg_dresult** out)
     if (!R->out64.ensure(std::max<uint64_t>(1, N) * 8)) { bg_dresult_free(R); ctx->set_error("device allocation failed"); return BG_ENOMEM; }
     ws.reset_events();
     ctx->launches = 0;
-    ctx->timing.cells = P.cells; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = P.cells_myers;
+    ctx->timing.cells = P.cells; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = P.cells_myers; ctx->timing.cells_refilled = 0;
     rc = run_edit(ctx, ws, B->residues.as<uint8_t>(), B->desc_edit.as<PairDesc>(), P, R->out64.as<uint64_t>(), B->edit_lut_ok ? B->edit_lut : nullptr);
     if (rc) { bg_dresult_free(R); return rc; }
     *out = R;
@@ -1362,7 +1533,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds_from_scan(scan, lo, hi);
     const int nchunks = (int)cb.size() - 1;
     const uint64_t ws_budget = ctx->trace_budget_words;   // per work set; three of them fit the B200's 180 GB many times over
-    const uint64_t wave_budget = std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
+    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
 
     // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
     // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon
@@ -1506,7 +1677,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         CU_TRY(ctx, cudaMemcpyAsync(fo.score + rel, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st_small));
         CU_TRY(ctx, cudaMemcpyAsync(fo.status + rel, ws.flags.p, n, cudaMemcpyDeviceToHost, st_small));
         CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st_small));
-        ctx->timing.cells += P.cells; ctx->timing.cells_packed16 += P.cells_half;
+        ctx->timing.cells += P.cells; ctx->timing.cells_packed16 += P.cells_half; ctx->timing.cells_refilled += P.cells_ckpt;
         ctx->timing.trace_bytes += pp.score_only ? 0 : P.total_trace_words * 4;
         return BG_OK;
     };
@@ -1688,7 +1859,7 @@ int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_resul
     rc = bg_sync(ctx);   // cached blocks may still be in use by device-resident work (see bg_dresult_free)
     if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
-    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0; ctx->timing.cells_refilled = 0;
 
     // upper bound of each device's share of the arena: 2*(n+m) per pair
     std::vector<uint64_t> ub(nd + 1, 0);
@@ -1744,7 +1915,7 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     rc = bg_sync(ctx);
     if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
-    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0; ctx->timing.cells_refilled = 0;
     // Alphabet from a sample of the batch: <= 4 byte values -> bit-parallel K4b.  The kernel flags any
     // byte outside the sampled alphabet, in which case the batch is redone with the general kernel.
     uint8_t lut[256];

@@ -46,6 +46,27 @@ struct __align__(16) EndCell {
     uint32_t flags;  // bit 0: semiglobal column branch (aligner.rs:389)
 };
 
+// A traceback walk suspended at a row-block boundary (bounded-memory traceback, k2_wave.cuh): everything
+// k3_walk_diag needs to go on in the next launch.
+struct __align__(16) WalkState {
+    uint32_t k, l, cur, pos, wops, flags;
+    uint32_t started;   // 0: the first launch initialises the walk from the end cell
+    uint32_t done;      // the walk has ended and its results are written
+    uint64_t it;
+    uint64_t pad_;
+};
+
+// Bounded-memory traceback: what one launch does for one slot (built by the host per launch).
+struct __align__(16) CkptSlot {
+    uint64_t ck_off;      // int2 offset of the slot's checkpoint rows
+    uint32_t ck_stride;   // elements per checkpoint row (len2 rounded up to 32)
+    uint32_t row0;        // the launch fills / walks DP rows row0 + 1 .. row0 + nrows (nrows == 0: nothing)
+    uint32_t nrows;
+    uint32_t every;       // checkpoint spacing of the slot, rows (multiple of 32)
+    uint32_t pad_[2];
+};
+static_assert(sizeof(CkptSlot) == 32, "CkptSlot layout");
+
 constexpr uint32_t WALK_UNDERFLOW = 1;  // reference would index seq[usize::MAX] (A.6)
 constexpr uint32_t WALK_HANG = 2;       // step bound exceeded (cannot happen with well-formed traces)
 

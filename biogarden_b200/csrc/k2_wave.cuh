@@ -18,6 +18,14 @@
 //     pairs' cell counts so that the pairs of a launch finish together, and a CTA moves on to its next
 //     pair as soon as its own bands are done -- there is no barrier between pairs.
 // The walk (K3) reads the trace exactly as for K1 with L = 32.
+//
+// Bounded-memory traceback (CKPT = true; pairs whose 0.5 B/cell trace does not fit the budget): the DP is run
+// twice.  Pass 1 keeps no direction codes; it leaves row CHECKPOINTS -- the register state (M + a, X) of every
+// column at the rows that are multiples of `ckpt_every` -- and the end cell.  Pass 2 goes through the row
+// blocks bottom-up: one launch re-fills rows (row0, row0 + nrows] starting from the checkpoint at row0, this
+// time storing the codes of just that block, and k3_walk_diag continues the walk through the block
+// (WalkState carries it from launch to launch).  Trace memory is ckpt_every x len2 / 2 bytes instead of
+// len1 x len2 / 2, checkpoints cost 8 B x len2 per block, and the cells are computed twice.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -52,6 +60,12 @@ struct WaveArgs {
     uint32_t n_rounds;
     uint32_t prog_stride;           // >= max(Q) * K2_WARPS + 1
     uint32_t cand_stride;           // >= max(Q) * K2_WARPS
+    // ---- bounded-memory traceback (k2_wave<.., CKPT = true> only) ----
+    const CkptSlot* cks;            // [slot]: the row block this launch fills, where the slot's checkpoints live
+    uint32_t ckpt_write;            // pass 1: store the checkpoints; pass 2: 0
+    uint32_t write_end;             // pass 1: publish the end cell; pass 2: 0
+    int2* ckpt;                     // per slot [row block][ck_stride]: (M + a, X) of row (block + 1) * every, by 0-based column
+    const WalkState* wstate;        // pass 2: skip pairs whose walk has already ended
 };
 
 constexpr int K2_MAX_Q = 12;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
@@ -71,7 +85,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     return v;
 }
 
-template <int C, bool IS_LOCAL, bool PROF4>
+template <int C, bool IS_LOCAL, bool PROF4, bool CKPT = false>
 __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     namespace cg = cooperative_groups;
     constexpr int L = 32;
@@ -100,7 +114,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     const uint32_t Q = as.Q, NW = Q * K2_WARPS, R = NW + 1;
     const uint32_t wk = (uint32_t)as.rank * K2_WARPS + (threadIdx.x >> 5);
     const PairDesc d = A.desc[slot];
-    const uint32_t n = d.n, m = d.m, nbands = d.nbands, steps = d.steps;
+    CkptSlot cs; cs.ck_off = 0; cs.ck_stride = cs.row0 = cs.nrows = 0; cs.every = 1;
+    if (CKPT) cs = W.cks[slot];
+    const uint32_t row0 = cs.row0;
+    // pass 2: nothing to do for empty blocks, blocks below the end cell, or after the walk has ended
+    if (CKPT && !W.write_end && (cs.nrows == 0 || W.wstate[slot].done || A.end[slot].k <= row0)) continue;
+    const uint32_t n = CKPT ? cs.nrows : d.n, m = d.m, nbands = d.nbands;
+    const uint32_t tstride = d.steps;                       // steps per band in the trace layout
+    const uint32_t steps = CKPT ? n + 31u : d.steps;        // steps this launch runs
     const uint32_t n_pad = (n + 31u) & ~31u;
     const int32_t a = A.a, b = A.b, one = A.one;
     const int mode = A.mode;
@@ -108,8 +129,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     const bool col_gap = (mode == M_GLOBAL);
     const bool track_col = (mode == M_SEMIGLOBAL || mode == M_FITTING);
     const bool track_row = (mode == M_SEMIGLOBAL || mode == M_OVERLAP);
-    const uint8_t* sa = A.residues + d.a_off;
+    const uint8_t* sa = A.residues + d.a_off + row0;
     const uint8_t* sb = A.residues + d.b_off;
+    const int2* ck_in = nullptr;
+    if (CKPT && row0 > 0) ck_in = W.ckpt + cs.ck_off + (uint64_t)(row0 / cs.every - 1u) * cs.ck_stride;
 
     const uint32_t band_cols = (uint32_t)(L * C);
     const uint32_t mcol0 = m ? m - 1 : 0;
@@ -167,13 +190,16 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
             }
             MuA[c] = border_row(row_gap, a, b, j0 + 1) + a;
             Xu[c] = NEG_INF;
+            if (CKPT && ck_in && j0 < m) { const int2 v = __ldcg(ck_in + j0); MuA[c] = v.x; Xu[c] = v.y; }
         }
         int32_t MdiagA = border_row(row_gap, a, b, jbase) + a;
+        if (CKPT && ck_in) MdiagA = (jbase == 0) ? border_col(col_gap, a, b, row0) + a : ((jbase - 1 < m) ? __ldcg(ck_in + jbase - 1).x : a);
         int32_t MlastA = a, Ylast = NEG_INF;
         uint32_t rcur = 0;
         uint32_t cur_blk = 0;
         int2 in_blk = make_int2(a, NEG_INF);    // boundary rows [t0, t0+32) of the band to the left
         int2 out_blk = make_int2(0, 0);         // this band's last column, rows collected over 32 steps
+        uint32_t next_ck = cs.every, ck_no = 0;  // CKPT pass 1: next checkpoint row of this lane, its index
 
         for (uint32_t t = 0; t < steps; ++t) {
             const uint32_t tq = t & 31u;
@@ -207,7 +233,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
             const bool active = i0 < n;
             if (p == 0) {
                 r = r0;
-                if (bd == 0) { MlA = border_col(col_gap, a, b, i0 + 1) + a; Yl = NEG_INF; }
+                if (bd == 0) { MlA = border_col(col_gap, a, b, row0 + i0 + 1) + a; Yl = NEG_INF; }
                 else { MlA = inM; Yl = inY; }
             }
             rcur = r;
@@ -246,9 +272,18 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
                 }
                 MlastA = leftA; Ylast = Y; MdiagA = MlA;
                 if (A.want_trace && lane_has_cols) {
-                    uint32_t* tp = A.trace + d.trace_off + ((uint64_t)bd * steps + t) * (uint64_t)(K * 32) + lane;
+                    uint32_t* tp = A.trace + d.trace_off + ((uint64_t)bd * tstride + t) * (uint64_t)(K * 32) + lane;
 #pragma unroll
                     for (int k = 0; k < K; ++k) tp[k * 32] = w[k];
+                }
+                if (CKPT && W.ckpt_write && i0 + 1 == next_ck) {
+                    if (next_ck < n) {
+                        int2* ck = W.ckpt + cs.ck_off + (uint64_t)(ck_no++) * cs.ck_stride + jbase;
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            if (jbase + c < m) __stcg(ck + c, make_int2(MuA[c], Xu[c]));
+                    }
+                    next_ck += cs.every;
                 }
                 if (track_col && bd == bd_m) {
                     int32_t v = MuA[0];
@@ -347,7 +382,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
             else { e.score = frb; e.k = n; e.l = frj; }
             break;
         }
-        A.end[slot] = e;
+        if (!CKPT || W.write_end) A.end[slot] = e;
     }
   }   // persistent loop
     if (bad_residue) atomicOr(A.err_flag, 1u);

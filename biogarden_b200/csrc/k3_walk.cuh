@@ -34,6 +34,11 @@ struct WalkArgs {
     int32_t* score;         // [pair]
     uint8_t* walk_flags;    // [pair]
     uint64_t* lens2;        // [2*pairs + 1]: lens2[2p] = lens2[2p+1] = aligned length
+    // bounded-memory traceback (k3_walk_diag only): the trace holds DP rows row0 + 1 .. of the pair; the walk is
+    // resumed from / suspended into wstate[slot] when it reaches row row0 > 0
+    const CkptSlot* cks = nullptr;
+    WalkState* wstate = nullptr;
+    uint32_t last_launch = 0;   // row block 0: every walk that is still open ends here
 };
 
 __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
@@ -473,19 +478,30 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
 
     uint32_t k = e.k, l = e.l, flags = 0;
     const bool colbr = (e.flags & 1u) != 0;
-    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
+    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
+    uint64_t it = 0;
+    uint32_t row0 = 0;
+    if (A.cks) {
+        const CkptSlot cs = A.cks[slot];
+        if (cs.nrows == 0 && !A.last_launch) return;      // this launch holds no rows of the pair
+        row0 = cs.row0;
+    }
+    WalkState* const ws_ = A.wstate ? A.wstate + slot : nullptr;
+    if (ws_ && ws_->started) {
+        if (ws_->done) return;
+        k = ws_->k; l = ws_->l; cur = ws_->cur; pos = ws_->pos; wops = ws_->wops; flags = ws_->flags; it = ws_->it;
+        __syncwarp();
+    } else if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
         if (colbr) push_run(1u, n - k); else push_run(2u, m - l);
     }
-    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
-    const uint64_t bound = 3ull * ((uint64_t)n + m) + 64;   // emits + state switches + one probe per window
-    uint64_t it = 0;
+    const uint64_t bound = 3ull * ((uint64_t)n + m) + 64 + 2ull * (n / DIAG_ROWS);   // emits + state switches + one probe per window
     uint32_t probe_skip = 0;
-    bool done = false;
+    bool done = false, suspended = false;
     while (!done) {
         // ---- load the window anchored at (k, l): row r is DP row k - r, blocks cb_c(r) - 4 .. cb_c(r) + 4 ----
         const uint32_t k_hi = k, l_hi = l;
-        if (k >= 1 && l >= 1) {
-            const uint32_t rows = min(k, (uint32_t)DIAG_ROWS);
+        if (k > row0 && l >= 1) {
+            const uint32_t rows = min(k - row0, (uint32_t)DIAG_ROWS);
             for (uint32_t x = q; x < rows * DIAG_WB; x += 32) {
                 const uint32_t rr = x / DIAG_WB, bx = x - rr * DIAG_WB;
                 const int32_t cb = (((int32_t)l_hi - (int32_t)rr - 1) >> 3) - DIAG_HALF + (int32_t)bx;
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
                     const uint32_t j0 = (uint32_t)cb << 3;
                     const uint32_t bd = j0 / band_cols, rem = j0 - bd * band_cols;
                     const uint32_t p = rem / C, c = rem - p * C;
-                    const uint32_t t = (i - 1) + p;
+                    const uint32_t t = (i - 1 - row0) + p;
                     const uint64_t idx = d.trace_off + ((uint64_t)bd * d.steps + t) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
                     wv = __ldg(A.trace + idx);
                 }
@@ -507,6 +523,7 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
         for (;;) {
             if (++it > bound) { flags |= WALK_HANG; done = true; break; }
             if (k != 0 && l != 0) {
+                if (k <= row0) { suspended = true; done = true; break; }             // the codes of this row belong to the next launch
                 const uint32_t rr = k_hi - k;
                 const int32_t bx = (int32_t)((l - 1) >> 3) - ((((int32_t)l_hi - (int32_t)rr - 1) >> 3) - DIAG_HALF);
                 if (rr >= (uint32_t)DIAG_ROWS || bx < 0 || bx >= DIAG_WB) break;     // left the window: re-anchor
@@ -515,7 +532,7 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
                     // bit set: 'R', and in local mode not the stop code) is emitted at once.  After a short run the
                     // next few steps go through the scalar path (unrelated sequences change state every 2-3 cells)
                     const uint32_t rq = rr + q;
-                    bool good = (q < k) && (q < l) && rq < (uint32_t)DIAG_ROWS;
+                    bool good = (q < k - row0) && (q < l) && rq < (uint32_t)DIAG_ROWS;
                     if (good) {
                         const uint32_t lq = l - q;
                         const int32_t bq = (int32_t)((lq - 1) >> 3) - ((((int32_t)l_hi - (int32_t)rq - 1) >> 3) - DIAG_HALF);
@@ -556,10 +573,18 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
         }
         __syncwarp();
     }
+    if (suspended) {
+        if (q == 0) {
+            ws_->k = k; ws_->l = l; ws_->cur = cur; ws_->pos = pos; ws_->wops = wops; ws_->flags = flags; ws_->it = it;
+            ws_->started = 1u; ws_->done = 0u;
+        }
+        return;
+    }
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
         if (colbr) { push_run(1u, k); k = 0; } else { push_run(2u, l); l = 0; }
     }
     if (q == 0) {
+        if (ws_) { ws_->started = 1u; ws_->done = 1u; }
         if (pos & 15u) ops[pos >> 4] = wops;
         slotw[0] = k; slotw[1] = l;
         const uint32_t len = n + m - pos;

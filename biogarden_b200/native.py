@@ -40,7 +40,7 @@ class bg_timing(C.Structure):
                 ("compact_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_uint64),
                 ("launches", C.c_uint64), ("trace_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("cells_packed16", C.c_uint64), ("cells_bitparallel", C.c_uint64),
-                ("fill_launches", C.c_uint64)]
+                ("fill_launches", C.c_uint64), ("cells_refilled", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -51,7 +51,7 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def lib():
     L.bg_batch_prepare.restype = ci; L.bg_batch_prepare.argtypes = [vp, vp, ci]
     L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
     L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
+    L.bg_set_long_trace_budget.restype = ci; L.bg_set_long_trace_budget.argtypes = [vp, u64]
     L.bg_score_table26.restype = C.POINTER(C.c_int8); L.bg_score_table26.argtypes = [C.c_char_p]
     L.bg_residue_histogram.restype = ci; L.bg_residue_histogram.argtypes = [C.POINTER(bg_batch), vp, vp]
     L.bg_ref_status.restype = ci; L.bg_ref_status.argtypes = [ci, u64, u64, i32, ci]
@@ -297,6 +298,10 @@ class Context:
 
     def set_trace_budget(self, nbytes):
         check(lib().bg_set_trace_budget(self.h, nbytes), self.h)
+
+    def set_long_trace_budget(self, nbytes):
+        """Trace memory per launch of the long-pair path; pairs that need more use bounded-memory traceback."""
+        check(lib().bg_set_long_trace_budget(self.h, nbytes), self.h)
 
 
 def synth_pairs(seed, first_pair, n_pairs, alphabet: bytes, len_lo, len_hi, resize_b=True) -> Batch:

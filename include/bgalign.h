@@ -117,6 +117,7 @@ typedef struct {
     uint64_t cells_packed16;    /* of `cells`: filled by the packed 16 x 2 kernel (two cells per lane instruction) */
     uint64_t cells_bitparallel; /* of `cells`: edit distance by the bit-parallel kernel (32 cells per word column) */
     uint64_t fill_launches;     /* DP fill kernel launches behind fill_ms */
+    uint64_t cells_refilled;    /* of `cells`: pairs aligned with bounded-memory traceback (their cells are filled twice) */
 } bg_timing;
 
 /* ---- lifetime ---------------------------------------------------------------------- */
@@ -163,6 +164,11 @@ int bg_batch_prepare(bg_ctx* ctx, bg_dbatch* b, int for_edit);
  * 0,0 = automatic by length class) and bound the per-launch trace buffer. */
 int bg_set_shape(bg_ctx* ctx, int lanes_per_pair, int cols_per_lane);
 int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes);
+/* Trace memory one launch of the long-pair path (pairs wider than 4096 columns) may use; 0 = automatic (60 % of
+ * the device).  A pair whose 0.5 B/cell trace does not fit is aligned with BOUNDED-MEMORY traceback: row
+ * checkpoints in a first pass, then re-fill + walk block by block (results are identical; the cells are
+ * computed twice).  This replaces the reference's "six full matrices or nothing" (aligner.rs:594-602). */
+int bg_set_long_trace_budget(bg_ctx* ctx, uint64_t bytes);
 
 /* ---- helpers for host mirrors ------------------------------------------------------ */
 /* The shipped scorers' 26x26 tables, indexed [a-'A'][b-'A'] (score.rs:5-35,45-75,82-111).

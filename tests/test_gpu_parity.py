@@ -251,12 +251,10 @@ def test_cfg5_small_long_pair(aligner):
     assert not problems, "\n".join(problems)
 
 
-def test_wavefront_kernel_long_pairs(aligner):
-    """K2 (pairs wider than 4096 columns: one pair per thread-block cluster, 1/2/4/8 CTAs per pair)
-    mixed with K1 classes in one batch; all modes against the lean oracle."""
-    rng = random.Random(99)
+def _mutated_long_pairs(shapes, seed):
+    rng = random.Random(seed)
     seqs = []
-    for n, m in [(5000, 4200), (3000, 9000), (9000, 17000), (7000, 33000), (300, 5000), (6000, 300), (4500, 4097)]:
+    for n, m in shapes:
         s1 = bytes(rng.choice(b"ACGT") for _ in range(n))
         s2 = bytearray()
         for c in s1:
@@ -272,7 +270,13 @@ def test_wavefront_kernel_long_pairs(aligner):
         while len(s2) < m:
             s2.append(rng.choice(b"ACGT"))
         seqs += [s1, bytes(s2[:m])]
-    batch = native.Batch.from_sequences(seqs)
+    return native.Batch.from_sequences(seqs)
+
+
+def test_wavefront_kernel_long_pairs(aligner):
+    """K2 (pairs wider than 4096 columns: one pair per thread-block cluster, 1/2/4/8 CTAs per pair)
+    mixed with K1 classes in one batch; all modes against the lean oracle."""
+    batch = _mutated_long_pairs([(5000, 4200), (3000, 9000), (9000, 17000), (7000, 33000), (300, 5000), (6000, 300), (4500, 4097)], 99)
     problems = []
     for mode, scorer, a, b in [("semiglobal", "unit", -1, -1), ("local", "blosum62", -11, -1), ("global", "unit", -2, -1),
                                ("overlap", "unit", -2, -2)]:
@@ -280,6 +284,43 @@ def test_wavefront_kernel_long_pairs(aligner):
         ora = _cmp.oracle_align(batch, mode, scorer, a, b, lean=True)
         problems += _cmp.diff(batch, eng, ora, "K2 %s/%s" % (mode, scorer))
         eng.close()
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("budget_mb", [1, 6])
+def test_bounded_memory_traceback(budget_mb):
+    """Pairs whose 4-bit trace exceeds the long-pair trace budget: row checkpoints + block-wise re-fill and a
+    walk resumed from block to block (k2_wave<.., CKPT>, k3_walk_diag with WalkState) must give exactly the
+    result of the unbounded path, i.e. the oracle's.  1 MiB: all pairs but the smallest are checkpointed, one or
+    two per launch group, in blocks of 64 rows and up (up to 141 blocks); 6 MiB: the two small pairs fit whole,
+    the five large ones form one group.  All modes:
+    the walk starts below / at / above block boundaries (local, fitting column maximum, semiglobal branches)."""
+    al = SequenceAligner()
+    al.context.set_long_trace_budget(budget_mb << 20)
+    batch = _mutated_long_pairs([(5000, 4200), (2100, 9000), (6100, 4500), (300, 5000), (4096, 4097), (1000, 4100), (9000, 17000)], 7)
+    problems = []
+    for mode, scorer, a, b in [("semiglobal", "unit", -1, -1), ("local", "blosum62", -11, -1), ("global", "unit", -2, -1),
+                               ("overlap", "unit", -2, -2), ("semiglobal", "blosum62", -1, -2)]:
+        eng = _cmp.engine_align(al, batch, mode, scorer, a, b)
+        ora = _cmp.oracle_align(batch, mode, scorer, a, b, lean=True)
+        problems += _cmp.diff(batch, eng, ora, "bounded %s/%s %d MiB" % (mode, scorer, budget_mb))
+        eng.close()
+        t = al.context.timing()
+        n, m = batch.lengths()
+        wave_cells = int(np.sum((n * m)[m > 4096]))
+        if budget_mb == 1:   # only the trace of (300, 5000) fits whole
+            assert t["cells_refilled"] == wave_cells - 300 * 5000, (t["cells_refilled"], wave_cells)
+        else:     # the five largest pairs are checkpointed, (1000, 4100) and (300, 5000) fit whole
+            assert t["cells_refilled"] == wave_cells - 1000 * 4100 - 300 * 5000, (t["cells_refilled"], wave_cells)
+    # the device-resident entry points go through the same plan
+    params = al.make_params(batch, "semiglobal", score_mod.unit, -1, -1)
+    db = al.context.upload(batch)
+    dres = al.context.align_device(db, params)
+    res = al.context.download(dres)
+    problems += _cmp.diff(batch, res, _cmp.oracle_align(batch, "semiglobal", "unit", -1, -1, lean=True), "bounded device path")
+    res.close()
+    al.context.free_result(dres)
+    al.context.free_batch(db)
     assert not problems, "\n".join(problems)
 
 
