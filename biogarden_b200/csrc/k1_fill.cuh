@@ -74,6 +74,46 @@ __device__ __forceinline__ void acc_local_bit0(uint32_t& w, int32_t mx, int32_t 
         : "+r"(w) : "r"(mx), "r"(X), "r"(Y), "r"(one), "r"(bit));
 }
 
+// if (x <= y) w += bit
+__device__ __forceinline__ void acc_if_le(uint32_t& w, int32_t x, int32_t y, int32_t one, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.s32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+        : "+r"(w) : "r"(x), "r"(y), "r"(one), "r"(bit));
+}
+// if (x == y) w += bit_y; else if (x == z) w += bit_z      (one compare feeds both)
+__device__ __forceinline__ void acc_eq_else_eq(uint32_t& w, int32_t x, int32_t y, int32_t z, int32_t one, uint32_t bit_y, uint32_t bit_z) {
+    asm("{\n\t.reg .pred py, pz;\n\tsetp.eq.s32 py, %1, %2;\n\tsetp.eq.and.s32 pz, %1, %3, !py;\n\t"
+        "@py mad.lo.u32 %0, %4, %5, %0;\n\t@pz mad.lo.u32 %0, %4, %6, %0;\n\t}"
+        : "+r"(w) : "r"(x), "r"(y), "r"(z), "r"(one), "r"(bit_y), "r"(bit_z));
+}
+// x * k + y on the FMA pipe (k only known at run time)
+__device__ __forceinline__ uint32_t fma_mad_u32(uint32_t x, uint32_t k, uint32_t y) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(k), "r"(y));
+    return d;
+}
+
+// One LOCAL-mode cell (aligner.rs:477-506), written so that the ALU pipe -- the binding one -- sees 9
+// instructions: the gap states are VIADDMNMX.RELU (add + max + clamp fused; the clamp comes after the trace
+// byte is decided, which reads the unclamped operands), their "opened here" tests compare the FMA-pipe sums
+// x_up + b <= m_up + a, bit 0 is accumulated from two disjoint predicates -- M == 0 (STOP; then M == Y == 0
+// because Y >= 0) and M == X != Y -- and the running first maximum is kept as one unsigned key
+// (M << 5 | 31 - column), decoded once per row instead of compare + three selects per cell.
+__device__ __forceinline__ void local_cell(uint32_t& w, uint32_t sh, int32_t upA, int32_t& Xc, int32_t& Y, int32_t leftA,
+                                           int32_t diag_plus_s, int32_t b, int32_t one, uint32_t k32, uint32_t colkey,
+                                           uint32_t& rowkey, int32_t& mx) {
+    const int32_t tx = fma_add(Xc, one, b);
+    acc_if_le(w, tx, upA, one, TR_XOPEN << sh);
+    const int32_t X = __viaddmax_s32_relu(Xc, b, upA);
+    const int32_t ty = fma_add(Y, one, b);
+    acc_if_le(w, ty, leftA, one, TR_YOPEN << sh);
+    Y = __viaddmax_s32_relu(Y, b, leftA);
+    mx = __vimax3_s32(diag_plus_s, X, Y);
+    acc_eq_else_eq(w, mx, Y, X, one, TR_YEQ << sh, TR_XEQ << sh);
+    acc_if_eq(w, mx, 0, one, TR_XEQ << sh);
+    rowkey = max(rowkey, fma_mad_u32((uint32_t)mx, k32, colkey));
+    Xc = X;
+}
+
 // M[0][j] and M[i][0].
 __device__ __forceinline__ int32_t border_row(bool row_gap, int32_t a, int32_t b, uint32_t j) {
     return (row_gap && j > 0) ? a + (int32_t)(j - 1) * b : 0;
@@ -119,6 +159,7 @@ __global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs
     const uint32_t nbands_w = __reduce_max_sync(FULL, my_nbands);
 
     const int32_t a = A.a, b = A.b, one = A.one;
+    const uint32_t k32 = (uint32_t)A.one << 5;
     const int mode = A.mode;
     const bool row_gap = (mode == M_GLOBAL || mode == M_FITTING);
     const bool col_gap = (mode == M_GLOBAL);
@@ -218,11 +259,23 @@ __global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs
                 uint32_t sel; const unsigned char* rowp;
                 if (PROF4) sel = r * 0x1111u + 0x8880u;
                 else rowp = reinterpret_cast<const unsigned char*>(s_tab) + r * (uint32_t)(ncol1 * 4);
+                uint32_t rowkey = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     uint32_t& wk = w[c >> 3];
                     const uint32_t sh = 4u * (c & 7);
                     const int32_t upA = MuA[c];
+                    if (IS_LOCAL) {
+                        int32_t sb_;   // s - a
+                        if (PROF4) sb_ = prmt_sx(cprof[c], sel);
+                        else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
+                        int32_t mx;
+                        local_cell(wk, sh, upA, Xu[c], Y, leftA, fma_add(diagA, one, sb_), b, one, k32, 31u - c, rowkey, mx);
+                        const int32_t mxA = fma_add(mx, one, a);
+                        diagA = upA; leftA = mxA;
+                        MuA[c] = mxA;
+                        continue;
+                    }
                     // aligner.rs:443-444 / 477-480: xo = M[i-1][j] + a is the register itself
                     int32_t X = __viaddmax_s32(Xu[c], b, upA);
                     acc_if_eq(wk, X, upA, one, TR_XOPEN << sh);
@@ -247,6 +300,10 @@ __global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs
                     MuA[c] = mxA; Xu[c] = X;
                 }
                 MlastA = leftA; Ylast = Y; MdiagA = MlA;
+                if (IS_LOCAL) {   // first maximum of this row's cells; strictly greater than everything above
+                    const int32_t v = (int32_t)(rowkey >> 5);
+                    if (v > best) { best = v; bi = i0 + 1; bj = jbase + 32u - (rowkey & 31u); }
+                }
                 if (A.want_trace && lane_has_cols) {
                     uint32_t* tp = A.trace + d.trace_off + ((uint64_t)(bd * d.steps + t) * K) * 32u + lane;
 #pragma unroll

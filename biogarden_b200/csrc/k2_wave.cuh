@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     const uint32_t steps = CKPT ? n + 31u : d.steps;        // steps this launch runs
     const uint32_t n_pad = (n + 31u) & ~31u;
     const int32_t a = A.a, b = A.b, one = A.one;
+    const uint32_t k32 = (uint32_t)A.one << 5;
     const int mode = A.mode;
     const bool row_gap = (mode == M_GLOBAL || mode == M_FITTING);
     const bool col_gap = (mode == M_GLOBAL);
@@ -245,11 +246,23 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
                 uint32_t sel; const unsigned char* rowp;
                 if (PROF4) sel = r * 0x1111u + 0x8880u;
                 else rowp = reinterpret_cast<const unsigned char*>(s_tab) + r * (uint32_t)(ncol1 * 4);
+                uint32_t rowkey = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     uint32_t& wk_ = w[c >> 3];
                     const uint32_t sh = 4u * (c & 7);
                     const int32_t upA = MuA[c];
+                    if (IS_LOCAL) {
+                        int32_t sb_;
+                        if (PROF4) sb_ = prmt_sx(cprof[c], sel);
+                        else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
+                        int32_t mx;
+                        local_cell(wk_, sh, upA, Xu[c], Y, leftA, fma_add(diagA, one, sb_), b, one, k32, 31u - c, rowkey, mx);
+                        const int32_t mxA = fma_add(mx, one, a);
+                        diagA = upA; leftA = mxA;
+                        MuA[c] = mxA;
+                        continue;
+                    }
                     int32_t X = __viaddmax_s32(Xu[c], b, upA);
                     acc_if_eq(wk_, X, upA, one, TR_XOPEN << sh);
                     Y = __viaddmax_s32(Y, b, leftA);
@@ -271,6 +284,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
                     MuA[c] = mxA; Xu[c] = X;
                 }
                 MlastA = leftA; Ylast = Y; MdiagA = MlA;
+                if (IS_LOCAL) {
+                    const int32_t v = (int32_t)(rowkey >> 5);
+                    if (v > best) { best = v; bi = row0 + i0 + 1; bj = jbase + 32u - (rowkey & 31u); }
+                }
                 if (A.want_trace && lane_has_cols) {
                     uint32_t* tp = A.trace + d.trace_off + ((uint64_t)bd * tstride + t) * (uint64_t)(K * 32) + lane;
 #pragma unroll
