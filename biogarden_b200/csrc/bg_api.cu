@@ -572,8 +572,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 for (uint32_t x = 0; x < ns; ++x) {                                  // slots are in largest-first order
                     PairDesc& d = dst[wc.slot_begin + x];
                     const double cells = (double)d.n * (double)d.m;
-                    uint32_t q = (uint32_t)std::max(1.0, std::floor(cells / ideal + 0.5));
-                    q = std::min<uint32_t>(q, std::max<uint32_t>(1, (d.nbands + K2_WARPS - 1) / K2_WARPS));
+                    // one warp per band: the whole pair is in flight at once (n + 64 * bands steps), and a warp whose pair
+                    // has no band left moves on to its CTA's next pair.  Measured on cfg5 (31 pairs per launch): groups
+                    // sized in proportion to the cells (one pair per group, ~5 CTAs) fill in 772 ms, 12 CTAs per pair in 682 ms.
+                    uint32_t q = std::max<uint32_t>(1, (d.nbands + K2_WARPS - 1) / K2_WARPS);
+                    (void)ideal;
                     uint32_t q_cap = K2_MAX_Q;
                     if (wc.ckpt_nb && ns == 1) {   // a single huge pair may own the machine; its boundary ring (q * 16 + 1 columns of n rows) is kept below 2 GiB
                         const uint64_t ring_q = ((2ull << 30) / sizeof(int2)) / ((((uint64_t)d.n + 31ull) & ~31ull) * K2_WARPS);
@@ -966,7 +969,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     if (l) {
                         Phase ph(ws, 2);
                         wk.cks = wa.cks; wk.last_launch = (l == NB) ? 1u : 0u;
-                        k3_walk_diag<<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(wk);
+                        k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(wk);
                     }
                     CU_TRY(ctx, cudaGetLastError());
                 }
@@ -1016,7 +1019,8 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     if (lc.long_walk) {
                         static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
                         // the window loaders map 8-column blocks onto trace words: need C % 8 == 0 (true for K2)
-                        if (lc.ops_fmt) k3_walk_diag<<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
+                        if (lc.ops_fmt && lc.sh.L == 32 && lc.sh.C == WAVE_C) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
+                        else if (lc.ops_fmt) k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
                         else if (walk_kind == 2 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
                         else k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, wst>>>(wa);
                     }
@@ -1301,7 +1305,7 @@ static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit, int32_t half_maxabs
     PinBuf stage;
     if (!stage.ensure(cap * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
     // long pairs (K2) need whole traces of several GB each: let them use most of the device
-    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
+    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.8 * (double)dv.total_mem) / 4);
     // with BG_OVERLAP: chunks of <= 2 GiB of trace so that walk(c) overlaps fill(c+1) (run_align); otherwise large
     // chunks -- the walk is latency-bound and wants as many pairs per launch as possible
     static const bool want_overlap = [] { const char* e = getenv("BG_OVERLAP"); return e && atoi(e) != 0; }();
@@ -1533,7 +1537,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds_from_scan(scan, lo, hi);
     const int nchunks = (int)cb.size() - 1;
     const uint64_t ws_budget = ctx->trace_budget_words;   // per work set; three of them fit the B200's 180 GB many times over
-    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.6 * (double)dv.total_mem) / 4);
+    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.8 * (double)dv.total_mem) / 4);
 
     // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
     // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon

@@ -68,7 +68,7 @@ struct WaveArgs {
     const WalkState* wstate;        // pass 2: skip pairs whose walk has already ended
 };
 
-constexpr int K2_MAX_Q = 12;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
+constexpr int K2_MAX_Q = 13;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
 
 constexpr int K2_WARPS = 16;        // warps per CTA
 

@@ -421,6 +421,11 @@ constexpr int DIAG_WB = 9;
 constexpr int DIAG_HALF = 4;          // blocks left of the diagonal's block
 constexpr int WALK_DIAG_WARPS = 4;
 
+// CT = 16: the K2 geometry (32 lanes x 16 columns) as compile-time constants -- the window loader's address
+// arithmetic (two divisions per word otherwise) is what a reload costs, not the memory round trip; CT = 0: any
+// geometry with C % 8 == 0.  The window height adapts: a path that drifts out sideways after a few rows
+// (unrelated sequences) gets short windows, a path that uses its window up gets tall ones.
+template <int CT>
 __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkArgs A) {
     __shared__ uint32_t s_tile[WALK_DIAG_WARPS][DIAG_ROWS * DIAG_WB];
     // interior-cell state machine as a table: [state * 16 + code] -> bit 0 emit, bits 1-2 op, bit 3 k--, bit 4 l--,
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
     if (d.pair_id == 0xFFFFFFFFu) return;
     const EndCell e = A.end[slot];
     const uint32_t n = d.n, m = d.m;
-    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
+    const uint32_t L = CT ? 32u : (uint32_t)A.L, C = CT ? (uint32_t)CT : (uint32_t)A.C;
     const uint32_t K = (C + 7) / 8;
     const uint32_t band_cols = L * C;
     const uint32_t lane_base = (slot % (32u / L)) * L;
@@ -496,12 +501,14 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
     }
     const uint64_t bound = 3ull * ((uint64_t)n + m) + 64 + 2ull * (n / DIAG_ROWS);   // emits + state switches + one probe per window
     uint32_t probe_skip = 0;
+    uint32_t win_rows = DIAG_ROWS;
     bool done = false, suspended = false;
     while (!done) {
         // ---- load the window anchored at (k, l): row r is DP row k - r, blocks cb_c(r) - 4 .. cb_c(r) + 4 ----
         const uint32_t k_hi = k, l_hi = l;
+        uint32_t rows = 0;
         if (k > row0 && l >= 1) {
-            const uint32_t rows = min(k - row0, (uint32_t)DIAG_ROWS);
+            rows = min(k - row0, win_rows);
             for (uint32_t x = q; x < rows * DIAG_WB; x += 32) {
                 const uint32_t rr = x / DIAG_WB, bx = x - rr * DIAG_WB;
                 const int32_t cb = (((int32_t)l_hi - (int32_t)rr - 1) >> 3) - DIAG_HALF + (int32_t)bx;
@@ -526,13 +533,14 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
                 if (k <= row0) { suspended = true; done = true; break; }             // the codes of this row belong to the next launch
                 const uint32_t rr = k_hi - k;
                 const int32_t bx = (int32_t)((l - 1) >> 3) - ((((int32_t)l_hi - (int32_t)rr - 1) >> 3) - DIAG_HALF);
-                if (rr >= (uint32_t)DIAG_ROWS || bx < 0 || bx >= DIAG_WB) break;     // left the window: re-anchor
+                if (rr >= rows) { win_rows = min(2u * win_rows, (uint32_t)DIAG_ROWS); break; }          // used the window up: re-anchor, taller
+                if (bx < 0 || bx >= DIAG_WB) { if (rr < win_rows / 2u) win_rows = max(win_rows / 2u, 32u); break; }   // drifted out: re-anchor
                 if (cur == 0 && probe_skip == 0) {
                     // vector probe: lane q looks at cell (k - q, l - q); a run of plain diagonal moves (neither tie
                     // bit set: 'R', and in local mode not the stop code) is emitted at once.  After a short run the
                     // next few steps go through the scalar path (unrelated sequences change state every 2-3 cells)
                     const uint32_t rq = rr + q;
-                    bool good = (q < k - row0) && (q < l) && rq < (uint32_t)DIAG_ROWS;
+                    bool good = (q < k - row0) && (q < l) && rq < rows;
                     if (good) {
                         const uint32_t lq = l - q;
                         const int32_t bq = (int32_t)((lq - 1) >> 3) - ((((int32_t)l_hi - (int32_t)rq - 1) >> 3) - DIAG_HALF);

@@ -164,7 +164,7 @@ int bg_batch_prepare(bg_ctx* ctx, bg_dbatch* b, int for_edit);
  * 0,0 = automatic by length class) and bound the per-launch trace buffer. */
 int bg_set_shape(bg_ctx* ctx, int lanes_per_pair, int cols_per_lane);
 int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes);
-/* Trace memory one launch of the long-pair path (pairs wider than 4096 columns) may use; 0 = automatic (60 % of
+/* Trace memory one launch of the long-pair path (pairs wider than 4096 columns) may use; 0 = automatic (80 % of
  * the device).  A pair whose 0.5 B/cell trace does not fit is aligned with BOUNDED-MEMORY traceback: row
  * checkpoints in a first pass, then re-fill + walk block by block (results are identical; the cells are
  * computed twice).  This replaces the reference's "six full matrices or nothing" (aligner.rs:594-602). */
