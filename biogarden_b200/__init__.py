@@ -15,7 +15,7 @@ __all__ = ["Sequence", "Tile", "fasta", "BioError", "InvalidArgumentRange", "Inv
 
 def __getattr__(name):
     # compute-facing modules load the native library on first use
-    if name in ("aligner", "score", "seq", "native", "synth"):
+    if name in ("aligner", "score", "seq", "stat", "native", "synth"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

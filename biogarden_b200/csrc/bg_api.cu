@@ -35,6 +35,7 @@
 #include "k2_wave.cuh"
 #include "k3_walk.cuh"
 #include "k4_edit.cuh"
+#include "k5_distance.cuh"
 
 using namespace bg;
 
@@ -56,7 +57,7 @@ struct Shape { int L, C; };
 #define BG_SHAPES(X) \
     X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 5) X(32, 8) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
 constexpr int MAX_SHAPES = 20;
-constexpr int PIPE_DEPTH = 3;
+constexpr int PIPE_DEPTH = 6;
 // Pairs wider than this run on K2 (one pair per thread-block cluster, bands of 32 * WAVE_C columns).
 constexpr uint32_t WAVE_MIN_COLS = 4096;
 constexpr int WAVE_C = 16;
@@ -290,6 +291,24 @@ int shape_index(Shape s) {
     return -1;
 }
 
+// Scratch vectors of build_plan, recycled across calls and threads.  A fresh 0.5 MB std::vector is an mmap
+// whose pages fault in one by one (~3 us each in this VM, serialised on the process's mmap lock when a dozen
+// plan threads do it at once): that was a third of the plan time.
+struct PlanScratch { std::vector<uint8_t> cls; std::vector<uint32_t> ids, tmp, cnt, slots; };
+struct PlanScratchPool {
+    std::mutex mu; std::vector<PlanScratch*> free_;
+    PlanScratch* get() {
+        { std::lock_guard<std::mutex> lk(mu); if (!free_.empty()) { PlanScratch* p = free_.back(); free_.pop_back(); return p; } }
+        return new PlanScratch();
+    }
+    void put(PlanScratch* p) { std::lock_guard<std::mutex> lk(mu); if (free_.size() < 64) free_.push_back(p); else delete p; }
+};
+PlanScratchPool& plan_scratch_pool() { static PlanScratchPool* p = new PlanScratchPool(); return *p; }
+struct PlanScratchLease {
+    PlanScratch* s; PlanScratchLease() : s(plan_scratch_pool().get()) {}
+    ~PlanScratchLease() { plan_scratch_pool().put(s); }
+};
+
 // K1h leaves the second slot of a lane group empty when the next pair has a different row count, so a
 // plan can hold up to two slots per pair.
 size_t plan_desc_capacity(uint64_t n_pairs) { return 2 * (size_t)n_pairs + 8 * MAX_SHAPES; }
@@ -315,8 +334,18 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     static_assert(MAX_SHAPES >= 15 + 1 + 3, "room for the pseudo classes");
     const int myers_si = nshape;
     shapes[nshape++] = Shape{32, 4}; shapes[nshape++] = Shape{32, 8}; shapes[nshape++] = Shape{32, 10};
+    static const bool plan_prof = getenv("BG_PLAN_PROF") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!plan_prof) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plan] %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+        tp0 = t;
+    };
     // pass 1: class of every pair
-    std::vector<uint8_t> cls(n_pairs);
+    PlanScratchLease scratch;
+    std::vector<uint8_t>& cls = scratch.s->cls;
+    cls.resize(n_pairs);
     size_t count[MAX_SHAPES] = {0};
     uint32_t cls_min_n[MAX_SHAPES], cls_max_n[MAX_SHAPES] = {0}, cls_max_m[MAX_SHAPES] = {0};
     for (int s = 0; s < MAX_SHAPES; ++s) cls_min_n[s] = 0xFFFFFFFFu;
@@ -338,8 +367,10 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         cls_max_m[last_si] = std::max<uint32_t>(cls_max_m[last_si], (uint32_t)m);
     }
     for (int s = 0; s < nshape; ++s) { P.max_n = std::max(P.max_n, cls_max_n[s]); P.max_m = std::max(P.max_m, cls_max_m[s]); }
+    lap("pass 1");
     // pass 2: bucket pair ids per class
-    std::vector<uint32_t> ids(n_pairs);
+    std::vector<uint32_t>& ids = scratch.s->ids;
+    ids.resize(n_pairs);
     size_t start[MAX_SHAPES + 1]; start[0] = 0;
     for (int s = 0; s < nshape; ++s) start[s + 1] = start[s] + count[s];
     {
@@ -349,6 +380,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     }
     uint64_t pad_off = 0, bnd_off = 0;
     size_t nd = 0;
+    lap("pass 2");
     for (int si = 0; si < nshape; ++si) {
         if (!count[si]) continue;
         uint32_t* cid = ids.data() + start[si];
@@ -381,7 +413,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             if (range <= (1u << 22) && range <= 4 * cn + 1024) {
                 // stable counting sort, descending by row count (a comparison sort of 10^6 ids costs more
                 // than the GPU needs for the whole chunk)
-                std::vector<uint32_t> cnt(range + 1, 0), tmp(cid, cid + cn);
+                std::vector<uint32_t>& cnt = scratch.s->cnt; std::vector<uint32_t>& tmp = scratch.s->tmp;
+                cnt.assign(range + 1, 0); tmp.assign(cid, cid + cn);
                 for (size_t k = 0; k < cn; ++k) cnt[nmax - len_n(tmp[k]) + 1]++;
                 for (uint64_t r = 0; r < range; ++r) cnt[r + 1] += cnt[r];
                 for (size_t k = 0; k < cn; ++k) cid[cnt[nmax - len_n(tmp[k])]++] = tmp[k];
@@ -392,7 +425,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         // launch slots of the class in order; K1h: the two pairs of a lane group must have the same row
         // count (k1h_fill.cuh), so a hole (HOLE) follows a pair whose successor differs
         constexpr uint32_t HOLE = 0xFFFFFFFFu;
-        std::vector<uint32_t> slots_h;
+        std::vector<uint32_t>& slots_h = scratch.s->slots;
+        slots_h.clear();
         if (half && !uniform) {
             slots_h.reserve(cn + cn / 8 + 16);
             for (size_t k = 0; k < cn; ++k) {
@@ -458,6 +492,17 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 k += S;
             }
         }
+        lap("class prologue");
+        // (a 32-bit division per pair is a third of the plan's cost: most classes have a single band)
+        const bool single_band = cls_max_m[si] <= band_cols;
+        auto bands_of = [&](uint32_t m_) -> uint32_t { return single_band ? (m_ ? 1u : 0u) : (m_ + band_cols - 1) / band_cols; };
+        // which walker the class gets (run_align): k3_walk (one thread per pair) or, for long pairs, k3_walk_diag (one
+        // warp per pair) -- both leave 2-bit ops in the slot (PairDesc::pad_ = 1); the older long-pair walkers
+        // (BG_LONG_WALK) leave characters
+        static const int long_walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
+        const bool long_walk_cls = !half && (wave || (uint64_t)P.max_n + P.max_m > 16384);
+        const bool ops_slots = !long_walk_cls || (long_walk_kind == 0 && (sh.C & 7) == 0);
+        lc.long_walk = long_walk_cls; lc.ops_fmt = ops_slots;
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
         const size_t nwarps = (sn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
@@ -467,7 +512,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 if (k >= sn) break;
                 if (sl[k] == HOLE) continue;
                 maxn = std::max(maxn, len_n(sl[k]));
-                maxb = std::max(maxb, (len_m(sl[k]) + band_cols - 1) / band_cols);
+                maxb = std::max(maxb, bands_of(len_m(sl[k])));
             }
             // K1h: row-block trace layout, HB_TB steps per block, CW words per lane and block
             const uint32_t steps = half ? ((maxn + sh.L - 1 + HB_TB - 1) / HB_TB) * HB_TB : maxn + sh.L - 1;
@@ -499,18 +544,20 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             }
             for (uint32_t gidx = 0; gidx < G; ++gidx) {
                 const size_t k = w * G + gidx;
-                PairDesc& d = dst[nd++];
+                PairDesc d;     // built in registers, stored once (field-wise stores into dst cannot be combined: dst may alias off)
                 d.pair_id = 0xFFFFFFFFu; d.steps = steps; d.trace_off = ch.trace_words;
-                d.a_off = d.b_off = d.bnd_off = d.pad_off = 0; d.n = d.m = d.nbands = d.pad_ = 0;
+                d.a_off = d.b_off = d.bnd_off = d.pad_off = 0; d.n = d.m = d.nbands = 0; d.pad_ = ops_slots ? 1u : 0u;
                 if (k < sn && sl[k] != HOLE) {
                     const uint64_t id = sl[k];
-                    d.a_off = off[2 * id] - base; d.b_off = off[2 * id + 1] - base;
-                    d.n = (uint32_t)(off[2 * id + 1] - off[2 * id]); d.m = (uint32_t)(off[2 * id + 2] - off[2 * id + 1]);
-                    d.nbands = (d.m + band_cols - 1) / band_cols;
+                    const uint64_t o0 = off[2 * id], o1 = off[2 * id + 1], o2 = off[2 * id + 2];
+                    d.a_off = o0 - base; d.b_off = o1 - base;
+                    d.n = (uint32_t)(o1 - o0); d.m = (uint32_t)(o2 - o1);
+                    d.nbands = bands_of(d.m);
                     d.pair_id = (uint32_t)id;
                     d.pad_off = pad_off; pad_off += 2ull * (((uint64_t)d.n + d.m + 3ull) & ~3ull) + 16ull;   // + header of an op slot (k3_walk.cuh)
                     if (!wave && d.nbands > 1) { d.bnd_off = bnd_off; bnd_off += d.n; }   // K2: assigned below, once the group sizes are known
                 }
+                dst[nd++] = d;
             }
             if (grp) {
                 PairDesc& d = dst[nd - 1];
@@ -604,20 +651,12 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 P.max_Q = std::max<int>(P.max_Q, (int)wc.max_Q);
             }
         }
+        lap("class slots");
         P.classes.push_back(lc);
     }
     P.n_slots = nd;
     P.pad_bytes = pad_off; P.bnd_elems = bnd_off;
-    // which walker a class gets (run_align): k3_walk (one thread per pair) or, for long pairs, k3_walk_diag (one
-    // warp per pair) -- both leave 2-bit ops in the slot; the older long-pair walkers (BG_LONG_WALK) characters
-    static const int long_walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
-    for (LaunchClass& lc : P.classes) {
-        lc.long_walk = !lc.half && (lc.wave || (uint64_t)P.max_n + P.max_m > 16384);
-        lc.ops_fmt = !lc.long_walk || (long_walk_kind == 0 && (lc.sh.C & 7) == 0);
-        if (lc.ops_fmt)
-            for (const Chunk& ch : lc.chunks)
-                for (uint32_t sidx = ch.slot_begin; sidx < ch.slot_end; ++sidx) dst[sidx].pad_ = 1u;
-    }
+    lap("epilogue");
     P.built = true;
     return BG_OK;
 }
@@ -713,7 +752,7 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
     const uint64_t nblocks = (N + SCAN_BLOCK - 1) / SCAN_BLOCK;
     S.block_cost.assign(nblocks, 0.0);
     unsigned nt = std::thread::hardware_concurrency();
-    nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(nt ? nt : 1, 8), nblocks / 8));
+    nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(nt ? nt : 1, 16), nblocks / 8));
     std::vector<BatchScan> part(nt);
     auto work = [&](unsigned t) {
         BatchScan& P = part[t];
@@ -758,7 +797,8 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
     const uint64_t blk_lo = lo / SCAN_BLOCK, blk_hi = (hi + SCAN_BLOCK - 1) / SCAN_BLOCK;
     double total = 0;
     for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
-    const double target = std::max(total / 8.0, 1.0e9);
+    static const double nchunk_target = [] { const char* e = getenv("BG_PIPE_CHUNKS"); return e ? std::max(1.0, atof(e)) : 5.0; }();
+    const double target = std::max(total / nchunk_target, 1.0e9);
     const uint64_t max_pairs = 262144;
     // every length class of a chunk becomes its own launch: keep >= ~4 waves of warps per launch
     const uint64_t min_pairs = 8192ull * (uint64_t)__builtin_popcount(S.class_mask ? S.class_mask : 1u);
@@ -771,7 +811,10 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
         // ... and ramp down: the last chunk's strings travel D2H after the GPU has gone idle, so the chunks
         // shrink towards the end (half of what is left, but not below a quarter of the regular size)
         const size_t nb = b.size();
-        const double scale = nb == 1 ? 0.25 : (nb == 2 || nb == 3) ? 0.5 : 1.0;
+        // (measured, cfg2: a plan costs ~28 ns per pair on one host thread, the GPU aligns a pair in ~12 ns; all plans
+        //  start together, so chunk c's plan is ready in time only if it is < ~0.4 of everything before it)
+        static const double ramp[] = {0.125, 0.1875, 0.25, 0.375, 0.5, 0.75};
+        const double scale = nb <= 6 ? ramp[nb - 1] : 1.0;
         const double left = total - done_cost;
         const double want = std::min(target * scale, std::max(left * 0.5, target * 0.25));
         if ((acc >= want && (double)(end - start) >= (double)min_pairs * scale) || (double)(end - start) >= (double)max_pairs * scale) {
@@ -1952,6 +1995,135 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
         if (rc) return rc;
     }
     return BG_ECUDA;
+}
+
+// ---- K5: hamming_distance batched / p_distance_matrix -----------------------------------
+// analysis::seq::hamming_distance for every pair (seq.rs:74-83).  Any pair with len1 != len2 makes the call
+// return BG_EINVAL_SIZE (the reference returns Err(InvalidInputSize) for that pair), out is then unspecified.
+int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
+    if (!ctx || !in || (!out && in->n_pairs)) return BG_EINVAL_ARG;
+    int rc = check_batch(ctx, in);
+    if (rc) return rc;
+    const uint64_t N = in->n_pairs;
+    if (!N) return BG_OK;
+    for (uint64_t q = 0; q < N; ++q)
+        if (in->seq_off[2 * q + 1] - in->seq_off[2 * q] != in->seq_off[2 * q + 2] - in->seq_off[2 * q + 1]) return BG_EINVAL_SIZE;
+    rc = bg_sync(ctx);
+    if (rc) return rc;
+    const int nd = (int)ctx->devs.size();
+    const std::vector<uint64_t> bounds = shard_bounds(in, nd);
+    std::vector<int> rcs(nd, BG_OK);
+    auto work = [&](int d) {
+        const uint64_t lo = bounds[d], hi = bounds[d + 1], n = hi - lo;
+        if (!n) return;
+        Device& dv = ctx->devs[d];
+        WorkSet& ws = dv.ws[0];
+        auto fail = [&](int code, const char* what) { ctx->set_error(what); rcs[d] = code; };
+        if (cudaSetDevice(dv.ordinal) != cudaSuccess) return fail(BG_ECUDA, "cudaSetDevice failed");
+        const uint64_t base = in->seq_off[2 * lo], nres = in->seq_off[2 * hi] - base;
+        // pieces of at most HAM_SPLIT bytes; offsets rebased to the shard
+        PinBuf stage;
+        if (!stage.ensure((2 * n + 1 + n + 1 + n) * 8)) return fail(BG_ENOMEM, "pinned staging allocation failed");
+        uint64_t* h_off = stage.as<uint64_t>(); uint64_t* h_first = h_off + 2 * n + 1; uint64_t* h_out = h_first + n + 1;
+        uint64_t pieces = 0;
+        for (uint64_t q = 0; q < n; ++q) {
+            h_off[2 * q] = in->seq_off[2 * (lo + q)] - base; h_off[2 * q + 1] = in->seq_off[2 * (lo + q) + 1] - base;
+            h_first[q] = pieces;
+            const uint64_t len = in->seq_off[2 * (lo + q) + 1] - in->seq_off[2 * (lo + q)];
+            pieces += std::max<uint64_t>(1, (len + HAM_SPLIT - 1) / HAM_SPLIT);
+        }
+        h_off[2 * n] = nres; h_first[n] = pieces;
+        if (!ws.residues.ensure(nres + 64) || !ws.off.ensure((2 * n + 1) * 8) || !ws.lens2.ensure((n + 1) * 8) || !ws.out64.ensure(n * 8) || !ws.err.ensure(4)) {
+            stage.release(); return fail(BG_ENOMEM, "device allocation failed (hamming)");
+        }
+        cudaStream_t st = ws.stream;
+        cudaError_t e = cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ws.off.p, h_off, (2 * n + 1) * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ws.lens2.p, h_first, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ws.out64.p, 0, n * 8, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ws.err.p, 0, 4, st);
+        if (e == cudaSuccess) {
+            HammingArgs ha{ws.residues.as<uint8_t>(), ws.off.as<uint64_t>(), n, ws.out64.as<uint64_t>(), ws.err.as<uint32_t>()};
+            const uint64_t blocks = std::min<uint64_t>((pieces + 7) / 8, (uint64_t)ctx->num_sms * 8);
+            k5_hamming<<<(unsigned)std::max<uint64_t>(1, blocks), 256, 0, st>>>(ha, ws.lens2.as<uint64_t>(), pieces);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { stage.release(); ctx->set_error(std::string("hamming: ") + cudaGetErrorString(e)); rcs[d] = BG_ECUDA; return; }
+        memcpy(out + lo, h_out, n * 8);
+        ctx->h2d += nres + (3 * n + 2) * 8; ctx->d2h += n * 8;
+        stage.release();
+    };
+    ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
+    if (nd == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
+        for (auto& t : th) t.join();
+    }
+    for (int r : rcs) if (r) return r;
+    return BG_OK;
+}
+
+// analysis::stat::p_distance_matrix (stat.rs:138-152): out[i * rows + j] = (#positions where row i and row j
+// differ, over the zip of the two rows) as f32 / (len(row 0) as f32); 0 on the diagonal.  rows == 0 is
+// BG_EINVAL_SIZE (the reference indexes data[0], tile.rs:32, and panics).  Runs on the context's first device.
+int bg_p_distance_matrix(bg_ctx* ctx, const uint8_t* residues, const uint64_t* seq_off, uint64_t rows, float* out) {
+    if (!ctx || !seq_off || !out) return BG_EINVAL_ARG;
+    if (rows == 0) return BG_EINVAL_SIZE;
+    for (uint64_t r = 0; r < rows; ++r) if (seq_off[r + 1] < seq_off[r]) { ctx->set_error("seq_off not monotone"); return BG_EINVAL_ARG; }
+    if (rows > (1ull << 20)) { ctx->set_error("p_distance_matrix: too many rows"); return BG_EUNSUPPORTED; }
+    int rc = bg_sync(ctx);
+    if (rc) return rc;
+    Device& dv = ctx->devs[0];
+    WorkSet& ws = dv.ws[0];
+    CU_TRY(ctx, cudaSetDevice(dv.ordinal));
+    const uint64_t base = seq_off[0], nres = seq_off[rows] - base;
+    if (nres && !residues) return BG_EINVAL_ARG;
+    PinBuf stage;
+    if (!stage.ensure((rows + 1) * 8 + rows * rows * 4)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+    uint64_t* h_off = stage.as<uint64_t>();
+    float* h_out = reinterpret_cast<float*>(h_off + rows + 1);
+    for (uint64_t r = 0; r <= rows; ++r) h_off[r] = seq_off[r] - base;
+    if (!ws.residues.ensure(nres + 64) || !ws.off.ensure((rows + 1) * 8) || !ws.arena.ensure(rows * rows * 4)) {
+        stage.release(); ctx->set_error("device allocation failed (p_distance_matrix)"); return BG_ENOMEM;
+    }
+    cudaStream_t st = ws.stream;
+    cudaError_t e = nres ? cudaMemcpyAsync(ws.residues.p, residues + base, nres, cudaMemcpyHostToDevice, st) : cudaSuccess;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws.off.p, h_off, (rows + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        PDistArgs pa{ws.residues.as<uint8_t>(), ws.off.as<uint64_t>(), rows, (float)(seq_off[1] - seq_off[0]), ws.arena.as<float>()};
+        const uint64_t items = rows * (rows + 1) / 2;
+        const uint64_t blocks = std::min<uint64_t>((items + 7) / 8, (uint64_t)ctx->num_sms * 8);
+        k5_pdist<<<(unsigned)std::max<uint64_t>(1, blocks), 256, 0, st>>>(pa);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, ws.arena.p, rows * rows * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { stage.release(); ctx->set_error(std::string("p_distance_matrix: ") + cudaGetErrorString(e)); return BG_ECUDA; }
+    memcpy(out, h_out, rows * rows * 4);
+    ctx->h2d = nres + (rows + 1) * 8; ctx->d2h = rows * rows * 4; ctx->launches = 1;
+    stage.release();
+    return BG_OK;
+}
+
+// Host-only diagnostic (no CUDA call): time of build_plan for n_pairs uniform pairs of len x len with traceback,
+// the way the host pipeline calls it.  Returns milliseconds (best of `reps`).
+double bg_debug_plan_ms(uint64_t n_pairs, uint32_t len, int half, int reps) {
+    bg_ctx ctx;
+    std::vector<uint64_t> off(2 * n_pairs + 1);
+    for (uint64_t i = 0; i <= 2 * n_pairs; ++i) off[i] = i * len;
+    std::vector<PairDesc> dst(plan_desc_capacity(n_pairs));
+    double best = 1e30;
+    for (int r = 0; r < std::max(1, reps); ++r) {
+        Plan P;
+        const auto t0 = std::chrono::steady_clock::now();
+        build_plan(&ctx, off.data(), 0, n_pairs, true, 8192ull << 18, 8192ull << 18, half ? 1 : 0, P, dst.data());
+        best = std::min(best, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+    return best;
 }
 
 const int8_t* bg_score_table26(const char* name) {

@@ -48,7 +48,7 @@ class bg_timing(C.Structure):
 
 # every symbol include/bgalign.h declares (tests check the library exports all of them)
 SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_version", "bg_align_batch",
-           "bg_result_free", "bg_edit_distance_batch", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
+           "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
            "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
@@ -87,6 +87,8 @@ def lib():
     L.bg_device_ordinal.restype = ci; L.bg_device_ordinal.argtypes = [vp, ci]
     L.bg_last_timing.restype = ci; L.bg_last_timing.argtypes = [vp, C.POINTER(bg_timing)]
     L.bg_batch_prepare.restype = ci; L.bg_batch_prepare.argtypes = [vp, vp, ci]
+    L.bg_hamming_distance_batch.restype = ci; L.bg_hamming_distance_batch.argtypes = [vp, C.POINTER(bg_batch), vp]
+    L.bg_p_distance_matrix.restype = ci; L.bg_p_distance_matrix.argtypes = [vp, vp, vp, u64, vp]
     L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
     L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
     L.bg_set_long_trace_budget.restype = ci; L.bg_set_long_trace_budget.argtypes = [vp, u64]
@@ -246,6 +248,21 @@ class Context:
     def edit_distance_batch(self, batch: Batch) -> np.ndarray:
         out = np.zeros(batch.n_pairs, np.uint64)
         check(lib().bg_edit_distance_batch(self.h, C.byref(batch.c), out.ctypes.data), self.h)
+        return out
+
+    def hamming_distance_batch(self, batch: Batch) -> np.ndarray:
+        """seq.rs:74-83 for every pair; raises InvalidInputSize when a pair has unequal lengths."""
+        out = np.zeros(batch.n_pairs, np.uint64)
+        check(lib().bg_hamming_distance_batch(self.h, C.byref(batch.c), out.ctypes.data), self.h)
+        return out
+
+    def p_distance_matrix(self, residues: np.ndarray, seq_off: np.ndarray) -> np.ndarray:
+        """stat.rs:138-152: rows x rows float32."""
+        residues = np.ascontiguousarray(residues, np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, np.uint64)
+        rows = len(seq_off) - 1
+        out = np.zeros((max(rows, 0), max(rows, 0)), np.float32)
+        check(lib().bg_p_distance_matrix(self.h, residues.ctypes.data, seq_off.ctypes.data, max(rows, 0), out.ctypes.data), self.h)
         return out
 
     # ---- device-resident path ----

@@ -139,6 +139,15 @@ void bg_result_free(bg_result* r);
  * fails on any byte content (the reference never errs). */
 int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out);
 
+/* ---- next to the hot path: position-wise compares ----------------------- */
+/* analysis::seq::hamming_distance for every pair (seq.rs:74-83): out[p] = #positions where the two sequences
+ * differ.  BG_EINVAL_SIZE if any pair has len1 != len2 (the reference's Err(InvalidInputSize)). */
+int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out);
+/* analysis::stat::p_distance_matrix (stat.rs:138-152) of `rows` sequences (row r = residues[seq_off[r] ..
+ * seq_off[r+1])): out is rows x rows f32, row-major; out[i][j] = mismatches over the zip of rows i and j, as
+ * f32, divided by (len(row 0) as f32); 0 on the diagonal.  rows == 0 -> BG_EINVAL_SIZE (the reference panics). */
+int bg_p_distance_matrix(bg_ctx* ctx, const uint8_t* residues, const uint64_t* seq_off, uint64_t rows, float* out);
+
 /* ---- the hot path, device-resident (benchmarks: inputs already in HBM) ------------- */
 typedef struct bg_dbatch bg_dbatch;   /* batch resident on one device of the context */
 typedef struct bg_dresult bg_dresult; /* results resident on that device */

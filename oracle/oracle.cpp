@@ -556,6 +556,40 @@ double orc_align_batch(int mode, const uint8_t* residues, const uint64_t* seq_of
     });
 }
 
+// analysis::seq::hamming_distance, src/analysis/seq.rs:74-83: length check, then zip + filter(a != b) + count.
+int orc_hamming_distance(const uint8_t* s1, size_t n, const uint8_t* s2, size_t m, uint64_t* out) {
+    if (n != m) return ORC_ERR_SIZE;                    // seq.rs:81
+    uint64_t c = 0;
+    for (size_t x = 0; x < n; ++x) if (s1[x] != s2[x]) ++c;   // seq.rs:76-80
+    *out = c;
+    return ORC_OK;
+}
+
+// analysis::stat::p_distance_matrix, src/analysis/stat.rs:138-152.  The reference visits every ordered pair
+// (i, j), counts mismatches over the zip of the two rows (zip ends with the shorter row), and stores
+// count as f32 / columns as f32 into both [i][j] and [j][i]; `columns` is the length of row 0 (tile.rs:31-33).
+int orc_p_distance_matrix(const uint8_t* residues, const uint64_t* seq_off, uint64_t rows, float* out) {
+    if (rows == 0) return ORC_PANIC;                    // self.data[0] (tile.rs:32)
+    const float columns = (float)(seq_off[1] - seq_off[0]);
+    for (uint64_t x = 0; x < rows * rows; ++x) out[x] = 0.0f;   // Array2::zeros (stat.rs:140)
+    for (uint64_t i = 0; i < rows; ++i) {
+        const uint8_t* a = residues + seq_off[i]; const uint64_t la = seq_off[i + 1] - seq_off[i];
+        for (uint64_t j = 0; j < rows; ++j) {
+            const uint8_t* b = residues + seq_off[j]; const uint64_t lb = seq_off[j + 1] - seq_off[j];
+            float p_dist = 0.0f;                                   // stat.rs:143
+            if (i != j) {
+                uint64_t c = 0;
+                const uint64_t len = la < lb ? la : lb;
+                for (uint64_t x = 0; x < len; ++x) if (a[x] != b[x]) ++c;
+                p_dist = (float)c;                                 // `.count() as f32` (stat.rs:145)
+            }
+            out[i * rows + j] = p_dist / columns;                  // stat.rs:147
+            out[j * rows + i] = p_dist / columns;                  // stat.rs:148
+        }
+    }
+    return ORC_OK;
+}
+
 double orc_edit_distance_batch(const uint8_t* residues, const uint64_t* seq_off, uint64_t n_pairs,
                                int n_threads, int lean, uint64_t* out) {
     return run_threads(n_pairs, n_threads, [&](int, uint64_t lo, uint64_t hi) {

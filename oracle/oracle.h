@@ -72,6 +72,13 @@ double orc_align_batch(int mode, const uint8_t* residues, const uint64_t* seq_of
                        int scorer, const int32_t* table, int32_t a, int32_t b, int n_threads, int lean,
                        int32_t* score, uint8_t* status, uint64_t* len, uint64_t* hash,
                        uint8_t* arena, const uint64_t* out_off);
+/* analysis::seq::hamming_distance (seq.rs:74-83): 0 and *out = #positions with s1[x] != s2[x]; ORC_ERR_SIZE when
+ * the lengths differ (Err(BioError::InvalidInputSize)). */
+int orc_hamming_distance(const uint8_t* s1, size_t n, const uint8_t* s2, size_t m, uint64_t* out);
+/* analysis::stat::p_distance_matrix (stat.rs:138-152) over `rows` sequences: the reference's double loop, f32
+ * arithmetic and all (out: rows x rows).  Returns nonzero for rows == 0 (the reference panics on data[0]). */
+int orc_p_distance_matrix(const uint8_t* residues, const uint64_t* seq_off, uint64_t rows, float* out);
+
 double orc_edit_distance_batch(const uint8_t* residues, const uint64_t* seq_off, uint64_t n_pairs,
                                int n_threads, int lean, uint64_t* out);
 

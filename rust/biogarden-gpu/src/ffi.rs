@@ -38,4 +38,7 @@ extern "C" {
     pub fn bg_align_batch(ctx: *mut bg_ctx, input: *const bg_batch, p: *const bg_params, out: *mut bg_result) -> c_int;
     pub fn bg_result_free(r: *mut bg_result);
     pub fn bg_edit_distance_batch(ctx: *mut bg_ctx, input: *const bg_batch, out: *mut u64) -> c_int;
+    /// Trace memory per launch of the long-pair path (0 = automatic); pairs that need more are aligned with
+    /// bounded-memory traceback (row checkpoints + block-wise re-fill), same results.
+    pub fn bg_set_long_trace_budget(ctx: *mut bg_ctx, bytes: u64) -> c_int;
 }

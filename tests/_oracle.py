@@ -47,6 +47,10 @@ def lib():
         L.orc_edit_distance_batch.restype = C.c_double
         L.orc_edit_distance_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         L.orc_hw_threads.restype = C.c_int
+        L.orc_hamming_distance.restype = C.c_int
+        L.orc_hamming_distance.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, u64p]
+        L.orc_p_distance_matrix.restype = C.c_int
+        L.orc_p_distance_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -85,6 +89,25 @@ def edit_distance(s1, s2, lean=False):
     f = L.orc_edit_distance_lean if lean else L.orc_edit_distance
     f(bytes(s1), len(s1), bytes(s2), len(s2), C.byref(out))
     return out.value
+
+
+def hamming_distance(s1, s2):
+    """(status, distance): status ORC_ERR_SIZE (2) when the lengths differ (seq.rs:81)."""
+    out = C.c_uint64(0)
+    st = lib().orc_hamming_distance(bytes(s1), len(s1), bytes(s2), len(s2), C.byref(out))
+    return st, out.value
+
+
+def p_distance_matrix(rows):
+    """rows: list of bytes -> float32 (R, R) array, the reference's arithmetic (stat.rs:138-152)."""
+    res = np.frombuffer(b"".join(bytes(r) for r in rows) or b"\0", dtype=np.uint8).copy()
+    off = np.zeros(len(rows) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    out = np.zeros((len(rows), len(rows)), np.float32)
+    st = lib().orc_p_distance_matrix(res.ctypes.data, off.ctypes.data, len(rows), out.ctypes.data)
+    if st:
+        raise RuntimeError("reference panics (empty matrix)")
+    return out
 
 
 def align_batch(mode, residues, seq_off, scorer, a, b, table=None, threads=1, lean=False, want_strings=True,

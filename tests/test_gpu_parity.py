@@ -431,3 +431,48 @@ def test_edit_distance_bit_parallel_and_fallback():
     want2, _ = orc.edit_distance_batch(big2.residues, big2.seq_off, threads=orc.hw_threads(), lean=True)
     assert np.array_equal(ctx.edit_distance_batch(big2), want2)
     ctx.close()
+
+
+def test_hamming_distance_goldens_and_random(kat, golden_dir):
+    """K5 hamming (seq.rs:74-83) through the C ABI: the reference's doctest and integration golden, then random
+    batches against the oracle -- every alignment of the two sequences relative to 16 / 4 bytes, lengths around
+    the vector width, empty pairs, pairs longer than one 64 KiB piece -- and the error for unequal lengths."""
+    from biogarden_b200.error import InvalidInputSize
+    d = kat["hamming_distance_doctest"]
+    assert seqmod.hamming_distance(Sequence(d["s1"]), Sequence(d["s2"])) == d["distance"]
+    t = kat["hamming_distance_integration"]
+    inp, _ = _fixture(golden_dir, t["fixture"])
+    assert seqmod.hamming_distance(inp[0], inp[1]) == t["distance"]
+    with pytest.raises(InvalidInputSize):
+        seqmod.hamming_distance(Sequence("ACGT"), Sequence("ACG"))
+    with pytest.raises(InvalidInputSize):
+        seqmod.hamming_distance_batch(Tile([Sequence("AC"), Sequence("AC"), Sequence("A"), Sequence("AC")]))
+    rng = random.Random(5)
+    seqs = []
+    for ln in list(range(0, 70)) + [127, 128, 129, 4095, 65535, 65536, 65537, 200001]:
+        s1 = bytes(rng.choice(b"ACGT") for _ in range(ln))
+        s2 = bytes(c if rng.random() < 0.8 else rng.choice(b"ACGT") for c in s1)
+        seqs += [s1, s2]
+    batch = native.Batch.from_sequences(seqs)
+    ctx = native.Context()
+    got = ctx.hamming_distance_batch(batch)
+    want = [orc.hamming_distance(seqs[2 * p], seqs[2 * p + 1])[1] for p in range(len(seqs) // 2)]
+    assert got.tolist() == want
+    ctx.close()
+
+
+def test_p_distance_matrix_vs_oracle():
+    """K5 p_distance_matrix (stat.rs:138-152): bit-exact f32 against the oracle, ragged rows (zip to the shorter
+    one), an empty row, one row only, a 300 x 2000 DNA matrix; empty Tile -> the reference panics."""
+    from biogarden_b200 import stat
+    rng = random.Random(11)
+    cases = [[b"ACGTACGTAC", b"ACGTTCGTAA", b"TTTTTTTTTT", b"ACGTACG", b""], [b"ACGT"],
+             [bytes(rng.choice(b"ACGT") for _ in range(2000)) for _ in range(300)],
+             [bytes(rng.choice(b"ACDEFGHIKL") for _ in range(rng.randint(1, 700))) for _ in range(41)]]
+    for rows in cases:
+        got = stat.p_distance_matrix(Tile([Sequence(r) for r in rows]))
+        want = orc.p_distance_matrix(rows)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(IndexError):
+        stat.p_distance_matrix(Tile([]))

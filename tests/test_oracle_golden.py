@@ -66,3 +66,29 @@ def test_config1_derived_value(golden_dir):
         return h
     assert "%016x" % fnv(a) == "48763f4161d42930"
     assert "%016x" % fnv(b) == "600db5c78f5408a0"
+
+
+def test_hamming_distance(kat, golden_dir):
+    """seq.rs:64-73 doctest (7) and tests/integration.rs:62-67 (477); unequal lengths are Err(InvalidInputSize)."""
+    d = kat["hamming_distance_doctest"]
+    assert orc.hamming_distance(d["s1"].encode(), d["s2"].encode()) == (orc.OK, d["distance"])
+    t = kat["hamming_distance_integration"]
+    inp, _ = _fixture(golden_dir, t["fixture"])
+    assert orc.hamming_distance(bytes(inp[0]), bytes(inp[1])) == (orc.OK, t["distance"])
+    assert orc.hamming_distance(b"ACGT", b"ACG")[0] == 2          # ORC_ERR_SIZE
+    assert orc.hamming_distance(b"", b"") == (orc.OK, 0)
+
+
+def test_p_distance_matrix_restatement():
+    """stat.rs:138-152 has no reference test; the restatement is checked against the definition written out with
+    numpy (f32 division, zip to the shorter row, columns = len(row 0))."""
+    import numpy as np
+    rows = [b"ACGTACGTAC", b"ACGTTCGTAA", b"TTTTTTTTTT", b"ACGTACG", b""]
+    got = orc.p_distance_matrix(rows)
+    want = np.zeros((5, 5), np.float32)
+    for i, a in enumerate(rows):
+        for j, b in enumerate(rows):
+            c = sum(1 for x, y in zip(a, b) if x != y) if i != j else 0
+            want[i, j] = np.float32(c) / np.float32(len(rows[0]))
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    assert got[0, 1] == np.float32(2) / np.float32(10) and got[0, 3] == 0 and got[2, 3] == np.float32(0.6)

@@ -6,7 +6,7 @@ committed because /root/reference does not exist on the GPU box.
 
 What it takes from the reference (data only, no code):
   * the FASTA fixtures the reference's own hot-path tests use
-    (tests/integration.rs:69-74, 234-312) -> tests/golden/fasta/{input,output}/
+    (tests/integration.rs:62-74, 234-312) -> tests/golden/fasta/{input,output}/
   * the three 26x26 substitution tables (src/alignment/score.rs:5-35, 45-75,
     82-111) parsed into tests/golden/score_tables.json
   * the doctest known answers (src/alignment/aligner.rs:75-82, 141-148,
@@ -30,6 +30,7 @@ FASTA = [
     "input/fitting_alignment.fasta", "output/fitting_alignment.fasta",
     "input/overlap_alignment.fasta", "output/overlap_alignment.fasta",
     "input/edit_distance.fasta",
+    "input/hamming_distance.fasta",
 ]
 
 
@@ -92,6 +93,10 @@ def main():
         ],
         "edit_distance_integration": {"ref": "tests/integration.rs:69-74",
                                       "fixture": "edit_distance", "distance": 299},
+        "hamming_distance_doctest": {"ref": "src/analysis/seq.rs:64-73",
+                                     "s1": "GAGCCTACTAACGGGAT", "s2": "CATCGTAATGACGGCCT", "distance": 7},
+        "hamming_distance_integration": {"ref": "tests/integration.rs:62-67",
+                                         "fixture": "hamming_distance", "distance": 477},
     }
     with open(os.path.join(OUT, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1)

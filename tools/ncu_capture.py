@@ -1,0 +1,25 @@
+"""One device-resident pass of a named workload at a given pair count -- the command ncu captures kernels from.
+
+  python tools/ncu_capture.py cfg2|cfg4|cfg5 N_PAIRS [REPS]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from biogarden_b200 import score, synth
+from biogarden_b200.aligner import SequenceAligner
+
+WL = {"cfg2": ("cfg2_dna150_global", "global", score.unit, -2, -1),
+      "cfg4": ("cfg4_protein_local", "local", score.blosum62, -11, -1),
+      "cfg5": ("cfg5_long_semiglobal", "semiglobal", score.unit, -1, -1)}
+name, n = sys.argv[1], int(sys.argv[2])
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+cfg, mode, sc, a, b = WL[name]
+batch = synth.make(cfg, n_pairs=n)
+al = SequenceAligner([0]); ctx = al.context
+params = al.make_params(batch, mode, sc, a, b)
+db = ctx.upload(batch, 0, prepare="align"); ctx.sync()
+for i in range(reps):
+    r = ctx.align_device(db, params); ctx.sync(); tm = ctx.timing(); ctx.free_result(r)
+print("%s %d pairs, %d cells: fill %.3f ms (%d launches), walk %.3f ms, compact %.3f ms" %
+      (name, n, batch.cells(), tm["fill_ms"], tm["fill_launches"], tm["walk_ms"], tm["compact_ms"]))
