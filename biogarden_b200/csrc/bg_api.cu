@@ -1165,6 +1165,7 @@ const char* bg_strerror(int err) {
         case BG_EINVAL_RESIDUE: return "residue without an entry in the score table";
         case BG_ENODEVICE: return "no usable CUDA device";
         case BG_EUNSUPPORTED: return "parameters outside the engine's supported range";
+        case BG_EINVAL_FASTA: return "Expected > at record start.";
         default: return "unknown error";
     }
 }

@@ -44,10 +44,12 @@ class Reader:
                 return
         if not self._line.startswith(">"):
             raise IOError("Expected > at record start.")
-        header = self._line[1:].rstrip().split(None, 1)
-        # splitn(2, whitespace) on a trimmed header: first field always exists (possibly empty)
-        record.id = header[0] if header else ""
-        record.desc = header[1] if len(header) > 1 else None
+        # splitn(2, char::is_whitespace) on the right-trimmed header: the id ends at the FIRST whitespace
+        # character (it is empty when the header starts with one), the description is everything after it
+        hdr = self._line[1:].rstrip()
+        cut = next((k for k, ch in enumerate(hdr) if ch.isspace()), None)
+        record.id = hdr if cut is None else hdr[:cut]
+        record.desc = None if cut is None else hdr[cut + 1:]
         parts = []
         while True:
             self._line = self._f.readline()
@@ -69,3 +71,39 @@ def read_tile(path) -> Tile:
     t = Tile()
     Reader.from_file(path).read_all(t)
     return t
+
+
+# ---- native ingest: FASTA text -> the C ABI's batch layout (csrc/fasta_ingest.cpp) ---------------------
+def parse_batch(text: bytes, n_threads: int = 0):
+    """io::fasta::Reader::read_all over `text`, done by the native multi-threaded parser, straight into the layout
+    the alignment entry points take.  Returns (ids, residues uint8 array, seq_off uint64[n + 1]).  Raises IOError
+    ("Expected > at record start.") like the reference."""
+    import ctypes as C
+    import numpy as np
+    from . import native
+    L = native.lib()
+    f = native.bg_fasta()
+    buf = bytes(text)
+    rc = L.bg_fasta_parse(buf, len(buf), n_threads, C.byref(f))
+    if rc == native.BG_EINVAL_FASTA:
+        raise IOError("Expected > at record start.")
+    native.check(rc)
+    try:
+        n = f.n_records
+        seq_off = np.ctypeslib.as_array(C.cast(f.seq_off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        id_off = np.ctypeslib.as_array(C.cast(f.id_off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        nres, nid = int(seq_off[n]), int(id_off[n])
+        residues = np.ctypeslib.as_array(C.cast(f.residues, C.POINTER(C.c_uint8)), shape=(max(nres, 1),))[:nres].copy()
+        idbytes = bytes(np.ctypeslib.as_array(C.cast(f.ids, C.POINTER(C.c_uint8)), shape=(max(nid, 1),))[:nid])
+        ids = [idbytes[int(id_off[r]):int(id_off[r + 1])].decode("utf-8", "replace") for r in range(n)]
+    finally:
+        L.bg_fasta_free(C.byref(f))
+    return ids, residues, seq_off
+
+
+def read_batch(path, n_threads: int = 0):
+    """FASTA file -> native.Batch of pairs (record 2p, record 2p + 1) plus the record ids."""
+    from . import native
+    with open(os.fspath(path), "rb") as fh:
+        ids, residues, seq_off = parse_batch(fh.read(), n_threads)
+    return native.Batch(residues, seq_off), ids

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbgalign.so")
 
 BG_OK, BG_EINVAL_RANGE, BG_EINVAL_SIZE, BG_ECUDA, BG_ENOMEM, BG_EINVAL_ARG, BG_EINVAL_RESIDUE, BG_ENODEVICE, \
-    BG_EUNSUPPORTED = range(9)
+    BG_EUNSUPPORTED, BG_EINVAL_FASTA = range(10)
 MODES = {"global": 0, "local": 1, "semiglobal": 2, "fitting": 3, "overlap": 4}
 F_SCORE_ONLY = 1
 ST_OK, ST_REF_UNDEFINED = 0, 1
@@ -35,6 +35,11 @@ class bg_result(C.Structure):
                 ("off", C.c_void_p), ("owner_", C.c_void_p)]
 
 
+class bg_fasta(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("residues", C.c_void_p), ("seq_off", C.c_void_p),
+                ("ids", C.c_void_p), ("id_off", C.c_void_p)]
+
+
 class bg_timing(C.Structure):
     _fields_ = [("encode_ms", C.c_double), ("fill_ms", C.c_double), ("walk_ms", C.c_double),
                 ("compact_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_uint64),
@@ -51,7 +56,7 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
 
 _lib = None
 
@@ -89,6 +94,8 @@ def lib():
     L.bg_batch_prepare.restype = ci; L.bg_batch_prepare.argtypes = [vp, vp, ci]
     L.bg_hamming_distance_batch.restype = ci; L.bg_hamming_distance_batch.argtypes = [vp, C.POINTER(bg_batch), vp]
     L.bg_p_distance_matrix.restype = ci; L.bg_p_distance_matrix.argtypes = [vp, vp, vp, u64, vp]
+    L.bg_fasta_parse.restype = ci; L.bg_fasta_parse.argtypes = [vp, u64, ci, C.POINTER(bg_fasta)]
+    L.bg_fasta_free.restype = None; L.bg_fasta_free.argtypes = [C.POINTER(bg_fasta)]
     L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
     L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
     L.bg_set_long_trace_budget.restype = ci; L.bg_set_long_trace_budget.argtypes = [vp, u64]

@@ -53,7 +53,8 @@ typedef enum {
     BG_EINVAL_RESIDUE = 6, /* a residue byte has no row/column in the score table (the shipped
                               scorers panic on such bytes, score.rs:40,79,115) */
     BG_ENODEVICE = 7,      /* no CUDA device / library built without the requested device */
-    BG_EUNSUPPORTED = 8    /* penalties or scores outside the engine's 32-bit-safe range */
+    BG_EUNSUPPORTED = 8,   /* penalties or scores outside the engine's 32-bit-safe range */
+    BG_EINVAL_FASTA = 9    /* "Expected > at record start." (io/fasta.rs:104-109) */
 } bg_err;
 
 /* Per-pair status.  BG_ST_REF_UNDEFINED: the reference itself panics or never returns on
@@ -138,6 +139,21 @@ void bg_result_free(bg_result* r);
 /* analysis::seq::edit_distance for every pair (seq.rs:105-130): out[p] = distance.  Never
  * fails on any byte content (the reference never errs). */
 int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out);
+
+/* ---- before the hot path: FASTA text -> batch layout -------------------- */
+/* io::fasta::Reader::read_all (fasta.rs:95-136) over a text held in memory, straight into the layout bg_batch
+ * takes: record r has residues[seq_off[r] .. seq_off[r+1]) and id ids[id_off[r] .. id_off[r+1]).  An alignment
+ * batch of pairs (2p, 2p+1) is then {n_records / 2, residues, seq_off}.  Library-allocated (malloc), freed by
+ * bg_fasta_free.  n_threads <= 0: all host cores.  Host code; needs no GPU. */
+typedef struct bg_fasta {
+    uint64_t n_records;
+    uint8_t* residues;
+    uint64_t* seq_off;    /* [n_records + 1] */
+    uint8_t* ids;
+    uint64_t* id_off;     /* [n_records + 1] */
+} bg_fasta;
+int bg_fasta_parse(const uint8_t* text, uint64_t len, int n_threads, bg_fasta* out);
+void bg_fasta_free(bg_fasta* f);
 
 /* ---- next to the hot path: position-wise compares ----------------------- */
 /* analysis::seq::hamming_distance for every pair (seq.rs:74-83): out[p] = #positions where the two sequences
