@@ -791,14 +791,14 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
 }
 
 // Pipeline chunks for pairs [lo, hi) at SCAN_BLOCK granularity, roughly equal cell counts.
-std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi) {
+std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi, double nchunk_override = 0.0) {
     std::vector<uint64_t> b{lo};
     if (hi == lo) { b.push_back(hi); return b; }
     const uint64_t blk_lo = lo / SCAN_BLOCK, blk_hi = (hi + SCAN_BLOCK - 1) / SCAN_BLOCK;
     double total = 0;
     for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
     static const double nchunk_target = [] { const char* e = getenv("BG_PIPE_CHUNKS"); return e ? std::max(1.0, atof(e)) : 5.0; }();
-    const double target = std::max(total / nchunk_target, 1.0e9);
+    const double target = nchunk_override > 0 ? std::max(total / nchunk_override, 1.0e8) : std::max(total / nchunk_target, 1.0e9);
     const uint64_t max_pairs = 262144;
     // every length class of a chunk becomes its own launch: keep >= ~4 waves of warps per launch
     const uint64_t min_pairs = 8192ull * (uint64_t)__builtin_popcount(S.class_mask ? S.class_mask : 1u);
@@ -1782,7 +1782,10 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
     const uint64_t* off = in->seq_off;
-    const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi);
+    // Edit distance is bound by the host plan (a pair costs the GPU ~3 ns and one host thread ~30-40 ns): many
+    // chunks, so that all cores plan at once and the first chunks are ready early.
+    static const double edit_chunks = [] { const char* e = getenv("BG_EDIT_CHUNKS"); return e ? std::max(1.0, atof(e)) : 24.0; }();
+    const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi, edit_chunks);
     const int nchunks = (int)cb.size() - 1;
     struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; std::thread th; };
     std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one host thread per chunk, consumed as they finish
@@ -1790,8 +1793,15 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         pre[c].th = std::thread([&, c] {
             const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+            const auto t0 = std::chrono::steady_clock::now();
             pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
+            if (getenv("BG_PROFILE_HOST"))
+                fprintf(stderr, "[bgalign]   edit plan of chunk %d (%llu pairs): %.2f ms\n", c, (unsigned long long)n,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         });
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     cudaStream_t st_comp = dv.ws[0].stream, st_h2d = dv.ws[1].stream, st_d2h = dv.ws[2].stream;
     cudaStream_t saved[PIPE_DEPTH];
     for (int s = 0; s < PIPE_DEPTH; ++s) { saved[s] = dv.ws[s].stream; dv.ws[s].stream = st_comp; dv.ws[s].reset_events(); }
@@ -1826,6 +1836,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
             } else {
                 int expect = BG_OK; rc_shared.compare_exchange_strong(expect, rc);
             }
+            if (prof) fprintf(stderr, "[bgalign]   edit chunk %d results on the host at %.2f ms\n", c, since());
             { std::lock_guard<std::mutex> lk(mu); finished = c + 1; }
             cv.notify_all();
         }
@@ -1867,7 +1878,9 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         }
         rc_all = rc_shared.load();
         if (rc_all) break;
+        const double t0 = prof ? since() : 0;
         rc_all = issue(s, c);
+        if (prof) fprintf(stderr, "[bgalign]   edit chunk %d (%llu pairs) issued %.2f .. %.2f ms\n", c, (unsigned long long)(cb[c + 1] - cb[c]), t0, since());
         if (rc_all) break;
         { std::lock_guard<std::mutex> lk(mu); issued = c + 1; }
         cv.notify_all();
