@@ -1802,9 +1802,12 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-    cudaStream_t st_comp = dv.ws[0].stream, st_h2d = dv.ws[1].stream, st_d2h = dv.ws[2].stream;
+    // Every work set computes on its OWN stream: a chunk is at most one partial wave of the bit-parallel kernel
+    // (one thread per pair, ~1.1 ms whatever the chunk size), so chunks must overlap on the GPU -- on one shared
+    // compute stream the pipeline ran at 1.15 ms per chunk regardless of its size (measured, cfg3).
+    cudaStream_t st_h2d = dv.ws[0].walk_stream, st_d2h = dv.ws[1].walk_stream;
     cudaStream_t saved[PIPE_DEPTH];
-    for (int s = 0; s < PIPE_DEPTH; ++s) { saved[s] = dv.ws[s].stream; dv.ws[s].stream = st_comp; dv.ws[s].reset_events(); }
+    for (int s = 0; s < PIPE_DEPTH; ++s) { saved[s] = dv.ws[s].stream; dv.ws[s].reset_events(); }
     cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH];
     for (int s = 0; s < PIPE_DEPTH; ++s) {
         cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming);
@@ -1857,6 +1860,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
         CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        cudaStream_t st_comp = ws.stream;
         CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         int rc = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);
         if (rc) return rc;
@@ -1889,7 +1893,8 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     cv.notify_all();
     finisher.join();
     if (rc_all == BG_OK) rc_all = rc_shared.load();
-    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_comp); cudaStreamSynchronize(st_d2h);
+    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_d2h);
+    for (int s = 0; s < PIPE_DEPTH; ++s) cudaStreamSynchronize(dv.ws[s].stream);
     for (auto& h : host_out) h.release();
     for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
     for (int s = 0; s < PIPE_DEPTH; ++s) { dv.ws[s].stream = saved[s]; cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); }
@@ -1984,7 +1989,7 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     if (in->n_pairs && !getenv("BG_NO_MYERS")) {
         const uint64_t b0 = in->seq_off[0], b1 = in->seq_off[2 * in->n_pairs];
         uint64_t hist[256] = {0};
-        const uint64_t span = b1 - b0, take = std::min<uint64_t>(span, 1u << 20);
+        const uint64_t span = b1 - b0, take = std::min<uint64_t>(span, 1u << 16);   // (2 x 1 MiB of byte increments cost 2 ms)
         for (uint64_t x = 0; x < take; ++x) hist[in->residues[b0 + x]]++;
         for (uint64_t x = 0; x < take; ++x) hist[in->residues[b1 - 1 - x]]++;
         use_lut = span > 0 && make_edit_lut(hist, lut);
