@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name -> (synth config, pairs per GPU)
+    "cfg1": ("cfg1_from_file", 1),             # the reference's example pair (9 559 x 8 457): a latency number
     "cfg2": ("cfg2_dna150_global", 1_000_000),
     "cfg4": ("cfg4_protein_local", 100_000),
     "cfg3": ("cfg3_edit_100_300", 1_250_000),
@@ -85,10 +86,24 @@ def reduce_over_ranks(dev_ms, e2e_ms, cells, world, device):
     return float(mx[0]), float(mx[1]), float(sm[2])
 
 
+def make_batch(cfg_name, n_pairs, first_pair=0):
+    """The workload's pairs: the seeded synthetic stream, or (config #1) the committed copy of the reference's
+    fixture repeated n_pairs times."""
+    from biogarden_b200 import fasta, native, synth
+    cfg = synth.CONFIGS[cfg_name]
+    if "fixture" in cfg:
+        import numpy as np
+        one, _ = fasta.read_batch(os.path.join(ROOT, "tests", "golden", "fasta", "input", cfg["fixture"] + ".fasta"))
+        res = np.tile(one.residues, n_pairs)
+        step = int(one.seq_off[2])
+        off = np.concatenate([one.seq_off[:2] + np.uint64(k * step) for k in range(n_pairs)] + [np.array([n_pairs * step], np.uint64)])
+        return native.Batch(res, off.astype(np.uint64))
+    return synth.make(cfg_name, n_pairs=n_pairs, first_pair=first_pair)
+
+
 def rank_batch(cfg_name, pairs_per_rank, rank):
     """Weak scaling: rank r owns pairs [r * pairs, (r + 1) * pairs) of the workload's seeded stream."""
-    from biogarden_b200 import synth
-    return synth.make(cfg_name, n_pairs=pairs_per_rank, first_pair=rank * pairs_per_rank)
+    return make_batch(cfg_name, pairs_per_rank, rank * pairs_per_rank)
 
 
 def int32_peak():
@@ -196,13 +211,15 @@ def run_reference(args, rank, world):
     cfg = synth.CONFIGS[cfg_name]
     cores = orc.hw_threads()
     sample = args.ref_pairs or {"cfg2": 15000, "cfg3": 3000, "cfg4": 120}.get(args.workload, 40) * cores   # ~5 s per step
+    if args.workload == "cfg1":
+        cores, sample = 1, 1
     if args.workload == "cfg5":
         from biogarden_b200 import native
         cores = min(cores, 8)
         sample = 4 * cores
         batch = native.synth_pairs(cfg["seed"], 0, sample, cfg["alphabet"], 10000, 10000, cfg["resize_b"])
     else:
-        batch = synth.make(cfg_name, n_pairs=sample)
+        batch = make_batch(cfg_name, sample)
     cells = batch.cells()
 
     def step():
@@ -232,7 +249,7 @@ def run_reference(args, rank, world):
 
 def workload_config(args, cfg, pairs_per_gpu, note=None):
     c = {"workload": "%s: %d synthetic %s pairs per GPU, len %d-%d, %s, scorer %s, open %d, extend %d, %s" % (
-        args.workload, pairs_per_gpu, "DNA" if cfg["alphabet"] == b"ACGT" else "protein", cfg["lo"], cfg["hi"],
+        args.workload, pairs_per_gpu, ("fixture %s.fasta DNA" % cfg["fixture"]) if "fixture" in cfg else "DNA" if cfg["alphabet"] == b"ACGT" else "protein", cfg["lo"], cfg["hi"],
         cfg["mode"], cfg["scorer"], cfg["a"], cfg["b"], "score only" if cfg["mode"] == "edit" else "with traceback"),
         "pairs_per_gpu": pairs_per_gpu, "seed": cfg["seed"], "parallelism": "independent pairs sharded per GPU, no collective",
         "l2": "inputs + trace larger than L2 (no flush needed)"}
@@ -374,13 +391,13 @@ def main():
         hbm, hbm_src = hbm_peak()
         kern = ("k4_myers (bit-parallel edit distance)" if cells_bitpar * 2 > cells else "k4_edit") if is_edit else \
                ("k1h_fill (packed 16x2 DP fill + direction codes)" if cells_packed * 2 > cells else
-                "k2_wave (wavefront DP fill + direction codes)" if args.workload == "cfg5" else "k1_fill (DP fill + direction codes)")
+                "k2_wave (wavefront DP fill + direction codes)" if args.workload in ("cfg5", "cfg1") else "k1_fill (DP fill + direction codes)")
         bytes_per_cell, cap = ncu_traffic(kern.split(" ")[0])
         line = {
             "metric": "GCUPS (cell updates/s, with traceback)" if not is_edit else "GCUPS (cell updates/s, score only)",
             "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
+            "dtype": "int32", "data": "reference fixture (tests/golden)" if "fixture" in cfg else "synthetic",
             "config": workload_config(args, cfg, pairs),
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "timed": "host wall clock around bg_align_batch (pinned host buffers in, pinned results out)"},
@@ -425,7 +442,9 @@ def cpu_baseline(args, cfg_name, cfg):
         sample = 8 * cores
         batch = native.synth_pairs(cfg["seed"], 0, sample, cfg["alphabet"], 10000, 10000, cfg["resize_b"])
     else:
-        batch = synth.make(cfg_name, n_pairs=sample)
+        if args.workload == "cfg1":
+            cores, sample = 1, 1
+        batch = make_batch(cfg_name, sample)
     t0 = time.perf_counter()
     if cfg["mode"] == "edit":
         _, secs = orc.edit_distance_batch(batch.residues, batch.seq_off, threads=cores, lean=False)

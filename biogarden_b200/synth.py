@@ -6,6 +6,9 @@ PROTEIN = b"ACDEFGHIKLMNPQRSTVWY"
 
 # name -> (seed, alphabet, len_lo, len_hi, resize_b, mode, scorer, a, b, full-size pair count)
 CONFIGS = {
+    # BASELINE config #1 is not synthetic: the reference's own fixture (examples/from_file.rs:20-31), one pair
+    "cfg1_from_file": dict(seed=0, alphabet=DNA, lo=9559, hi=8457, resize_b=False, mode="semiglobal",
+                           scorer="blosum62", a=-1, b=-2, n_pairs=1, fixture="semiglobal_alignment"),
     "cfg2_dna150_global": dict(seed=2, alphabet=DNA, lo=150, hi=150, resize_b=True, mode="global",
                                scorer="unit", a=-2, b=-1, n_pairs=1_000_000),
     "cfg3_edit_100_300": dict(seed=3, alphabet=DNA, lo=100, hi=300, resize_b=True, mode="edit",

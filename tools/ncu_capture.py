@@ -1,6 +1,6 @@
 """One device-resident pass of a named workload at a given pair count -- the command ncu captures kernels from.
 
-  python tools/ncu_capture.py cfg2|cfg4|cfg5 N_PAIRS [REPS]
+  python tools/ncu_capture.py cfg2|cfg4|cfg4u|cfg5 N_PAIRS [REPS]
 """
 import os
 import sys
@@ -14,8 +14,13 @@ WL = {"cfg2": ("cfg2_dna150_global", "global", score.unit, -2, -1),
       "cfg5": ("cfg5_long_semiglobal", "semiglobal", score.unit, -1, -1)}
 name, n = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-cfg, mode, sc, a, b = WL[name]
-batch = synth.make(cfg, n_pairs=n)
+if name == "cfg4u":      # one length class of config #4: uniform 600 aa protein pairs -> a single k1_fill<32,20,local> launch
+    from biogarden_b200 import native
+    mode, sc, a, b = "local", score.blosum62, -11, -1
+    batch = native.synth_pairs(4, 0, n, synth.PROTEIN, 600, 600, True)
+else:
+    cfg, mode, sc, a, b = WL[name]
+    batch = synth.make(cfg, n_pairs=n)
 al = SequenceAligner([0]); ctx = al.context
 params = al.make_params(batch, mode, sc, a, b)
 db = ctx.upload(batch, 0, prepare="align"); ctx.sync()

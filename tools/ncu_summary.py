@@ -41,7 +41,10 @@ def main():
     for spec in sys.argv[2:]:
         parts = spec.split(":")
         rep, cells, note = parts[0], float(parts[1]), (parts[2] if len(parts) > 2 else "")
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # REPORT may also be the `ncu -i X.ncu-rep --page raw --csv` text itself (made on the GPU box: the reports are
+        # too large to travel back)
+        raw = open(rep).read() if rep.endswith(".csv") else \
+            subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
         for vals in rows[2:]:
