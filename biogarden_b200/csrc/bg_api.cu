@@ -1012,7 +1012,9 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     if (l) {
                         Phase ph(ws, 2);
                         wk.cks = wa.cks; wk.last_launch = (l == NB) ? 1u : 0u;
-                        k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(wk);
+                        static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
+                        if (old_diag) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(wk);
+                        else k3_walk_skew<WAVE_C><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, st>>>(wk);
                     }
                     CU_TRY(ctx, cudaGetLastError());
                 }
@@ -1062,8 +1064,13 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     if (lc.long_walk) {
                         static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
                         // the window loaders map 8-column blocks onto trace words: need C % 8 == 0 (true for K2)
-                        if (lc.ops_fmt && lc.sh.L == 32 && lc.sh.C == WAVE_C) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
-                        else if (lc.ops_fmt) k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
+                        static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
+                        if (lc.ops_fmt && old_diag) {
+                            if (lc.sh.L == 32 && lc.sh.C == WAVE_C) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
+                            else k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
+                        }
+                        else if (lc.ops_fmt && lc.sh.L == 32 && lc.sh.C == WAVE_C) k3_walk_skew<WAVE_C><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, wst>>>(wa);
+                        else if (lc.ops_fmt) k3_walk_skew<0><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, wst>>>(wa);
                         else if (walk_kind == 2 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
                         else k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, wst>>>(wa);
                     }

@@ -603,6 +603,241 @@ __global__ void __launch_bounds__(WALK_DIAG_WARPS * 32) k3_walk_diag(const WalkA
     }
 }
 
+// K3, skewed-window long-pair form (the default for long pairs): k3_walk_diag's window, stored so that a walk
+// step is ONE shared-memory byte load and a handful of ALU instructions.
+//   * the window is kept as BYTES in diagonal coordinates: row r (DP row k_hi - r), offset d = l - (l_hi - r) + 36,
+//     i.e. the anchor's diagonal is column 36 of every row and a path may drift 35 cells to either side;
+//     a diagonal move is idx += 72, a move up (gap in seq2) idx += 73, a move left idx -= 1 -- no row / column /
+//     word / shift arithmetic in the loop, and (k, l) are recovered from idx only when the window is left;
+//   * the byte of a cell is the state machine's input pre-digested while the window is filled (in parallel, by
+//     all lanes): bits 0-1 the move of state 'M' (0 diagonal, 1 up, 2 left; the reference tests M == Y first),
+//     bit 2 "state 'X' keeps extending", bit 3 "state 'Y' keeps extending"; 0xFF = not in the window (borders,
+//     outside the matrix, rows of another launch, the frame) and 0xFE = local-mode stop (aligner.rs:181), so one
+//     compare ends the fast loop, and everything rare -- borders, re-anchoring, suspension at a row-block
+//     boundary -- is handled between windows by the same code as in k3_walk_diag;
+//   * ops are accumulated by shifting (first emitted = highest position), converted from / to the positional
+//     format of WalkState / push_run at the window boundaries.
+// The scalar step was ~75 SASS instructions with two dependent shared-memory reads (~300 cycles on the one warp a
+// pair has); this one is ~15 with one.  Same op output, same WalkState: interchangeable with k3_walk_diag.
+constexpr int SKEW_W = 72;
+constexpr int SKEW_C0 = 36;
+constexpr int SKEW_ROWS = 256;
+constexpr int SKEW_WORDS = 10;        // 8-column trace words per window row (covers 70 + 7 columns at any alignment)
+constexpr int WALK_SKEW_WARPS = 2;
+constexpr int SKEW_BATCH = 16;        // independent trace-word loads in flight per lane while a window is filled
+
+template <int CT>
+__global__ void __launch_bounds__(WALK_SKEW_WARPS * 32) k3_walk_skew(const WalkArgs A) {
+    __shared__ __align__(16) uint8_t s_tile[WALK_SKEW_WARPS][(SKEW_ROWS + 1) * SKEW_W + 8];
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * WALK_SKEW_WARPS + wib;
+    const uint32_t q = threadIdx.x & 31;
+    constexpr unsigned FULL = 0xffffffffu;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const EndCell e = A.end[slot];
+    const uint32_t n = d.n, m = d.m;
+    const uint32_t L = CT ? 32u : (uint32_t)A.L, C = CT ? (uint32_t)CT : (uint32_t)A.C;
+    const uint32_t K = (C + 7) / 8;
+    const uint32_t band_cols = L * C;
+    const uint32_t lane_base = (slot % (32u / L)) * L;
+    const int mode = A.mode;
+    uint8_t* tile = s_tile[wib];
+    uint32_t* slotw = reinterpret_cast<uint32_t*>(A.pad + d.pad_off);
+    uint32_t* ops = slotw + 2;
+    uint32_t pos = n + m;
+    uint32_t wops = 0;
+    auto push = [&](uint32_t op) {     // every lane tracks pos / wops, lane 0 stores
+        --pos;
+        wops |= op << ((pos & 15u) * 2u);
+        if ((pos & 15u) == 0) { if (q == 0) ops[pos >> 4] = wops; wops = 0; }
+    };
+    auto push_run = [&](uint32_t op, uint32_t count) {
+        const uint32_t pattern = op * 0x55555555u;
+        while (count) {
+            const uint32_t hi = (pos & 15u) ? (pos & 15u) : 16u;
+            const uint32_t take = min(count, hi), lo = hi - take;
+            const uint32_t mask = (take == 16u) ? 0xffffffffu : (((1u << (2u * take)) - 1u) << (2u * lo));
+            wops |= pattern & mask;
+            pos -= take; count -= take;
+            if ((pos & 15u) == 0) { if (q == 0) ops[pos >> 4] = wops; wops = 0; }
+        }
+    };
+
+    uint32_t k = e.k, l = e.l, flags = 0;
+    const bool colbr = (e.flags & 1u) != 0;
+    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
+    uint64_t it = 0;
+    uint32_t row0 = 0;
+    if (A.cks) {
+        const CkptSlot cs = A.cks[slot];
+        if (cs.nrows == 0 && !A.last_launch) return;
+        row0 = cs.row0;
+    }
+    WalkState* const ws_ = A.wstate ? A.wstate + slot : nullptr;
+    if (ws_ && ws_->started) {
+        if (ws_->done) return;
+        k = ws_->k; l = ws_->l; cur = ws_->cur; pos = ws_->pos; wops = ws_->wops; flags = ws_->flags; it = ws_->it;
+        __syncwarp();
+    } else if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
+        if (colbr) push_run(1u, n - k); else push_run(2u, m - l);
+    }
+    const uint64_t bound = 3ull * ((uint64_t)n + m) + 64 + 4ull * (n / 32u);   // emits + state switches + windows
+    uint32_t win_rows = SKEW_ROWS;
+    uint32_t probe_skip = 0;
+    bool done = false, suspended = false;
+    while (!done) {
+        if (++it > bound) { flags |= WALK_HANG; break; }
+        if (k == 0 || l == 0) {
+            // border cells: the reference's border trace values (aligner.rs:107-108, 52)
+            bool valid;
+            switch (mode) {
+                case M_GLOBAL: valid = (k != 0 || l != 0); break;
+                case M_LOCAL: valid = false; break;
+                case M_SEMIGLOBAL: valid = false; break;
+                default: valid = (l != 0); break;
+            }
+            if (!valid) break;
+            if (cur == 0) {
+                if (l == 0) { push(1u); --k; cur = 1; }
+                else { push(2u); --l; cur = 2; }
+            } else if (cur == 1) {
+                if (k == 0) { flags |= WALK_UNDERFLOW; break; }
+                push(1u); --k;
+            } else {
+                if (l == 0) { flags |= WALK_UNDERFLOW; break; }
+                push(2u); --l;
+            }
+            continue;
+        }
+        if (k <= row0) { suspended = true; break; }              // the codes of this row belong to the next launch
+        // ---- fill the window anchored at (k, l) ----
+        const uint32_t k_hi = k, l_hi = l;
+        const uint32_t rows = min(k - row0, win_rows);
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(tile);
+            const uint32_t n16 = ((rows + 1u) * SKEW_W + 15u) / 16u;
+            for (uint32_t x = q; x < n16; x += 32) t4[x] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        }
+        __syncwarp();
+        // The words are fetched in batches of SKEW_BATCH independent loads per lane (one memory round trip per
+        // batch; a load-use loop paid one per word: 80 x ~0.7 us per window, which WAS the walk time).
+        auto word_of = [&](uint32_t x, uint32_t& rr, uint32_t& j0, int32_t& d0, uint64_t& idxw) -> bool {
+            if (x >= rows * SKEW_WORDS) return false;
+            rr = x / SKEW_WORDS;
+            const uint32_t wx = x - rr * SKEW_WORDS;
+            const int32_t ldiag = (int32_t)l_hi - (int32_t)rr;                   // column on the anchor's diagonal in this row
+            const int32_t cb = ((ldiag - (SKEW_C0 - 1) - 1) >> 3) + (int32_t)wx;   // word holding column ldiag - 35 (offset 1), then the next ones
+            if (cb < 0 || ((uint32_t)cb << 3) >= m) return false;
+            const uint32_t i = k_hi - rr;
+            j0 = (uint32_t)cb << 3;
+            if (CT == 16) {
+                idxw = d.trace_off + ((uint64_t)(j0 >> 9) * d.steps + (i - 1 - row0) + ((j0 >> 4) & 31u)) * 64u + ((j0 >> 3) & 1u) * 32u + ((j0 >> 4) & 31u);
+            } else {
+                const uint32_t bd = j0 / band_cols, rem = j0 - bd * band_cols;
+                const uint32_t p = rem / C, c = rem - p * C;
+                idxw = d.trace_off + ((uint64_t)bd * d.steps + (i - 1 - row0) + p) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
+            }
+            d0 = (int32_t)j0 + 1 - ldiag + SKEW_C0;                               // offset of the word's first column
+            return true;
+        };
+        for (uint32_t base = 0; base < rows * SKEW_WORDS; base += 32u * SKEW_BATCH) {
+            uint32_t wv[SKEW_BATCH];
+#pragma unroll
+            for (int u = 0; u < SKEW_BATCH; ++u) {
+                uint32_t rr, j0; int32_t d0; uint64_t idxw;
+                wv[u] = word_of(base + (uint32_t)u * 32u + q, rr, j0, d0, idxw) ? __ldg(A.trace + idxw) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < SKEW_BATCH; ++u) {
+                uint32_t rr, j0; int32_t d0; uint64_t idxw;
+                if (!word_of(base + (uint32_t)u * 32u + q, rr, j0, d0, idxw)) continue;
+                uint32_t w = wv[u];
+                uint8_t* rowp = tile + rr * SKEW_W;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const uint32_t nib = w & 15u; w >>= 4;
+                    const int32_t dd = d0 + c8;
+                    if (dd >= 1 && dd <= SKEW_W - 2 && j0 + (uint32_t)c8 < m) {
+                        uint32_t bb = ((nib & TR_YEQ) ? 2u : (nib & TR_XEQ)) | ((nib & TR_XOPEN) ? 0u : 4u) | ((nib & TR_YOPEN) ? 0u : 8u);
+                        if (mode == M_LOCAL && (nib & 3u) == 3u) bb = 0xFEu;
+                        rowp[dd] = (uint8_t)bb;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- fast walk inside the window (all lanes redundantly; lane 0 stores) ----
+        uint32_t idx = SKEW_C0;
+        uint32_t cnt = (pos & 15u) ? (pos & 15u) : 16u;            // free op fields of the current word
+        uint32_t sw = (cnt == 16u) ? 0u : (wops >> (2u * cnt));    // its ops so far, shifted form
+        uint32_t budget = 4u * (rows + SKEW_W) + 16u;
+        uint32_t last = 0xFFu;
+        for (;;) {
+            if (--budget == 0) { flags |= WALK_HANG; done = true; break; }
+            if (cur == 0 && probe_skip == 0) {
+                // vector probe: lane q looks at the cell q diagonal steps ahead; a run of plain diagonal moves goes out at once
+                const uint32_t pi = idx + (uint32_t)SKEW_W * q;
+                const bool good = pi < (rows + 1u) * SKEW_W && (tile[pi] & 0xF3u) == 0u;     // in the window, not a sentinel, move 0
+                const uint32_t mask = __ballot_sync(FULL, good);
+                uint32_t run = (mask == FULL) ? 32u : (uint32_t)(__ffs((int)~mask) - 1);
+                if (run < 4u) probe_skip = 8u;
+                idx += SKEW_W * run;
+                while (run) {
+                    const uint32_t take = min(run, cnt);
+                    sw = (take == 16u) ? 0u : (sw << (2u * take));
+                    cnt -= take; pos -= take; run -= take;
+                    if (cnt == 0) { if (q == 0) ops[pos >> 4] = sw; sw = 0; cnt = 16u; }
+                }
+            } else if (probe_skip) --probe_skip;
+            const uint32_t b = tile[idx];
+            if (b >= 0xFEu) { last = b; break; }
+            const uint32_t op = cur ? cur : (b & 3u);
+            const uint32_t emit = cur ? ((b >> (cur + 1u)) & 1u) : 1u;
+            if (emit) {
+                sw = (sw << 2) | op;
+                --pos;
+                if (--cnt == 0) { if (q == 0) ops[pos >> 4] = sw; sw = 0; cnt = 16u; }
+                idx += (op == 0u) ? (uint32_t)SKEW_W : (op == 1u) ? (uint32_t)(SKEW_W + 1) : 0xffffffffu;
+                cur = op;
+            } else {
+                cur = 0;
+            }
+        }
+        wops = (cnt == 16u) ? 0u : (sw << (2u * cnt));
+        {
+            const uint32_t rr = idx / SKEW_W, dd = idx - rr * SKEW_W;
+            k = k_hi - rr;
+            l = (uint32_t)((int32_t)dd - SKEW_C0 + (int32_t)l_hi - (int32_t)rr);
+            if (rr >= rows) win_rows = min(2u * win_rows, (uint32_t)SKEW_ROWS);
+            else if (rr < win_rows / 2u) win_rows = max(win_rows / 2u, 32u);
+        }
+        if (last == 0xFEu) break;                                  // local: M == 0 here (aligner.rs:181)
+        __syncwarp();
+    }
+    if (suspended) {
+        if (q == 0) {
+            ws_->k = k; ws_->l = l; ws_->cur = cur; ws_->pos = pos; ws_->wops = wops; ws_->flags = flags; ws_->it = it;
+            ws_->started = 1u; ws_->done = 0u;
+        }
+        return;
+    }
+    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
+        if (colbr) { push_run(1u, k); k = 0; } else { push_run(2u, l); l = 0; }
+    }
+    if (q == 0) {
+        if (ws_) { ws_->started = 1u; ws_->done = 1u; }
+        if (pos & 15u) ops[pos >> 4] = wops;
+        slotw[0] = k; slotw[1] = l;
+        const uint32_t len = n + m - pos;
+        A.score[d.pair_id] = e.score;
+        A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
+        A.lens2[2ull * d.pair_id] = len;
+        A.lens2[2ull * d.pair_id + 1] = len;
+    }
+}
+
 // Score-only epilogue when no traceback is requested.
 __global__ void k_scores_only(const PairDesc* desc, const EndCell* end, uint32_t n_slots, int32_t* score,
                               uint8_t* walk_flags, int mode) {
