@@ -169,6 +169,8 @@ struct WorkSet {
     cudaStream_t stream = nullptr;
     cudaStream_t walk_stream = nullptr;   // traceback walks of chunk c run here, next to the fill of chunk c+1
     cudaStream_t post_stream = nullptr;   // host-buffer pipeline: walk + scan + gather of this set's chunk go here (next to the next chunk's fill)
+    cudaStream_t fill2_stream = nullptr;  // host-buffer pipeline: every other fill launch of a chunk goes here, so that the tail of
+                                          // one length class's launch overlaps the head of the next (their traces are disjoint)
     BlockCache* cache = nullptr;
     DevBuf trace2;                        // second trace buffer (chunks alternate)
     DevBuf trace, end, bnd, pad, table, codes, err, cubtmp, progress, cand;   // scratch + parameters
@@ -952,6 +954,12 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     if (overlap && !ws.trace2.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4)) { ctx->set_error("device allocation failed (second trace buffer)"); return BG_ENOMEM; }
     cudaStream_t wst = overlap ? ws.walk_stream : split ? ws.post_stream : st;
     cudaStream_t pst = split ? ws.post_stream : st;
+    cudaStream_t st2 = (split && ws.fill2_stream && n_chunks >= 2) ? ws.fill2_stream : nullptr;
+    if (st2) {
+        cudaEvent_t ev0 = ws.get_event();
+        CU_TRY(ctx, cudaEventRecord(ev0, st));
+        CU_TRY(ctx, cudaStreamWaitEvent(st2, ev0, 0));       // inputs, parameters and memsets issued on the main stream so far
+    }
     cudaEvent_t ev_walk_done[2] = {nullptr, nullptr};
     if (overlap) {
         cudaEvent_t ev0 = ws.get_event();
@@ -974,6 +982,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             fa.end = ws.end.as<EndCell>() + ch.slot_begin;
             fa.n_slots = ns;
             const uint32_t nwarps = (ns + G - 1) / G;
+            cudaStream_t fst = st;          // stream of this launch's fill
             if (lc.wave && ch.ckpt_nb) {
                 // ---- bounded-memory traceback: pass 1 (checkpoints + end cells), then row block by row block,
                 //      bottom-up, re-fill with direction codes + resume the walks (k2_wave.cuh) ----
@@ -1035,17 +1044,19 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 Phase ph(ws, 1);
                 CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, pp.smem, st, wa));
             } else if (lc.half) {
-                Phase ph(ws, 1);
+                fst = (st2 && (chunk_no & 1)) ? st2 : st;
+                Phase ph(ws, 1, fst);
                 const uint32_t nw2 = (ns + 2 * G - 1) / (2 * G);
-                if (!dispatch_k1h(lc.sh, pp.mode != BG_GLOBAL, dim3((nw2 + 3) / 4), st, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
+                if (!dispatch_k1h(lc.sh, pp.mode != BG_GLOBAL, dim3((nw2 + 3) / 4), fst, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
             } else {
-                Phase ph(ws, 1);
-                dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, st, fa);
+                fst = (st2 && (chunk_no & 1)) ? st2 : st;
+                Phase ph(ws, 1, fst);
+                dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, fst, fa);
             }
             CU_TRY(ctx, cudaGetLastError());
             if (overlap || split) {
                 cudaEvent_t evf = ws.get_event();
-                CU_TRY(ctx, cudaEventRecord(evf, st));
+                CU_TRY(ctx, cudaEventRecord(evf, fst));
                 CU_TRY(ctx, cudaStreamWaitEvent(wst, evf, 0));
             }
             {
@@ -1616,6 +1627,9 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         saved[s] = dv.ws[s].stream; dv.ws[s].stream = st_comp; dv.ws[s].reset_events();
         dv.ws[s].post_stream = (st_post == st_comp) ? nullptr : st_post;
     }
+    static const bool no_fill2 = getenv("BG_NO_FILL2") != nullptr;
+    cudaStream_t st_fill2 = (PIPE_DEPTH > 3 && !no_fill2 && st_post != st_comp) ? saved[3] : nullptr;   // an otherwise idle work-set stream
+    for (int s = 0; s < PIPE_DEPTH; ++s) dv.ws[s].fill2_stream = st_fill2;
     cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH], ev_arena[PIPE_DEPTH];
     for (int s = 0; s < PIPE_DEPTH; ++s) {
         cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming);
@@ -1773,8 +1787,9 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     }
     for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
     cudaStreamSynchronize(st_post);
+    if (st_fill2) cudaStreamSynchronize(st_fill2);
     for (int s = 0; s < PIPE_DEPTH; ++s) {
-        dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr;
+        dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr; dv.ws[s].fill2_stream = nullptr;
         cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); cudaEventDestroy(ev_arena[s]);
     }
     *total_out = arena_base;
