@@ -2066,11 +2066,12 @@ int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
         PinBuf stage;
         if (!stage.ensure((2 * n + 1 + n + 1 + n) * 8)) return fail(BG_ENOMEM, "pinned staging allocation failed");
         uint64_t* h_off = stage.as<uint64_t>(); uint64_t* h_first = h_off + 2 * n + 1; uint64_t* h_out = h_first + n + 1;
-        uint64_t pieces = 0;
+        uint64_t pieces = 0, max_len = 0;
         for (uint64_t q = 0; q < n; ++q) {
             h_off[2 * q] = in->seq_off[2 * (lo + q)] - base; h_off[2 * q + 1] = in->seq_off[2 * (lo + q) + 1] - base;
             h_first[q] = pieces;
             const uint64_t len = in->seq_off[2 * (lo + q) + 1] - in->seq_off[2 * (lo + q)];
+            max_len = std::max(max_len, len);
             pieces += std::max<uint64_t>(1, (len + HAM_SPLIT - 1) / HAM_SPLIT);
         }
         h_off[2 * n] = nres; h_first[n] = pieces;
@@ -2086,7 +2087,16 @@ int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
         if (e == cudaSuccess) {
             HammingArgs ha{ws.residues.as<uint8_t>(), ws.off.as<uint64_t>(), n, ws.out64.as<uint64_t>(), ws.err.as<uint32_t>()};
             const uint64_t blocks = std::min<uint64_t>((pieces + 7) / 8, (uint64_t)ctx->num_sms * 8);
-            k5_hamming<<<(unsigned)std::max<uint64_t>(1, blocks), 256, 0, st>>>(ha, ws.lens2.as<uint64_t>(), pieces);
+            {
+                Phase ph(ws, 1);     // bg_last_timing().fill_ms = the compare kernel alone
+                if (pieces == n) {   // no pair longer than one piece: one lane group per pair
+                    if (max_len <= 256) k5_hamming_direct<8><<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(ha);
+                    else if (max_len <= 1024) k5_hamming_direct<16><<<(unsigned)((n * 16 + 255) / 256), 256, 0, st>>>(ha);
+                    else k5_hamming_direct<32><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(ha);
+                } else {
+                    k5_hamming<<<(unsigned)std::max<uint64_t>(1, blocks), 256, 0, st>>>(ha, ws.lens2.as<uint64_t>(), pieces);
+                }
+            }
             e = cudaGetLastError();
             ctx->launches++;
         }
@@ -2098,6 +2108,9 @@ int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
         stage.release();
     };
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
+    for (auto& dv : ctx->devs) for (WorkSet& w : dv.ws) w.reset_events();
+    ctx->timing = bg_timing{};
+    ctx->timing.cells = in->seq_off[2 * N] - in->seq_off[0];      // bytes compared x 2 (both sequences): HBM bytes the kernel reads
     if (nd == 1) work(0);
     else {
         std::vector<std::thread> th;
