@@ -175,6 +175,57 @@ inline uint64_t edit_distance(alignment::aligner::SequenceAligner& al, const ds:
     return edit_distance_batch(al, t)[0];
 }
 
+// analysis::seq::hamming_distance (seq.rs:74-83): Err(InvalidInputSize) when the lengths differ.
+inline std::vector<uint64_t> hamming_distance_batch(alignment::aligner::SequenceAligner& al, const ds::Tile& pairs) {
+    if (pairs.len() % 2) throw BioError(BioError::InvalidInputSize, "Provided inputs have invalid size!");
+    std::vector<uint8_t> res; std::vector<uint64_t> off{0};
+    for (const auto& s : pairs.data) { res.insert(res.end(), s.chain.begin(), s.chain.end()); off.push_back(res.size()); }
+    bg_batch batch{pairs.len() / 2, res.data(), off.data()};
+    std::vector<uint64_t> out(batch.n_pairs);
+    const int err = bg_hamming_distance_batch(al.context(), &batch, out.data());
+    if (err == BG_EINVAL_SIZE) throw BioError(BioError::InvalidInputSize, "Provided inputs have invalid size!");
+    if (err != BG_OK) throw BioError(BioError::Engine, bg_strerror(err));
+    return out;
+}
+inline uint64_t hamming_distance(alignment::aligner::SequenceAligner& al, const ds::Sequence& a, const ds::Sequence& b) {
+    ds::Tile t; t.push(a); t.push(b);
+    return hamming_distance_batch(al, t)[0];
+}
+
 }}  // namespace analysis::seq
+
+namespace analysis { namespace stat {
+
+// analysis::stat::p_distance_matrix (stat.rs:138-152): rows x rows, row-major f32.
+inline std::vector<float> p_distance_matrix(alignment::aligner::SequenceAligner& al, const ds::Tile& matrix) {
+    if (matrix.len() == 0) throw std::out_of_range("p_distance_matrix of an empty Tile (the reference panics on data[0])");
+    std::vector<uint8_t> res; std::vector<uint64_t> off{0};
+    for (const auto& s : matrix.data) { res.insert(res.end(), s.chain.begin(), s.chain.end()); off.push_back(res.size()); }
+    std::vector<float> out(matrix.len() * matrix.len());
+    const int err = bg_p_distance_matrix(al.context(), res.data(), off.data(), matrix.len(), out.data());
+    if (err != BG_OK) throw BioError(BioError::Engine, bg_strerror(err));
+    return out;
+}
+
+}}  // namespace analysis::stat
+
+namespace io { namespace fasta {
+
+// io::fasta::Reader::read_all over a text in memory (fasta.rs:95-136) by the native parser; ids are kept.
+inline ds::Tile read_all(const std::string& text, std::vector<std::string>* ids = nullptr) {
+    bg_fasta f{};
+    const int err = bg_fasta_parse(reinterpret_cast<const uint8_t*>(text.data()), text.size(), 0, &f);
+    if (err == BG_EINVAL_FASTA) throw std::runtime_error("Expected > at record start.");
+    if (err != BG_OK) throw BioError(BioError::Engine, bg_strerror(err));
+    ds::Tile t;
+    for (uint64_t r = 0; r < f.n_records; ++r) {
+        t.push(ds::Sequence(std::vector<uint8_t>(f.residues + f.seq_off[r], f.residues + f.seq_off[r + 1])));
+        if (ids) ids->emplace_back(reinterpret_cast<const char*>(f.ids) + f.id_off[r], f.ids + f.id_off[r + 1] - (f.ids + f.id_off[r]));
+    }
+    bg_fasta_free(&f);
+    return t;
+}
+
+}}  // namespace io::fasta
 }  // namespace biogarden
 #endif

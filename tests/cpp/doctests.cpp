@@ -35,6 +35,18 @@ int main() {
         CHECK(score == 4); CHECK(a1 == Sequence("TAGCA-CTTGGATTCTCGG")); CHECK(a2 == Sequence("---CAGCGTGG--------"));
     }
     CHECK(biogarden::analysis::seq::edit_distance(al, Sequence("ACTGGATTC"), Sequence("ACGT")) == 5);
+    // seq.rs:64-73
+    CHECK(biogarden::analysis::seq::hamming_distance(al, Sequence("GAGCCTACTAACGGGAT"), Sequence("CATCGTAATGACGGCCT")) == 7);
+    try { biogarden::analysis::seq::hamming_distance(al, Sequence("ACGT"), Sequence("ACG")); CHECK(false); }
+    catch (const biogarden::BioError& e) { CHECK(e.kind == biogarden::BioError::InvalidInputSize); }
+    {   // stat.rs:138-152 and io/fasta.rs:95-136 through the native ingest
+        std::vector<std::string> ids;
+        auto t = biogarden::io::fasta::read_all(">a first\nACGT\nACGT\n>b\nACGTTCGA\r\n>c\nTTTTTTTT\n", &ids);
+        CHECK(t.len() == 3); CHECK(ids.size() == 3 && ids[0] == "a" && ids[2] == "c");
+        CHECK(t.data[0] == Sequence("ACGTACGT"));
+        auto d = biogarden::analysis::stat::p_distance_matrix(al, t);
+        CHECK(d.size() == 9 && d[0] == 0.0f && d[1] == 2.0f / 8.0f && d[3] == d[1] && d[2] == 6.0f / 8.0f && d[5] == 6.0f / 8.0f);
+    }
     // error behaviour: Err(InvalidArgumentRange) / Err(InvalidInputSize) under the reference's conditions
     try { al.global_alignment(Sequence("AC"), Sequence("AC"), score::unit, 1, -1); CHECK(false); }
     catch (const biogarden::BioError& e) { CHECK(e.kind == biogarden::BioError::InvalidArgumentRange); }
