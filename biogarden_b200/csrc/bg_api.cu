@@ -392,8 +392,8 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         const uint32_t K = words_per_lane_step(sh.C), band_cols = sh.L * sh.C;
         // K1h (two pairs per lane group, 16-bit halves): short single-band classes whose scores provably fit
         bool half = false;
-        // (every single-band shape up to 512 columns has a packed instantiation: BG_HALF_SHAPES)
-        if (with_trace && half_maxabs > 0 && !wave && (sh.L == 8 || (sh.L == 16 && (sh.C == 10 || sh.C == 16)) || (sh.L == 32 && (sh.C == 12 || sh.C == 16)))) {
+        // (every single-band shape except (32,5) / (32,8) has a packed instantiation: BG_HALF_SHAPES)
+        if (with_trace && half_maxabs > 0 && !wave && (sh.L == 8 || (sh.L == 16 && (sh.C == 10 || sh.C == 16)) || (sh.L == 32 && sh.C >= 12))) {
             const uint32_t cmn = cls_max_n[si], cmm = cls_max_m[si];
             half = cmm <= band_cols && ((int64_t)cmn + cmm + 2) * half_maxabs <= HB_RANGE;
         }
@@ -684,10 +684,10 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
 // pair groups: Q consecutive CTAs work on one pair.  (Thread-block clusters would give the same
 // guarantee, but clusters of 4 must sit inside one GPC and strand 16 of the B200's 148 SMs:
 // 33 resident clusters instead of 37 groups -- measured, see profiles/.)
-#define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 12) X(32, 16)
+#define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
 // Blocks per SM by columns per lane (registers ~ 4 C + 60; measured on cfg2: (16,10) with 6 blocks/SM and
 // 4 of the 8 accumulations on the ALU pipe fills 11 % faster than (8,19) with 3 blocks/SM).
-constexpr int k1h_minb(int C) { return C <= 10 ? 6 : C <= 12 ? 4 : 3; }
+constexpr int k1h_minb(int C) { return C <= 10 ? 6 : C <= 12 ? 4 : C <= 24 ? 3 : 2; }
 bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a) {
 #define X(L_, C_) if (sh.L == L_ && sh.C == C_) { \
         if (track) k1h_fill<L_, C_, true, 0x55, k1h_minb(C_)><<<grid, 128, 0, st>>>(a); \

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from biogarden_b200 import native, score
 from biogarden_b200.aligner import SequenceAligner
 al = SequenceAligner([0]); ctx = al.context
-for ln, n in ((150, 400000), (250, 200000), (350, 120000), (500, 60000)):
+for ln, n in ((150, 400000), (250, 200000), (350, 120000), (500, 60000), (700, 30000), (1000, 16000)):
     batch = native.synth_pairs(2, 0, n, b"ACGT", ln, ln, True)
     params = al.make_params(batch, "global", score.unit, -2, -1)
     db = ctx.upload(batch, 0, prepare="align"); ctx.sync()
