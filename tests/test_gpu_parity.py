@@ -276,7 +276,10 @@ def _mutated_long_pairs(shapes, seed):
 def test_wavefront_kernel_long_pairs(aligner):
     """K2 (pairs wider than 4096 columns: one pair per thread-block cluster, 1/2/4/8 CTAs per pair)
     mixed with K1 classes in one batch; all modes against the lean oracle."""
-    batch = _mutated_long_pairs([(5000, 4200), (3000, 9000), (9000, 17000), (7000, 33000), (300, 5000), (6000, 300), (4500, 4097)], 99)
+    # (9000, 500), (8000, 200), (20000, 60): K1 classes (32,16), (16,16), (8,8) whose pairs are walked by the long-pair
+    # walker's generic-geometry instantiation (several pairs per warp: lane_base) because the batch holds long pairs
+    batch = _mutated_long_pairs([(5000, 4200), (3000, 9000), (9000, 17000), (7000, 33000), (300, 5000), (6000, 300), (4500, 4097),
+                                 (9000, 500), (8000, 200), (8100, 190), (20000, 60)], 99)
     problems = []
     for mode, scorer, a, b in [("semiglobal", "unit", -1, -1), ("local", "blosum62", -11, -1), ("global", "unit", -2, -1),
                                ("overlap", "unit", -2, -2)]:
