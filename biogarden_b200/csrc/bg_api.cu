@@ -21,6 +21,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
+#include <memory>
 #include <map>
 #include <mutex>
 #include <string>
@@ -310,6 +313,50 @@ struct PlanScratchLease {
     PlanScratch* s; PlanScratchLease() : s(plan_scratch_pool().get()) {}
     ~PlanScratchLease() { plan_scratch_pool().put(s); }
 };
+
+// Host worker pool: the batch scan and the per-chunk launch plans of every call run here.  Creating a dozen
+// std::threads per bg_align_batch call cost ~0.4 ms before the first chunk could be issued.
+struct TaskHandle {
+    std::shared_ptr<std::atomic<int>> done;
+    bool joinable() const { return (bool)done; }
+    void join();
+};
+class HostPool {
+  public:
+    HostPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        const unsigned nt = std::max(4u, std::min(hw ? hw : 8u, 32u));
+        for (unsigned t = 0; t < nt; ++t) std::thread([this] { run(); }).detach();
+    }
+    TaskHandle submit(std::function<void()> fn) {
+        TaskHandle h; h.done = std::make_shared<std::atomic<int>>(0);
+        { std::lock_guard<std::mutex> lk(mu_); q_.emplace_back(std::move(fn), h.done); }
+        cv_.notify_one();
+        return h;
+    }
+    void wait(const std::shared_ptr<std::atomic<int>>& d) {
+        std::unique_lock<std::mutex> lk(mu_done_);
+        cv_done_.wait(lk, [&] { return d->load(std::memory_order_acquire) != 0; });
+    }
+  private:
+    void run() {
+        for (;;) {
+            std::pair<std::function<void()>, std::shared_ptr<std::atomic<int>>> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return !q_.empty(); });
+                job = std::move(q_.front()); q_.pop_front();
+            }
+            job.first();
+            { std::lock_guard<std::mutex> lk(mu_done_); job.second->store(1, std::memory_order_release); }
+            cv_done_.notify_all();
+        }
+    }
+    std::mutex mu_, mu_done_; std::condition_variable cv_, cv_done_;
+    std::deque<std::pair<std::function<void()>, std::shared_ptr<std::atomic<int>>>> q_;
+};
+HostPool& host_pool() { static HostPool* p = new HostPool(); return *p; }   // never destroyed: its threads end with the process
+void TaskHandle::join() { if (done) { host_pool().wait(done); done.reset(); } }
 
 // K1h leaves the second slot of a lane group empty when the next pair has a different row count, so a
 // plan can hold up to two slots per pair.
@@ -761,6 +808,7 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
         BatchScan& P = part[t];
         const uint64_t b_lo = nblocks * t / nt, b_hi = nblocks * (t + 1) / nt;
         const uint64_t* off = in->seq_off;
+        uint64_t last_m = ~0ull;
         for (uint64_t blk = b_lo; blk < b_hi; ++blk) {
             const uint64_t q_hi = std::min(N, (blk + 1) * SCAN_BLOCK);
             double cost = 0;
@@ -770,8 +818,11 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                 const uint64_t n = o1 - o0, m = o2 - o1;
                 if (n < m) P.fitting_violation = true;
                 if (m > WAVE_MIN_COLS) P.has_wide = true;
-                P.class_mask |= 1u << (m <= 64 ? 0 : m <= 96 ? 1 : m <= 128 ? 2 : m <= 160 ? 3 : m <= 192 ? 4 : m <= 256 ? 5 : m <= 384 ? 6 :
-                                       m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
+                if (m != last_m) {
+                    last_m = m;
+                    P.class_mask |= 1u << (m <= 64 ? 0 : m <= 96 ? 1 : m <= 128 ? 2 : m <= 160 ? 3 : m <= 192 ? 4 : m <= 256 ? 5 : m <= 384 ? 6 :
+                                           m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
+                }
                 P.max_len_sum = std::max(P.max_len_sum, n + m);
                 cost += (double)n * (double)m + 64.0;
             }
@@ -780,8 +831,9 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
     };
     if (nt == 1) work(0);
     else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        std::vector<TaskHandle> th;
+        for (unsigned t = 1; t < nt; ++t) th.push_back(host_pool().submit([&work, t] { work(t); }));
+        work(0);
         for (auto& x : th) x.join();
     }
     for (auto& P : part) {
@@ -1605,10 +1657,10 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
     // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon
     // as ITS plan is ready, so the GPU starts after the (small) first chunk's plan.
-    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; std::thread th; };
+    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; TaskHandle th; };
     std::vector<Prebuilt> pre(nchunks);
     for (int c = 0; c < nchunks; ++c)
-        pre[c].th = std::thread([&, c] {
+        pre[c].th = host_pool().submit([&, c] {
             const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
             const auto t0 = std::chrono::steady_clock::now();
@@ -1810,10 +1862,10 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     static const double edit_chunks = [] { const char* e = getenv("BG_EDIT_CHUNKS"); return e ? std::max(1.0, atof(e)) : 24.0; }();
     const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi, edit_chunks);
     const int nchunks = (int)cb.size() - 1;
-    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; std::thread th; };
-    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one host thread per chunk, consumed as they finish
+    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; TaskHandle th; };
+    std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one pool task per chunk, consumed as they finish
     for (int c = 0; c < nchunks; ++c)
-        pre[c].th = std::thread([&, c] {
+        pre[c].th = host_pool().submit([&, c] {
             const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
             const auto t0 = std::chrono::steady_clock::now();
