@@ -891,18 +891,29 @@ __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
         uint32_t ia = slotw[0], ib = slotw[1];
         const uint32_t pos0 = d.n + d.m - len;
         const uint32_t lt = (1u << lane) - 1u;
-        for (uint32_t base = 0; base < len; base += 32) {
-            const uint32_t x = base + lane;
-            const bool valid = x < len;
-            uint32_t op = 3u;
-            if (valid) { const uint32_t q = pos0 + x; op = (ops[q >> 4] >> ((q & 15u) * 2u)) & 3u; }
-            const bool useA = valid && op != 2u, useB = valid && op != 1u;
-            const uint32_t bA = __ballot_sync(0xffffffffu, useA), bB = __ballot_sync(0xffffffffu, useB);
-            if (valid) {
-                A.arena[o0 + x] = useA ? sa[ia + __popc(bA & lt)] : (uint8_t)'-';
-                A.arena[o1 + x] = useB ? sb[ib + __popc(bB & lt)] : (uint8_t)'-';
-            }
-            ia += __popc(bA); ib += __popc(bB);
+        // Two groups of 32 characters per iteration: the op words and then all four residue loads are issued
+        // before anything is stored (a load-use-store loop of one group had one memory round trip per group
+        // on its critical path: ncu long-scoreboard 18 stalls per issue).
+        for (uint32_t base = 0; base < len; base += 64) {
+            const uint32_t x0 = base + lane, x1 = x0 + 32;
+            const bool v0 = x0 < len, v1 = x1 < len;
+            uint32_t w0 = 0, w1 = 0;
+            const uint32_t q0 = pos0 + x0, q1 = pos0 + x1;
+            if (v0) w0 = __ldg(ops + (q0 >> 4));
+            if (v1) w1 = __ldg(ops + (q1 >> 4));
+            const uint32_t op0 = v0 ? (w0 >> ((q0 & 15u) * 2u)) & 3u : 3u, op1 = v1 ? (w1 >> ((q1 & 15u) * 2u)) & 3u : 3u;
+            const bool a0 = v0 && op0 != 2u, b0 = v0 && op0 != 1u, a1 = v1 && op1 != 2u, b1 = v1 && op1 != 1u;
+            const uint32_t bA0 = __ballot_sync(0xffffffffu, a0), bB0 = __ballot_sync(0xffffffffu, b0);
+            const uint32_t bA1 = __ballot_sync(0xffffffffu, a1), bB1 = __ballot_sync(0xffffffffu, b1);
+            const uint32_t ia1 = ia + __popc(bA0), ib1 = ib + __popc(bB0);
+            uint8_t ca0 = '-', cb0 = '-', ca1 = '-', cb1 = '-';
+            if (a0) ca0 = __ldg(sa + ia + __popc(bA0 & lt));
+            if (b0) cb0 = __ldg(sb + ib + __popc(bB0 & lt));
+            if (a1) ca1 = __ldg(sa + ia1 + __popc(bA1 & lt));
+            if (b1) cb1 = __ldg(sb + ib1 + __popc(bB1 & lt));
+            if (v0) { A.arena[o0 + x0] = ca0; A.arena[o1 + x0] = cb0; }
+            if (v1) { A.arena[o0 + x1] = ca1; A.arena[o1 + x1] = cb1; }
+            ia = ia1 + __popc(bA1); ib = ib1 + __popc(bB1);
         }
         return;
     }
