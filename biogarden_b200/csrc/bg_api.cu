@@ -745,6 +745,21 @@ bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillAr
     return false;
 }
 
+// One-thread-per-pair walker with the launch's geometry compiled in (k3_walk.cuh).
+void dispatch_walk(Shape sh, bool half, uint32_t ns, cudaStream_t st, const WalkArgs& a) {
+    const dim3 grid((ns + 127) / 128);
+    if (half) {
+#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k3_walk<L_, C_, true><<<grid, 128, 0, st>>>(a); return; }
+        BG_HALF_SHAPES(X)
+#undef X
+    } else {
+#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k3_walk<L_, C_, false><<<grid, 128, 0, st>>>(a); return; }
+        BG_SHAPES(X)
+#undef X
+    }
+    k3_walk<0, 0, false><<<grid, 128, 0, st>>>(a);
+}
+
 template <class Kern>
 cudaError_t launch_k2_impl(Kern kern, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a) {
     cudaLaunchConfig_t cfg{};
@@ -1138,7 +1153,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                         else if (walk_kind == 2 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
                         else k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, wst>>>(wa);
                     }
-                    else k3_walk<<<(ns + 127) / 128, 128, 0, wst>>>(wa);
+                    else dispatch_walk(lc.sh, lc.half, ns, wst, wa);
                 }
                 cudaEvent_t pb = ws.get_event();
                 cudaEventRecord(pb, wst);

@@ -41,6 +41,11 @@ struct WalkArgs {
     uint32_t last_launch = 0;   // row block 0: every walk that is still open ends here
 };
 
+// LT / CT != 0: the launch's geometry as compile-time constants (HALF: K1h's packed row-block layout).  The cell
+// address is two divisions and a handful of multiplies by the geometry; with run-time operands that was most
+// of the ~100 instructions a walk step cost (ncu: 29 k warp instructions per warp of 300-step walks, issue
+// slots 57 % busy).  <0, 0, false> is the generic form.
+template <int LT, int CT, bool HALF>
 __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= A.n_slots) return;
@@ -48,10 +53,10 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     if (d.pair_id == 0xFFFFFFFFu) return;
     const EndCell e = A.end[slot];
     const uint32_t n = d.n, m = d.m;
-    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
+    const uint32_t L = LT ? (uint32_t)LT : (uint32_t)A.L, C = CT ? (uint32_t)CT : (uint32_t)A.C;
     const uint32_t K = (C + 7) / 8;
     const uint32_t band_cols = L * C;
-    const uint32_t H = (uint32_t)A.H;
+    const uint32_t H = LT ? (HALF ? 2u : 1u) : (uint32_t)A.H;
     const uint32_t lane_base = ((slot % (H * (32u / L))) / H) * L;
     const uint32_t half = slot % H;
     // Output: the walk only records WHAT it did -- one 2-bit op per step (0 both residues, 1 seq1 residue
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
         wops |= op << ((pos & 15u) * 2u);
         if ((pos & 15u) == 0) { ops[pos >> 4] = wops; wops = 0; }
     };
-    const uint32_t CW = (uint32_t)A.CW;
+    const uint32_t CW = LT ? (HALF ? (uint32_t)((CT + 3) & ~3) : 0u) : (uint32_t)A.CW;
     uint64_t quad_idx = ~0ull; uint4 quad = make_uint4(0, 0, 0, 0);
     auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
         const uint32_t j0 = j - 1;
