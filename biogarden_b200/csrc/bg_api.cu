@@ -161,6 +161,7 @@ struct Plan {
     uint32_t max_n = 0, max_m = 0;
     int32_t half_maxabs = 0;          // > 0: short classes were laid out for K1h (packed 16 x 2) with this max |score|
     bool myers = false;               // edit distance: pairs with len2 <= 320 laid out one per thread for K4b
+    bool compact = false;             // host pipeline, all classes K4b: the staged descriptors are MyersSlot (16 B), not PairDesc
     bool built = false;
 };
 
@@ -1208,6 +1209,7 @@ int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* 
             if (lc.myers_W) {
                 MyersArgs ma;
                 ma.desc = desc + ch.slot_begin; ma.n_slots = ns; ma.residues = residues; ma.lut = ws.codes.as<uint8_t>();
+                ma.cdesc = P.compact ? reinterpret_cast<const MyersSlot*>(desc) + ch.slot_begin : nullptr;
                 ma.out = out; ma.err_flag = ws.err.as<uint32_t>();
                 if (lc.myers_W == 4) launch_myers<4>(ns, ws.stream, ma);
                 else if (lc.myers_W == 8) launch_myers<8>(ns, ws.stream, ma);
@@ -1877,6 +1879,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     static const double edit_chunks = [] { const char* e = getenv("BG_EDIT_CHUNKS"); return e ? std::max(1.0, atof(e)) : 24.0; }();
     const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi, edit_chunks);
     const int nchunks = (int)cb.size() - 1;
+    static const bool no_compact = getenv("BG_NO_COMPACT") != nullptr;
     struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; TaskHandle th; };
     std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one pool task per chunk, consumed as they finish
     for (int c = 0; c < nchunks; ++c)
@@ -1885,6 +1888,25 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
             const auto t0 = std::chrono::steady_clock::now();
             pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
+            if (pre[c].rc == BG_OK && !no_compact) {
+                // all classes bit-parallel and the arena offsets fit 48 bits: shrink the slots in place (slot i is read
+                // at byte 64 i before anything at or beyond byte 16 i is written)
+                Plan& P = pre[c].plan;
+                bool all = P.myers && !P.classes.empty();
+                for (const LaunchClass& lc : P.classes) all = all && lc.myers_W > 0;
+                const PairDesc* src = pre[c].stage.as<PairDesc>();
+                for (size_t x = 0; all && x < P.n_slots; ++x)
+                    all = src[x].pair_id == 0xFFFFFFFFu || (src[x].a_off < (1ull << 48) && src[x].m <= 0xFFFFu && src[x].b_off == src[x].a_off + src[x].n);
+                if (all) {
+                    MyersSlot* dst = pre[c].stage.as<MyersSlot>();
+                    for (size_t x = 0; x < P.n_slots; ++x) {
+                        const PairDesc f = src[x];
+                        MyersSlot ms; ms.a_off_lo = (uint32_t)f.a_off; ms.a_off_hi = (uint16_t)(f.a_off >> 32); ms.pair_id = f.pair_id; ms.n = f.n; ms.m = (uint16_t)f.m;
+                        dst[x] = ms;
+                    }
+                    P.compact = true;
+                }
+            }
             if (getenv("BG_PROFILE_HOST"))
                 fprintf(stderr, "[bgalign]   edit plan of chunk %d (%llu pairs): %.2f ms\n", c, (unsigned long long)n,
                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
@@ -1947,9 +1969,10 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
             ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM;
         }
         if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
-        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
+        const size_t slot_bytes = P.compact ? sizeof(MyersSlot) : sizeof(PairDesc);
+        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * slot_bytes, cudaMemcpyHostToDevice, st_h2d));
         CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
-        ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        ctx->h2d += nres + P.n_slots * slot_bytes;
         cudaStream_t st_comp = ws.stream;
         CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         int rc = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);

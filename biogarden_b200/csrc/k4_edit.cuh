@@ -117,8 +117,17 @@ __global__ void __launch_bounds__(128) k4_edit(const EditArgs A) {
 // len2 > 32 * W or richer alphabets take the systolic kernel above.
 namespace bg {
 
+// Compact launch slot of the host pipeline (16 bytes instead of PairDesc's 64: the pipeline is bound by the H2D
+// copy): seq2 follows seq1 in the arena, so b_off = a_off + n; m <= 320 in the bit-parallel classes.
+struct __align__(16) MyersSlot {
+    uint32_t a_off_lo; uint32_t pair_id;   // pair_id 0xFFFFFFFF = empty slot
+    uint32_t n; uint16_t m; uint16_t a_off_hi;
+};
+static_assert(sizeof(MyersSlot) == 16, "MyersSlot layout");
+
 struct MyersArgs {
     const PairDesc* desc;
+    const MyersSlot* cdesc;  // != nullptr: compact slots instead of desc
     uint32_t n_slots;
     const uint8_t* residues;
     const uint8_t* lut;      // [256] byte -> code 0..3, 0xFF = not in the 4-symbol alphabet (device)
@@ -133,7 +142,14 @@ __global__ void __launch_bounds__(128) k4_myers(const MyersArgs A) {
     __syncthreads();
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= A.n_slots) return;
-    const PairDesc d = A.desc[slot];
+    struct { uint64_t a_off, b_off; uint32_t n, m, pair_id; } d;
+    if (A.cdesc) {
+        const MyersSlot c = A.cdesc[slot];
+        d.a_off = ((uint64_t)c.a_off_hi << 32) | c.a_off_lo; d.n = c.n; d.m = c.m; d.pair_id = c.pair_id; d.b_off = d.a_off + c.n;
+    } else {
+        const PairDesc f = A.desc[slot];
+        d.a_off = f.a_off; d.b_off = f.b_off; d.n = f.n; d.m = f.m; d.pair_id = f.pair_id;
+    }
     if (d.pair_id == 0xFFFFFFFFu) return;
     const uint32_t n = d.n, m = d.m;
     if (m == 0 || n == 0) { A.out[d.pair_id] = (uint64_t)(m == 0 ? n : m); return; }
