@@ -325,8 +325,16 @@ struct TaskHandle {
 class HostPool {
   public:
     HostPool() {
+        // One worker per core this process can count on: under a one-process-per-GPU launcher (torchrun / MPI
+        // export the number of local ranks) the cores are shared, and 8 ranks x 14 concurrent plan tasks on 32 cores
+        // made every rank's FIRST chunks late (N = 8: host-to-host step 15 -> 47 ms).  Tasks are taken in FIFO
+        // order, so a smaller pool finishes the early chunks' plans first.  BG_HOST_THREADS overrides.
         unsigned hw = std::thread::hardware_concurrency();
-        const unsigned nt = std::max(4u, std::min(hw ? hw : 8u, 32u));
+        unsigned share = 1;
+        for (const char* v : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "SLURM_NTASKS_PER_NODE"})
+            if (const char* e = getenv(v)) { const int x = atoi(e); if (x > 1) { share = (unsigned)x; break; } }
+        unsigned nt = std::max(3u, std::min(hw ? hw : 8u, 32u) / share);
+        if (const char* e = getenv("BG_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
         for (unsigned t = 0; t < nt; ++t) std::thread([this] { run(); }).detach();
     }
     TaskHandle submit(std::function<void()> fn) {
