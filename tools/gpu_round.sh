@@ -1,6 +1,6 @@
 # Full GPU validation pass of a round: parity tests, smoke, benches of every config, ncu launch list and captures.
 # The .ncu-rep files are turned into raw CSV pages on the box and deleted (gpurun_out may carry 64 MiB back).
-O=gpurun_out/r01b; mkdir -p $O
+O=gpurun_out/r01d; mkdir -p $O
 (time python -m pytest tests -m gpu -x -q) > $O/pytest.log 2>&1
 python __graft_entry__.py smoke > $O/smoke.log 2>&1
 python bench.py > $O/bench_cfg2.log 2>&1
@@ -19,6 +19,6 @@ cap() {  # name, workload, pairs, kernel regex, skip, count
 }
 cap k1h_fill_cfg2 cfg2 200000 "k1h_fill|k3_walk|k_gather" 3 3
 cap k1_fill_local_cfg4u cfg4u 20000 "k1_fill" 1 1
-cap k2_wave_cfg5 cfg5 32 "k2_wave|k3_walk_diag" 2 2
+cap k2_wave_cfg5 cfg5 32 "k2_wave|k3_walk_skew" 2 2
 tail -n 3 $O/pytest.log $O/smoke.log $O/cap_*plain.log
 ls -la $O
