@@ -777,64 +777,39 @@ __global__ void __launch_bounds__(WALK_SKEW_WARPS * 32) k3_walk_skew(const WalkA
         uint32_t idx = SKEW_C0;
         uint32_t cnt = (pos & 15u) ? (pos & 15u) : 16u;            // free op fields of the current word
         uint32_t sw = (cnt == 16u) ? 0u : (wops >> (2u * cnt));    // its ops so far, shifted form
-        uint32_t widx = (pos - 1u) >> 4;                           // the word being filled (pos >= 1 whenever an op can still come)
         uint32_t budget = 4u * (rows + SKEW_W) + 16u;
         uint32_t last = 0xFFu;
-        bool hang = false;
-#define SKEW_EMIT(op_) do { sw = (sw << 2) | (op_); if (--cnt == 0) { if (q == 0) ops[widx] = sw; --widx; sw = 0; cnt = 16u; } } while (0)
-        // One loop per state of the reference's machine: the common step is a byte load, a sentinel
-        // test, the op into the shift register and a constant index delta.
         for (;;) {
-            if (cur == 0) {
-                for (;;) {
-                    if (--budget == 0) { hang = true; break; }
-                    if (probe_skip == 0) {
-                        // vector probe: lane q looks at the cell q diagonal steps ahead; a run of plain diagonal moves goes out at once
-                        const uint32_t pi = idx + (uint32_t)SKEW_W * q;
-                        const bool good = pi < (rows + 1u) * SKEW_W && (tile[pi] & 0xF3u) == 0u;     // in the window, not a sentinel, move 0
-                        const uint32_t mask = __ballot_sync(FULL, good);
-                        uint32_t run = (mask == FULL) ? 32u : (uint32_t)(__ffs((int)~mask) - 1);
-                        if (run < 4u) probe_skip = 8u;
-                        idx += SKEW_W * run;
-                        while (run) {
-                            const uint32_t take = min(run, cnt);
-                            sw = (take == 16u) ? 0u : (sw << (2u * take));
-                            cnt -= take; run -= take;
-                            if (cnt == 0) { if (q == 0) ops[widx] = sw; --widx; sw = 0; cnt = 16u; }
-                        }
-                    } else --probe_skip;
-                    last = tile[idx];
-                    if (last >= 0xFEu) break;
-                    const uint32_t op = last & 3u;
-                    SKEW_EMIT(op);
-                    if (op == 0u) { idx += SKEW_W; continue; }
-                    if (op == 1u) { idx += SKEW_W + 1; cur = 1; } else { idx -= 1; cur = 2; }
-                    break;
+            if (--budget == 0) { flags |= WALK_HANG; done = true; break; }
+            if (cur == 0 && probe_skip == 0) {
+                // vector probe: lane q looks at the cell q diagonal steps ahead; a run of plain diagonal moves goes out at once
+                const uint32_t pi = idx + (uint32_t)SKEW_W * q;
+                const bool good = pi < (rows + 1u) * SKEW_W && (tile[pi] & 0xF3u) == 0u;     // in the window, not a sentinel, move 0
+                const uint32_t mask = __ballot_sync(FULL, good);
+                uint32_t run = (mask == FULL) ? 32u : (uint32_t)(__ffs((int)~mask) - 1);
+                if (run < 4u) probe_skip = 8u;
+                idx += SKEW_W * run;
+                while (run) {
+                    const uint32_t take = min(run, cnt);
+                    sw = (take == 16u) ? 0u : (sw << (2u * take));
+                    cnt -= take; pos -= take; run -= take;
+                    if (cnt == 0) { if (q == 0) ops[pos >> 4] = sw; sw = 0; cnt = 16u; }
                 }
-            } else if (cur == 1) {
-                for (;;) {
-                    if (--budget == 0) { hang = true; break; }
-                    last = tile[idx];
-                    if (last >= 0xFEu) break;
-                    if (!(last & 4u)) { cur = 0; break; }           // the gap was opened here: back to 'M' at the same cell
-                    SKEW_EMIT(1u);
-                    idx += SKEW_W + 1;
-                }
+            } else if (probe_skip) --probe_skip;
+            const uint32_t b = tile[idx];
+            if (b >= 0xFEu) { last = b; break; }
+            const uint32_t op = cur ? cur : (b & 3u);
+            const uint32_t emit = cur ? ((b >> (cur + 1u)) & 1u) : 1u;
+            if (emit) {
+                sw = (sw << 2) | op;
+                --pos;
+                if (--cnt == 0) { if (q == 0) ops[pos >> 4] = sw; sw = 0; cnt = 16u; }
+                idx += (op == 0u) ? (uint32_t)SKEW_W : (op == 1u) ? (uint32_t)(SKEW_W + 1) : 0xffffffffu;
+                cur = op;
             } else {
-                for (;;) {
-                    if (--budget == 0) { hang = true; break; }
-                    last = tile[idx];
-                    if (last >= 0xFEu) break;
-                    if (!(last & 8u)) { cur = 0; break; }
-                    SKEW_EMIT(2u);
-                    idx -= 1;
-                }
+                cur = 0;
             }
-            if (hang || last >= 0xFEu) break;
         }
-#undef SKEW_EMIT
-        if (hang) { flags |= WALK_HANG; done = true; last = 0xFFu; }
-        pos = widx * 16u + cnt;
         wops = (cnt == 16u) ? 0u : (sw << (2u * cnt));
         {
             const uint32_t rr = idx / SKEW_W, dd = idx - rr * SKEW_W;
