@@ -2262,6 +2262,23 @@ int bg_p_distance_matrix(bg_ctx* ctx, const uint8_t* residues, const uint64_t* s
     return BG_OK;
 }
 
+// Page-lock / unlock caller memory (cudaHostRegister): the host-buffer entry points copy straight out of the
+// caller's residue arena, which is a true asynchronous DMA only when that memory is pinned; from pageable memory
+// the driver stages every copy synchronously (measured: see INTEGRATION.md).  A shim pins its arena once.
+int bg_pin_host(const void* ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return BG_EINVAL_ARG;
+    const cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return BG_OK; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return e == cudaErrorMemoryAllocation ? BG_ENOMEM : BG_ECUDA; }
+    return BG_OK;
+}
+int bg_unpin_host(const void* ptr) {
+    if (!ptr) return BG_EINVAL_ARG;
+    const cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return BG_ECUDA; }
+    return BG_OK;
+}
+
 // Host-only diagnostic (no CUDA call): time of build_plan for n_pairs uniform pairs of len x len with traceback,
 // the way the host pipeline calls it.  Returns milliseconds (best of `reps`).
 double bg_debug_plan_ms(uint64_t n_pairs, uint32_t len, int half, int reps) {

@@ -56,7 +56,7 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
 
 _lib = None
 
@@ -96,6 +96,8 @@ def lib():
     L.bg_p_distance_matrix.restype = ci; L.bg_p_distance_matrix.argtypes = [vp, vp, vp, u64, vp]
     L.bg_fasta_parse.restype = ci; L.bg_fasta_parse.argtypes = [vp, u64, ci, C.POINTER(bg_fasta)]
     L.bg_fasta_free.restype = None; L.bg_fasta_free.argtypes = [C.POINTER(bg_fasta)]
+    L.bg_pin_host.restype = ci; L.bg_pin_host.argtypes = [vp, u64]
+    L.bg_unpin_host.restype = ci; L.bg_unpin_host.argtypes = [vp]
     L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
     L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
     L.bg_set_long_trace_budget.restype = ci; L.bg_set_long_trace_budget.argtypes = [vp, u64]

@@ -195,6 +195,12 @@ int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes);
  * computed twice).  This replaces the reference's "six full matrices or nothing" (aligner.rs:594-602). */
 int bg_set_long_trace_budget(bg_ctx* ctx, uint64_t bytes);
 
+/* Page-lock / unlock caller memory (cudaHostRegister).  The host-buffer entry points read the caller's residue
+ * arena directly: pinned, that is an asynchronous DMA overlapped with the kernels; pageable, the driver stages it
+ * synchronously.  Results are always returned in library-owned pinned memory. */
+int bg_pin_host(const void* ptr, uint64_t bytes);
+int bg_unpin_host(const void* ptr);
+
 /* ---- helpers for host mirrors ------------------------------------------------------ */
 /* The shipped scorers' 26x26 tables, indexed [a-'A'][b-'A'] (score.rs:5-35,45-75,82-111).
  * name = "blosum62" | "pam250" | "unit"; returns NULL for anything else. */

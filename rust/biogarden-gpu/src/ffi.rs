@@ -41,4 +41,7 @@ extern "C" {
     /// Trace memory per launch of the long-pair path (0 = automatic); pairs that need more are aligned with
     /// bounded-memory traceback (row checkpoints + block-wise re-fill), same results.
     pub fn bg_set_long_trace_budget(ctx: *mut bg_ctx, bytes: u64) -> c_int;
+    /// Page-lock the arena a Tile was flattened into (once), so that the H2D copy is an asynchronous DMA.
+    pub fn bg_pin_host(ptr: *const c_void, bytes: u64) -> c_int;
+    pub fn bg_unpin_host(ptr: *const c_void) -> c_int;
 }
