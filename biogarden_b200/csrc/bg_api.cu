@@ -315,6 +315,16 @@ struct PlanScratchLease {
     ~PlanScratchLease() { plan_scratch_pool().put(s); }
 };
 
+// Is this caller memory pageable (neither allocated pinned nor registered)?  Copies out of pageable memory are staged
+// synchronously by the driver (32 ms instead of 14 ms per 10^6-pair call), so the pipelines stage such chunks
+// themselves: the chunk's plan task also copies its residues into pinned staging, in parallel with the other chunks.
+bool host_is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 // Host worker pool: the batch scan and the per-chunk launch plans of every call run here.  Creating a dozen
 // std::threads per bg_align_batch call cost ~0.4 ms before the first chunk could be issued.
 struct TaskHandle {
@@ -1682,12 +1692,19 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
     // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
     // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon
     // as ITS plan is ready, so the GPU starts after the (small) first chunk's plan.
-    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; TaskHandle th; };
+    struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; };
     std::vector<Prebuilt> pre(nchunks);
+    static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
+    const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues + off[2 * lo]);
     for (int c = 0; c < nchunks; ++c)
         pre[c].th = host_pool().submit([&, c] {
             const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+            if (stage_res) {
+                const uint64_t b0 = off[2 * c_lo], nb = off[2 * (c_lo + n)] - b0;
+                if (!pre[c].res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+                memcpy(pre[c].res.p, in->residues + b0, nb);
+            }
             const auto t0 = std::chrono::steady_clock::now();
             pre[c].rc = build_plan(ctx, off + 2 * c_lo, off[2 * c_lo], n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs,
                                    pre[c].plan, pre[c].stage.as<PairDesc>());
@@ -1783,7 +1800,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         if (!pp.score_only)
             ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((2 * n + 1) * 8) && ws.arena.ensure(std::max<uint64_t>(1, P.pad_bytes));
         if (!ok) { ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM; }
-        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
+        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, stage_res ? (const uint8_t*)pre[c].res.p : in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
         if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
         CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
@@ -1863,7 +1880,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
                 fprintf(stderr, "[bgalign]   gpu ws%d phase %d: start %.3f ms, %.3f ms\n", s, ev.phase, t_a, dur);
             }
     }
-    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
+    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); pb.res.release(); }
     cudaStreamSynchronize(st_post);
     if (st_fill2) cudaStreamSynchronize(st_fill2);
     for (int s = 0; s < PIPE_DEPTH; ++s) {
@@ -1888,12 +1905,19 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi, edit_chunks);
     const int nchunks = (int)cb.size() - 1;
     static const bool no_compact = getenv("BG_NO_COMPACT") != nullptr;
-    struct Prebuilt { Plan plan; PinBuf stage; int rc = BG_OK; TaskHandle th; };
+    struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; };
     std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one pool task per chunk, consumed as they finish
+    static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
+    const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues + off[2 * lo]);
     for (int c = 0; c < nchunks; ++c)
         pre[c].th = host_pool().submit([&, c] {
             const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+            if (stage_res) {
+                const uint64_t b0 = off[2 * lo2], nb = off[2 * (lo2 + n)] - b0;
+                if (!pre[c].res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+                memcpy(pre[c].res.p, in->residues + b0, nb);
+            }
             const auto t0 = std::chrono::steady_clock::now();
             pre[c].rc = build_plan(ctx, off + 2 * lo2, off[2 * lo2], n, false, 0, 0, 0, pre[c].plan, pre[c].stage.as<PairDesc>(), lut != nullptr);
             if (pre[c].rc == BG_OK && !no_compact) {
@@ -1976,7 +2000,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(std::max<uint64_t>(1, n) * 8)) {
             ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM;
         }
-        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
+        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, stage_res ? (const uint8_t*)pre[c].res.p : in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
         const size_t slot_bytes = P.compact ? sizeof(MyersSlot) : sizeof(PairDesc);
         if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * slot_bytes, cudaMemcpyHostToDevice, st_h2d));
         CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
@@ -2017,7 +2041,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_d2h);
     for (int s = 0; s < PIPE_DEPTH; ++s) cudaStreamSynchronize(dv.ws[s].stream);
     for (auto& h : host_out) h.release();
-    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); }
+    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); pb.res.release(); }
     for (int s = 0; s < PIPE_DEPTH; ++s) { dv.ws[s].stream = saved[s]; cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); }
     return rc_all;
 }
