@@ -173,6 +173,7 @@ struct WorkSet {
     cudaStream_t stream = nullptr;
     cudaStream_t walk_stream = nullptr;   // traceback walks of chunk c run here, next to the fill of chunk c+1
     cudaStream_t post_stream = nullptr;   // host-buffer pipeline: walk + scan + gather of this set's chunk go here (next to the next chunk's fill)
+    uint64_t split_cap_words = (6ull << 30) / 4;   // all launches of a plan get their own trace region up to this total
     cudaStream_t fill2_stream = nullptr;  // host-buffer pipeline: every other fill launch of a chunk goes here, so that the tail of
                                           // one length class's launch overlaps the head of the next (their traces are disjoint)
     BlockCache* cache = nullptr;
@@ -1007,7 +1008,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     // (integer-pipe bound) overlaps the walk / scan / gather of the previous launch (latency bound, small
     // grids).  Every launch then needs its own trace region, which pipeline chunks can afford.
     const bool split = ws.post_stream != nullptr && !pp.score_only && P.max_wave_slots == 0 &&
-                       (n_chunks == 1 || P.total_trace_words <= (6ull << 30) / 4);
+                       (n_chunks == 1 || P.total_trace_words <= ws.split_cap_words);
     if (!pp.score_only) {
         ok = ok && ws.trace.ensure(std::max<uint64_t>(1, split ? P.total_trace_words : P.max_trace_words) * 4);
         ok = ok && ws.pad.ensure(std::max<uint64_t>(1, P.pad_bytes));
@@ -1384,12 +1385,29 @@ int bg_last_timing(const bg_ctx* cctx, bg_timing* out) {
         double ph[4] = {0, 0, 0, 0}, tot = 0;
         for (WorkSet& ws : dv.ws) {
             CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+            // A phase's time is the UNION of its kernels' intervals: launches of one phase can run side by side (fills
+            // alternate between two streams, walks run next to the following fill), and a sum would count that time twice.
+            std::vector<std::pair<double, double>> iv[4];
+            double t_min = 0, t_max = 0; bool any = false;
             for (auto& ev : ws.evs) {
-                float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
-                ph[ev.phase] += ms;
+                float s0 = 0, dur = 0;
+                cudaEventElapsedTime(&s0, ws.evs.front().a, ev.a); cudaEventElapsedTime(&dur, ev.a, ev.b);
+                iv[ev.phase].emplace_back((double)s0, (double)s0 + dur);
+                if (!any || s0 < t_min) t_min = s0;
+                if (!any || s0 + dur > t_max) t_max = (double)s0 + dur;
+                any = true;
                 if (ev.phase == 1) t.fill_launches++;
             }
-            if (!ws.evs.empty()) { float ms = 0; cudaEventElapsedTime(&ms, ws.evs.front().a, ws.evs.back().b); tot = std::max<double>(tot, ms); }
+            for (int k = 0; k < 4; ++k) {
+                std::sort(iv[k].begin(), iv[k].end());
+                double cur_a = 0, cur_b = -1;
+                for (auto& x : iv[k]) {
+                    if (cur_b < cur_a || x.first > cur_b) { if (cur_b > cur_a) ph[k] += cur_b - cur_a; cur_a = x.first; cur_b = x.second; }
+                    else cur_b = std::max(cur_b, x.second);
+                }
+                if (cur_b > cur_a) ph[k] += cur_b - cur_a;
+            }
+            if (any) tot = std::max<double>(tot, t_max - t_min);
         }
         // devices run concurrently: report the slowest
         t.encode_ms = std::max(t.encode_ms, ph[0]); t.fill_ms = std::max(t.fill_ms, ph[1]);
@@ -1522,7 +1540,25 @@ int bg_align_device(bg_ctx* ctx, const bg_dbatch* cin, const bg_params* p, bg_dr
     rc = upload_params(ctx, ws, pp);
     AlignIO io{B->residues.as<uint8_t>(), B->desc_align.as<PairDesc>(), &P, N,
                R->score.as<int32_t>(), R->flags.as<uint8_t>(), R->lens2.as<uint64_t>(), R->off.as<uint64_t>(), R->arena.as<uint8_t>()};
+    // Device-resident batches: when the traces of ALL launches fit next to each other (45 % of the device), every
+    // launch keeps its own trace region, so the walk / gather of launch c run on the high-priority stream next to
+    // the fill of launch c + 1 (the walk is a latency-bound chain of dependent loads that leaves the integer pipes
+    // idle) and the fills alternate between two streams.  The main stream then waits for the post stream, so that
+    // everything ordered after this call on the main stream -- the next call's fills included -- sees the results.
+    static const bool no_dev_split = getenv("BG_NO_DEV_SPLIT") != nullptr;
+    const uint64_t cap_saved = ws.split_cap_words;
+    const bool dev_split = !no_dev_split && !pp.score_only && P.max_wave_slots == 0 &&
+                           (double)P.total_trace_words * 4.0 <= 0.45 * (double)dv.total_mem;
+    if (dev_split) {
+        ws.post_stream = ws.walk_stream; ws.fill2_stream = dv.ws[1].stream;
+        ws.split_cap_words = P.total_trace_words;
+    }
     if (!rc) rc = run_align(ctx, ws, io, pp);
+    if (dev_split) {
+        cudaEvent_t evj = ws.get_event();
+        if (cudaEventRecord(evj, ws.post_stream) != cudaSuccess || cudaStreamWaitEvent(ws.stream, evj, 0) != cudaSuccess) { if (!rc) { ctx->set_error("stream join failed"); rc = BG_ECUDA; } }
+        ws.post_stream = nullptr; ws.fill2_stream = nullptr; ws.split_cap_words = cap_saved;
+    }
     if (rc) { bg_dresult_free(R); return rc; }
     *out = R;
     return BG_OK;
@@ -1815,7 +1851,7 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         size_t n_launch = 0;
         for (const LaunchClass& lc : P.classes) n_launch += lc.chunks.size();
         cudaStream_t st_last = (ws.post_stream && !pp.score_only && P.max_wave_slots == 0 &&
-                                (n_launch == 1 || P.total_trace_words <= (6ull << 30) / 4)) ? ws.post_stream : st_comp;
+                                (n_launch == 1 || P.total_trace_words <= ws.split_cap_words)) ? ws.post_stream : st_comp;
         if (!pp.score_only) {   // chunk-relative offsets -> offsets into the caller's arena, on the device
             if (st_last != st_post && st_post != st_comp) {   // keep the running base stream-ordered on st_post
                 CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_last));
