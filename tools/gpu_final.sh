@@ -1,4 +1,4 @@
-O=gpurun_out/r01c; mkdir -p $O
+O=gpurun_out/r01e; mkdir -p $O
 (time python -m pytest tests -m gpu -x -q) > $O/pytest.log 2>&1
 python __graft_entry__.py smoke > $O/smoke.log 2>&1
 python bench.py > $O/bench_cfg2.log 2>&1
