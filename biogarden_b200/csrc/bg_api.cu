@@ -2322,6 +2322,54 @@ int bg_p_distance_matrix(bg_ctx* ctx, const uint8_t* residues, const uint64_t* s
     return BG_OK;
 }
 
+// Host-only diagnostic (no CUDA call): plans a batch of long pairs (lens = n0, m0, n1, m1, ...) under a long-pair
+// trace budget and checks the bounded-memory layout it produces.  out[0] = launches (chunks with slots), out[1] =
+// bounded-memory chunks, out[2] = largest block count, out[3] = cells on the bounded path, out[4] = violations:
+// a chunk whose trace exceeds the budget, a block below 64 rows, a launch table whose blocks do not tile the pair's
+// rows exactly once bottom-up, or checkpoint regions that overlap.
+int bg_debug_plan_long(const uint64_t* lens, uint64_t n_pairs, uint64_t budget_bytes, uint64_t* out) {
+    if (!lens || !out) return BG_EINVAL_ARG;
+    bg_ctx ctx;
+    std::vector<uint64_t> off(2 * n_pairs + 1, 0);
+    for (uint64_t i = 0; i < 2 * n_pairs; ++i) off[i + 1] = off[i] + lens[i];
+    std::vector<PairDesc> dst(plan_desc_capacity(n_pairs));
+    Plan P;
+    const int rc = build_plan(&ctx, off.data(), 0, n_pairs, true, 8192ull << 18, budget_bytes / 4, 0, P, dst.data());
+    if (rc) return rc;
+    uint64_t launches = 0, ck_chunks = 0, max_nb = 0, viol = 0;
+    for (const LaunchClass& lc : P.classes)
+        for (const Chunk& ch : lc.chunks) {
+            const uint32_t ns = ch.slot_end - ch.slot_begin;
+            if (!ns) continue;
+            ++launches;
+            if (lc.wave && ch.trace_words * 4 > budget_bytes && !(ns == 1 && !ch.ckpt_nb)) ++viol;   // (one whole pair that fits nowhere else is checkpointed, never oversized)
+            if (!ch.ckpt_nb) continue;
+            ++ck_chunks; max_nb = std::max<uint64_t>(max_nb, ch.ckpt_nb);
+            if (ch.trace_words * 4 > budget_bytes) ++viol;
+            uint64_t next_off = 0;
+            for (uint32_t x = 0; x < ns; ++x) {
+                const PairDesc& d = dst[ch.slot_begin + x];
+                uint64_t covered = 0, expect_hi = d.n;
+                const CkptSlot& p1 = ch.ck_table[x];
+                if (p1.row0 != 0 || p1.nrows != d.n || p1.every < 64 || (p1.every & 31u)) ++viol;
+                if (p1.ck_off != next_off) ++viol;
+                next_off += (uint64_t)(ch.ckpt_nb - 1) * p1.ck_stride;
+                if (p1.ck_stride < d.m) ++viol;
+                if (d.steps != p1.every + 31u) ++viol;
+                for (uint32_t l = 1; l <= ch.ckpt_nb; ++l) {          // bottom-up
+                    const CkptSlot& e = ch.ck_table[(size_t)l * ns + x];
+                    if (e.nrows == 0) continue;
+                    if ((uint64_t)e.row0 + e.nrows != expect_hi || e.nrows > e.every || e.row0 % e.every) ++viol;
+                    expect_hi = e.row0; covered += e.nrows;
+                }
+                if (covered != d.n || expect_hi != 0) ++viol;
+            }
+            if (next_off != ch.ckpt_elems) ++viol;
+        }
+    out[0] = launches; out[1] = ck_chunks; out[2] = max_nb; out[3] = P.cells_ckpt; out[4] = viol;
+    return BG_OK;
+}
+
 // Page-lock / unlock caller memory (cudaHostRegister): the host-buffer entry points copy straight out of the
 // caller's residue arena, which is a true asynchronous DMA only when that memory is pinned; from pageable memory
 // the driver stages every copy synchronously (measured: see INTEGRATION.md).  A shim pins its arena once.

@@ -126,3 +126,42 @@ def test_batch_layout_and_odd_tile():
     assert b.n_pairs == 2 and list(b.seq_off) == [0, 3, 3, 4, 8] and b.cells() == 4
     with pytest.raises(InvalidInputSize):
         native.Batch.from_sequences([b"A", b"C", b"G"])
+
+
+def test_bounded_memory_plan_layout():
+    """The launch plan of long pairs under a trace budget (host logic of the bounded-memory traceback, no GPU):
+    with room for everything nothing is checkpointed; under a small budget pairs are grouped and cut into row
+    blocks of >= 64 rows whose traces fit the budget, every pair's blocks tile its rows exactly once bottom-up, the
+    checkpoint regions do not overlap; pairs that fit whole stay on the unbounded path."""
+    import ctypes as C
+    from biogarden_b200 import native
+    L = native.lib()
+    L.bg_debug_plan_long.restype = C.c_int
+    L.bg_debug_plan_long.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+
+    def plan(lens, budget):
+        a = np.array(lens, np.uint64).reshape(-1)
+        out = np.zeros(5, np.uint64)
+        assert L.bg_debug_plan_long(a.ctypes.data, len(a) // 2, budget, out.ctypes.data) == 0
+        return [int(x) for x in out]
+
+    pairs = [(5000, 4200), (2100, 9000), (6100, 4500), (300, 5000), (4096, 4097), (1000, 4100), (9000, 17000)]
+    cells = lambda ps: sum(n * m for n, m in ps)
+    launches, ck, nb, refilled, viol = plan(pairs, 100 << 30)
+    assert (ck, refilled, viol) == (0, 0, 0) and launches >= 1
+    launches, ck, nb, refilled, viol = plan(pairs, 1 << 20)
+    assert viol == 0 and ck >= 3 and nb >= 32 and refilled == cells(pairs) - 300 * 5000
+    launches, ck, nb, refilled, viol = plan(pairs, 6 << 20)
+    assert viol == 0 and ck == 1 and refilled == cells(pairs) - 1000 * 4100 - 300 * 5000
+    # cfg5-like: 40 pairs of 50-100 kbp under 16 GiB
+    rng = np.random.default_rng(5)
+    big = [(int(n), int(m)) for n, m in rng.integers(50_000, 100_001, size=(40, 2))]
+    launches, ck, nb, refilled, viol = plan(big, 16 << 30)
+    # the largest pairs (fewer than six of them fit together) are checkpointed, the smallest ones fit six at a time
+    assert viol == 0 and ck >= 1 and 0 < refilled < cells(big) and 2 <= nb <= 64
+    launches, ck, nb, refilled, viol = plan(big, 1 << 30)
+    assert viol == 0 and refilled == cells(big)
+    # a budget below one 64-row block of the widest pair is refused
+    a = np.array([(9000, 170000)], np.uint64).reshape(-1)
+    out = np.zeros(5, np.uint64)
+    assert L.bg_debug_plan_long(a.ctypes.data, 1, 1 << 20, out.ctypes.data) == native.BG_ENOMEM
