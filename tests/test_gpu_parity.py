@@ -479,3 +479,23 @@ def test_p_distance_matrix_vs_oracle():
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     with pytest.raises(IndexError):
         stat.p_distance_matrix(Tile([]))
+
+
+def test_user_closure_scorer(aligner):
+    """A scorer that is not one of the shipped tables (any `Fn(&u8,&u8)->i32`): match +5 /
+    mismatch -4 through the table materialisation, every mode, against the oracle driven by the same 256x256 table;
+    DNA (packed kernel for the non-local modes) and a 20-letter alphabet (int32 kernel, dense table in shared memory)."""
+    rng = random.Random(21)
+    problems = []
+    for alpha, max_len in ((b"ACGT", 300), (b"ACDEFGHIKLMNPQRSTVWY", 260)):
+        batch = _random_batch(rng, 300, alpha, max_len)
+        for mode, a, b in (("global", -10, -1), ("local", -6, -2), ("semiglobal", -3, -3), ("overlap", -5, -1), ("fitting", -10, -1)):
+            if mode == "fitting":
+                n, m = batch.lengths()
+                if np.any(n < m):
+                    continue
+            eng = _cmp.engine_align(aligner, batch, mode, None, a, b, match_mismatch=(5, -4))
+            ora = _cmp.oracle_align(batch, mode, None, a, b, match_mismatch=(5, -4))
+            problems += _cmp.diff(batch, eng, ora, "closure %s %s" % (mode, alpha[:4]))
+            eng.close()
+    assert not problems, "\n".join(problems)
