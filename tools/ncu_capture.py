@@ -1,6 +1,6 @@
 """One device-resident pass of a named workload at a given pair count -- the command ncu captures kernels from.
 
-  python tools/ncu_capture.py cfg2|cfg4|cfg4u|cfg5 N_PAIRS [REPS]
+  python tools/ncu_capture.py cfg2|cfg3|cfg4|cfg4u|cfg5 N_PAIRS [REPS]
 """
 import os
 import sys
@@ -14,6 +14,15 @@ WL = {"cfg2": ("cfg2_dna150_global", "global", score.unit, -2, -1),
       "cfg5": ("cfg5_long_semiglobal", "semiglobal", score.unit, -1, -1)}
 name, n = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+if name == "cfg3":        # edit distance, score only (bit-parallel kernel, one launch per 32-column-block class)
+    batch = synth.make("cfg3_edit_100_300", n_pairs=n)
+    from biogarden_b200 import native
+    ctx = native.Context([0])
+    db = ctx.upload(batch, 0, prepare="edit"); ctx.sync()
+    for i in range(reps):
+        r = ctx.edit_distance_device(db); ctx.sync(); tm = ctx.timing(); ctx.free_result(r)
+    print("cfg3 %d pairs, %d cells: fill %.3f ms (%d launches)" % (n, batch.cells(), tm["fill_ms"], tm["fill_launches"]))
+    sys.exit(0)
 if name == "cfg4u":      # one length class of config #4: uniform 600 aa protein pairs -> a single k1_fill<32,20,local> launch
     from biogarden_b200 import native
     mode, sc, a, b = "local", score.blosum62, -11, -1
