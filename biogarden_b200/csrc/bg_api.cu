@@ -30,15 +30,8 @@
 #include <thread>
 #include <vector>
 
-#include <cub/device/device_scan.cuh>
-
-#include "bg_common.cuh"
-#include "k1_fill.cuh"
-#include "k1h_fill.cuh"
-#include "k2_wave.cuh"
-#include "k3_walk.cuh"
-#include "k4_edit.cuh"
-#include "k5_distance.cuh"
+#include "bg_args.cuh"
+#include "launch.h"
 
 using namespace bg;
 
@@ -54,16 +47,10 @@ using namespace bg;
 
 namespace {
 
-struct Shape { int L, C; };
-
-// Kernel shapes compiled in: (lanes per pair, columns per lane).  A band is L*C columns.
-#define BG_SHAPES(X) \
-    X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 5) X(32, 8) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
 constexpr int MAX_SHAPES = 20;
 constexpr int PIPE_DEPTH = 6;
 // Pairs wider than this run on K2 (one pair per thread-block cluster, bands of 32 * WAVE_C columns).
 constexpr uint32_t WAVE_MIN_COLS = 4096;
-constexpr int WAVE_C = 16;
 
 // Size-keyed free lists so that steady-state calls never hit cudaMalloc / cudaFree / cudaHostAlloc
 // (each of which synchronises the device or pins pages: milliseconds to 100s of milliseconds).
@@ -731,90 +718,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     return BG_OK;
 }
 
-// ------------------------------------------------------------------------------ launches
-template <int L, int C>
-void launch_k1(bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a) {
-    if (local) {
-        if (prof4) k1_fill<L, C, true, true><<<grid, 128, smem, st>>>(a);
-        else k1_fill<L, C, true, false><<<grid, 128, smem, st>>>(a);
-    } else {
-        if (prof4) k1_fill<L, C, false, true><<<grid, 128, smem, st>>>(a);
-        else k1_fill<L, C, false, false><<<grid, 128, smem, st>>>(a);
-    }
-}
-void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a) {
-#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { launch_k1<L_, C_>(local, prof4, grid, smem, st, a); return; }
-    BG_SHAPES(X)
-#undef X
-}
-// K2 is launched COOPERATIVELY (all CTAs co-resident, which its spin waits need) as a persistent grid of
-// pair groups: Q consecutive CTAs work on one pair.  (Thread-block clusters would give the same
-// guarantee, but clusters of 4 must sit inside one GPC and strand 16 of the B200's 148 SMs:
-// 33 resident clusters instead of 37 groups -- measured, see profiles/.)
-#define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
-// Blocks per SM by columns per lane (registers ~ 4 C + 60; measured on cfg2: (16,10) with 6 blocks/SM and
-// 4 of the 8 accumulations on the ALU pipe fills 11 % faster than (8,19) with 3 blocks/SM).
-constexpr int k1h_minb(int C) { return C <= 10 ? 6 : C <= 12 ? 4 : C <= 24 ? 3 : 2; }
-bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a) {
-#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { \
-        if (track) k1h_fill<L_, C_, true, 0x55, k1h_minb(C_)><<<grid, 128, 0, st>>>(a); \
-        else k1h_fill<L_, C_, false, 0x55, k1h_minb(C_)><<<grid, 128, 0, st>>>(a); \
-        return true; }
-    BG_HALF_SHAPES(X)
-#undef X
-    return false;
-}
-
-// One-thread-per-pair walker with the launch's geometry compiled in (k3_walk.cuh).
-void dispatch_walk(Shape sh, bool half, uint32_t ns, cudaStream_t st, const WalkArgs& a) {
-    const dim3 grid((ns + 127) / 128);
-    if (half) {
-#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k3_walk<L_, C_, true><<<grid, 128, 0, st>>>(a); return; }
-        BG_HALF_SHAPES(X)
-#undef X
-    } else {
-#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k3_walk<L_, C_, false><<<grid, 128, 0, st>>>(a); return; }
-        BG_SHAPES(X)
-#undef X
-    }
-    k3_walk<0, 0, false><<<grid, 128, 0, st>>>(a);
-}
-
-template <class Kern>
-cudaError_t launch_k2_impl(Kern kern, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)n_cta);          // one CTA per SM (launch bounds: 1 block of 16 warps per SM)
-    cfg.blockDim = dim3(K2_WARPS * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a);
-}
-cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false) {
-    if (ckpt) {
-        if (local) {
-            if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true, true>, n_cta, smem, st, a);
-            return launch_k2_impl(k2_wave<WAVE_C, true, false, true>, n_cta, smem, st, a);
-        }
-        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true, true>, n_cta, smem, st, a);
-        return launch_k2_impl(k2_wave<WAVE_C, false, false, true>, n_cta, smem, st, a);
-    }
-    if (local) {
-        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_cta, smem, st, a);
-        return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_cta, smem, st, a);
-    }
-    if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_cta, smem, st, a);
-    return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_cta, smem, st, a);
-}
-void dispatch_k4(Shape sh, dim3 grid, cudaStream_t st, const EditArgs& a) {
-#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k4_edit<L_, C_><<<grid, 128, 0, st>>>(a); return; }
-    BG_SHAPES(X)
-#undef X
-}
-
+// ------------------------------------------------------------------------------ launches (launch.h, l_*.cu)
 struct Phase {
     WorkSet& ws; int phase; cudaEvent_t a;
     cudaStream_t st;
@@ -1110,8 +1014,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                         Phase ph(ws, 2);
                         wk.cks = wa.cks; wk.last_launch = (l == NB) ? 1u : 0u;
                         static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
-                        if (old_diag) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(wk);
-                        else k3_walk_skew<WAVE_C><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, st>>>(wk);
+                        launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, true, ns, st, wk);
                     }
                     CU_TRY(ctx, cudaGetLastError());
                 }
@@ -1151,7 +1054,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 cudaEvent_t pa = ws.get_event();
                 cudaEventRecord(pa, wst);
                 if (pp.score_only) {
-                    k_scores_only<<<(ns + 127) / 128, 128, 0, wst>>>(fa.desc, fa.end, ns, io.score, io.flags, pp.mode);
+                    launch_scores_only(fa.desc, fa.end, ns, io.score, io.flags, pp.mode, wst);
                 } else {
                     WalkArgs wa;
                     wa.desc = fa.desc; wa.end = fa.end; wa.n_slots = ns; wa.residues = fa.residues;
@@ -1164,14 +1067,9 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                         static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
                         // the window loaders map 8-column blocks onto trace words: need C % 8 == 0 (true for K2)
                         static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
-                        if (lc.ops_fmt && old_diag) {
-                            if (lc.sh.L == 32 && lc.sh.C == WAVE_C) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
-                            else k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, wst>>>(wa);
-                        }
-                        else if (lc.ops_fmt && lc.sh.L == 32 && lc.sh.C == WAVE_C) k3_walk_skew<WAVE_C><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, wst>>>(wa);
-                        else if (lc.ops_fmt) k3_walk_skew<0><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, wst>>>(wa);
-                        else if (walk_kind == 2 || (lc.sh.C & 7)) k3_walk_warp<<<(ns + 3) / 4, 128, 0, wst>>>(wa);
-                        else k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, wst>>>(wa);
+                        const bool k2geo = lc.sh.L == 32 && lc.sh.C == WAVE_C;
+                        if (lc.ops_fmt) launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, k2geo, ns, wst, wa);
+                        else launch_long_walk((walk_kind == 2 || (lc.sh.C & 7)) ? LW_WARP : LW_TILE, false, ns, wst, wa);
                     }
                     else dispatch_walk(lc.sh, lc.half, ns, wst, wa);
                 }
@@ -1190,24 +1088,21 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     if (!pp.score_only) {
         Phase ph(ws, 3, pst);
         size_t tmp = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
+        scan_lengths(nullptr, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
         if (!ws.cubtmp.ensure(tmp + 16)) { ctx->set_error("device allocation failed (scan)"); return BG_ENOMEM; }
-        cub::DeviceScan::ExclusiveSum(ws.cubtmp.p, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
+        scan_lengths(ws.cubtmp.p, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
         ctx->launches += 2;
         if (P.n_slots) {
             GatherArgs ga;
             ga.desc = io.desc; ga.n_slots = (uint32_t)P.n_slots; ga.pad = ws.pad.as<uint8_t>();
             ga.off = io.off; ga.arena = io.arena; ga.residues = io.residues;
-            k_gather<<<(unsigned)((P.n_slots + 3) / 4), 128, 0, pst>>>(ga);
+            launch_gather(ga, pst);
             ctx->launches++;
         }
         CU_TRY(ctx, cudaGetLastError());
     }
     return BG_OK;
 }
-
-template <int W>
-void launch_myers(uint32_t ns, cudaStream_t st, const MyersArgs& a) { k4_myers<W><<<(ns + 127) / 128, 128, 0, st>>>(a); }
 
 // lut: host [256] byte -> code 0..3 / 0xFF, only needed when the plan has K4b classes.
 int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* desc, const Plan& P, uint64_t* out,
@@ -1230,9 +1125,7 @@ int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* 
                 ma.desc = desc + ch.slot_begin; ma.n_slots = ns; ma.residues = residues; ma.lut = ws.codes.as<uint8_t>();
                 ma.cdesc = P.compact ? reinterpret_cast<const MyersSlot*>(desc) + ch.slot_begin : nullptr;
                 ma.out = out; ma.err_flag = ws.err.as<uint32_t>();
-                if (lc.myers_W == 4) launch_myers<4>(ns, ws.stream, ma);
-                else if (lc.myers_W == 8) launch_myers<8>(ns, ws.stream, ma);
-                else launch_myers<10>(ns, ws.stream, ma);
+                launch_myers(lc.myers_W, ns, ws.stream, ma);
             } else {
                 ea.desc = desc + ch.slot_begin; ea.n_slots = ns;
                 const uint32_t nwarps = (ns + G - 1) / G;
@@ -1483,7 +1376,7 @@ static int ensure_plan(bg_ctx* ctx, bg_dbatch* B, bool edit, int32_t half_maxabs
         // which byte values occur at all?  (<= 4 -> bit-parallel K4b)
         if (!ws.cubtmp.ensure(1024) || !ws.scalars.ensure(1024)) { stage.release(); ctx->set_error("allocation failed"); return BG_ENOMEM; }
         CU_TRY(ctx, cudaMemsetAsync(ws.cubtmp.p, 0, 1024, ws.stream));
-        k_byte_hist<<<ctx->num_sms * 4, 256, 0, ws.stream>>>(B->residues.as<uint8_t>(), B->n_residues, ws.cubtmp.as<unsigned int>());
+        launch_byte_hist(B->residues.as<uint8_t>(), B->n_residues, ws.cubtmp.as<unsigned int>(), ctx->num_sms * 4, ws.stream);
         CU_TRY(ctx, cudaMemcpyAsync(ws.scalars.p, ws.cubtmp.p, 1024, cudaMemcpyDeviceToHost, ws.stream));
         CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
         uint64_t hist[256];
@@ -1858,8 +1751,8 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
                 CU_TRY(ctx, cudaStreamWaitEvent(st_post, ev_comp[s], 0));
                 st_last = st_post;
             }
-            k_rebase<<<(unsigned)((2 * n + 1 + 255) / 256), 256, 0, st_last>>>(ws.off.as<uint64_t>(), 2 * n + 1, d_base);
-            k_bump<<<1, 1, 0, st_last>>>(d_base, ws.off.as<uint64_t>() + 2 * n, ws.run.as<uint64_t>());
+            launch_rebase(ws.off.as<uint64_t>(), 2 * n + 1, d_base, st_last);
+            launch_bump(d_base, ws.off.as<uint64_t>() + 2 * n, ws.run.as<uint64_t>(), st_last);
             CU_TRY(ctx, cudaGetLastError());
             ctx->launches += 2;
         } else {
@@ -2249,11 +2142,9 @@ int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
             {
                 Phase ph(ws, 1);     // bg_last_timing().fill_ms = the compare kernel alone
                 if (pieces == n) {   // no pair longer than one piece: one lane group per pair
-                    if (max_len <= 256) k5_hamming_direct<8><<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(ha);
-                    else if (max_len <= 1024) k5_hamming_direct<16><<<(unsigned)((n * 16 + 255) / 256), 256, 0, st>>>(ha);
-                    else k5_hamming_direct<32><<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(ha);
+                    launch_hamming_direct(max_len <= 256 ? 8 : max_len <= 1024 ? 16 : 32, n, st, ha);
                 } else {
-                    k5_hamming<<<(unsigned)std::max<uint64_t>(1, blocks), 256, 0, st>>>(ha, ws.lens2.as<uint64_t>(), pieces);
+                    launch_hamming_pieces((unsigned)std::max<uint64_t>(1, blocks), st, ha, ws.lens2.as<uint64_t>(), pieces);
                 }
             }
             e = cudaGetLastError();
@@ -2310,7 +2201,7 @@ int bg_p_distance_matrix(bg_ctx* ctx, const uint8_t* residues, const uint64_t* s
         PDistArgs pa{ws.residues.as<uint8_t>(), ws.off.as<uint64_t>(), rows, (float)(seq_off[1] - seq_off[0]), ws.arena.as<float>()};
         const uint64_t items = rows * (rows + 1) / 2;
         const uint64_t blocks = std::min<uint64_t>((items + 7) / 8, (uint64_t)ctx->num_sms * 8);
-        k5_pdist<<<(unsigned)std::max<uint64_t>(1, blocks), 256, 0, st>>>(pa);
+        launch_pdist((unsigned)std::max<uint64_t>(1, blocks), st, pa);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, ws.arena.p, rows * rows * 4, cudaMemcpyDeviceToHost, st);

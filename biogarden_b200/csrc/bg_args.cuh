@@ -1,0 +1,146 @@
+// bg_args.cuh -- kernel argument structs and launch constants shared by the host side (bg_api.cu) and the
+// kernel translation units (l_*.cu); the kernels themselves live in k*.cuh, each included by exactly one l_*.cu.
+#pragma once
+#include "bg_common.cuh"
+
+namespace bg {
+
+struct FillArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* residues;
+    const int32_t* table;      // n_rows x n_cols (device)
+    int32_t n_rows, n_cols;
+    const uint8_t* row_code;   // [256] (device)
+    const uint8_t* col_code;   // [256]
+    int32_t a, b;              // gap open / extend
+    int32_t mode;
+    int32_t want_trace;
+    uint32_t* trace;
+    int2* bnd;
+    EndCell* end;
+    uint32_t* err_flag;        // bit 0: residue without a table row/column
+    int32_t one;               // == 1 at run time; keeps the FMA-pipe adds below as IMADs (see k1_fill)
+    int32_t tg_shift;          // K1h trace tiling (k1h_fill.cuh)
+};
+
+// ---- K1h (k1h_fill.cuh) ----
+constexpr int32_t HB_BIAS = 1 << 15;
+constexpr int32_t HB_NEG = 1 << 8;       // biased "minus infinity": below every value a cell can take (>= 2^15 - 2*HB_RANGE - 3*HB_MAXABS)
+constexpr int32_t HB_RANGE = 15000;      // max (len1 + len2 + 2) * max|score| the host admits: |H| and the frame shift each stay below it
+constexpr int32_t HB_MAXABS = 512;       // max |a|, |b|, |s|
+constexpr int HB_TB = 4;                 // systolic steps per trace row block
+constexpr int HB_TG_MAX = 4;             // FillArgs::tg_shift <= 2: 2^tg_shift row blocks of one lane are stored back to back
+__host__ __device__ inline uint32_t hb_words_per_lane_block(int C) { return (uint32_t)((C + 3) & ~3); }
+
+// ---- K2 (k2_wave.cuh) ----
+struct WaveCand {          // one worker's end-cell candidates (SURVEY A.5 tie rules applied when merged)
+    int32_t best; uint32_t bi, bj;        // local
+    int32_t rbest; uint32_t rj;           // last row, last max
+    int32_t cbest; uint32_t ci;           // last column, first max (valid iff has_col)
+    int32_t corner;                       // M[n][m] (valid iff has_col)
+    uint32_t has_col;
+    uint32_t pad_[7];
+};
+static_assert(sizeof(WaveCand) == 64, "WaveCand layout");
+// Which pair a CTA works on in round r of a launch, as which member of the pair's CTA group.  The host
+// sizes the groups in proportion to the pairs' cell counts (a launch holds only as many pairs as their
+// traces fit in memory -- about as many as the machine has SMs / 4 -- so equal groups would leave the SMs
+// of the small pairs idle until the largest pair is done) and hands every CTA its list.
+struct WaveAssign { uint32_t slot; uint16_t rank; uint16_t Q; };   // Q == 0: idle in this round
+struct WaveArgs {
+    FillArgs f;
+    unsigned long long* progress;   // [slot][prog_stride], zeroed before launch
+    WaveCand* cand;                 // [slot][cand_stride]
+    uint32_t* done;                 // [slot] workers that have finished the pair (zeroed before launch)
+    uint32_t* next_band;            // [slot] next unclaimed band of the pair (zeroed before launch)
+    const WaveAssign* assign;       // [n_rounds][gridDim.x]
+    uint32_t n_rounds;
+    uint32_t prog_stride;           // >= max(Q) * K2_WARPS + 1
+    uint32_t cand_stride;           // >= max(Q) * K2_WARPS
+    // ---- bounded-memory traceback (k2_wave<.., CKPT = true> only) ----
+    const CkptSlot* cks;            // [slot]: the row block this launch fills, where the slot's checkpoints live
+    uint32_t ckpt_write;            // pass 1: store the checkpoints; pass 2: 0
+    uint32_t write_end;             // pass 1: publish the end cell; pass 2: 0
+    int2* ckpt;                     // per slot [row block][ck_stride]: (M + a, X) of row (block + 1) * every, by 0-based column
+    const WalkState* wstate;        // pass 2: skip pairs whose walk has already ended
+};
+constexpr int K2_MAX_Q = 13;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
+constexpr int K2_WARPS = 16;        // warps per CTA
+
+// ---- K3 (k3_walk.cuh) ----
+struct WalkArgs {
+    const PairDesc* desc;
+    const EndCell* end;
+    uint32_t n_slots;
+    const uint8_t* residues;
+    const uint32_t* trace;
+    int32_t mode;
+    int32_t L, C;           // geometry K1 used for this launch
+    int32_t H;              // pairs per lane group: 1 (K1 / K2) or 2 (K1h, packed 16 x 2)
+    int32_t tg_shift;       // K1h trace tiling
+    int32_t CW;             // 0: step-major trace words (bg_common.cuh); > 0: K1h row blocks, CW words per lane and block (k1h_fill.cuh)
+    uint8_t* pad;           // padded output slots
+    int32_t* score;         // [pair]
+    uint8_t* walk_flags;    // [pair]
+    uint64_t* lens2;        // [2*pairs + 1]: lens2[2p] = lens2[2p+1] = aligned length
+    // bounded-memory traceback (k3_walk_diag only): the trace holds DP rows row0 + 1 .. of the pair; the walk is
+    // resumed from / suspended into wstate[slot] when it reaches row row0 > 0
+    const CkptSlot* cks = nullptr;
+    WalkState* wstate = nullptr;
+    uint32_t last_launch = 0;   // row block 0: every walk that is still open ends here
+};
+struct GatherArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* pad;
+    const uint64_t* off;   // exclusive scan of lens2
+    uint8_t* arena;
+    const uint8_t* residues;
+};
+
+// ---- K4 (k4_edit.cuh) ----
+struct EditArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* residues;
+    int32_t* bnd;        // band-boundary column scratch (multi-band pairs only), int32 per row
+    uint64_t* out;       // [pair]
+};
+// Compact launch slot of the host pipeline (16 bytes instead of PairDesc's 64: the pipeline is bound by the H2D
+// copy): seq2 follows seq1 in the arena, so b_off = a_off + n; m <= 320 in the bit-parallel classes.
+struct __align__(16) MyersSlot {
+    uint32_t a_off_lo; uint32_t pair_id;   // pair_id 0xFFFFFFFF = empty slot
+    uint32_t n; uint16_t m; uint16_t a_off_hi;
+};
+static_assert(sizeof(MyersSlot) == 16, "MyersSlot layout");
+struct MyersArgs {
+    const PairDesc* desc;
+    const MyersSlot* cdesc;  // != nullptr: compact slots instead of desc
+    uint32_t n_slots;
+    const uint8_t* residues;
+    const uint8_t* lut;      // [256] byte -> code 0..3, 0xFF = not in the 4-symbol alphabet (device)
+    uint64_t* out;           // [pair]
+    uint32_t* err_flag;      // bit 1: a byte outside the alphabet was met (the caller then reruns with K4)
+};
+
+// ---- K5 (k5_distance.cuh) ----
+struct HammingArgs {
+    const uint8_t* residues;
+    const uint64_t* seq_off;   // [2 * n_pairs + 1], relative to residues
+    uint64_t n_pairs;
+    uint64_t* out;             // [n_pairs]
+    uint32_t* err_flag;        // bit 1: a pair with len1 != len2 (the reference returns Err(InvalidInputSize))
+};
+// One warp per pair; pairs longer than HAM_SPLIT bytes are cut into pieces handled by different warps of a grid-
+// stride loop and accumulated with one atomic per piece (out zeroed before launch).
+constexpr uint64_t HAM_SPLIT = 1u << 16;
+struct PDistArgs {
+    const uint8_t* residues;
+    const uint64_t* seq_off;   // [rows + 1]
+    uint64_t rows;
+    float columns;             // (columns as f32) = len of row 0 (stat.rs:139,147)
+    float* out;                // rows x rows, row-major
+};
+
+}  // namespace bg

@@ -24,28 +24,10 @@
 //   * pairs longer than one band loop over bands; the band's last column (M, Y) per row goes
 //     through a small global scratch column (written by lane L-1, prefetched by lane 0).
 #pragma once
-#include "bg_common.cuh"
+#include "bg_args.cuh"
 
 namespace bg {
 
-struct FillArgs {
-    const PairDesc* desc;
-    uint32_t n_slots;
-    const uint8_t* residues;
-    const int32_t* table;      // n_rows x n_cols (device)
-    int32_t n_rows, n_cols;
-    const uint8_t* row_code;   // [256] (device)
-    const uint8_t* col_code;   // [256]
-    int32_t a, b;              // gap open / extend
-    int32_t mode;
-    int32_t want_trace;
-    uint32_t* trace;
-    int2* bnd;
-    EndCell* end;
-    uint32_t* err_flag;        // bit 0: residue without a table row/column
-    int32_t one;               // == 1 at run time; keeps the FMA-pipe adds below as IMADs (see k1_fill)
-    int32_t tg_shift;          // K1h trace tiling (k1h_fill.cuh)
-};
 
 __device__ __forceinline__ int32_t prmt_sx(uint32_t packed, uint32_t sel) {
     int32_t d;

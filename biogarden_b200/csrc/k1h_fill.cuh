@@ -44,20 +44,13 @@
 // Restrictions (the host falls back to K1 otherwise -- still GPU, never CPU): not local mode,
 // <= 4 distinct residues per side, single band, (len1 + len2 + 2) * max|score| <= HB_RANGE.
 #pragma once
-#include "bg_common.cuh"
+#include "bg_args.cuh"
 #include "k1_fill.cuh"
 
 namespace bg {
 
-constexpr int32_t HB_BIAS = 1 << 15;
-constexpr int32_t HB_NEG = 1 << 8;       // biased "minus infinity": below every value a cell can take (>= 2^15 - 2*HB_RANGE - 3*HB_MAXABS)
-constexpr int32_t HB_RANGE = 15000;      // max (len1 + len2 + 2) * max|score| the host admits: |H| and the frame shift each stay below it
-constexpr int32_t HB_MAXABS = 512;       // max |a|, |b|, |s|
-constexpr int HB_TB = 4;                 // systolic steps per trace row block
-constexpr int HB_TG_MAX = 4;             // FillArgs::tg_shift <= 2: 2^tg_shift row blocks of one lane are stored back to back
 // HB_PIPES (template argument below): two bits per max (X, Y, m1, M): low / high half accumulates on the ALU pipe
 
-__host__ __device__ inline uint32_t hb_words_per_lane_block(int C) { return (uint32_t)((C + 3) & ~3); }
 
 __device__ __forceinline__ uint32_t hb_pack(int32_t v) { return (uint32_t)v * 65537u; }   // same value in both halves
 __device__ __forceinline__ int32_t hb_half(uint32_t v, int h) { return (int32_t)((v >> (16 * h)) & 0xffffu); }

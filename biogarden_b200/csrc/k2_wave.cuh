@@ -29,48 +29,15 @@
 #pragma once
 #include <cooperative_groups.h>
 
-#include "bg_common.cuh"
+#include "bg_args.cuh"
 #include "k1_fill.cuh"
 
 namespace bg {
 
-struct WaveCand {          // one worker's end-cell candidates (SURVEY A.5 tie rules applied when merged)
-    int32_t best; uint32_t bi, bj;        // local
-    int32_t rbest; uint32_t rj;           // last row, last max
-    int32_t cbest; uint32_t ci;           // last column, first max (valid iff has_col)
-    int32_t corner;                       // M[n][m] (valid iff has_col)
-    uint32_t has_col;
-    uint32_t pad_[7];
-};
-static_assert(sizeof(WaveCand) == 64, "WaveCand layout");
 
-// Which pair a CTA works on in round r of a launch, as which member of the pair's CTA group.  The host
-// sizes the groups in proportion to the pairs' cell counts (a launch holds only as many pairs as their
-// traces fit in memory -- about as many as the machine has SMs / 4 -- so equal groups would leave the SMs
-// of the small pairs idle until the largest pair is done) and hands every CTA its list.
-struct WaveAssign { uint32_t slot; uint16_t rank; uint16_t Q; };   // Q == 0: idle in this round
 
-struct WaveArgs {
-    FillArgs f;
-    unsigned long long* progress;   // [slot][prog_stride], zeroed before launch
-    WaveCand* cand;                 // [slot][cand_stride]
-    uint32_t* done;                 // [slot] workers that have finished the pair (zeroed before launch)
-    uint32_t* next_band;            // [slot] next unclaimed band of the pair (zeroed before launch)
-    const WaveAssign* assign;       // [n_rounds][gridDim.x]
-    uint32_t n_rounds;
-    uint32_t prog_stride;           // >= max(Q) * K2_WARPS + 1
-    uint32_t cand_stride;           // >= max(Q) * K2_WARPS
-    // ---- bounded-memory traceback (k2_wave<.., CKPT = true> only) ----
-    const CkptSlot* cks;            // [slot]: the row block this launch fills, where the slot's checkpoints live
-    uint32_t ckpt_write;            // pass 1: store the checkpoints; pass 2: 0
-    uint32_t write_end;             // pass 1: publish the end cell; pass 2: 0
-    int2* ckpt;                     // per slot [row block][ck_stride]: (M + a, X) of row (block + 1) * every, by 0-based column
-    const WalkState* wstate;        // pass 2: skip pairs whose walk has already ended
-};
 
-constexpr int K2_MAX_Q = 13;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
 
-constexpr int K2_WARPS = 16;        // warps per CTA
 
 // Boundary hand-over flags: release / acquire at GPU scope on the counter itself.  The producer's 32
 // lanes write their block, __syncwarp() orders those writes before lane 0's release store; the consumer's

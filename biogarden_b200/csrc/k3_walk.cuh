@@ -11,7 +11,7 @@
 // Characters are produced back to front into a padded slot of 2*round_up(n+m,4) bytes; k_gather then
 // packs all strings densely (offsets from a device-side scan of the lengths).
 #pragma once
-#include "bg_common.cuh"
+#include "bg_args.cuh"
 
 namespace bg {
 
@@ -19,27 +19,6 @@ namespace bg {
 #define K3_MINB 16
 #endif
 
-struct WalkArgs {
-    const PairDesc* desc;
-    const EndCell* end;
-    uint32_t n_slots;
-    const uint8_t* residues;
-    const uint32_t* trace;
-    int32_t mode;
-    int32_t L, C;           // geometry K1 used for this launch
-    int32_t H;              // pairs per lane group: 1 (K1 / K2) or 2 (K1h, packed 16 x 2)
-    int32_t tg_shift;       // K1h trace tiling
-    int32_t CW;             // 0: step-major trace words (bg_common.cuh); > 0: K1h row blocks, CW words per lane and block (k1h_fill.cuh)
-    uint8_t* pad;           // padded output slots
-    int32_t* score;         // [pair]
-    uint8_t* walk_flags;    // [pair]
-    uint64_t* lens2;        // [2*pairs + 1]: lens2[2p] = lens2[2p+1] = aligned length
-    // bounded-memory traceback (k3_walk_diag only): the trace holds DP rows row0 + 1 .. of the pair; the walk is
-    // resumed from / suspended into wstate[slot] when it reaches row row0 > 0
-    const CkptSlot* cks = nullptr;
-    WalkState* wstate = nullptr;
-    uint32_t last_launch = 0;   // row block 0: every walk that is still open ends here
-};
 
 // LT / CT != 0: the launch's geometry as compile-time constants (HALF: K1h's packed row-block layout).  The cell
 // address is two divisions and a handful of multiplies by the geometry; with run-time operands that was most
@@ -871,14 +850,6 @@ __global__ void k_bump(uint64_t* base, const uint64_t* chunk_total_entry, uint64
 // a copy for the long-pair walkers (character slots), and for k3_walk's op slots (PairDesc::pad_ == 1) the
 // materialisation -- op q reads seq1[first_a + #(ops before q that consume seq1)] resp. seq2 likewise, the
 // counts coming from warp ballots.
-struct GatherArgs {
-    const PairDesc* desc;
-    uint32_t n_slots;
-    const uint8_t* pad;
-    const uint64_t* off;   // exclusive scan of lens2
-    uint8_t* arena;
-    const uint8_t* residues;
-};
 
 __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
     const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

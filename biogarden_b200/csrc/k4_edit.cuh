@@ -6,17 +6,10 @@
 // on raw bytes (the reference compares bytes, any alphabet).  The reference's u128 table is an
 // artefact of its container type: distances are bounded by max(len1, len2) < 2^32.
 #pragma once
-#include "bg_common.cuh"
+#include "bg_args.cuh"
 
 namespace bg {
 
-struct EditArgs {
-    const PairDesc* desc;
-    uint32_t n_slots;
-    const uint8_t* residues;
-    int32_t* bnd;        // band-boundary column scratch (multi-band pairs only), int32 per row
-    uint64_t* out;       // [pair]
-};
 
 template <int L, int C>
 __global__ void __launch_bounds__(128) k4_edit(const EditArgs A) {
@@ -117,23 +110,7 @@ __global__ void __launch_bounds__(128) k4_edit(const EditArgs A) {
 // len2 > 32 * W or richer alphabets take the systolic kernel above.
 namespace bg {
 
-// Compact launch slot of the host pipeline (16 bytes instead of PairDesc's 64: the pipeline is bound by the H2D
-// copy): seq2 follows seq1 in the arena, so b_off = a_off + n; m <= 320 in the bit-parallel classes.
-struct __align__(16) MyersSlot {
-    uint32_t a_off_lo; uint32_t pair_id;   // pair_id 0xFFFFFFFF = empty slot
-    uint32_t n; uint16_t m; uint16_t a_off_hi;
-};
-static_assert(sizeof(MyersSlot) == 16, "MyersSlot layout");
 
-struct MyersArgs {
-    const PairDesc* desc;
-    const MyersSlot* cdesc;  // != nullptr: compact slots instead of desc
-    uint32_t n_slots;
-    const uint8_t* residues;
-    const uint8_t* lut;      // [256] byte -> code 0..3, 0xFF = not in the 4-symbol alphabet (device)
-    uint64_t* out;           // [pair]
-    uint32_t* err_flag;      // bit 1: a byte outside the alphabet was met (the caller then reruns with K4)
-};
 
 template <int W>
 __global__ void __launch_bounds__(128) k4_myers(const MyersArgs A) {

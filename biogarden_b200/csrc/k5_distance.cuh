@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bg_args.cuh"
+
 namespace bg {
 
 __host__ __device__ __forceinline__ uint64_t umin64(uint64_t x, uint64_t y) { return x < y ? x : y; }
@@ -64,17 +66,7 @@ __device__ __forceinline__ uint32_t warp_mismatches(const uint8_t* a, const uint
     return group_mismatches<32>(a, b, len, lane);
 }
 
-struct HammingArgs {
-    const uint8_t* residues;
-    const uint64_t* seq_off;   // [2 * n_pairs + 1], relative to residues
-    uint64_t n_pairs;
-    uint64_t* out;             // [n_pairs]
-    uint32_t* err_flag;        // bit 1: a pair with len1 != len2 (the reference returns Err(InvalidInputSize))
-};
 
-// One warp per pair; pairs longer than HAM_SPLIT bytes are cut into pieces handled by different warps of a grid-
-// stride loop and accumulated with one atomic per piece (out zeroed before launch).
-constexpr uint64_t HAM_SPLIT = 1u << 16;
 
 __global__ void __launch_bounds__(256) k5_hamming(const HammingArgs A, const uint64_t* piece_first /* [n_pairs + 1] */, uint64_t n_pieces) {
     const uint32_t lane = threadIdx.x & 31;
@@ -113,13 +105,6 @@ __global__ void __launch_bounds__(256) k5_hamming_direct(const HammingArgs A) {
     if (p < A.n_pairs && lane == 0) A.out[p] = c;
 }
 
-struct PDistArgs {
-    const uint8_t* residues;
-    const uint64_t* seq_off;   // [rows + 1]
-    uint64_t rows;
-    float columns;             // (columns as f32) = len of row 0 (stat.rs:139,147)
-    float* out;                // rows x rows, row-major
-};
 
 // One warp per unordered pair (i, j), i < j: count over the zip of the two rows (zip stops at the shorter one,
 // stat.rs:145), divide in f32 exactly as the reference does (IEEE division, round to nearest), write both

@@ -1,0 +1,55 @@
+// l_k3.cu -- instantiations of K3 (k3_walk.cuh): traceback walks, string assembly, offset scan.
+#include <cub/device/device_scan.cuh>
+
+#include "launch.h"
+#include "k3_walk.cuh"
+
+namespace bg {
+
+// One-thread-per-pair walker with the launch's geometry compiled in.
+void dispatch_walk(Shape sh, bool half, uint32_t ns, cudaStream_t st, const WalkArgs& a) {
+    const dim3 grid((ns + 127) / 128);
+    if (half) {
+#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k3_walk<L_, C_, true><<<grid, 128, 0, st>>>(a); return; }
+        BG_HALF_SHAPES(X)
+#undef X
+    } else {
+#define X(L_, C_) if (sh.L == L_ && sh.C == C_) { k3_walk<L_, C_, false><<<grid, 128, 0, st>>>(a); return; }
+        BG_SHAPES(X)
+#undef X
+    }
+    k3_walk<0, 0, false><<<grid, 128, 0, st>>>(a);
+}
+
+// Long pairs: one warp per pair.  k2_geometry: the (32 lanes x WAVE_C columns) geometry as compile-time constants.
+void launch_long_walk(LongWalk kind, bool k2_geometry, uint32_t ns, cudaStream_t st, const WalkArgs& a) {
+    switch (kind) {
+    case LW_SKEW:
+        if (k2_geometry) k3_walk_skew<WAVE_C><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, st>>>(a);
+        else k3_walk_skew<0><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, st>>>(a);
+        break;
+    case LW_DIAG:
+        if (k2_geometry) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(a);
+        else k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(a);
+        break;
+    case LW_TILE: k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, st>>>(a); break;
+    default: k3_walk_warp<<<(ns + 3) / 4, 128, 0, st>>>(a); break;
+    }
+}
+
+void launch_scores_only(const PairDesc* desc, const EndCell* end, uint32_t ns, int32_t* score, uint8_t* flags, int mode, cudaStream_t st) {
+    k_scores_only<<<(ns + 127) / 128, 128, 0, st>>>(desc, end, ns, score, flags, mode);
+}
+void launch_gather(const GatherArgs& a, cudaStream_t st) { k_gather<<<(unsigned)((a.n_slots + 3) / 4), 128, 0, st>>>(a); }
+void launch_rebase(uint64_t* off, uint64_t count, const uint64_t* base, cudaStream_t st) {
+    k_rebase<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(off, count, base);
+}
+void launch_bump(uint64_t* base, const uint64_t* chunk_total_entry, uint64_t* chunk_total_out, cudaStream_t st) {
+    k_bump<<<1, 1, 0, st>>>(base, chunk_total_entry, chunk_total_out);
+}
+// Exclusive scan of the aligned lengths (tmp == nullptr: size query)
+cudaError_t scan_lengths(void* tmp, size_t& tmp_bytes, const uint64_t* lens, uint64_t* off, int count, cudaStream_t st) {
+    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lens, off, count, st);
+}
+
+}  // namespace bg

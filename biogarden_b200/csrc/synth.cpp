@@ -2,7 +2,7 @@
 //
 // Every pair has its own splitmix64 stream derived from (seed, pair index), so any rank can
 // generate any sub-range of a workload and get the same bytes as a single-process run.
-#include "../../include/bgalign.h"
+#include "../../include/bgsynth.h"
 
 #include <algorithm>
 #include <thread>
@@ -61,7 +61,7 @@ inline void gen_pair(uint64_t seed, uint64_t pair, const char* alpha, uint32_t n
 extern "C" int bg_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pairs, const char* alphabet, int alphabet_len,
                               uint32_t len_lo, uint32_t len_hi, int resize_b,
                               uint8_t* residues, uint64_t* seq_off, uint64_t* n_residues) {
-    if (!alphabet || alphabet_len <= 0 || len_hi < len_lo || !seq_off) return BG_EINVAL_ARG;
+    if (!alphabet || alphabet_len <= 0 || len_hi < len_lo || !seq_off) return 5;   /* BG_EINVAL_ARG */
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
     nt = (unsigned)std::min<uint64_t>(nt, std::max<uint64_t>(1, n_pairs / 4096));
@@ -93,30 +93,5 @@ extern "C" int bg_synth_pairs(uint64_t seed, uint64_t first_pair, uint64_t n_pai
     }
     if (n_residues) *n_residues = seq_off[2 * n_pairs];
     if (residues) pass(true);
-    return BG_OK;
-}
-
-extern "C" int bg_residue_histogram(const bg_batch* in, uint64_t* hist_a, uint64_t* hist_b) {
-    if (!in || !hist_a || !hist_b || (in->n_pairs && (!in->seq_off || !in->residues))) return BG_EINVAL_ARG;
-    for (int i = 0; i < 256; ++i) hist_a[i] = hist_b[i] = 0;
-    const uint64_t N = in->n_pairs;
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt == 0) nt = 1;
-    nt = (unsigned)std::min<uint64_t>(nt, std::max<uint64_t>(1, N / 8192));
-    std::vector<std::vector<uint64_t>> part(nt, std::vector<uint64_t>(512, 0));
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) {
-        const uint64_t lo = N * t / nt, hi = N * (t + 1) / nt;
-        th.emplace_back([&, t, lo, hi] {
-            uint64_t* h = part[t].data();
-            for (uint64_t p = lo; p < hi; ++p) {
-                for (uint64_t x = in->seq_off[2 * p]; x < in->seq_off[2 * p + 1]; ++x) h[in->residues[x]]++;
-                for (uint64_t x = in->seq_off[2 * p + 1]; x < in->seq_off[2 * p + 2]; ++x) h[256 + in->residues[x]]++;
-            }
-        });
-    }
-    for (auto& x : th) x.join();
-    for (unsigned t = 0; t < nt; ++t)
-        for (int i = 0; i < 256; ++i) { hist_a[i] += part[t][i]; hist_b[i] += part[t][256 + i]; }
-    return BG_OK;
+    return 0;
 }

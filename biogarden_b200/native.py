@@ -56,7 +56,7 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status", "bg_synth_pairs"]
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status"]
 
 _lib = None
 
@@ -104,8 +104,6 @@ def lib():
     L.bg_score_table26.restype = C.POINTER(C.c_int8); L.bg_score_table26.argtypes = [C.c_char_p]
     L.bg_residue_histogram.restype = ci; L.bg_residue_histogram.argtypes = [C.POINTER(bg_batch), vp, vp]
     L.bg_ref_status.restype = ci; L.bg_ref_status.argtypes = [ci, u64, u64, i32, ci]
-    L.bg_synth_pairs.restype = ci
-    L.bg_synth_pairs.argtypes = [u64, u64, u64, C.c_char_p, ci, u32, u32, ci, vp, vp, C.POINTER(u64)]
     _lib = L
     return L
 
@@ -330,14 +328,38 @@ class Context:
         check(lib().bg_set_long_trace_budget(self.h, nbytes), self.h)
 
 
+_synth = None
+SYNTH_LIB_PATH = os.path.join(_HERE, "libbgsynth.so")
+
+
+def synth_lib():
+    """libbgsynth.so (include/bgsynth.h): the workload generator of tests and bench.py -- tooling, kept out of the
+    product library so that a process that only generates inputs (bench.py --impl reference) never maps libbgalign.so."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise EngineError("libbgsynth.so not built (%s): run `make -C biogarden_b200/csrc`" % SYNTH_LIB_PATH)
+        S = C.CDLL(SYNTH_LIB_PATH)
+        S.bg_synth_pairs.restype = C.c_int
+        S.bg_synth_pairs.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        _synth = S
+    return _synth
+
+
+def _check_synth(rc):
+    if rc:
+        raise EngineError("bg_synth_pairs: invalid argument")
+
+
 def synth_pairs(seed, first_pair, n_pairs, alphabet: bytes, len_lo, len_hi, resize_b=True) -> Batch:
     """Deterministic synthetic workload (SURVEY 8d generator)."""
-    L = lib()
+    L = synth_lib()
     off = np.zeros(2 * n_pairs + 1, np.uint64)
     tot = C.c_uint64(0)
-    check(L.bg_synth_pairs(seed, first_pair, n_pairs, alphabet, len(alphabet), len_lo, len_hi, int(resize_b), None,
-                           off.ctypes.data, C.byref(tot)))
+    _check_synth(L.bg_synth_pairs(seed, first_pair, n_pairs, alphabet, len(alphabet), len_lo, len_hi, int(resize_b), None,
+                                  off.ctypes.data, C.byref(tot)))
     res = np.zeros(max(1, tot.value), np.uint8)
-    check(L.bg_synth_pairs(seed, first_pair, n_pairs, alphabet, len(alphabet), len_lo, len_hi, int(resize_b),
-                           res.ctypes.data, off.ctypes.data, C.byref(tot)))
+    _check_synth(L.bg_synth_pairs(seed, first_pair, n_pairs, alphabet, len(alphabet), len_lo, len_hi, int(resize_b),
+                                  res.ctypes.data, off.ctypes.data, C.byref(tot)))
     return Batch(res[:tot.value], off)
