@@ -33,6 +33,10 @@
 #include "bg_args.cuh"
 #include "launch.h"
 
+namespace bg {
+// host_expand.cpp: 2-bit alignment ops -> the two aligned strings (AVX-512 VBMI2 or portable code)
+void expand_ops(const uint8_t* s1, const uint8_t* s2, const uint32_t* ops, uint64_t len, uint8_t* a_out, uint8_t* b_out);
+}
 using namespace bg;
 
 // ----------------------------------------------------------------------------- utilities
@@ -134,7 +138,7 @@ struct Chunk {
     std::vector<CkptSlot> ck_table;       // [ckpt_nb + 1][slots]: pass 1, then the blocks bottom-up
     uint64_t ckpt_elems = 0;
 };
-struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; bool half = false; int myers_W = 0; bool ops_fmt = false, long_walk = false; };
+struct LaunchClass { Shape sh; std::vector<Chunk> chunks; bool wave = false; bool half = false; int myers_W = 0; bool long_walk = false; };
 
 struct Plan {
     std::vector<LaunchClass> classes;
@@ -169,7 +173,8 @@ struct WorkSet {
     DevBuf residues, desc, score, flags, lens2, off, arena, out64;     // pipeline mode: chunk in / out
     DevBuf assign;                                                     // K2: CTA assignment table of the launch
     DevBuf ckpt, wstate, ckslots;                                      // K2 bounded-memory traceback: row checkpoints, suspended walks, launch table
-    DevBuf run;                                                        // pipeline mode: [0] this chunk's string bytes, [1] (work set 0) running arena base
+    DevBuf run;                                                        // (unused by the alignment pipeline since results travel as ops)
+    DevBuf len, first, ops;                                            // pipeline mode: compact results of the chunk (k_pack_ops)
     PinBuf stage;                                                     // descriptor staging
     PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
     cudaEvent_t ev_scan = nullptr;
@@ -182,7 +187,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots};
+        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots, &len, &first, &ops};
     }
 };
 
@@ -207,7 +212,44 @@ struct Prepared {
 
 }  // namespace
 
+// A persistent host thread that runs one job at a time (the per-device drivers / finishers of multi-device and
+// pipelined calls: spawning std::threads per call cost more than a small batch takes).
+struct Worker {
+    std::mutex mu; std::condition_variable cv;
+    std::function<void()> job; bool has = false, done = true, quit = false;
+    std::thread th;
+    Worker() : th([this] { loop(); }) {}
+    ~Worker() { { std::lock_guard<std::mutex> lk(mu); quit = true; } cv.notify_all(); th.join(); }
+    void loop() {
+        for (;;) {
+            std::function<void()> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return has || quit; });
+                if (!has && quit) return;
+                j = std::move(job); has = false;
+            }
+            j();
+            { std::lock_guard<std::mutex> lk(mu); done = true; }
+            cv.notify_all();
+        }
+    }
+    void run(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(mu); job = std::move(f); has = true; done = false; }
+        cv.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done; }); }
+};
+
 struct bg_ctx {
+    std::vector<std::unique_ptr<Worker>> workers;   // [2 d] driver of device d (d >= 1), [2 d + 1] its finisher; created on first use
+    Worker& worker(size_t i) {
+        if (workers.size() <= i) workers.resize(i + 1);
+        if (!workers[i]) workers[i].reset(new Worker());
+        return *workers[i];
+    }
+    Worker& dev_worker(int d) { return worker(2 * (size_t)d); }
+    Worker& fin_worker(int d) { return worker(2 * (size_t)d + 1); }
     std::vector<Device> devs;
     std::string last_error;
     std::mutex err_mu;
@@ -248,41 +290,13 @@ struct HostResultOwner {
         if (q) pinned.emplace_back(q, got);
         return q;
     }
+    void release_all() { for (auto& q : pinned) pinned_cache().put(q.first, q.second); pinned.clear(); }
 };
 
 // ------------------------------------------------------------------------------ planning
-// Length class -> kernel shape.  Short pairs use few lanes per pair (the systolic pipeline costs
-// L-1 fill/drain steps per pair) and many columns per lane; wide pairs use a full warp, and pairs
-// wider than 1024 columns loop over bands of the L=32 shape that wastes the fewest padded columns.
-Shape pick_shape(const bg_ctx* ctx, uint32_t m, bool half_ok = false) {
+Shape pick_shape(const bg_ctx* ctx, uint32_t m, bool half_ok = false, bool c8 = false) {
     if (ctx->force_L) return Shape{ctx->force_L, ctx->force_C};
-    if (half_ok && m > 128 && m <= 160) return Shape{16, 10};   // K1h: more resident warps beat the longer pipeline ramp
-    if (m <= 64) return Shape{8, 8};
-    if (m <= 96) return Shape{8, 12};
-    if (m <= 128) return Shape{8, 16};
-    if (m <= 152) return Shape{8, 19};
-    if (m <= 192) return Shape{8, 24};
-    if (m <= 256) return Shape{16, 16};
-    if (m <= 384) return Shape{32, 12};
-    if (m <= 512) return Shape{32, 16};
-    if (m <= 640) return Shape{32, 20};
-    if (m <= 768) return Shape{32, 24};
-    if (m <= 1024) return Shape{32, 32};
-    Shape best{32, 32};
-    uint64_t best_cols = ~0ull;
-    for (int c : {32, 24, 20, 16}) {
-        const uint64_t band = 32ull * c, cols = (m + band - 1) / band * band;
-        if (cols < best_cols) { best_cols = cols; best = Shape{32, c}; }
-    }
-    return best;
-}
-
-int shape_index(Shape s) {
-    int i = 0;
-#define X(L_, C_) if (s.L == L_ && s.C == C_) return i; ++i;
-    BG_SHAPES(X)
-#undef X
-    return -1;
+    return pick_shape_m(m, half_ok, c8);
 }
 
 // Scratch vectors of build_plan, recycled across calls and threads.  A fresh 0.5 MB std::vector is an mmap
@@ -405,15 +419,16 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     size_t count[MAX_SHAPES] = {0};
     uint32_t cls_min_n[MAX_SHAPES], cls_max_n[MAX_SHAPES] = {0}, cls_max_m[MAX_SHAPES] = {0};
     for (int s = 0; s < MAX_SHAPES; ++s) cls_min_n[s] = 0xFFFFFFFFu;
-    uint32_t last_m = 0xFFFFFFFFu; int last_si = -1;
+    uint32_t last_m = 0xFFFFFFFFu; int last_si = -1; bool last_long = false;
     for (uint64_t p = 0; p < n_pairs; ++p) {
         const uint64_t n = off[2 * p + 1] - off[2 * p], m = off[2 * p + 2] - off[2 * p + 1];
         if (n > 0x7FFFFFF0ull || m > 0x7FFFFFF0ull) { ctx->set_error("sequence longer than 2^31"); return BG_EUNSUPPORTED; }
-        if ((uint32_t)m != last_m) {
-            last_m = (uint32_t)m;
+        const bool is_long = with_trace && n + m > LONG_WALK_LEN;
+        if ((uint32_t)m != last_m || is_long != last_long) {
+            last_m = (uint32_t)m; last_long = is_long;
             if (with_trace && m > WAVE_MIN_COLS && !ctx->force_L) last_si = wave_si;
             else if (myers && m <= 320) last_si = myers_si + (m <= 128 ? 0 : m <= 256 ? 1 : 2);
-            else last_si = shape_index(pick_shape(ctx, last_m, with_trace && half_maxabs > 0));
+            else last_si = shape_index(pick_shape(ctx, last_m, with_trace && half_maxabs > 0 && !is_long, is_long));
             if (last_si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
         }
         cls[p] = (uint8_t)last_si; count[last_si]++;
@@ -553,13 +568,10 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
         // (a 32-bit division per pair is a third of the plan's cost: most classes have a single band)
         const bool single_band = cls_max_m[si] <= band_cols;
         auto bands_of = [&](uint32_t m_) -> uint32_t { return single_band ? (m_ ? 1u : 0u) : (m_ + band_cols - 1) / band_cols; };
-        // which walker the class gets (run_align): k3_walk (one thread per pair) or, for long pairs, k3_walk_diag (one
-        // warp per pair) -- both leave 2-bit ops in the slot (PairDesc::pad_ = 1); the older long-pair walkers
-        // (BG_LONG_WALK) leave characters
-        static const int long_walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
-        const bool long_walk_cls = !half && (wave || (uint64_t)P.max_n + P.max_m > 16384);
-        const bool ops_slots = !long_walk_cls || (long_walk_kind == 0 && (sh.C & 7) == 0);
-        lc.long_walk = long_walk_cls; lc.ops_fmt = ops_slots;
+        // which walker the class gets (run_align): k3_walk (one thread per pair) or, when the class holds long pairs,
+        // k3_walk_skew (one warp per pair; needs C % 8 == 0, which pick_shape guarantees for long pairs unless a shape
+        // is forced).  Both leave 2-bit ops in the pair's slot.
+        lc.long_walk = !half && (sh.C & 7) == 0 && (wave || (uint64_t)cls_max_n[si] + cls_max_m[si] > LONG_WALK_LEN);
         Chunk ch; ch.slot_begin = (uint32_t)nd; ch.trace_words = 0;
         const size_t nwarps = (sn + G - 1) / G;
         for (size_t w = 0; w < nwarps; ++w) {
@@ -603,7 +615,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 const size_t k = w * G + gidx;
                 PairDesc d;     // built in registers, stored once (field-wise stores into dst cannot be combined: dst may alias off)
                 d.pair_id = 0xFFFFFFFFu; d.steps = steps; d.trace_off = ch.trace_words;
-                d.a_off = d.b_off = d.bnd_off = d.pad_off = 0; d.n = d.m = d.nbands = 0; d.pad_ = ops_slots ? 1u : 0u;
+                d.a_off = d.b_off = d.bnd_off = d.pad_off = 0; d.n = d.m = d.nbands = 0; d.pad_ = 1u;
                 if (k < sn && sl[k] != HOLE) {
                     const uint64_t id = sl[k];
                     const uint64_t o0 = off[2 * id], o1 = off[2 * id + 1], o2 = off[2 * id + 2];
@@ -785,14 +797,15 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
 }
 
 // Pipeline chunks for pairs [lo, hi) at SCAN_BLOCK granularity, roughly equal cell counts.
-std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi, double nchunk_override = 0.0) {
+// nd > 1: the chunks feed a queue that nd devices share -- nd times as many chunks, and the ramp goes by rounds of nd.
+std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi, double nchunk_override = 0.0, int nd = 1) {
     std::vector<uint64_t> b{lo};
     if (hi == lo) { b.push_back(hi); return b; }
     const uint64_t blk_lo = lo / SCAN_BLOCK, blk_hi = (hi + SCAN_BLOCK - 1) / SCAN_BLOCK;
     double total = 0;
     for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
     static const double nchunk_target = [] { const char* e = getenv("BG_PIPE_CHUNKS"); return e ? std::max(1.0, atof(e)) : 5.0; }();
-    const double target = nchunk_override > 0 ? std::max(total / nchunk_override, 1.0e8) : std::max(total / nchunk_target, 1.0e9);
+    const double target = nchunk_override > 0 ? std::max(total / nchunk_override, 1.0e8) : std::max(total / (nchunk_target * nd), 1.0e9);
     const uint64_t max_pairs = 262144;
     // every length class of a chunk becomes its own launch: keep >= ~4 waves of warps per launch
     const uint64_t min_pairs = 8192ull * (uint64_t)__builtin_popcount(S.class_mask ? S.class_mask : 1u);
@@ -804,7 +817,7 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
         // ramp: the first two chunks are a quarter / a half of the rest, so planning + H2D of chunk 0 is short
         // ... and ramp down: the last chunk's strings travel D2H after the GPU has gone idle, so the chunks
         // shrink towards the end (half of what is left, but not below a quarter of the regular size)
-        const size_t nb = b.size();
+        const size_t nb = (b.size() - 1) / (size_t)nd + 1;
         // (measured, cfg2: a plan costs ~28 ns per pair on one host thread, the GPU aligns a pair in ~12 ns; all plans
         //  start together, so chunk c's plan is ready in time only if it is < ~0.4 of everything before it)
         static const double ramp[] = {0.125, 0.1875, 0.25, 0.375, 0.5, 0.75};
@@ -887,6 +900,10 @@ int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_
 struct AlignIO {
     const uint8_t* residues; const PairDesc* desc; const Plan* plan; uint64_t N;
     int32_t* score; uint8_t* flags; uint64_t* lens2; uint64_t* off; uint8_t* arena;
+    // compact results (host-buffer entry points): ops != nullptr -> instead of strings in `arena`, the pairs' 2-bit
+    // ops are packed densely into `ops` at word offsets `off` ([N + 1], exclusive scan of ceil(len / 16)), next to
+    // len / first; `lens2` is still the walkers' output
+    uint32_t* len = nullptr; uint32_t* first = nullptr; uint32_t* ops = nullptr;
 };
 
 // Uploads the score table / code maps into the work set and clears its error flag.
@@ -978,7 +995,6 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
             if (lc.wave && ch.ckpt_nb) {
                 // ---- bounded-memory traceback: pass 1 (checkpoints + end cells), then row block by row block,
                 //      bottom-up, re-fill with direction codes + resume the walks (k2_wave.cuh) ----
-                if (!lc.ops_fmt) { ctx->set_error("bounded-memory traceback needs the default long-pair walker"); return BG_EUNSUPPORTED; }
                 const uint32_t NB = ch.ckpt_nb;
                 if (!ws.ckpt.ensure(std::max<uint64_t>(1, ch.ckpt_elems) * sizeof(int2)) || !ws.wstate.ensure(ns * sizeof(WalkState)) ||
                     !ws.ckslots.ensure(ch.ck_table.size() * sizeof(CkptSlot)) ||
@@ -1064,12 +1080,8 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     wa.pad = ws.pad.as<uint8_t>(); wa.score = io.score; wa.walk_flags = io.flags; wa.lens2 = io.lens2;
                     // long pairs: one warp per pair with a trace window in shared memory; short pairs: one thread per pair
                     if (lc.long_walk) {
-                        static const int walk_kind = [] { const char* e = getenv("BG_LONG_WALK"); return !e ? 0 : !strcmp(e, "tile") ? 1 : !strcmp(e, "vec") ? 2 : 0; }();
-                        // the window loaders map 8-column blocks onto trace words: need C % 8 == 0 (true for K2)
                         static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
-                        const bool k2geo = lc.sh.L == 32 && lc.sh.C == WAVE_C;
-                        if (lc.ops_fmt) launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, k2geo, ns, wst, wa);
-                        else launch_long_walk((walk_kind == 2 || (lc.sh.C & 7)) ? LW_WARP : LW_TILE, false, ns, wst, wa);
+                        launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, lc.sh.L == 32 && lc.sh.C == WAVE_C, ns, wst, wa);
                     }
                     else dispatch_walk(lc.sh, lc.half, ns, wst, wa);
                 }
@@ -1085,7 +1097,27 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     if (overlap)
         for (int b2 = 0; b2 < 2; ++b2)
             if (ev_walk_done[b2]) CU_TRY(ctx, cudaStreamWaitEvent(st, ev_walk_done[b2], 0));   // scan / gather need every walk
-    if (!pp.score_only) {
+    if (!pp.score_only && io.ops) {
+        // words[p] = ceil(len / 16) -> exclusive scan -> the pairs' op runs, packed densely (the word counts live behind
+        // the scan's temporary storage in ws.cubtmp)
+        Phase ph(ws, 3, pst);
+        size_t tmp = 0;
+        scan_lengths(nullptr, tmp, io.off, io.off, (int)(N + 1), pst);
+        const size_t tmp_al = (tmp + 255) & ~(size_t)255;
+        if (!ws.cubtmp.ensure(tmp_al + (N + 1) * 8)) { ctx->set_error("device allocation failed (scan)"); return BG_ENOMEM; }
+        uint64_t* words = reinterpret_cast<uint64_t*>(ws.cubtmp.as<unsigned char>() + tmp_al);
+        launch_ops_words(io.lens2, N, words, pst);
+        scan_lengths(ws.cubtmp.p, tmp, words, io.off, (int)(N + 1), pst);
+        ctx->launches += 2;
+        if (P.n_slots) {
+            PackOpsArgs pa;
+            pa.desc = io.desc; pa.n_slots = (uint32_t)P.n_slots; pa.pad = ws.pad.as<uint8_t>(); pa.lens2 = io.lens2;
+            pa.woff = io.off; pa.len = io.len; pa.first = io.first; pa.ops = io.ops;
+            launch_pack_ops(pa, (uint64_t)P.max_n + P.max_m > 4096, pst);
+            ctx->launches++;
+        }
+        CU_TRY(ctx, cudaGetLastError());
+    } else if (!pp.score_only) {
         Phase ph(ws, 3, pst);
         size_t tmp = 0;
         scan_lengths(nullptr, tmp, io.lens2, io.off, (int)(2 * N + 1), pst);
@@ -1541,7 +1573,7 @@ void bg_result_free(bg_result* r) {
     if (!r) return;
     if (r->owner_) {
         HostResultOwner* own = (HostResultOwner*)r->owner_;
-        for (auto& q : own->pinned) pinned_cache().put(q.first, q.second);
+        own->release_all();
         delete own;
     }
     memset(r, 0, sizeof *r);
@@ -1589,58 +1621,137 @@ std::vector<uint64_t> shard_bounds_from_scan(const BatchScan& S, uint64_t N, int
     return b;
 }
 
-struct FinalOut {      // the caller-visible arrays of one device's pair range
-    int32_t* score; uint8_t* status; uint64_t* off; uint8_t* arena; uint64_t arena_cap;
+// ---- host-buffer alignment -------------------------------------------------------------------------------
+// Results leave the device in compact form -- score, status, aligned length, start cell and 2-bit ops per pair
+// (k_pack_ops) -- and the strings are rebuilt on the host from the caller's own residues (host_expand.cpp).  D2H
+// is the scarce direction of the 8-GPU box (profiles/pcie_roof_r02.json), and the host pass also writes every
+// string at its final, dense position whatever device or chunk it came from, so there is nothing to stitch.
+struct OpsOut {        // compact result arrays of the whole batch (pinned, caller order)
+    int32_t* score = nullptr; uint8_t* status = nullptr; uint32_t* len = nullptr; uint32_t* first = nullptr;
+    uint32_t* ops = nullptr; uint64_t* ops_off = nullptr; uint64_t ops_cap_words = 0;
 };
 
-// One device's share of bg_align_batch: chunks of pairs [lo, hi) flow through the three work sets as a
-// classic three-stage pipeline on dedicated streams --
-//     H2D stream:      residues + launch descriptors of chunk c
-//     compute stream:  all kernels, strictly chunk after chunk (each chunk gets the whole GPU; with one
-//                      stream per chunk the kernels of three chunks time-share the SMs, all three finish
-//                      together and the copy engines then sit idle: measured 17 ms instead of 11 for cfg2)
-//     D2H streams:     scores / status / offsets, then the dense strings once their size is known
-// driven by two host threads: the caller's thread issues chunks as work sets become free, a finisher
-// thread waits for each chunk's results, issues the string copy and post-processes (status rules).
-int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const Prepared& pp,
-                   const BatchScan& scan, const FinalOut& fo, uint64_t* total_out) {
+// One unit of device work: pairs [lo, lo + n) of the caller's batch (pipeline mode), or a set of pairs gathered
+// into staging (long pairs dealt to devices by size; map[q] = caller index of local pair q).
+struct WorkItem {
+    uint64_t lo = 0, n = 0;
+    const uint8_t* res = nullptr;       // host residues; sequence s of the item at res[off[s] - off[0]]
+    const uint64_t* off = nullptr;      // [2n + 1]
+    const uint32_t* map = nullptr;
+    uint64_t ops_base = 0, ops_cap = 0; // the item's region of OpsOut::ops (upper-bound layout), words
+    uint64_t words = 0;                 // op words the item really produced
+    uint64_t cols = 0;                  // sum of aligned lengths (set by finish_item)
+    PinBuf gather;                      // long mode: gathered residues | offsets | map | per-pair outputs
+    int32_t* t_score = nullptr; uint8_t* t_status = nullptr; uint32_t* t_len = nullptr; uint32_t* t_first = nullptr;   // long mode
+};
+
+struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; };
+
+struct AlignJob {
+    std::vector<Prebuilt> pre;                  // per item
+    bg_ctx* ctx = nullptr; const bg_batch* in = nullptr; const Prepared* pp = nullptr; const BatchScan* scan = nullptr;
+    OpsOut oo;
+    std::vector<WorkItem> items;
+    bool long_mode = false;
+    std::vector<std::vector<int>> dev_items;   // long mode: items per device; pipeline mode: empty (shared queue)
+    std::atomic<int> next_item{0};
+    std::atomic<int> rc{BG_OK};
+    // string expansion (bg_align_batch only): items are expanded in caller order as soon as every earlier item's
+    // column total is known
+    bool want_strings = false;
+    uint64_t* off = nullptr; uint8_t* arena = nullptr; uint64_t arena_cap = 0;
+    std::mutex mu; std::condition_variable cv;
+    std::vector<char> arrived; int frontier = 0; uint64_t arena_base = 0;
+    int pending = 0;                            // expansion tasks in flight
+    void fail(int code) { int expect = BG_OK; rc.compare_exchange_strong(expect, code); }
+};
+
+// Expands pairs [p_lo, p_hi) (caller order): off[2p] holds the pair's a_align offset relative to `base`.
+void expand_pairs(AlignJob& J, uint64_t p_lo, uint64_t p_hi, uint64_t base) {
+    const bg_batch* in = J.in;
+    for (uint64_t p = p_lo; p < p_hi; ++p) {
+        const uint64_t len = J.oo.len[p], o = J.off[2 * p] + base;
+        J.off[2 * p] = o; J.off[2 * p + 1] = o + len;
+        if (!len) continue;
+        if (o + 2 * len > J.arena_cap) { J.ctx->set_error("internal: arena bound exceeded"); J.fail(BG_ECUDA); return; }
+        expand_ops(in->residues + in->seq_off[2 * p] + J.oo.first[2 * p], in->residues + in->seq_off[2 * p + 1] + J.oo.first[2 * p + 1],
+                   J.oo.ops + J.oo.ops_off[p], len, J.arena + o, J.arena + o + len);
+    }
+}
+
+// Hands pairs [p_lo, p_hi) to the host pool in pieces of similar column counts.  Caller holds J.mu.
+void submit_expand_locked(AlignJob& J, uint64_t p_lo, uint64_t p_hi, uint64_t base, uint64_t cols) {
+    const uint64_t per_task = std::max<uint64_t>(1ull << 20, cols / 64 + 1);
+    uint64_t start = p_lo, acc = 0;
+    for (uint64_t p = p_lo; p < p_hi; ++p) {
+        acc += J.oo.len[p];
+        if (acc >= per_task || p + 1 == p_hi) {
+            const uint64_t a = start, b = p + 1;
+            ++J.pending;
+            host_pool().submit([&J, a, b, base] {
+                expand_pairs(J, a, b, base);
+                { std::lock_guard<std::mutex> lk(J.mu); --J.pending; }
+                J.cv.notify_all();
+            });
+            start = p + 1; acc = 0;
+        }
+    }
+}
+
+// The item's results are on the host: op offsets, and (strings wanted) relative string offsets + expansion.
+void finish_item(AlignJob& J, int c) {
+    WorkItem& it = J.items[c];
+    OpsOut& oo = J.oo;
+    uint64_t w = it.ops_base, cols = 0;
+    if (it.map) {   // long mode: scatter the per-pair outputs to caller order
+        for (uint64_t q = 0; q < it.n; ++q) {
+            const uint64_t p = it.map[q];
+            oo.score[p] = it.t_score[q]; oo.status[p] = it.t_status[q];
+            if (oo.len) {
+                oo.len[p] = it.t_len[q]; oo.first[2 * p] = it.t_first[2 * q]; oo.first[2 * p + 1] = it.t_first[2 * q + 1];
+                oo.ops_off[p] = w; w += ((uint64_t)it.t_len[q] + 15) >> 4;
+            }
+        }
+    } else if (oo.len) {
+        for (uint64_t p = it.lo; p < it.lo + it.n; ++p) {
+            const uint64_t len = oo.len[p];
+            oo.ops_off[p] = w; w += (len + 15) >> 4;
+            if (J.want_strings) J.off[2 * p] = 2 * cols;     // relative to the item's arena base
+            cols += len;
+        }
+    }
+    it.cols = cols;
+    if (oo.len && w - it.ops_base != it.words) { J.ctx->set_error("internal: op word count mismatch"); J.fail(BG_ECUDA); }
+    if (!J.want_strings || J.long_mode) return;       // long mode: expanded after all items (caller order is scattered)
+    std::lock_guard<std::mutex> lk(J.mu);
+    J.arrived[c] = 1;
+    while (J.frontier < (int)J.items.size() && J.arrived[J.frontier]) {
+        WorkItem& f = J.items[J.frontier];
+        if (J.rc.load() == BG_OK) submit_expand_locked(J, f.lo, f.lo + f.n, J.arena_base, f.cols);
+        J.arena_base += 2 * f.cols;
+        ++J.frontier;
+    }
+}
+
+// One device's share of a job: its items flow through the work sets as a pipeline on dedicated streams --
+//     H2D stream:      residues + launch descriptors of item c
+//     compute stream:  all kernels, strictly item after item (each item gets the whole GPU; with one stream per
+//                      item the kernels of three items time-share the SMs, all three finish together and the copy
+//                      engines then sit idle: measured 17 ms instead of 11 for cfg2)
+//     D2H streams:     per-pair results, then the packed ops once their size is known
+// driven by two host threads: the issuer takes the next item (pipeline mode: from the queue all devices share, so a
+// faster or less loaded device simply takes more chunks) as a work set becomes free, a finisher waits for each
+// item's results, issues the ops copy and hands the item to finish_item.
+int device_pipeline(AlignJob& J, int d) {
+    bg_ctx* ctx = J.ctx;
+    const Prepared& pp = *J.pp;
     Device& dv = ctx->devs[d];
     if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
-    const uint64_t* off = in->seq_off;
-    // Batches with long pairs (K2 class) are not cut into pipeline chunks: their traces take GBs per
-    // pair, the copies are negligible next to the fill, and every launch should see as many pairs as
-    // memory allows.  Everything else flows through the chunk pipeline.
-    bool long_mode = false;
-    if (scan.has_wide)
-        for (uint64_t q = lo; q < hi && !long_mode; ++q) long_mode = (off[2 * q + 2] - off[2 * q + 1]) > WAVE_MIN_COLS;
-    std::vector<uint64_t> cb = long_mode ? std::vector<uint64_t>{lo, hi} : chunk_bounds_from_scan(scan, lo, hi);
-    const int nchunks = (int)cb.size() - 1;
-    const uint64_t ws_budget = ctx->trace_budget_words;   // per work set; three of them fit the B200's 180 GB many times over
-    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.8 * (double)dv.total_mem) / 4);
+    const bool long_mode = J.long_mode;
+    const bool ops_mode = J.oo.len != nullptr;
 
-    // Launch plans of all chunks are built by one host thread per chunk, straight into pinned staging
-    // (planning a 125k-pair chunk takes longer than the GPU needs to align it); chunk c is issued as soon
-    // as ITS plan is ready, so the GPU starts after the (small) first chunk's plan.
-    struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; };
-    std::vector<Prebuilt> pre(nchunks);
-    static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
-    const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues + off[2 * lo]);
-    for (int c = 0; c < nchunks; ++c)
-        pre[c].th = host_pool().submit([&, c] {
-            const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
-            if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
-            if (stage_res) {
-                const uint64_t b0 = off[2 * c_lo], nb = off[2 * (c_lo + n)] - b0;
-                if (!pre[c].res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
-                memcpy(pre[c].res.p, in->residues + b0, nb);
-            }
-            const auto t0 = std::chrono::steady_clock::now();
-            pre[c].rc = build_plan(ctx, off + 2 * c_lo, off[2 * c_lo], n, !pp.score_only, ws_budget, wave_budget, pp.half_maxabs,
-                                   pre[c].plan, pre[c].stage.as<PairDesc>());
-            if (getenv("BG_PROFILE_HOST"))
-                fprintf(stderr, "[bgalign]   plan of chunk %d (%llu pairs): %.2f ms\n", c, (unsigned long long)n,
-                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-        });
+    std::vector<Prebuilt>& pre = J.pre;   // launch plans, built by the host pool from the start of the job on
+    const int nitems = (int)J.items.size();
 
     // streams: the work sets' own streams are borrowed for the stages; kernels of every work set go to st_comp
     cudaStream_t st_comp = dv.ws[0].stream, st_h2d = dv.ws[1].stream, st_small = dv.ws[2].stream, st_arena = dv.ws[0].walk_stream;
@@ -1660,144 +1771,144 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
         cudaEventCreateWithFlags(&ev_comp[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_arena[s], cudaEventDisableTiming);
     }
-
     static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-    // running arena base of this call (device scalar next to work set 0's chunk total)
-    uint64_t* d_base = nullptr;
-    if (dv.ws[0].run.ensure(16)) { d_base = dv.ws[0].run.as<uint64_t>() + 1; cudaMemsetAsync(d_base, 0, 8, st_comp); }
 
-    // issuer -> finisher hand-over
+    // issuer -> finisher hand-over (k-th item this device took -> work set k % PIPE_DEPTH)
     std::mutex mu; std::condition_variable cv;
-    int issued = 0;                       // chunks handed to the finisher
-    int finished = 0;                     // chunks whose work set is free again
-    bool issuer_done = false;
-    std::atomic<int> rc_shared{BG_OK};
-    uint64_t arena_base = 0;              // finisher only
+    std::vector<int> taken;               // item index of the k-th item issued here
+    int issued = 0, finished = 0; bool issuer_done = false;
 
-    std::thread finisher([&] {
+    Worker& finisher = ctx->fin_worker(d);
+    finisher.run([&] {
         cudaSetDevice(dv.ordinal);
-        for (int c = 0;; ++c) {
+        for (int k = 0;; ++k) {
+            int c;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return issued > c || issuer_done; });
-                if (issued <= c) break;
+                cv.wait(lk, [&] { return issued > k || issuer_done; });
+                if (issued <= k) break;
+                c = taken[k];
             }
-            const int s = c % PIPE_DEPTH;
+            const int s = k % PIPE_DEPTH;
             WorkSet& ws = dv.ws[s];
-            const uint64_t c_n = cb[c + 1] - cb[c];
+            WorkItem& it = J.items[c];
             uint64_t* h_total = ws.scalars.as<uint64_t>();
             uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
             int rc = BG_OK;
             if (cudaEventSynchronize(ws.ev_scan) != cudaSuccess) { ctx->set_error("cudaEventSynchronize failed"); rc = BG_ECUDA; }
-            uint64_t total = 0;
             if (!rc && (*h_err & 1u)) { ctx->set_error("a residue byte has no row/column in the score table"); rc = BG_EINVAL_RESIDUE; }
-            if (!rc) {
-                total = pp.score_only ? 0 : *h_total;
-                if (total) {
-                    if (arena_base + total > fo.arena_cap) { ctx->set_error("internal: arena bound exceeded"); rc = BG_ECUDA; }
-                    else if (cudaMemcpyAsync(fo.arena + arena_base, ws.arena.p, total, cudaMemcpyDeviceToHost, st_arena) != cudaSuccess ||
-                             cudaEventRecord(ev_arena[s], st_arena) != cudaSuccess || cudaEventSynchronize(ev_arena[s]) != cudaSuccess) {
-                        ctx->set_error("string copy failed"); rc = BG_ECUDA;
-                    }
+            if (!rc && ops_mode) {
+                it.words = *h_total;
+                if (it.words > it.ops_cap) { ctx->set_error("internal: op arena bound exceeded"); rc = BG_ECUDA; }
+                else if (it.words &&
+                         (cudaMemcpyAsync(J.oo.ops + it.ops_base, ws.ops.p, it.words * 4, cudaMemcpyDeviceToHost, st_arena) != cudaSuccess ||
+                          cudaEventRecord(ev_arena[s], st_arena) != cudaSuccess || cudaEventSynchronize(ev_arena[s]) != cudaSuccess)) {
+                    ctx->set_error("ops copy failed"); rc = BG_ECUDA;
                 }
             }
-            if (prof) fprintf(stderr, "[bgalign]   chunk %d results on the host at %.2f ms\n", c, since());
+            if (prof) fprintf(stderr, "[bgalign]   dev %d item %d results on the host at %.2f ms\n", d, c, since());
             if (!rc) {
-                ctx->d2h += c_n * 5 + (pp.score_only ? 0 : 2 * c_n * 8 + total);
-                arena_base += total;   // offsets were rebased and the status rules applied on the device
+                ctx->d2h += it.n * 5 + (ops_mode ? it.n * 12 + it.words * 4 + 8 : 0);
+                finish_item(J, c);
             } else {
-                int expect = BG_OK; rc_shared.compare_exchange_strong(expect, rc);
+                J.fail(rc);
             }
-            { std::lock_guard<std::mutex> lk(mu); finished = c + 1; }
+            { std::lock_guard<std::mutex> lk(mu); finished = k + 1; }
             cv.notify_all();
         }
     });
 
     auto issue = [&](int s, int c) -> int {
         WorkSet& ws = dv.ws[s];
-        const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
-        const uint64_t base = off[2 * c_lo], nres = off[2 * (c_lo + n)] - base, rel = c_lo - lo;
+        WorkItem& it = J.items[c];
+        const uint64_t n = it.n;
+        const uint64_t base = it.off[0], nres = it.off[2 * n] - base;
         if (!ws.scalars.ensure(16)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
-        if (pre[c].th.joinable()) pre[c].th.join();
-        int rc = pre[c].rc;
+        Prebuilt& pb = pre[c];
+        if (pb.th.joinable()) pb.th.join();
+        int rc = pb.rc;
         if (rc) return rc;
-        const Plan& P = pre[c].plan;
-        bool ok = ws.run.ensure(16) && ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
-                  ws.score.ensure(n * 4) && ws.flags.ensure(n);
-        if (!pp.score_only)
-            ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((2 * n + 1) * 8) && ws.arena.ensure(std::max<uint64_t>(1, P.pad_bytes));
+        const Plan& P = pb.plan;
+        bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
+                  ws.score.ensure(std::max<uint64_t>(1, n) * 4) && ws.flags.ensure(std::max<uint64_t>(1, n));
+        if (ops_mode)
+            ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((n + 1) * 8) && ws.len.ensure(std::max<uint64_t>(1, n) * 4) &&
+                 ws.first.ensure(std::max<uint64_t>(1, n) * 8) && ws.ops.ensure(std::max<uint64_t>(1, it.ops_cap) * 4);
         if (!ok) { ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM; }
-        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, stage_res ? (const uint8_t*)pre[c].res.p : in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
-        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
+        const uint8_t* src = pb.res.p ? (const uint8_t*)pb.res.p : it.res;
+        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, src, nres, cudaMemcpyHostToDevice, st_h2d));
+        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pb.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
         CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
         ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
         CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         rc = upload_params(ctx, ws, pp);
         if (rc) return rc;
         AlignIO io{ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), &P, n,
-                   ws.score.as<int32_t>(), ws.flags.as<uint8_t>(), ws.lens2.as<uint64_t>(), ws.off.as<uint64_t>(), ws.arena.as<uint8_t>()};
+                   ws.score.as<int32_t>(), ws.flags.as<uint8_t>(), ws.lens2.as<uint64_t>(), ws.off.as<uint64_t>(), nullptr};
+        if (ops_mode) { io.len = ws.len.as<uint32_t>(); io.first = ws.first.as<uint32_t>(); io.ops = ws.ops.as<uint32_t>(); }
         rc = run_align(ctx, ws, io, pp);
         if (rc) return rc;
-        // which stream the chunk's last kernels went to (run_align: post stream unless the plan has several launches)
+        // which stream the item's last kernels went to (run_align: post stream unless the plan has several launches)
         size_t n_launch = 0;
         for (const LaunchClass& lc : P.classes) n_launch += lc.chunks.size();
         cudaStream_t st_last = (ws.post_stream && !pp.score_only && P.max_wave_slots == 0 &&
                                 (n_launch == 1 || P.total_trace_words <= ws.split_cap_words)) ? ws.post_stream : st_comp;
-        if (!pp.score_only) {   // chunk-relative offsets -> offsets into the caller's arena, on the device
-            if (st_last != st_post && st_post != st_comp) {   // keep the running base stream-ordered on st_post
-                CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_last));
-                CU_TRY(ctx, cudaStreamWaitEvent(st_post, ev_comp[s], 0));
-                st_last = st_post;
-            }
-            launch_rebase(ws.off.as<uint64_t>(), 2 * n + 1, d_base, st_last);
-            launch_bump(d_base, ws.off.as<uint64_t>() + 2 * n, ws.run.as<uint64_t>(), st_last);
-            CU_TRY(ctx, cudaGetLastError());
-            ctx->launches += 2;
-        } else {
-            memset(fo.off + 2 * rel, 0, 2 * n * 8);
-        }
         CU_TRY(ctx, cudaEventRecord(ev_comp[s], st_last));
         CU_TRY(ctx, cudaStreamWaitEvent(st_small, ev_comp[s], 0));
         uint64_t* h_total = ws.scalars.as<uint64_t>();
         uint32_t* h_err = reinterpret_cast<uint32_t*>(h_total + 1);
+        *h_total = 0;
         CU_TRY(ctx, cudaMemcpyAsync(h_err, ws.err.p, 4, cudaMemcpyDeviceToHost, st_small));
-        if (!pp.score_only) {
-            CU_TRY(ctx, cudaMemcpyAsync(h_total, ws.run.p, 8, cudaMemcpyDeviceToHost, st_small));
-            CU_TRY(ctx, cudaMemcpyAsync(fo.off + 2 * rel, ws.off.p, 2 * n * 8, cudaMemcpyDeviceToHost, st_small));
+        int32_t* o_score = it.map ? it.t_score : J.oo.score + it.lo;
+        uint8_t* o_status = it.map ? it.t_status : J.oo.status + it.lo;
+        if (ops_mode) {
+            CU_TRY(ctx, cudaMemcpyAsync(h_total, ws.off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st_small));
+            if (n) {
+                CU_TRY(ctx, cudaMemcpyAsync(it.map ? it.t_len : J.oo.len + it.lo, ws.len.p, n * 4, cudaMemcpyDeviceToHost, st_small));
+                CU_TRY(ctx, cudaMemcpyAsync(it.map ? it.t_first : J.oo.first + 2 * it.lo, ws.first.p, n * 8, cudaMemcpyDeviceToHost, st_small));
+            }
         }
-        CU_TRY(ctx, cudaMemcpyAsync(fo.score + rel, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st_small));
-        CU_TRY(ctx, cudaMemcpyAsync(fo.status + rel, ws.flags.p, n, cudaMemcpyDeviceToHost, st_small));
+        if (n) {
+            CU_TRY(ctx, cudaMemcpyAsync(o_score, ws.score.p, n * 4, cudaMemcpyDeviceToHost, st_small));
+            CU_TRY(ctx, cudaMemcpyAsync(o_status, ws.flags.p, n, cudaMemcpyDeviceToHost, st_small));
+        }
         CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st_small));
-        ctx->timing.cells += P.cells; ctx->timing.cells_packed16 += P.cells_half; ctx->timing.cells_refilled += P.cells_ckpt;
-        ctx->timing.trace_bytes += pp.score_only ? 0 : P.total_trace_words * 4;
+        {
+            std::lock_guard<std::mutex> lk(ctx->err_mu);   // (devices share the context's counters)
+            ctx->timing.cells += P.cells; ctx->timing.cells_packed16 += P.cells_half; ctx->timing.cells_refilled += P.cells_ckpt;
+            ctx->timing.trace_bytes += pp.score_only ? 0 : P.total_trace_words * 4;
+        }
         return BG_OK;
     };
 
     int rc_all = BG_OK;
-    for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
-        const int s = c % PIPE_DEPTH;
-        {   // work set s is free once chunk c - PIPE_DEPTH has left it
+    for (int k = 0; rc_all == BG_OK; ++k) {
+        int c;
+        if (long_mode) { if (k >= (int)J.dev_items[d].size()) break; c = J.dev_items[d][k]; }
+        else { c = J.next_item.fetch_add(1); if (c >= nitems) break; }
+        const int s = k % PIPE_DEPTH;
+        {   // work set s is free once the item that used it last has left it
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return finished >= c - PIPE_DEPTH + 1; });
+            cv.wait(lk, [&] { return finished >= k - PIPE_DEPTH + 1; });
         }
-        rc_all = rc_shared.load();
+        rc_all = J.rc.load();
         if (rc_all) break;
         const double t0 = prof ? since() : 0;
         rc_all = issue(s, c);
-        if (prof) fprintf(stderr, "[bgalign]   chunk %d (%llu pairs) issued %.2f .. %.2f ms\n", c, (unsigned long long)(cb[c + 1] - cb[c]), t0, since());
+        if (prof) fprintf(stderr, "[bgalign]   dev %d item %d (%llu pairs) issued %.2f .. %.2f ms\n", d, c, (unsigned long long)J.items[c].n, t0, since());
         if (rc_all) break;
-        { std::lock_guard<std::mutex> lk(mu); issued = c + 1; }
+        { std::lock_guard<std::mutex> lk(mu); taken.push_back(c); issued = k + 1; }
         cv.notify_all();
     }
+    if (rc_all) J.fail(rc_all);
     { std::lock_guard<std::mutex> lk(mu); issuer_done = true; }
     cv.notify_all();
-    finisher.join();
-    if (rc_all == BG_OK) rc_all = rc_shared.load();
+    finisher.wait();
     cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_comp); cudaStreamSynchronize(st_small); cudaStreamSynchronize(st_arena);
     if (prof) {
-        fprintf(stderr, "[bgalign] drained at %.2f ms\n", since());
+        fprintf(stderr, "[bgalign] dev %d drained at %.2f ms\n", d, since());
         // GPU-side timeline of the kernels (events on the compute stream), relative to the first one
         cudaEvent_t e0 = nullptr;
         for (int s = 0; s < PIPE_DEPTH && !e0; ++s) if (!dv.ws[s].evs.empty()) e0 = dv.ws[s].evs.front().a;
@@ -1809,15 +1920,13 @@ int align_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t
                 fprintf(stderr, "[bgalign]   gpu ws%d phase %d: start %.3f ms, %.3f ms\n", s, ev.phase, t_a, dur);
             }
     }
-    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); pb.res.release(); }
     cudaStreamSynchronize(st_post);
     if (st_fill2) cudaStreamSynchronize(st_fill2);
     for (int s = 0; s < PIPE_DEPTH; ++s) {
         dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr; dv.ws[s].fill2_stream = nullptr;
         cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); cudaEventDestroy(ev_arena[s]);
     }
-    *total_out = arena_base;
-    return rc_all;
+    return J.rc.load();
 }
 
 constexpr int EDIT_RETRY_GENERAL = -77;   // internal: a byte outside the sampled 4-symbol alphabet turned up
@@ -1975,6 +2084,168 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     return rc_all;
 }
 
+// Builds the job's items, starts the plan tasks, runs the devices and (strings wanted) the host expansion.
+// oo's arrays and (want_strings) off / arena are allocated by the caller.
+int run_align_job(AlignJob& J) {
+    bg_ctx* ctx = J.ctx;
+    const bg_batch* in = J.in;
+    const Prepared& pp = *J.pp;
+    const BatchScan& scan = *J.scan;
+    const uint64_t N = in->n_pairs;
+    const uint64_t* off = in->seq_off;
+    const int nd = (int)ctx->devs.size();
+    const bool ops_mode = J.oo.len != nullptr;
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    // Batches with long pairs (K2 class) are not cut into pipeline chunks: their traces take GBs per pair, the
+    // copies are negligible next to the fill, and every launch should see as many pairs as memory allows.  With
+    // several devices the pairs are dealt by size instead -- largest first, each to the device with the least
+    // work so far (1 000 pairs of 2.5e9 .. 1e10 cells: a contiguous split leaves the tail to chance).
+    J.long_mode = scan.has_wide;
+    if (N == 0) { if (J.want_strings) J.off[0] = 0; return BG_OK; }
+    if (!J.long_mode) {
+        const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, 0, N, 0.0, nd);
+        J.items.resize(cb.size() - 1);
+        for (size_t c = 0; c + 1 < cb.size(); ++c) {
+            WorkItem& it = J.items[c];
+            it.lo = cb[c]; it.n = cb[c + 1] - cb[c];
+            it.res = in->residues + off[2 * it.lo]; it.off = off + 2 * it.lo;
+            // upper-bound layout of the op arena: B(p) = residues before pair p / 16 + p  (ceil((n + m) / 16) words per pair at most)
+            it.ops_base = ((off[2 * it.lo] - off[0]) >> 4) + it.lo;
+            it.ops_cap = ((off[2 * cb[c + 1]] - off[0]) >> 4) + cb[c + 1] - it.ops_base;
+        }
+    } else if (nd == 1) {
+        J.items.resize(1);
+        WorkItem& it = J.items[0];
+        it.lo = 0; it.n = N; it.res = in->residues + off[0]; it.off = off;
+        it.ops_base = 0; it.ops_cap = ((off[2 * N] - off[0]) >> 4) + N;
+        J.dev_items.assign(1, std::vector<int>{0});
+    } else {
+        std::vector<uint32_t> order(N);
+        for (uint64_t p = 0; p < N; ++p) order[p] = (uint32_t)p;
+        auto cells = [&](uint32_t p) { return (double)(off[2ull * p + 1] - off[2ull * p]) * (double)(off[2ull * p + 2] - off[2ull * p + 1]) + 64.0; };
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cells(x) > cells(y); });
+        std::vector<double> load(nd, 0.0);
+        std::vector<std::vector<uint32_t>> sets(nd);
+        for (uint32_t p : order) {
+            int best = 0;
+            for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
+            sets[best].push_back(p); load[best] += cells(p);
+        }
+        J.dev_items.assign(nd, std::vector<int>());
+        uint64_t ops_base = 0;
+        for (int d = 0; d < nd; ++d) {
+            if (sets[d].empty()) continue;
+            std::sort(sets[d].begin(), sets[d].end());
+            J.items.emplace_back();
+            J.dev_items[d].push_back((int)J.items.size() - 1);
+        }
+        int k = 0;
+        for (int d = 0; d < nd; ++d) {
+            if (sets[d].empty()) continue;
+            WorkItem& it = J.items[k++];
+            const uint64_t n = sets[d].size();
+            uint64_t nres = 0;
+            for (uint32_t p : sets[d]) nres += off[2ull * p + 2] - off[2ull * p];
+            const uint64_t res_al = (nres + 63) & ~63ull;
+            const uint64_t bytes = res_al + (2 * n + 1) * 8 + n * 4 /*map*/ + n * 4 /*score*/ + n * 4 /*len*/ + n * 8 /*first*/ + n + 64;
+            if (!it.gather.ensure(bytes)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+            uint8_t* base = it.gather.as<uint8_t>();
+            uint64_t* g_off = reinterpret_cast<uint64_t*>(base + res_al);
+            uint32_t* g_map = reinterpret_cast<uint32_t*>(g_off + 2 * n + 1);
+            it.t_score = reinterpret_cast<int32_t*>(g_map + n);
+            it.t_len = reinterpret_cast<uint32_t*>(it.t_score + n);
+            it.t_first = it.t_len + n;
+            it.t_status = reinterpret_cast<uint8_t*>(it.t_first + 2 * n);
+            uint64_t w = 0;
+            for (uint64_t q = 0; q < n; ++q) {
+                const uint64_t p = sets[d][q];
+                const uint64_t l1 = off[2 * p + 1] - off[2 * p], l2 = off[2 * p + 2] - off[2 * p + 1];
+                memcpy(base + w, in->residues + off[2 * p], l1 + l2);
+                g_off[2 * q] = w; g_off[2 * q + 1] = w + l1; w += l1 + l2;
+                g_map[q] = (uint32_t)p;
+            }
+            g_off[2 * n] = w;
+            it.lo = 0; it.n = n; it.res = base; it.off = g_off; it.map = g_map;
+            it.ops_base = ops_base; it.ops_cap = (nres >> 4) + n + 1; ops_base += it.ops_cap;
+        }
+    }
+    const int nitems = (int)J.items.size();
+    J.arrived.assign(nitems, 0);
+    if (ops_mode && nitems && J.items.back().ops_base + J.items.back().ops_cap > J.oo.ops_cap_words) { ctx->set_error("internal: op arena too small"); return BG_ECUDA; }
+
+    // launch plans of all items, one pool task each, in item order (the first items' plans finish first)
+    const uint64_t ws_budget = ctx->trace_budget_words;   // per work set; several fit the B200's 180 GB many times over
+    const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.8 * (double)ctx->devs[0].total_mem) / 4);
+    static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
+    const bool stage_res = !no_stage && !J.long_mode && host_is_pageable(in->residues + off[0]);
+    J.pre = std::vector<Prebuilt>(nitems);
+    for (int c = 0; c < nitems; ++c)
+        J.pre[c].th = host_pool().submit([&J, c, ctx, ws_budget, wave_budget, stage_res] {
+            WorkItem& it = J.items[c];
+            Prebuilt& pb = J.pre[c];
+            if (!pb.stage.ensure(plan_desc_capacity(it.n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
+            if (stage_res) {
+                const uint64_t nb = it.off[2 * it.n] - it.off[0];
+                if (!pb.res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
+                memcpy(pb.res.p, it.res, nb);
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            pb.rc = build_plan(ctx, it.off, it.off[0], it.n, !J.pp->score_only, ws_budget, wave_budget, J.pp->half_maxabs, pb.plan, pb.stage.as<PairDesc>());
+            if (getenv("BG_PROFILE_HOST"))
+                fprintf(stderr, "[bgalign]   plan of item %d (%llu pairs): %.2f ms\n", c, (unsigned long long)it.n,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        });
+
+    // one driver per device: the caller's thread takes device 0, the context's persistent workers the others
+    std::vector<int> rcs(nd, BG_OK);
+    for (int d = 1; d < nd; ++d) ctx->dev_worker(d).run([&J, &rcs, d] { rcs[d] = device_pipeline(J, d); });
+    rcs[0] = device_pipeline(J, 0);
+    for (int d = 1; d < nd; ++d) ctx->dev_worker(d).wait();
+    for (auto& pb : J.pre) { if (pb.th.joinable()) pb.th.join(); pb.stage.release(); pb.res.release(); }
+    int rc = J.rc.load();
+    for (int d = 0; d < nd && !rc; ++d) rc = rcs[d];
+
+    if (!rc && J.want_strings && ops_mode) {
+        std::unique_lock<std::mutex> lk(J.mu);
+        if (J.long_mode) {   // items hold scattered pairs: lay the strings out in caller order now
+            uint64_t cols = 0;
+            for (uint64_t p = 0; p < N; ++p) { J.off[2 * p] = 2 * cols; cols += J.oo.len[p]; }
+            submit_expand_locked(J, 0, N, 0, cols);
+            J.arena_base = 2 * cols;
+        } else if (J.frontier != nitems) { ctx->set_error("internal: items missing at the end of the job"); rc = BG_ECUDA; }
+        J.cv.wait(lk, [&] { return J.pending == 0; });
+        J.off[2 * N] = J.arena_base;
+        if (!rc) rc = J.rc.load();
+    } else {
+        std::unique_lock<std::mutex> lk(J.mu);
+        J.cv.wait(lk, [&] { return J.pending == 0; });
+    }
+    for (WorkItem& it : J.items) it.gather.release();
+    if (prof) fprintf(stderr, "[bgalign] job done, rc %d\n", rc);
+    return rc;
+}
+
+// Validates, prepares and sizes: the part bg_align_batch and bg_align_batch_ops share.
+int begin_align_call(bg_ctx* ctx, const bg_batch* in, const bg_params* p, BatchScan& scan, Prepared& pp) {
+    int rc = check_batch(ctx, in, &scan);
+    if (rc) return rc;
+    static const uint64_t zero_off[1] = {0};
+    rc = prepare_params(ctx, p, in->n_pairs ? in->seq_off : zero_off, in->n_pairs, pp, &scan);
+    if (rc) return rc;
+    rc = bg_sync(ctx);   // cached blocks may still be in use by device-resident work (see bg_dresult_free)
+    if (rc) return rc;
+    ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
+    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0; ctx->timing.cells_refilled = 0;
+    return BG_OK;
+}
+
+// op words the compact result arrays need for this batch (upper-bound layout, see run_align_job)
+uint64_t ops_capacity_words(const bg_batch* in, int nd) {
+    const uint64_t N = in->n_pairs;
+    if (!N) return 1;
+    return ((in->seq_off[2 * N] - in->seq_off[0]) >> 4) + N + (uint64_t)nd + 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1986,63 +2257,77 @@ int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_resul
     const auto t_enter = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count(); };
     BatchScan scan;
-    int rc = check_batch(ctx, in, &scan);
-    if (rc) return rc;
-    if (prof) fprintf(stderr, "[bgalign] scan done at %.2f ms\n", since());
-    const uint64_t N = in->n_pairs;
     Prepared pp;
-    static const uint64_t zero_off[1] = {0};
-    rc = prepare_params(ctx, p, N ? in->seq_off : zero_off, N, pp, &scan);
+    int rc = begin_align_call(ctx, in, p, scan, pp);
     if (rc) return rc;
-    const int nd = (int)ctx->devs.size();
-    const std::vector<uint64_t> bounds = (N < 8ull * SCAN_BLOCK * nd) ? shard_bounds(in, nd) : shard_bounds_from_scan(scan, N, nd);
-    rc = bg_sync(ctx);   // cached blocks may still be in use by device-resident work (see bg_dresult_free)
-    if (rc) return rc;
-    ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
-    ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0; ctx->timing.cells_refilled = 0;
+    if (prof) fprintf(stderr, "[bgalign] scan + parameters done at %.2f ms\n", since());
+    const uint64_t N = in->n_pairs;
+    const uint64_t nres = N ? in->seq_off[2 * N] - in->seq_off[0] : 0;
 
-    // upper bound of each device's share of the arena: 2*(n+m) per pair
-    std::vector<uint64_t> ub(nd + 1, 0);
-    for (int d = 0; d < nd; ++d) {
-        uint64_t s = 0;
-        if (!pp.score_only && bounds[d + 1] > bounds[d]) s = 2 * (in->seq_off[2 * bounds[d + 1]] - in->seq_off[2 * bounds[d]]);
-        ub[d + 1] = ub[d] + s;
-    }
     HostResultOwner* own = new HostResultOwner();
+    HostResultOwner tmp;   // the compact arrays: only needed until the strings are written
     out->n_pairs = N; out->owner_ = own;
     out->score = (int32_t*)own->grab(N * 4); out->status = (uint8_t*)own->grab(N);
-    out->off = (uint64_t*)own->grab((2 * N + 1) * 8); out->arena = (uint8_t*)own->grab(ub[nd]);
-    if (!out->score || !out->status || !out->off || !out->arena) { bg_result_free(out); ctx->set_error("pinned host allocation failed"); return BG_ENOMEM; }
-
+    out->off = (uint64_t*)own->grab((2 * N + 1) * 8);
+    out->arena = (uint8_t*)own->grab(pp.score_only ? 1 : 2 * nres);   // a pair's strings are at most len1 + len2 long each
+    AlignJob J;
+    J.ctx = ctx; J.in = in; J.pp = &pp; J.scan = &scan;
+    J.oo.score = out->score; J.oo.status = out->status;
+    bool ok = out->score && out->status && out->off && out->arena;
+    if (!pp.score_only) {
+        J.oo.ops_cap_words = ops_capacity_words(in, (int)ctx->devs.size());
+        J.oo.len = (uint32_t*)tmp.grab(std::max<uint64_t>(1, N) * 4); J.oo.first = (uint32_t*)tmp.grab(std::max<uint64_t>(1, N) * 8);
+        J.oo.ops = (uint32_t*)tmp.grab(J.oo.ops_cap_words * 4 + 64); J.oo.ops_off = (uint64_t*)tmp.grab((N + 1) * 8);
+        ok = ok && J.oo.len && J.oo.first && J.oo.ops && J.oo.ops_off;
+        J.want_strings = true; J.off = out->off; J.arena = out->arena; J.arena_cap = 2 * nres;
+    }
+    if (!ok) { tmp.release_all(); bg_result_free(out); ctx->set_error("pinned host allocation failed"); return BG_ENOMEM; }
     if (prof) fprintf(stderr, "[bgalign] pipelines start at %.2f ms\n", since());
-    std::vector<int> rcs(nd, BG_OK);
-    std::vector<uint64_t> totals(nd, 0);
-    auto work = [&](int d) {
-        FinalOut fo{out->score + bounds[d], out->status + bounds[d], out->off + 2 * bounds[d], out->arena + ub[d], ub[d + 1] - ub[d]};
-        rcs[d] = align_pipeline(ctx, d, in, bounds[d], bounds[d + 1], pp, scan, fo, &totals[d]);
-    };
-    if (nd == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
-        for (auto& t : th) t.join();
-    }
-    for (int d = 0; d < nd; ++d)
-        if (rcs[d]) { bg_result_free(out); return rcs[d]; }
-    // close the gaps between the devices' arena regions (device 0's region is already in place)
-    uint64_t base = totals[0];
-    for (int d = 1; d < nd; ++d) {
-        if (totals[d]) {
-            if (ub[d] != base) memmove(out->arena + base, out->arena + ub[d], totals[d]);
-            for (uint64_t s = 2 * bounds[d]; s < 2 * bounds[d + 1]; ++s) out->off[s] += base;
-        } else {
-            for (uint64_t s = 2 * bounds[d]; s < 2 * bounds[d + 1]; ++s) out->off[s] = base;
-        }
-        base += totals[d];
-    }
-    out->off[2 * N] = base;
+    rc = run_align_job(J);
+    tmp.release_all();
+    if (rc) { bg_result_free(out); return rc; }
+    if (pp.score_only) memset(out->off, 0, (2 * N + 1) * 8);
     if (prof) fprintf(stderr, "[bgalign] bg_align_batch returns at %.2f ms\n", since());
     return BG_OK;
+}
+
+// Compact form of bg_align_batch: the same alignments as 2-bit ops (see bgalign.h).  A shim that builds its own
+// containers (Vec<u8> per Sequence, ds/sequence.rs:10-13) expands each pair straight into them with bg_expand_ops.
+int bg_align_batch_ops(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_ops_result* out) {
+    if (!ctx || !in || !p || !out) return BG_EINVAL_ARG;
+    memset(out, 0, sizeof *out);
+    if (p->flags & BG_F_SCORE_ONLY) { ctx->set_error("bg_align_batch_ops: use bg_align_batch for score-only calls"); return BG_EINVAL_ARG; }
+    BatchScan scan;
+    Prepared pp;
+    int rc = begin_align_call(ctx, in, p, scan, pp);
+    if (rc) return rc;
+    const uint64_t N = in->n_pairs;
+    HostResultOwner* own = new HostResultOwner();
+    AlignJob J;
+    J.ctx = ctx; J.in = in; J.pp = &pp; J.scan = &scan;
+    J.oo.ops_cap_words = ops_capacity_words(in, (int)ctx->devs.size());
+    J.oo.score = (int32_t*)own->grab(N * 4); J.oo.status = (uint8_t*)own->grab(N);
+    J.oo.len = (uint32_t*)own->grab(std::max<uint64_t>(1, N) * 4); J.oo.first = (uint32_t*)own->grab(std::max<uint64_t>(1, N) * 8);
+    J.oo.ops = (uint32_t*)own->grab(J.oo.ops_cap_words * 4 + 64); J.oo.ops_off = (uint64_t*)own->grab((N + 1) * 8);
+    out->n_pairs = N; out->owner_ = own;
+    out->score = J.oo.score; out->status = J.oo.status; out->len = J.oo.len; out->first = J.oo.first; out->ops = J.oo.ops; out->ops_off = J.oo.ops_off;
+    if (!out->score || !out->status || !out->len || !out->first || !out->ops || !out->ops_off) {
+        bg_ops_result_free(out); ctx->set_error("pinned host allocation failed"); return BG_ENOMEM;
+    }
+    rc = run_align_job(J);
+    if (rc) { bg_ops_result_free(out); return rc; }
+    out->ops_off[N] = J.oo.ops_cap_words;
+    return BG_OK;
+}
+
+void bg_ops_result_free(bg_ops_result* r) {
+    if (!r) return;
+    if (r->owner_) {
+        HostResultOwner* own = (HostResultOwner*)r->owner_;
+        own->release_all();
+        delete own;
+    }
+    memset(r, 0, sizeof *r);
 }
 
 int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {

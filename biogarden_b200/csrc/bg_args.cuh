@@ -24,6 +24,33 @@ struct FillArgs {
     int32_t tg_shift;          // K1h trace tiling (k1h_fill.cuh)
 };
 
+// ---- K0 (k0_plan.cuh): launch descriptors built on the device ----
+// The host only classifies (it reads the offsets once anyway to validate them) and sizes; which pair sits in which
+// launch slot, the K1h holes, the trace / output / scratch offsets are computed on the GPU from the offsets alone.
+constexpr int PLAN_MAX_CLS = 16;
+struct PlanCls {
+    int32_t L, C;                    // kernel shape of the class
+    uint32_t half;                   // 1: K1h -- two pairs per lane group with equal row counts, so runs of equal
+                                     //    len1 are padded to even length with empty slots ("holes")
+    uint32_t G2;                     // slots per warp
+    uint32_t sorted_begin, count;    // the class's range in the sorted pair order (class, then len1 descending)
+    uint32_t slot_begin, slot_cap;   // its descriptor range; cap = upper bound incl. holes, a multiple of G2
+    uint64_t pad_base;               // bytes: exact (the host sums the slot sizes per class)
+    uint64_t bnd_base;               // int2 elements: exact
+};
+struct PlanArgs {
+    const uint64_t* off;             // [2n + 1] sequence offsets of the item (device copy of the caller's slice)
+    uint64_t base;                   // off[0]: the item's residues start at device offset 0
+    uint32_t n_pairs, n_cls;
+    uint32_t half_ok;                // as in pick_shape_m
+    int32_t force_si;                // >= 0: every pair uses this shape (bg_set_shape)
+    uint64_t* keys;                  // [n] sort keys: class rank << 32 | (0x7fffffff - len1)
+    uint32_t* ids;                   // [n] pair ids in key order (nullptr: identity -- one class, one len1)
+    PairDesc* desc;
+    int8_t rank_of_shape[16];        // shape number -> class rank in cls[] (-1: not present)
+    PlanCls cls[PLAN_MAX_CLS];
+};
+
 // ---- K1h (k1h_fill.cuh) ----
 constexpr int32_t HB_BIAS = 1 << 15;
 constexpr int32_t HB_NEG = 1 << 8;       // biased "minus infinity": below every value a cell can take (>= 2^15 - 2*HB_RANGE - 3*HB_MAXABS)
@@ -97,6 +124,16 @@ struct GatherArgs {
     const uint64_t* off;   // exclusive scan of lens2
     uint8_t* arena;
     const uint8_t* residues;
+};
+struct PackOpsArgs {
+    const PairDesc* desc;
+    uint32_t n_slots;
+    const uint8_t* pad;      // op slots written by the walkers
+    const uint64_t* lens2;   // [2 * pairs + 1]: aligned length of pair p at [2p]
+    const uint64_t* woff;    // [pairs + 1]: exclusive scan of ceil(len / 16)
+    uint32_t* len;           // [pairs]
+    uint32_t* first;         // [2 * pairs]: (first_a, first_b) -- the strings start at seq1[first_a], seq2[first_b]
+    uint32_t* ops;           // dense op words
 };
 
 // ---- K4 (k4_edit.cuh) ----

@@ -8,8 +8,9 @@
 //
 // One thread per pair: the walk is a serial chain of dependent 4-byte loads, so the way to
 // keep the machine busy is many independent walks per SM, not lanes cooperating on one.
-// Characters are produced back to front into a padded slot of 2*round_up(n+m,4) bytes; k_gather then
-// packs all strings densely (offsets from a device-side scan of the lengths).
+// Every walker records one 2-bit op per alignment column, back to front, into the pair's slot; from there either
+// k_gather materialises the two strings on the device (device-resident results), or k_pack_ops packs the ops
+// densely for the trip to the host, where host_expand.cpp turns them into strings (host-buffer entry points).
 #pragma once
 #include "bg_args.cuh"
 
@@ -128,275 +129,12 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     A.lens2[2ull * d.pair_id + 1] = len;
 }
 
-// K3, long-pair form: one WARP per pair.  A walk over a 100 kbp pair is ~150k dependent steps; one
-// thread pays a full memory round trip for each.  Here the 32 lanes fetch the direction codes of the
-// next 32 cells the walk would visit if it kept doing what it is doing -- along the diagonal in state
-// 'M', up the column in state 'X', along the row in state 'Y' -- and the whole run that really
-// continues is emitted at once with coalesced stores (the codes decide, exactly as in the scalar walk;
-// nothing is recomputed).  Whatever stops a run is handled by one iteration of the scalar state
-// machine, so the emitted path is the reference's path, character for character.
-__global__ void __launch_bounds__(128) k3_walk_warp(const WalkArgs A) {
-    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t q = threadIdx.x & 31;
-    constexpr unsigned FULL = 0xffffffffu;
-    if (slot >= A.n_slots) return;
-    const PairDesc d = A.desc[slot];
-    if (d.pair_id == 0xFFFFFFFFu) return;
-    const EndCell e = A.end[slot];
-    const uint32_t n = d.n, m = d.m;
-    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
-    const uint32_t K = (C + 7) / 8;
-    const uint32_t band_cols = L * C;
-    const uint32_t lane_base = (slot % (32u / L)) * L;
-    const uint8_t* sa = A.residues + d.a_off;
-    const uint8_t* sb = A.residues + d.b_off;
-    const uint32_t cap4 = (n + m + 3u) & ~3u;
-    uint8_t* outA = A.pad + d.pad_off;
-    uint8_t* outB = outA + cap4;
-    uint32_t pos = cap4;
-    const int mode = A.mode;
-
-    auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
-        const uint32_t j0 = j - 1;
-        const uint32_t bd = j0 / band_cols, rr = j0 - bd * band_cols;
-        const uint32_t p = rr / C, c = rr - p * C;
-        const uint32_t t = (i - 1) + p;
-        const uint64_t idx = d.trace_off + ((uint64_t)bd * d.steps + t) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
-        return (__ldg(A.trace + idx) >> ((c & 7u) * 4u)) & 15u;
-    };
-    auto valid_at = [&](int64_t kk, int64_t ll, uint32_t nib) -> bool {
-        if (kk < 0 || ll < 0) return false;
-        const bool interior = (kk != 0 && ll != 0);
-        switch (mode) {
-            case M_GLOBAL: return (kk != 0 || ll != 0);
-            case M_LOCAL: return interior && (nib & 3u) != 3u;
-            case M_SEMIGLOBAL: return interior;
-            default: return ll != 0;
-        }
-    };
-
-    uint32_t k = e.k, l = e.l, flags = 0;
-    const bool colbr = (e.flags & 1u) != 0;
-    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404, emitted 32 characters at a time
-        if (colbr) { for (uint32_t i = n; i > k; ) { const uint32_t cnt = min(32u, i - k); if (q < cnt) { outA[pos - 1 - q] = sa[i - 1 - q]; outB[pos - 1 - q] = '-'; } pos -= cnt; i -= cnt; } }
-        else       { for (uint32_t i = m; i > l; ) { const uint32_t cnt = min(32u, i - l); if (q < cnt) { outA[pos - 1 - q] = '-'; outB[pos - 1 - q] = sb[i - 1 - q]; } pos -= cnt; i -= cnt; } }
-    }
-    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
-    const uint64_t bound = 2ull * ((uint64_t)n + m) + 8;
-    for (uint64_t it = 0;; ++it) {
-        if (it > bound) { flags |= WALK_HANG; break; }
-        // ---- vector phase: how far does the current kind of move continue? ----
-        const int64_t kq = (int64_t)k - ((cur == 2) ? 0 : (int64_t)q);
-        const int64_t lq = (int64_t)l - ((cur == 1) ? 0 : (int64_t)q);
-        const bool inb = (kq >= 1 && lq >= 1);
-        // the residues this lane would emit are fetched together with its direction code, so one memory
-        // round trip per iteration is on the critical path, not two
-        const uint8_t ra = (cur != 2 && kq >= 1) ? __ldg(sa + kq - 1) : (uint8_t)'-';
-        const uint8_t rb = (cur != 1 && lq >= 1) ? __ldg(sb + lq - 1) : (uint8_t)'-';
-        const uint32_t nib = inb ? nib_at((uint32_t)kq, (uint32_t)lq) : 0u;
-        const bool vq = valid_at(kq, lq, nib);
-        bool cont;
-        if (cur == 0) cont = vq && inb && (nib & 3u) == 0;                      // 'R'
-        else if (cur == 1) cont = vq && kq >= 1 && !(inb && (nib & TR_XOPEN));   // keep extending the gap in seq2
-        else cont = vq && lq >= 1 && !(inb && (nib & TR_YOPEN));
-        const uint32_t stopmask = ~__ballot_sync(FULL, cont);
-        const uint32_t run = stopmask ? (uint32_t)__ffs((int)stopmask) - 1u : 32u;   // leading lanes that continue (0..32)
-        if (run > 0) {
-            if (q < run) { outA[pos - 1 - q] = ra; outB[pos - 1 - q] = rb; }
-            pos -= run;
-            if (cur != 2) k -= run;
-            if (cur != 1) l -= run;
-            continue;
-        }
-        // ---- scalar phase: one iteration of backtrack() at (k, l); lane 0 holds its code ----
-        const uint32_t nib0 = __shfl_sync(FULL, nib, 0);
-        const bool interior = (k != 0 && l != 0);
-        if (!valid_at(k, l, nib0)) break;
-        uint8_t ea = 0, eb = 0; bool emit = false;
-        if (cur == 0) {
-            uint32_t t;
-            if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib0 & TR_YEQ) ? 2u : (nib0 & TR_XEQ);
-            emit = true;   // lane 0's ra / rb are the residues at (k, l) in state 'M'
-            if (t == 0) { ea = ra; eb = rb; --k; --l; }
-            else if (t == 1) { ea = ra; eb = '-'; --k; cur = 1; }
-            else { ea = '-'; eb = rb; --l; cur = 2; }
-        } else if (cur == 1) {
-            if (interior && (nib0 & TR_XOPEN)) cur = 0;
-            else if (k == 0) { flags |= WALK_UNDERFLOW; break; }
-            else { emit = true; ea = ra; eb = '-'; --k; }
-        } else {
-            if (interior && (nib0 & TR_YOPEN)) cur = 0;
-            else if (l == 0) { flags |= WALK_UNDERFLOW; break; }
-            else { emit = true; ea = '-'; eb = rb; --l; }
-        }
-        if (emit) { --pos; if (q == 0) { outA[pos] = ea; outB[pos] = eb; } }
-    }
-    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
-        if (colbr) { for (uint32_t i = k; i > 0; ) { const uint32_t cnt = min(32u, i); if (q < cnt) { outA[pos - 1 - q] = sa[i - 1 - q]; outB[pos - 1 - q] = '-'; } pos -= cnt; i -= cnt; } }
-        else       { for (uint32_t i = l; i > 0; ) { const uint32_t cnt = min(32u, i); if (q < cnt) { outA[pos - 1 - q] = '-'; outB[pos - 1 - q] = sb[i - 1 - q]; } pos -= cnt; i -= cnt; } }
-    }
-    if (q == 0) {
-        const uint32_t len = cap4 - pos;
-        A.score[d.pair_id] = e.score;
-        A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
-        A.lens2[2ull * d.pair_id] = len;
-        A.lens2[2ull * d.pair_id + 1] = len;
-    }
-}
-
-// K3, tiled long-pair form: one warp per pair keeps a WINDOW of the trace in shared memory.
-// The walk only ever moves up and/or left, so the codes it will need next lie in the TILE_H x TILE_W
-// cell window whose bottom-right corner is the current cell.  The 32 lanes fetch that window with
-// independent loads (one memory latency for ~100 walk steps instead of one per step), then the
-// reference's scalar state machine runs against shared memory until it steps out of the window.
-// Unlike the run-lookahead form above this is insensitive to how gappy the path is (two unrelated
-// 75 kbp sequences change state every 2-3 cells).
-constexpr int TILE_H = 64;            // rows per window
-constexpr int TILE_WB = 9;            // 8-column blocks per window (covers >= 64 columns at any alignment)
-constexpr int WALK_TILE_WARPS = 4;
-
-__global__ void __launch_bounds__(WALK_TILE_WARPS * 32) k3_walk_tile(const WalkArgs A) {
-    __shared__ uint32_t s_tile[WALK_TILE_WARPS][TILE_H * TILE_WB];
-    __shared__ uint8_t s_outA[WALK_TILE_WARPS][2 * (TILE_H + 8 * TILE_WB) + 8];
-    __shared__ uint8_t s_outB[WALK_TILE_WARPS][2 * (TILE_H + 8 * TILE_WB) + 8];
-    __shared__ uint8_t s_resA[WALK_TILE_WARPS][TILE_H];             // seq1 residues of the window's rows
-    __shared__ uint8_t s_resB[WALK_TILE_WARPS][8 * TILE_WB];         // seq2 residues of the window's columns
-    const uint32_t wib = threadIdx.x >> 5;
-    const uint32_t slot = blockIdx.x * WALK_TILE_WARPS + wib;
-    const uint32_t q = threadIdx.x & 31;
-    if (slot >= A.n_slots) return;
-    const PairDesc d = A.desc[slot];
-    if (d.pair_id == 0xFFFFFFFFu) return;
-    const EndCell e = A.end[slot];
-    const uint32_t n = d.n, m = d.m;
-    const uint32_t L = (uint32_t)A.L, C = (uint32_t)A.C;
-    const uint32_t K = (C + 7) / 8;
-    const uint32_t band_cols = L * C;
-    const uint32_t lane_base = (slot % (32u / L)) * L;
-    const uint8_t* sa = A.residues + d.a_off;
-    const uint8_t* sb = A.residues + d.b_off;
-    const uint32_t cap4 = (n + m + 3u) & ~3u;
-    uint8_t* outA = A.pad + d.pad_off;
-    uint8_t* outB = outA + cap4;
-    uint32_t pos = cap4;
-    const int mode = A.mode;
-    uint32_t* tile = s_tile[wib];
-    uint8_t* bufA = s_outA[wib];
-    uint8_t* bufB = s_outB[wib];
-    uint8_t* resA = s_resA[wib];
-    uint8_t* resB = s_resB[wib];
-    constexpr uint32_t BUFCAP = 2 * (TILE_H + 8 * TILE_WB);
-
-    // coalesced block emission helper (semiglobal tail / prefix)
-    auto emit_run = [&](const uint8_t* src, uint32_t hi, uint32_t lo, bool into_a) {   // src[hi-1] .. src[lo] , descending
-        for (uint32_t i = hi; i > lo; ) {
-            const uint32_t cnt = min(32u, i - lo);
-            if (q < cnt) {
-                const uint8_t ch = src[i - 1 - q];
-                outA[pos - 1 - q] = into_a ? ch : (uint8_t)'-';
-                outB[pos - 1 - q] = into_a ? (uint8_t)'-' : ch;
-            }
-            pos -= cnt; i -= cnt;
-        }
-    };
-
-    uint32_t k = e.k, l = e.l, flags = 0;
-    const bool colbr = (e.flags & 1u) != 0;
-    if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
-        if (colbr) emit_run(sa, n, k, true); else emit_run(sb, m, l, false);
-    }
-    uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
-    const uint64_t bound = 3ull * ((uint64_t)n + m) + 64;   // emits + state switches + one probe per window
-    uint64_t it = 0;
-    bool done = false;
-    while (!done) {
-        // ---- load the window: rows (i_lo, k], 8-column blocks [cb_lo, cb_hi] ----
-        uint32_t i_lo = 0, cb_lo = 0;   // window covers rows i_lo+1 .. k, columns cb_lo*8+1 .. l
-        if (k >= 1 && l >= 1) {
-            i_lo = (k > (uint32_t)TILE_H) ? k - TILE_H : 0;
-            const uint32_t cb_hi = (l - 1) >> 3;
-            cb_lo = (cb_hi + 1 > (uint32_t)TILE_WB) ? cb_hi + 1 - TILE_WB : 0;
-            const uint32_t rows = k - i_lo, nb = cb_hi - cb_lo + 1;
-            for (uint32_t x = q; x < rows * nb; x += 32) {
-                const uint32_t rr = x / nb, cb = cb_lo + (x - rr * nb);
-                const uint32_t i = i_lo + 1 + rr;
-                const uint32_t j0 = cb << 3;
-                const uint32_t bd = j0 / band_cols, rem = j0 - bd * band_cols;
-                const uint32_t p = rem / C, c = rem - p * C;
-                const uint32_t t = (i - 1) + p;
-                const uint64_t idx = d.trace_off + ((uint64_t)bd * d.steps + t) * (uint64_t)(K * 32u) + (uint64_t)(c >> 3) * 32u + lane_base + p;
-                tile[rr * TILE_WB + (cb - cb_lo)] = __ldg(A.trace + idx);
-            }
-            for (uint32_t x = q; x < rows; x += 32) resA[x] = sa[i_lo + x];                                   // row i_lo+1+x
-            for (uint32_t x = q; x < nb * 8; x += 32) { const uint32_t j0 = (cb_lo << 3) + x; resB[x] = (j0 < m) ? sb[j0] : 0; }
-        }
-        __syncwarp();
-        const uint32_t j_lo = cb_lo << 3;   // columns j_lo+1 .. l are cached
-        const uint32_t k_hi = k, l_hi = l;  // window anchor
-        auto ra_at = [&](uint32_t kk) -> uint8_t { return (kk > i_lo && kk <= k_hi && l_hi >= 1 && k_hi >= 1) ? resA[kk - i_lo - 1] : sa[kk - 1]; };
-        auto rb_at = [&](uint32_t ll) -> uint8_t { return (ll > j_lo && ll <= l_hi && l_hi >= 1 && k_hi >= 1) ? resB[ll - j_lo - 1] : sb[ll - 1]; };
-        // ---- scalar walk inside the window (all lanes execute it redundantly; lane 0 emits) ----
-        uint32_t nbuf = 0;
-        for (;;) {
-            if (++it > bound) { flags |= WALK_HANG; done = true; break; }
-            const bool interior = (k != 0 && l != 0);
-            if (interior && (k <= i_lo || l <= j_lo)) break;            // stepped out of the window: reload
-            uint32_t nib = 0;
-            if (interior) nib = (tile[(k - i_lo - 1) * TILE_WB + (((l - 1) >> 3) - cb_lo)] >> (((l - 1) & 7u) * 4u)) & 15u;
-            bool valid;
-            switch (mode) {
-                case M_GLOBAL: valid = (k != 0 || l != 0); break;
-                case M_LOCAL: valid = interior && (nib & 3u) != 3u; break;
-                case M_SEMIGLOBAL: valid = interior; break;
-                default: valid = (l != 0); break;
-            }
-            if (!valid) { done = true; break; }
-            uint8_t ea = 0, eb = 0; bool emit = false;
-            if (cur == 0) {
-                uint32_t t;
-                if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib & TR_YEQ) ? 2u : (nib & TR_XEQ);
-                emit = true;
-                if (t == 0) { ea = ra_at(k); eb = rb_at(l); --k; --l; }
-                else if (t == 1) { ea = ra_at(k); eb = '-'; --k; cur = 1; }
-                else { ea = '-'; eb = rb_at(l); --l; cur = 2; }
-            } else if (cur == 1) {
-                if (interior && (nib & TR_XOPEN)) cur = 0;
-                else if (k == 0) { flags |= WALK_UNDERFLOW; done = true; break; }
-                else { emit = true; ea = ra_at(k); eb = '-'; --k; }
-            } else {
-                if (interior && (nib & TR_YOPEN)) cur = 0;
-                else if (l == 0) { flags |= WALK_UNDERFLOW; done = true; break; }
-                else { emit = true; ea = '-'; eb = rb_at(l); --l; }
-            }
-            if (emit) {
-                if (q == 0) { bufA[nbuf] = ea; bufB[nbuf] = eb; }
-                if (++nbuf == BUFCAP) break;                           // flush (cannot happen inside one window, kept as a guard)
-            }
-        }
-        __syncwarp();
-        // ---- flush the characters of this window, coalesced ----
-        for (uint32_t x = q; x < nbuf; x += 32) { outA[pos - 1 - x] = bufA[x]; outB[pos - 1 - x] = bufB[x]; }
-        pos -= nbuf;
-        __syncwarp();
-    }
-    if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
-        if (colbr) emit_run(sa, k, 0, true); else emit_run(sb, l, 0, false);
-    }
-    if (q == 0) {
-        const uint32_t len = cap4 - pos;
-        A.score[d.pair_id] = e.score;
-        A.walk_flags[d.pair_id] = (uint8_t)ref_status(mode, n, m, e.score, flags);
-        A.lens2[2ull * d.pair_id] = len;
-        A.lens2[2ull * d.pair_id + 1] = len;
-    }
-}
-
 // K3, diagonal-window long-pair form: one warp per pair, 2-bit op output.
 // A walk over a long pair is ~(n + m) dependent steps; what limits it is how many steps it gets out of one
 // round of memory latency.  The path of two related sequences hugs a diagonal, so the window follows the
 // diagonal: DIAG_ROWS rows tall, and in row k - r the 9 eight-column blocks around column l - r (+-32
 // columns of drift).  The 32 lanes fetch the window with independent loads (one latency for up to
-// DIAG_ROWS steps; the square window of k3_walk_tile gave 64), then the reference's scalar state machine
+// DIAG_ROWS steps; a square 64 x 64 window, the first design, gave 64), then the reference's scalar state machine
 // runs against shared memory until the path leaves the window (long gap runs, drift) and the window is
 // re-anchored at the current cell.  Like k3_walk the walk only records 2-bit ops; k_gather turns them into
 // strings.  Needs C % 8 == 0 (an eight-column block is one trace word), true for K2 and the wide K1 shapes.
@@ -846,10 +584,8 @@ __global__ void k_bump(uint64_t* base, const uint64_t* chunk_total_entry, uint64
     *base += t;
 }
 
-// Dense packing: one warp per slot writes a_align then b_align to arena[off[2p]..], arena[off[2p+1]..]:
-// a copy for the long-pair walkers (character slots), and for k3_walk's op slots (PairDesc::pad_ == 1) the
-// materialisation -- op q reads seq1[first_a + #(ops before q that consume seq1)] resp. seq2 likewise, the
-// counts coming from warp ballots.
+// Dense packing: one warp per slot writes a_align then b_align to arena[off[2p]..], arena[off[2p+1]..]: op q reads
+// seq1[first_a + #(ops before q that consume seq1)] resp. seq2 likewise, the counts coming from warp ballots.
 
 __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
     const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -859,7 +595,7 @@ __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
     if (d.pair_id == 0xFFFFFFFFu) return;
     const uint64_t o0 = A.off[2ull * d.pair_id], o1 = A.off[2ull * d.pair_id + 1];
     const uint32_t len = (uint32_t)(o1 - o0);
-    if (d.pad_ == 1u) {
+    {
         const uint32_t* slotw = reinterpret_cast<const uint32_t*>(A.pad + d.pad_off);
         const uint32_t* ops = slotw + 2;
         const uint8_t* sa = A.residues + d.a_off;
@@ -891,14 +627,46 @@ __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
             if (v1) { A.arena[o0 + x1] = ca1; A.arena[o1 + x1] = cb1; }
             ia = ia1 + __popc(bA1); ib = ib1 + __popc(bB1);
         }
-        return;
     }
-    const uint32_t cap4 = (d.n + d.m + 3u) & ~3u;
-    const uint8_t* srcA = A.pad + d.pad_off + (cap4 - len);
-    const uint8_t* srcB = srcA + cap4;
-    for (uint32_t x = lane; x < len; x += 32) {
-        A.arena[o0 + x] = srcA[x];
-        A.arena[o1 + x] = srcB[x];
+}
+
+// Compact results for the trip to the host (host-buffer entry points): instead of strings, every pair's ops are
+// moved to the front of a dense, word-aligned run -- out word j of pair p holds columns 16 j .. 16 j + 15, column 0
+// being the first alignment column -- next to its length and start cell.  About 0.3 B per column travels D2H
+// instead of 2 B; host_expand.cpp rebuilds the strings from the caller's own residues.
+//   words[p] = ceil(len / 16) is scanned by the caller between k_ops_words and k_pack_ops.
+__global__ void k_ops_words(const uint64_t* lens2, uint64_t n_pairs, uint64_t* words) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_pairs) words[p] = (lens2[2 * p] + 15ull) >> 4;
+    if (p == n_pairs) words[p] = 0;
+}
+
+template <int G>   // lanes per slot
+__global__ void __launch_bounds__(128) k_pack_ops(const PackOpsArgs A) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t lane = threadIdx.x % G;
+    if (slot >= A.n_slots) return;
+    const PairDesc d = A.desc[slot];
+    if (d.pair_id == 0xFFFFFFFFu) return;
+    const uint32_t* slotw = reinterpret_cast<const uint32_t*>(A.pad + d.pad_off);
+    const uint32_t* ops = slotw + 2;
+    const uint32_t len = (uint32_t)A.lens2[2ull * d.pair_id];
+    const uint32_t pos0 = d.n + d.m - len;
+    const uint32_t cap_words = (d.n + d.m + 15u) >> 4;
+    if (lane == 0) {
+        A.len[d.pair_id] = len;
+        A.first[2ull * d.pair_id] = slotw[0];
+        A.first[2ull * d.pair_id + 1] = slotw[1];
+    }
+    const uint32_t nw = (len + 15u) >> 4, w0 = pos0 >> 4, sh = (pos0 & 15u) * 2u;
+    uint32_t* dst = A.ops + A.woff[d.pair_id];
+    for (uint32_t j = lane; j < nw; j += G) {
+        const uint32_t lo = __ldg(ops + w0 + j);
+        const uint32_t hi = (sh && w0 + j + 1 < cap_words) ? __ldg(ops + w0 + j + 1) : 0u;
+        uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
+        const uint32_t left = len - 16u * j;                 // columns from this word on
+        if (left < 16u) v &= (1u << (2u * left)) - 1u;       // deterministic tail bits
+        dst[j] = v;
     }
 }
 

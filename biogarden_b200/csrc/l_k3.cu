@@ -32,8 +32,6 @@ void launch_long_walk(LongWalk kind, bool k2_geometry, uint32_t ns, cudaStream_t
         if (k2_geometry) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(a);
         else k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(a);
         break;
-    case LW_TILE: k3_walk_tile<<<(ns + WALK_TILE_WARPS - 1) / WALK_TILE_WARPS, WALK_TILE_WARPS * 32, 0, st>>>(a); break;
-    default: k3_walk_warp<<<(ns + 3) / 4, 128, 0, st>>>(a); break;
     }
 }
 
@@ -41,6 +39,13 @@ void launch_scores_only(const PairDesc* desc, const EndCell* end, uint32_t ns, i
     k_scores_only<<<(ns + 127) / 128, 128, 0, st>>>(desc, end, ns, score, flags, mode);
 }
 void launch_gather(const GatherArgs& a, cudaStream_t st) { k_gather<<<(unsigned)((a.n_slots + 3) / 4), 128, 0, st>>>(a); }
+void launch_ops_words(const uint64_t* lens2, uint64_t n_pairs, uint64_t* words, cudaStream_t st) {
+    k_ops_words<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(lens2, n_pairs, words);
+}
+void launch_pack_ops(const PackOpsArgs& a, bool long_pairs, cudaStream_t st) {
+    if (long_pairs) k_pack_ops<32><<<(unsigned)(((uint64_t)a.n_slots * 32 + 127) / 128), 128, 0, st>>>(a);
+    else k_pack_ops<8><<<(unsigned)(((uint64_t)a.n_slots * 8 + 127) / 128), 128, 0, st>>>(a);
+}
 void launch_rebase(uint64_t* off, uint64_t count, const uint64_t* base, cudaStream_t st) {
     k_rebase<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(off, count, base);
 }

@@ -35,6 +35,11 @@ class bg_result(C.Structure):
                 ("off", C.c_void_p), ("owner_", C.c_void_p)]
 
 
+class bg_ops_result(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("score", C.c_void_p), ("status", C.c_void_p), ("len", C.c_void_p),
+                ("first", C.c_void_p), ("ops", C.c_void_p), ("ops_off", C.c_void_p), ("owner_", C.c_void_p)]
+
+
 class bg_fasta(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("residues", C.c_void_p), ("seq_off", C.c_void_p),
                 ("ids", C.c_void_p), ("id_off", C.c_void_p)]
@@ -56,7 +61,8 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status"]
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status",
+           "bg_align_batch_ops", "bg_ops_result_free", "bg_expand_ops", "bg_expand_kind"]
 
 _lib = None
 
@@ -79,6 +85,12 @@ def lib():
     L.bg_align_batch.restype = ci
     L.bg_align_batch.argtypes = [vp, C.POINTER(bg_batch), C.POINTER(bg_params), C.POINTER(bg_result)]
     L.bg_result_free.restype = None; L.bg_result_free.argtypes = [C.POINTER(bg_result)]
+    L.bg_align_batch_ops.restype = ci
+    L.bg_align_batch_ops.argtypes = [vp, C.POINTER(bg_batch), C.POINTER(bg_params), C.POINTER(bg_ops_result)]
+    L.bg_ops_result_free.restype = None; L.bg_ops_result_free.argtypes = [C.POINTER(bg_ops_result)]
+    L.bg_expand_ops.restype = ci; L.bg_expand_ops.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.bg_expand_ops_impl.restype = ci; L.bg_expand_ops_impl.argtypes = [ci, vp, vp, vp, u64, vp, vp]
+    L.bg_expand_kind.restype = C.c_char_p; L.bg_expand_kind.argtypes = []
     L.bg_edit_distance_batch.restype = ci; L.bg_edit_distance_batch.argtypes = [vp, C.POINTER(bg_batch), vp]
     L.bg_batch_upload.restype = ci; L.bg_batch_upload.argtypes = [vp, ci, C.POINTER(bg_batch), C.POINTER(vp)]
     L.bg_dbatch_free.restype = None; L.bg_dbatch_free.argtypes = [vp]
@@ -218,6 +230,71 @@ class Result:
             pass
 
 
+def _view(ptr, dtype, count):
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype)
+    buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class OpsResult:
+    """Owns a bg_ops_result (compact results: 2-bit ops per alignment column); numpy views valid until close()."""
+
+    def __init__(self, c_res: bg_ops_result, batch: "Batch"):
+        self._c = c_res
+        self.batch = batch
+        n = int(c_res.n_pairs)
+        self.n_pairs = n
+        self.score = _view(c_res.score, np.int32, n)
+        self.status = _view(c_res.status, np.uint8, n)
+        self.len = _view(c_res.len, np.uint32, n)
+        self.first = _view(c_res.first, np.uint32, 2 * n)
+        self.ops_off = _view(c_res.ops_off, np.uint64, n + 1)
+        self.ops = _view(c_res.ops, np.uint32, int(self.ops_off[-1]) if n else 0)
+
+    def strings(self, p, impl=None):
+        """(a_align, b_align) of pair p through bg_expand_ops (impl: None = the library's choice, 0 scalar, 1 AVX-512)."""
+        ln = int(self.len[p])
+        a = np.zeros(max(1, ln), np.uint8); b = np.zeros(max(1, ln), np.uint8)
+        bt = self.batch
+        s1 = bt.residues.ctypes.data + int(bt.seq_off[2 * p]) + int(self.first[2 * p])
+        s2 = bt.residues.ctypes.data + int(bt.seq_off[2 * p + 1]) + int(self.first[2 * p + 1])
+        ops = self.ops.ctypes.data + 4 * int(self.ops_off[p]) if self.ops.size else None
+        if impl is None:
+            check(lib().bg_expand_ops(s1, s2, ops, ln, a.ctypes.data, b.ctypes.data))
+        else:
+            check(lib().bg_expand_ops_impl(impl, s1, s2, ops, ln, a.ctypes.data, b.ctypes.data))
+        return bytes(a[:ln]), bytes(b[:ln])
+
+    def close(self):
+        if self._c is not None:
+            lib().bg_ops_result_free(C.byref(self._c))
+            self._c = None
+            self.score = self.status = self.len = self.first = self.ops = self.ops_off = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def expand_ops(s1: bytes, s2: bytes, ops: np.ndarray, length: int, impl=None):
+    """bg_expand_ops on host buffers (s1 / s2 start at the first residue the alignment consumes)."""
+    ops = np.ascontiguousarray(ops, np.uint32)
+    a = np.zeros(max(1, length), np.uint8); b = np.zeros(max(1, length), np.uint8)
+    b1 = np.frombuffer(s1 + b"\0", np.uint8); b2 = np.frombuffer(s2 + b"\0", np.uint8)
+    if impl is None:
+        check(lib().bg_expand_ops(b1.ctypes.data, b2.ctypes.data, ops.ctypes.data, length, a.ctypes.data, b.ctypes.data))
+    else:
+        check(lib().bg_expand_ops_impl(impl, b1.ctypes.data, b2.ctypes.data, ops.ctypes.data, length, a.ctypes.data, b.ctypes.data))
+    return bytes(a[:length]), bytes(b[:length])
+
+
+def expand_kind() -> str:
+    return lib().bg_expand_kind().decode()
+
+
 class Context:
     """bg_ctx: one engine instance (SequenceAligner::new, aligner.rs:44)."""
 
@@ -251,6 +328,11 @@ class Context:
         r = bg_result()
         check(lib().bg_align_batch(self.h, C.byref(batch.c), C.byref(params.c), C.byref(r)), self.h)
         return Result(r)
+
+    def align_batch_ops(self, batch: Batch, params: Params) -> OpsResult:
+        r = bg_ops_result()
+        check(lib().bg_align_batch_ops(self.h, C.byref(batch.c), C.byref(params.c), C.byref(r)), self.h)
+        return OpsResult(r, batch)
 
     def edit_distance_batch(self, batch: Batch) -> np.ndarray:
         out = np.zeros(batch.n_pairs, np.uint64)

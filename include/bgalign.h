@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BG_API_VERSION 1
+#define BG_API_VERSION 2
 
 typedef struct bg_ctx bg_ctx;
 
@@ -135,6 +135,34 @@ int bg_version(void);
  * (aligner.rs:84,150,216,290,351).  H2D of the batch, all kernels, D2H of the results. */
 int bg_align_batch(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_result* out);
 void bg_result_free(bg_result* r);
+
+/* ---- the hot path, compact results ---------------------------------------------------- */
+/* The same alignments as bg_align_batch, but as WHAT backtrack() emitted instead of the emitted characters: one
+ * 2-bit op per alignment column -- 0: both residues (aligner.rs:531-536), 1: seq1 residue over '-' (:537-541,
+ * :561-565), 2: '-' over seq2 residue (:542-547, :578-582) -- 16 ops per little-endian word, column q of pair p at
+ * bits [2 (q & 15), +2) of ops[ops_off[p] + (q >> 4)], column 0 first.  The strings are
+ *     a_align = expand(seq1 from first[2p], ops), b_align = expand(seq2 from first[2p+1], ops), both len[p] long,
+ * which bg_expand_ops does (AVX-512 VBMI2 when the host has it).  A shim that owns its containers expands every
+ * pair straight into them; bg_align_batch does exactly that into its arena.  D2H traffic is ~0.3 B per column
+ * instead of 2 B.  ops_off leaves gaps between pipeline chunks; ops_off[n_pairs] = size of ops in words. */
+typedef struct {
+    uint64_t n_pairs;
+    int32_t* score;    /* [n_pairs] */
+    uint8_t* status;   /* [n_pairs] bg_status */
+    uint32_t* len;     /* [n_pairs] aligned length in columns */
+    uint32_t* first;   /* [2 * n_pairs] index of the first residue of seq1 / seq2 inside the alignment */
+    uint32_t* ops;
+    uint64_t* ops_off; /* [n_pairs + 1] word offsets into ops */
+    void* owner_;      /* private */
+} bg_ops_result;
+int bg_align_batch_ops(bg_ctx* ctx, const bg_batch* in, const bg_params* p, bg_ops_result* out);
+void bg_ops_result_free(bg_ops_result* r);
+/* Expands `len` ops into a_out / b_out (len bytes each).  seq1_from / seq2_from point at the first residue the
+ * alignment consumes, i.e. residues + seq_off[2p] + first[2p] resp. residues + seq_off[2p+1] + first[2p+1]. */
+int bg_expand_ops(const uint8_t* seq1_from, const uint8_t* seq2_from, const uint32_t* ops, uint64_t len,
+                  uint8_t* a_out, uint8_t* b_out);
+/* "avx512-vbmi2" or "scalar": which implementation bg_expand_ops uses on this host. */
+const char* bg_expand_kind(void);
 
 /* analysis::seq::edit_distance for every pair (seq.rs:105-130): out[p] = distance.  Never
  * fails on any byte content (the reference never errs). */

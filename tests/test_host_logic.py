@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(native.SYMBOLS) == declared
-    assert L.bg_version() == 1
+    assert L.bg_version() == 2
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
@@ -165,3 +165,34 @@ def test_bounded_memory_plan_layout():
     a = np.array([(9000, 170000)], np.uint64).reshape(-1)
     out = np.zeros(5, np.uint64)
     assert L.bg_debug_plan_long(a.ctypes.data, 1, 1 << 20, out.ctypes.data) == native.BG_ENOMEM
+
+
+def test_host_expander_matches_definition():
+    """bg_expand_ops (host_expand.cpp): 2-bit ops -> aligned strings, both implementations (portable and, when the
+    host has it, AVX-512 VBMI2) against the definition written out in Python; lengths around the 16-op word and the
+    64-column vector width, all-gap runs, empty alignment.  Pure host code: no GPU involved."""
+    import random
+    rng = random.Random(3)
+    impls = [0] + ([1] if native.expand_kind() == "avx512-vbmi2" else [])
+    for ln in list(range(0, 70)) + [127, 128, 129, 191, 192, 193, 1000, 4097]:
+        for bias in (0.05, 0.5):
+            ops_list = [0 if rng.random() > bias else rng.choice((1, 2)) for _ in range(ln)]
+            na = sum(1 for o in ops_list if o != 2); nb = sum(1 for o in ops_list if o != 1)
+            s1 = bytes(rng.choice(b"ACGT") for _ in range(na)); s2 = bytes(rng.choice(b"ACGT") for _ in range(nb))
+            words = np.zeros((ln + 15) // 16 + 1, np.uint32)
+            for q, o in enumerate(ops_list):
+                words[q >> 4] |= np.uint32(o << (2 * (q & 15)))
+            ia = ib = 0
+            wa, wb = bytearray(), bytearray()
+            for o in ops_list:
+                if o != 2:
+                    wa.append(s1[ia]); ia += 1
+                else:
+                    wa.append(45)
+                if o != 1:
+                    wb.append(s2[ib]); ib += 1
+                else:
+                    wb.append(45)
+            for impl in impls + [None]:
+                got = native.expand_ops(s1, s2, words, ln, impl)
+                assert got == (bytes(wa), bytes(wb)), (ln, bias, impl)
