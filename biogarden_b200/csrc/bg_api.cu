@@ -165,6 +165,8 @@ struct WorkSet {
     cudaStream_t walk_stream = nullptr;   // traceback walks of chunk c run here, next to the fill of chunk c+1
     cudaStream_t post_stream = nullptr;   // host-buffer pipeline: walk + scan + gather of this set's chunk go here (next to the next chunk's fill)
     uint64_t split_cap_words = (6ull << 30) / 4;   // all launches of a plan get their own trace region up to this total
+    int launch_parity = -1;               // host-buffer pipeline: >= 0 -> this item's first fill goes to the main (0) or the second (1) fill stream, so that
+                                          // the fills of consecutive items alternate and the tail of one overlaps the head of the next
     cudaStream_t fill2_stream = nullptr;  // host-buffer pipeline: every other fill launch of a chunk goes here, so that the tail of
                                           // one length class's launch overlaps the head of the next (their traces are disjoint)
     BlockCache* cache = nullptr;
@@ -175,6 +177,9 @@ struct WorkSet {
     DevBuf ckpt, wstate, ckslots;                                      // K2 bounded-memory traceback: row checkpoints, suspended walks, launch table
     DevBuf run;                                                        // (unused by the alignment pipeline since results travel as ops)
     DevBuf len, first, ops;                                            // pipeline mode: compact results of the chunk (k_pack_ops)
+    DevBuf samples;                                                    // pipeline mode: sampled offset scans of the chunk
+    PinBuf samples_h;
+    DevBuf poff, pkeys, pids, psort;                                   // pipeline mode: device-side planner (offsets of the chunk, sort keys / ids / scratch)
     PinBuf stage;                                                     // descriptor staging
     PinBuf scalars;                                                   // [0] total bytes (u64), [1] err flag
     cudaEvent_t ev_scan = nullptr;
@@ -187,7 +192,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots, &len, &first, &ops};
+        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots, &len, &first, &ops, &poff, &pkeys, &pids, &psort, &samples};
     }
 };
 
@@ -258,6 +263,7 @@ struct bg_ctx {
     uint64_t trace_budget_words = 0;
     uint64_t long_budget_words = 0;   // K2 pairs; 0 = automatic (most of the device)
     int force_L = 0, force_C = 0;
+    bool host_plan = false;           // build every launch plan on the host (default: pipeline chunks are planned on the device, k0_plan.cuh)
     int num_sms = 148;
     void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu); last_error = s; }
 };
@@ -345,7 +351,10 @@ class HostPool {
         unsigned share = 1;
         for (const char* v : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "SLURM_NTASKS_PER_NODE"})
             if (const char* e = getenv(v)) { const int x = atoi(e); if (x > 1) { share = (unsigned)x; break; } }
-        unsigned nt = std::max(3u, std::min(hw ? hw : 8u, 32u) / share);
+        // (two cores are left to the threads that drive the GPU -- issuer and finisher of the pipeline: with every core busy
+        //  expanding strings their wake-ups came up to 0.7 ms late, measured at the end of a cfg2 call)
+        const unsigned avail = std::min(hw ? hw : 8u, 32u) / share;
+        unsigned nt = std::max(3u, avail > 4 ? avail - 2 : avail);
         if (const char* e = getenv("BG_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
         for (unsigned t = 0; t < nt; ++t) std::thread([this] { run(); }).detach();
     }
@@ -742,16 +751,30 @@ struct Phase {
 // (cells) of every block of SCAN_BLOCK pairs -- everything the host-buffer entry points need before
 // they can start cutting chunks.  (Three separate serial passes cost ~8 ms per million pairs.)
 constexpr uint64_t SCAN_BLOCK = 4096;
+// What the device-side planner (k0_plan.cuh) needs to know about the pairs of one kernel shape, per SCAN_BLOCK pairs:
+// counted in the same pass that validates the offsets.
+struct ClassStat {
+    uint64_t count = 0, pad_bytes = 0, bnd_elems = 0, cells = 0;
+    uint32_t min_n = 0xFFFFFFFFu, max_n = 0, max_m = 0;
+    void add(const ClassStat& o) {
+        count += o.count; pad_bytes += o.pad_bytes; bnd_elems += o.bnd_elems; cells += o.cells;
+        min_n = std::min(min_n, o.min_n); max_n = std::max(max_n, o.max_n); max_m = std::max(max_m, o.max_m);
+    }
+};
 struct BatchScan {
     bool monotone = true, fitting_violation = false, has_wide = false;
     uint32_t class_mask = 0;          // length classes present (by len2)
     uint64_t max_len_sum = 0;
     std::vector<double> block_cost;   // per SCAN_BLOCK pairs
+    bool with_stats = false;          // block_cls filled (alignment calls with traceback)
+    bool half_ok = false; int force_si = -1;
+    std::vector<ClassStat> block_cls; // [block][BG_N_SHAPES]
 };
 void scan_batch(const bg_batch* in, BatchScan& S) {
     const uint64_t N = in->n_pairs;
     const uint64_t nblocks = (N + SCAN_BLOCK - 1) / SCAN_BLOCK;
     S.block_cost.assign(nblocks, 0.0);
+    if (S.with_stats) S.block_cls.assign(nblocks * BG_N_SHAPES, ClassStat());
     unsigned nt = std::thread::hardware_concurrency();
     nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(nt ? nt : 1, 16), nblocks / 8));
     std::vector<BatchScan> part(nt);
@@ -760,15 +783,31 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
         const uint64_t b_lo = nblocks * t / nt, b_hi = nblocks * (t + 1) / nt;
         const uint64_t* off = in->seq_off;
         uint64_t last_m = ~0ull;
+        uint64_t st_m = ~0ull; bool st_long = false; int st_si = 0; uint32_t st_band = 1;
         for (uint64_t blk = b_lo; blk < b_hi; ++blk) {
             const uint64_t q_hi = std::min(N, (blk + 1) * SCAN_BLOCK);
             double cost = 0;
+            ClassStat* cs = S.with_stats ? &S.block_cls[blk * BG_N_SHAPES] : nullptr;
             for (uint64_t q = blk * SCAN_BLOCK; q < q_hi; ++q) {
                 const uint64_t o0 = off[2 * q], o1 = off[2 * q + 1], o2 = off[2 * q + 2];
                 if (o1 < o0 || o2 < o1) { P.monotone = false; continue; }
                 const uint64_t n = o1 - o0, m = o2 - o1;
                 if (n < m) P.fitting_violation = true;
                 if (m > WAVE_MIN_COLS) P.has_wide = true;
+                if (cs && m <= WAVE_MIN_COLS && n < 0x7FFFFFF0ull) {
+                    const bool is_long = n + m > LONG_WALK_LEN;
+                    if (m != st_m || is_long != st_long) {
+                        st_m = m; st_long = is_long;
+                        const Shape sh = S.force_si >= 0 ? shape_at(S.force_si) : pick_shape_m((uint32_t)m, S.half_ok && !is_long, is_long);
+                        st_si = shape_index(sh); st_band = (uint32_t)(sh.L * sh.C);
+                    }
+                    ClassStat& c = cs[st_si];
+                    c.count++; c.cells += n * m;
+                    c.pad_bytes += 2ull * ((n + m + 3ull) & ~3ull) + 16ull;
+                    if (m > st_band) c.bnd_elems += n;
+                    c.min_n = std::min<uint32_t>(c.min_n, (uint32_t)n); c.max_n = std::max<uint32_t>(c.max_n, (uint32_t)n);
+                    c.max_m = std::max<uint32_t>(c.max_m, (uint32_t)m);
+                }
                 if (m != last_m) {
                     last_m = m;
                     P.class_mask |= 1u << (m <= 64 ? 0 : m <= 96 ? 1 : m <= 128 ? 2 : m <= 160 ? 3 : m <= 192 ? 4 : m <= 256 ? 5 : m <= 384 ? 6 :
@@ -832,6 +871,76 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
     return b;
 }
 
+// Launch plan of pairs [lo, hi) (lo a multiple of SCAN_BLOCK; hi a multiple or the batch end) for the DEVICE-side
+// planner: classes, descriptor ranges and trace regions sized from the scan's per-class statistics (upper bounds
+// where the exact value depends on the order the device will establish: K1h holes, per-warp step counts).  Returns
+// false when the item needs the host planner: a forced split into several launches per class (trace budget), too
+// many pairs, no statistics.
+bool plan_from_stats(const bg_ctx* ctx, const BatchScan& S, uint64_t lo, uint64_t hi, uint64_t budget_words, int32_t half_maxabs,
+                     Plan& P, PlanArgs& A, bool& need_sort) {
+    if (!S.with_stats || hi <= lo || (lo % SCAN_BLOCK) != 0 || hi - lo >= 0x7FFFFFF0ull) return false;
+    ClassStat cls[BG_N_SHAPES];
+    for (uint64_t blk = lo / SCAN_BLOCK; blk * SCAN_BLOCK < hi; ++blk)
+        for (int s = 0; s < BG_N_SHAPES; ++s) cls[s].add(S.block_cls[blk * BG_N_SHAPES + s]);
+    uint64_t counted = 0;
+    for (int s = 0; s < BG_N_SHAPES; ++s) counted += cls[s].count;
+    if (counted != hi - lo) return false;          // pairs outside the K1 / K1h classes (wide pairs, oversize)
+    P = Plan();
+    P.half_maxabs = half_maxabs;
+    A = PlanArgs();
+    A.n_pairs = (uint32_t)(hi - lo); A.half_ok = S.half_ok ? 1u : 0u; A.force_si = S.force_si; A.n_cls = 0;
+    for (int s = 0; s < 16; ++s) A.rank_of_shape[s] = -1;
+    uint64_t nd = 0, pad_off = 0, bnd_off = 0, sorted = 0;
+    int n_present = 0; bool uniform_n = true;
+    for (int si = 0; si < BG_N_SHAPES; ++si) {
+        const ClassStat& c = cls[si];
+        if (!c.count) continue;
+        if (A.n_cls >= PLAN_MAX_CLS) return false;
+        ++n_present;
+        if (c.min_n != c.max_n) uniform_n = false;
+        const Shape sh = shape_at(si);
+        const uint32_t K = words_per_lane_step(sh.C), band_cols = (uint32_t)(sh.L * sh.C);
+        bool half = false;
+        if (half_maxabs > 0 && shape_has_half(sh))
+            half = c.max_m <= band_cols && ((int64_t)c.max_n + c.max_m + 2) * half_maxabs <= HB_RANGE;
+        const uint32_t G2 = (half ? 2u : 1u) * (32u / (uint32_t)sh.L);
+        const uint64_t holes_ub = half ? std::min<uint64_t>(c.count, (uint64_t)c.max_n - c.min_n + 1) : 0;
+        const uint64_t slot_cap = (c.count + holes_ub + G2 - 1) / G2 * G2;
+        const uint64_t nwarps = slot_cap / G2;
+        uint64_t warp_words;
+        if (half) {
+            const uint32_t steps = ((c.max_n + sh.L - 1 + HB_TB - 1) / HB_TB) * HB_TB;
+            warp_words = (uint64_t)((steps / HB_TB + HB_TG_MAX - 1) / HB_TG_MAX) * HB_TG_MAX * 32ull * hb_words_per_lane_block(sh.C);
+        } else {
+            const uint64_t maxb = c.max_m ? (c.max_m + band_cols - 1) / band_cols : 0;
+            warp_words = maxb * ((uint64_t)c.max_n + sh.L - 1) * K * 32ull;
+        }
+        const uint64_t trace_words = nwarps * warp_words;
+        if (trace_words > budget_words || nd + slot_cap >= 0xFFFFFFF0ull) return false;
+        LaunchClass lc; lc.sh = sh; lc.half = half;
+        lc.long_walk = !half && (sh.C & 7) == 0 && (uint64_t)c.max_n + c.max_m > LONG_WALK_LEN;
+        Chunk ch; ch.slot_begin = (uint32_t)nd; ch.slot_end = (uint32_t)(nd + slot_cap); ch.trace_words = trace_words;
+        lc.chunks.push_back(ch);
+        P.classes.push_back(lc);
+        PlanCls& pc = A.cls[A.n_cls];
+        pc.L = sh.L; pc.C = sh.C; pc.half = half ? 1u : 0u; pc.G2 = G2;
+        pc.sorted_begin = (uint32_t)sorted; pc.count = (uint32_t)c.count;
+        pc.slot_begin = (uint32_t)nd; pc.slot_cap = (uint32_t)slot_cap;
+        pc.pad_base = pad_off; pc.bnd_base = bnd_off;
+        A.rank_of_shape[si] = (int8_t)A.n_cls;
+        ++A.n_cls;
+        nd += slot_cap; sorted += c.count; pad_off += c.pad_bytes; bnd_off += c.bnd_elems;
+        P.cells += c.cells; if (half) P.cells_half += c.cells;
+        P.total_trace_words += trace_words; P.max_trace_words = std::max(P.max_trace_words, trace_words);
+        P.max_n = std::max(P.max_n, c.max_n); P.max_m = std::max(P.max_m, c.max_m);
+    }
+    P.n_slots = nd; P.pad_bytes = pad_off; P.bnd_elems = bnd_off;
+    P.built = true;
+    (void)ctx;
+    need_sort = !(n_present == 1 && uniform_n);
+    return true;
+}
+
 // scan != nullptr: the host-buffer entry points validate and measure the batch in one multi-threaded pass.
 int check_batch(bg_ctx* ctx, const bg_batch* in, BatchScan* scan = nullptr) {
     if (!in || (in->n_pairs && (!in->seq_off || (!in->residues && in->seq_off[2 * in->n_pairs] != in->seq_off[0])))) {
@@ -845,6 +954,15 @@ int check_batch(bg_ctx* ctx, const bg_batch* in, BatchScan* scan = nullptr) {
     for (uint64_t s = 0; s < 2 * in->n_pairs; ++s)
         if (in->seq_off[s + 1] < in->seq_off[s]) { ctx->set_error("seq_off not monotone"); return BG_EINVAL_ARG; }
     return BG_OK;
+}
+
+// > 0: the packed 16 x 2 kernel (K1h) may be used with these parameters, with this bound on |score| (0: not).
+int32_t half_maxabs_of(const bg_params* p) {
+    if (!p || !p->table || p->n_rows <= 0 || p->n_cols <= 0 || p->n_rows > 4 || p->n_cols > 4) return 0;
+    if (p->mode == BG_LOCAL || (p->flags & BG_F_SCORE_ONLY) || getenv("BG_NO_HALF")) return 0;
+    int64_t maxabs = std::max<int64_t>(llabs((long long)p->gap_open), llabs((long long)p->gap_extend));
+    for (int i = 0; i < p->n_rows * p->n_cols; ++i) maxabs = std::max<int64_t>(maxabs, llabs((long long)p->table[i]));
+    return maxabs <= HB_MAXABS ? (int32_t)std::max<int64_t>(1, maxabs) : 0;
 }
 
 // Validates bg_params against the reference's rules and the engine's numeric range.
@@ -887,8 +1005,7 @@ int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_
     pp.smem = 512 + (size_t)p->n_rows * (p->n_cols + 1) * 4;
     if (pp.smem > 48 * 1024) { ctx->set_error("score table too large for shared memory"); return BG_EUNSUPPORTED; }
     pp.prof4 = fits8 && p->n_rows <= 4;
-    if (mode != BG_LOCAL && p->n_rows <= 4 && p->n_cols <= 4 && maxabs <= HB_MAXABS && !pp.score_only && !getenv("BG_NO_HALF"))
-        pp.half_maxabs = (int32_t)std::max<int64_t>(1, maxabs);
+    pp.half_maxabs = half_maxabs_of(p);
     memcpy(pp.codes, p->row_code, 256); memcpy(pp.codes + 256, p->col_code, 256);
     for (int i = 0; i < 256; ++i) {
         if (pp.codes[i] != 0xFF && pp.codes[i] >= p->n_rows) { ctx->set_error("row_code entry out of range"); return BG_EINVAL_ARG; }
@@ -904,6 +1021,7 @@ struct AlignIO {
     // ops are packed densely into `ops` at word offsets `off` ([N + 1], exclusive scan of ceil(len / 16)), next to
     // len / first; `lens2` is still the walkers' output
     uint32_t* len = nullptr; uint32_t* first = nullptr; uint32_t* ops = nullptr;
+    ulonglong2* samples = nullptr; uint64_t sample_stride = 0;   // every sample_stride-th entry of the {op words, columns} scan + totals
 };
 
 // Uploads the score table / code maps into the work set and clears its error flag.
@@ -963,7 +1081,8 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     if (overlap && !ws.trace2.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4)) { ctx->set_error("device allocation failed (second trace buffer)"); return BG_ENOMEM; }
     cudaStream_t wst = overlap ? ws.walk_stream : split ? ws.post_stream : st;
     cudaStream_t pst = split ? ws.post_stream : st;
-    cudaStream_t st2 = (split && ws.fill2_stream && n_chunks >= 2) ? ws.fill2_stream : nullptr;
+    cudaStream_t st2 = (split && ws.fill2_stream && (n_chunks >= 2 || ws.launch_parity >= 0)) ? ws.fill2_stream : nullptr;
+    const size_t parity = ws.launch_parity > 0 ? 1 : 0;
     if (st2) {
         cudaEvent_t ev0 = ws.get_event();
         CU_TRY(ctx, cudaEventRecord(ev0, st));
@@ -1051,12 +1170,12 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 Phase ph(ws, 1);
                 CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, pp.smem, st, wa));
             } else if (lc.half) {
-                fst = (st2 && (chunk_no & 1)) ? st2 : st;
+                fst = (st2 && ((chunk_no + parity) & 1)) ? st2 : st;
                 Phase ph(ws, 1, fst);
                 const uint32_t nw2 = (ns + 2 * G - 1) / (2 * G);
                 if (!dispatch_k1h(lc.sh, pp.mode != BG_GLOBAL, dim3((nw2 + 3) / 4), fst, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
             } else {
-                fst = (st2 && (chunk_no & 1)) ? st2 : st;
+                fst = (st2 && ((chunk_no + parity) & 1)) ? st2 : st;
                 Phase ph(ws, 1, fst);
                 dispatch_k1(lc.sh, pp.local, pp.prof4, dim3((nwarps + 3) / 4), pp.smem, fst, fa);
             }
@@ -1098,24 +1217,27 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
         for (int b2 = 0; b2 < 2; ++b2)
             if (ev_walk_done[b2]) CU_TRY(ctx, cudaStreamWaitEvent(st, ev_walk_done[b2], 0));   // scan / gather need every walk
     if (!pp.score_only && io.ops) {
-        // words[p] = ceil(len / 16) -> exclusive scan -> the pairs' op runs, packed densely (the word counts live behind
-        // the scan's temporary storage in ws.cubtmp)
+        // counts[p] = {ceil(len / 16), len} -> exclusive scan (into io.off, [N + 1] x 16 B) -> the pairs' op runs, packed
+        // densely; the counts live behind the scan's temporary storage in ws.cubtmp
         Phase ph(ws, 3, pst);
+        ulonglong2* scan_out = reinterpret_cast<ulonglong2*>(io.off);
         size_t tmp = 0;
-        scan_lengths(nullptr, tmp, io.off, io.off, (int)(N + 1), pst);
+        scan_counts(nullptr, tmp, scan_out, scan_out, (int)(N + 1), pst);
         const size_t tmp_al = (tmp + 255) & ~(size_t)255;
-        if (!ws.cubtmp.ensure(tmp_al + (N + 1) * 8)) { ctx->set_error("device allocation failed (scan)"); return BG_ENOMEM; }
-        uint64_t* words = reinterpret_cast<uint64_t*>(ws.cubtmp.as<unsigned char>() + tmp_al);
-        launch_ops_words(io.lens2, N, words, pst);
-        scan_lengths(ws.cubtmp.p, tmp, words, io.off, (int)(N + 1), pst);
+        if (!ws.cubtmp.ensure(tmp_al + (N + 1) * 16)) { ctx->set_error("device allocation failed (scan)"); return BG_ENOMEM; }
+        ulonglong2* counts = reinterpret_cast<ulonglong2*>(ws.cubtmp.as<unsigned char>() + tmp_al);
+        launch_ops_counts(io.lens2, N, counts, pst);
+        scan_counts(ws.cubtmp.p, tmp, counts, scan_out, (int)(N + 1), pst);
         ctx->launches += 2;
         if (P.n_slots) {
             PackOpsArgs pa;
             pa.desc = io.desc; pa.n_slots = (uint32_t)P.n_slots; pa.pad = ws.pad.as<uint8_t>(); pa.lens2 = io.lens2;
-            pa.woff = io.off; pa.len = io.len; pa.first = io.first; pa.ops = io.ops;
+            pa.woff = scan_out; pa.len = io.len; pa.first = io.first; pa.ops = io.ops;
             launch_pack_ops(pa, (uint64_t)P.max_n + P.max_m > 4096, pst);
             ctx->launches++;
         }
+        launch_ops_sample(scan_out, N, io.sample_stride, io.samples, pst);
+        ctx->launches++;
         CU_TRY(ctx, cudaGetLastError());
     } else if (!pp.score_only) {
         Phase ph(ws, 3, pst);
@@ -1211,7 +1333,7 @@ void bg_destroy(bg_ctx* ctx) {
         for (WorkSet& ws : dv.ws) {
             if (ws.stream) cudaStreamSynchronize(ws.stream);
             for (DevBuf* b : ws.all_bufs()) b->release();
-            ws.stage.release(); ws.scalars.release();
+            ws.stage.release(); ws.scalars.release(); ws.samples_h.release();
             for (auto e : ws.ev_pool) cudaEventDestroy(e);
             if (ws.ev_scan) cudaEventDestroy(ws.ev_scan);
             if (ws.walk_stream) cudaStreamDestroy(ws.walk_stream);
@@ -1256,6 +1378,7 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
     if (const char* e = getenv("BG_TRACE_BUDGET_MB")) budget_mb = strtoull(e, nullptr, 10);
     ctx->trace_budget_words = budget_mb * (1024ull * 1024ull / 4ull);
     if (const char* e = getenv("BG_LONG_TRACE_BUDGET_MB")) ctx->long_budget_words = strtoull(e, nullptr, 10) * (1024ull * 1024ull / 4ull);
+    if (const char* e = getenv("BG_HOST_PLAN")) ctx->host_plan = atoi(e) != 0;
     if (const char* e = getenv("BG_FORCE_SHAPE")) {   // "L,C" -- experiments / tests
         int l = 0, c = 0;
         if (sscanf(e, "%d,%d", &l, &c) == 2) { ctx->force_L = l; ctx->force_C = c; }
@@ -1284,6 +1407,12 @@ int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes) {
     return BG_OK;
 }
 
+int bg_set_host_plan(bg_ctx* ctx, int on) {
+    if (!ctx) return BG_EINVAL_ARG;
+    ctx->host_plan = on != 0;
+    return BG_OK;
+}
+
 int bg_set_long_trace_budget(bg_ctx* ctx, uint64_t bytes) {   // 0 = automatic
     if (!ctx || (bytes && bytes < 4096)) return BG_EINVAL_ARG;
     ctx->long_budget_words = bytes / 4;
@@ -1307,12 +1436,12 @@ int bg_last_timing(const bg_ctx* cctx, bg_timing* out) {
     t.h2d_bytes = ctx->h2d; t.d2h_bytes = ctx->d2h; t.launches = ctx->launches; t.fill_launches = 0;
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.ordinal);
-        double ph[4] = {0, 0, 0, 0}, tot = 0;
+        double ph[6] = {0, 0, 0, 0, 0, 0}, tot = 0;   // 0 encode, 1 fill, 2 walk, 3 compact, 4 H2D, 5 device-side plan
         for (WorkSet& ws : dv.ws) {
             CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
             // A phase's time is the UNION of its kernels' intervals: launches of one phase can run side by side (fills
             // alternate between two streams, walks run next to the following fill), and a sum would count that time twice.
-            std::vector<std::pair<double, double>> iv[4];
+            std::vector<std::pair<double, double>> iv[6];
             double t_min = 0, t_max = 0; bool any = false;
             for (auto& ev : ws.evs) {
                 float s0 = 0, dur = 0;
@@ -1323,7 +1452,7 @@ int bg_last_timing(const bg_ctx* cctx, bg_timing* out) {
                 any = true;
                 if (ev.phase == 1) t.fill_launches++;
             }
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 6; ++k) {
                 std::sort(iv[k].begin(), iv[k].end());
                 double cur_a = 0, cur_b = -1;
                 for (auto& x : iv[k]) {
@@ -1640,12 +1769,14 @@ struct WorkItem {
     const uint32_t* map = nullptr;
     uint64_t ops_base = 0, ops_cap = 0; // the item's region of OpsOut::ops (upper-bound layout), words
     uint64_t words = 0;                 // op words the item really produced
-    uint64_t cols = 0;                  // sum of aligned lengths (set by finish_item)
+    uint64_t cols = 0;                  // sum of aligned lengths
+    uint64_t stride = 4096;             // pairs per expansion task; the device samples its offset scans at this stride
+    std::vector<ulonglong2> samples;    // [nsub + 1]: {op words, columns} before sub-block i of the item; [nsub] = totals
     PinBuf gather;                      // long mode: gathered residues | offsets | map | per-pair outputs
     int32_t* t_score = nullptr; uint8_t* t_status = nullptr; uint32_t* t_len = nullptr; uint32_t* t_first = nullptr;   // long mode
 };
 
-struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; };
+struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; bool dev_plan = false, need_sort = false; PlanArgs pa; };
 
 struct AlignJob {
     std::vector<Prebuilt> pre;                  // per item
@@ -1698,12 +1829,53 @@ void submit_expand_locked(AlignJob& J, uint64_t p_lo, uint64_t p_hi, uint64_t ba
     }
 }
 
-// The item's results are on the host: op offsets, and (strings wanted) relative string offsets + expansion.
+// Sub-block i of a pipeline item (pairs [lo + i * stride, ...)): op offsets of its pairs and, when strings are wanted,
+// their final arena offsets + the strings themselves.  The sub-block's starting offsets come from the device's scans
+// (WorkItem::samples), so sub-blocks are independent of each other and no serial pass over the item exists.
+void expand_sub(AlignJob& J, int c, uint64_t i, uint64_t arena_base, bool strings) {
+    const WorkItem& it = J.items[c];
+    const bg_batch* in = J.in;
+    OpsOut& oo = J.oo;
+    const uint64_t p_lo = it.lo + i * it.stride, p_hi = std::min(it.lo + it.n, p_lo + it.stride);
+    uint64_t w = it.ops_base + it.samples[i].x, o = arena_base + 2 * it.samples[i].y;
+    for (uint64_t p = p_lo; p < p_hi; ++p) {
+        const uint64_t len = oo.len[p];
+        oo.ops_off[p] = w;
+        if (strings) {
+            J.off[2 * p] = o; J.off[2 * p + 1] = o + len;
+            if (len) {
+                if (o + 2 * len > J.arena_cap) { J.ctx->set_error("internal: arena bound exceeded"); J.fail(BG_ECUDA); return; }
+                expand_ops(in->residues + in->seq_off[2 * p] + oo.first[2 * p], in->residues + in->seq_off[2 * p + 1] + oo.first[2 * p + 1],
+                           oo.ops + w, len, J.arena + o, J.arena + o + len);
+            }
+        }
+        w += (len + 15) >> 4; o += 2 * len;
+    }
+}
+
+// Caller holds J.mu.
+void submit_item_locked(AlignJob& J, int c, uint64_t arena_base, bool strings) {
+    const WorkItem& it = J.items[c];
+    const uint64_t nsub = (it.n + it.stride - 1) / it.stride;
+    for (uint64_t i = 0; i < nsub; ++i) {
+        ++J.pending;
+        host_pool().submit([&J, c, i, arena_base, strings] {
+            expand_sub(J, c, i, arena_base, strings);
+            { std::lock_guard<std::mutex> lk(J.mu); --J.pending; }
+            J.cv.notify_all();
+        });
+    }
+}
+
+// The item's results are on the host.  Pipeline items: hand their sub-blocks to the host pool -- at once when only the
+// op offsets are wanted, in caller order when strings are (an item's arena base is the column total of everything
+// before it).  Long-mode items hold scattered pairs: scatter their per-pair outputs to caller order here; the strings
+// are laid out after the last item (run_align_job).
 void finish_item(AlignJob& J, int c) {
     WorkItem& it = J.items[c];
     OpsOut& oo = J.oo;
-    uint64_t w = it.ops_base, cols = 0;
-    if (it.map) {   // long mode: scatter the per-pair outputs to caller order
+    if (it.map) {
+        uint64_t w = it.ops_base;
         for (uint64_t q = 0; q < it.n; ++q) {
             const uint64_t p = it.map[q];
             oo.score[p] = it.t_score[q]; oo.status[p] = it.t_status[q];
@@ -1712,23 +1884,20 @@ void finish_item(AlignJob& J, int c) {
                 oo.ops_off[p] = w; w += ((uint64_t)it.t_len[q] + 15) >> 4;
             }
         }
-    } else if (oo.len) {
-        for (uint64_t p = it.lo; p < it.lo + it.n; ++p) {
-            const uint64_t len = oo.len[p];
-            oo.ops_off[p] = w; w += (len + 15) >> 4;
-            if (J.want_strings) J.off[2 * p] = 2 * cols;     // relative to the item's arena base
-            cols += len;
-        }
+        if (oo.len && w - it.ops_base != it.words) { J.ctx->set_error("internal: op word count mismatch"); J.fail(BG_ECUDA); }
+        return;
     }
-    it.cols = cols;
-    if (oo.len && w - it.ops_base != it.words) { J.ctx->set_error("internal: op word count mismatch"); J.fail(BG_ECUDA); }
-    if (!J.want_strings || J.long_mode) return;       // long mode: expanded after all items (caller order is scattered)
+    if (!oo.len) return;                               // score-only
     std::lock_guard<std::mutex> lk(J.mu);
+    if (J.long_mode) {                                  // one device, one item, caller order: op offsets now, strings at the end
+        if (J.rc.load() == BG_OK) submit_item_locked(J, c, 0, false);
+        return;
+    }
+    if (!J.want_strings) { if (J.rc.load() == BG_OK) submit_item_locked(J, c, 0, false); return; }
     J.arrived[c] = 1;
     while (J.frontier < (int)J.items.size() && J.arrived[J.frontier]) {
-        WorkItem& f = J.items[J.frontier];
-        if (J.rc.load() == BG_OK) submit_expand_locked(J, f.lo, f.lo + f.n, J.arena_base, f.cols);
-        J.arena_base += 2 * f.cols;
+        if (J.rc.load() == BG_OK) submit_item_locked(J, J.frontier, J.arena_base, true);
+        J.arena_base += 2 * J.items[J.frontier].cols;
         ++J.frontier;
     }
 }
@@ -1755,6 +1924,7 @@ int device_pipeline(AlignJob& J, int d) {
 
     // streams: the work sets' own streams are borrowed for the stages; kernels of every work set go to st_comp
     cudaStream_t st_comp = dv.ws[0].stream, st_h2d = dv.ws[1].stream, st_small = dv.ws[2].stream, st_arena = dv.ws[0].walk_stream;
+    cudaStream_t st_plan = dv.ws[2].walk_stream;     // high priority, like the post stream
     static const bool no_split = getenv("BG_NO_SPLIT") != nullptr;
     cudaStream_t st_post = (long_mode || no_split) ? st_comp : dv.ws[1].walk_stream;
     cudaStream_t saved[PIPE_DEPTH];
@@ -1765,11 +1935,12 @@ int device_pipeline(AlignJob& J, int d) {
     static const bool no_fill2 = getenv("BG_NO_FILL2") != nullptr;
     cudaStream_t st_fill2 = (PIPE_DEPTH > 3 && !no_fill2 && st_post != st_comp) ? saved[3] : nullptr;   // an otherwise idle work-set stream
     for (int s = 0; s < PIPE_DEPTH; ++s) dv.ws[s].fill2_stream = st_fill2;
-    cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH], ev_arena[PIPE_DEPTH];
+    cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH], ev_arena[PIPE_DEPTH], ev_plan[PIPE_DEPTH];
     for (int s = 0; s < PIPE_DEPTH; ++s) {
         cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_comp[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev_arena[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_plan[s], cudaEventDisableTiming);
     }
     static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -1800,7 +1971,10 @@ int device_pipeline(AlignJob& J, int d) {
             if (cudaEventSynchronize(ws.ev_scan) != cudaSuccess) { ctx->set_error("cudaEventSynchronize failed"); rc = BG_ECUDA; }
             if (!rc && (*h_err & 1u)) { ctx->set_error("a residue byte has no row/column in the score table"); rc = BG_EINVAL_RESIDUE; }
             if (!rc && ops_mode) {
-                it.words = *h_total;
+                const uint64_t nsub = (it.n + it.stride - 1) / it.stride;
+                const ulonglong2* sh = ws.samples_h.as<ulonglong2>();
+                it.samples.assign(sh, sh + nsub + 1);
+                it.words = sh[nsub].x; it.cols = sh[nsub].y;
                 if (it.words > it.ops_cap) { ctx->set_error("internal: op arena bound exceeded"); rc = BG_ECUDA; }
                 else if (it.words &&
                          (cudaMemcpyAsync(J.oo.ops + it.ops_base, ws.ops.p, it.words * 4, cudaMemcpyDeviceToHost, st_arena) != cudaSuccess ||
@@ -1810,8 +1984,9 @@ int device_pipeline(AlignJob& J, int d) {
             }
             if (prof) fprintf(stderr, "[bgalign]   dev %d item %d results on the host at %.2f ms\n", d, c, since());
             if (!rc) {
-                ctx->d2h += it.n * 5 + (ops_mode ? it.n * 12 + it.words * 4 + 8 : 0);
+                ctx->d2h += it.n * 5 + (ops_mode ? it.n * 12 + it.words * 4 + (it.samples.size()) * 16 : 0);
                 finish_item(J, c);
+                if (prof) fprintf(stderr, "[bgalign]   dev %d item %d finished at %.2f ms\n", d, c, since());
             } else {
                 J.fail(rc);
             }
@@ -1820,8 +1995,10 @@ int device_pipeline(AlignJob& J, int d) {
         }
     });
 
-    auto issue = [&](int s, int c) -> int {
+    static const bool no_alt = getenv("BG_NO_ALT_FILL") != nullptr;
+    auto issue = [&](int s, int c, int k) -> int {
         WorkSet& ws = dv.ws[s];
+        ws.launch_parity = no_alt ? -1 : ((k + 1) & 1);   // (chunk_no is 1 at the first launch of a plan: item 0 starts on the main stream)
         WorkItem& it = J.items[c];
         const uint64_t n = it.n;
         const uint64_t base = it.off[0], nres = it.off[2 * n] - base;
@@ -1834,20 +2011,54 @@ int device_pipeline(AlignJob& J, int d) {
         bool ok = ws.residues.ensure(nres + 16) && ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) &&
                   ws.score.ensure(std::max<uint64_t>(1, n) * 4) && ws.flags.ensure(std::max<uint64_t>(1, n));
         if (ops_mode)
-            ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((n + 1) * 8) && ws.len.ensure(std::max<uint64_t>(1, n) * 4) &&
+            ok = ok && ws.lens2.ensure((2 * n + 1) * 8) && ws.off.ensure((n + 1) * 16) && ws.len.ensure(std::max<uint64_t>(1, n) * 4) &&
                  ws.first.ensure(std::max<uint64_t>(1, n) * 8) && ws.ops.ensure(std::max<uint64_t>(1, it.ops_cap) * 4);
         if (!ok) { ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM; }
         const uint8_t* src = pb.res.p ? (const uint8_t*)pb.res.p : it.res;
+        cudaEvent_t pe_a = nullptr;
+        if (prof) { pe_a = ws.get_event(); cudaEventRecord(pe_a, st_h2d); }
         if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, src, nres, cudaMemcpyHostToDevice, st_h2d));
-        if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pb.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
-        CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
-        ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        if (pb.dev_plan) {
+            // the chunk's 16 B/pair offsets instead of 64 B/pair descriptors; the planner runs on its own high-priority
+            // stream next to the previous chunk's fill and hands the descriptors to the compute stream
+            const size_t scratch_bytes = plan_scratch_bytes((uint32_t)n, (uint32_t)P.n_slots);
+            if (!ws.poff.ensure((2 * n + 1) * 8) || !ws.psort.ensure(scratch_bytes)) { ctx->set_error("device allocation failed (planner buffers)"); return BG_ENOMEM; }
+            CU_TRY(ctx, cudaMemcpyAsync(ws.poff.p, pb.stage.p ? pb.stage.p : (const void*)it.off, (2 * n + 1) * 8, cudaMemcpyHostToDevice, st_h2d));
+            CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
+            if (prof) { cudaEvent_t pe_b = ws.get_event(); cudaEventRecord(pe_b, st_h2d); ws.evs.push_back(PhaseEv{pe_a, pe_b, 4}); }
+            CU_TRY(ctx, cudaStreamWaitEvent(st_plan, ev_h2d[s], 0));
+            cudaEvent_t pp_a = nullptr;
+            if (prof) { pp_a = ws.get_event(); cudaEventRecord(pp_a, st_plan); }
+            PlanArgs pa = pb.pa;
+            pa.off = ws.poff.as<uint64_t>(); pa.base = base; pa.desc = ws.desc.as<PairDesc>();
+            CU_TRY(ctx, launch_plan(pa, pb.need_sort, (uint32_t)P.n_slots, ws.psort.p, scratch_bytes, st_plan));
+            if (prof) { cudaEvent_t pp_b = ws.get_event(); cudaEventRecord(pp_b, st_plan); ws.evs.push_back(PhaseEv{pp_a, pp_b, 5}); }
+            CU_TRY(ctx, cudaEventRecord(ev_plan[s], st_plan));
+            CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_plan[s], 0));
+            ctx->h2d += nres + (2 * n + 1) * 8;
+            ctx->launches += pb.need_sort ? 16 : 10;
+        } else {
+            if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pb.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
+            CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
+            ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+        }
         CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         rc = upload_params(ctx, ws, pp);
         if (rc) return rc;
         AlignIO io{ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), &P, n,
                    ws.score.as<int32_t>(), ws.flags.as<uint8_t>(), ws.lens2.as<uint64_t>(), ws.off.as<uint64_t>(), nullptr};
-        if (ops_mode) { io.len = ws.len.as<uint32_t>(); io.first = ws.first.as<uint32_t>(); io.ops = ws.ops.as<uint32_t>(); }
+        uint64_t nsub = 0;
+        if (ops_mode) {
+            // expansion tasks of ~256k columns: pairs per task from the item's mean length, a power of two
+            const uint64_t mean = std::max<uint64_t>(1, nres / (2 * std::max<uint64_t>(1, n)));
+            uint64_t stride = 64;
+            while (stride < 8192 && stride * mean < (256u << 10)) stride *= 2;
+            it.stride = stride;
+            nsub = (n + stride - 1) / stride;
+            if (!ws.samples.ensure((nsub + 1) * 16) || !ws.samples_h.ensure((nsub + 1) * 16)) { ctx->set_error("allocation failed (offset samples)"); return BG_ENOMEM; }
+            io.len = ws.len.as<uint32_t>(); io.first = ws.first.as<uint32_t>(); io.ops = ws.ops.as<uint32_t>();
+            io.samples = ws.samples.as<ulonglong2>(); io.sample_stride = stride;
+        }
         rc = run_align(ctx, ws, io, pp);
         if (rc) return rc;
         // which stream the item's last kernels went to (run_align: post stream unless the plan has several launches)
@@ -1864,7 +2075,7 @@ int device_pipeline(AlignJob& J, int d) {
         int32_t* o_score = it.map ? it.t_score : J.oo.score + it.lo;
         uint8_t* o_status = it.map ? it.t_status : J.oo.status + it.lo;
         if (ops_mode) {
-            CU_TRY(ctx, cudaMemcpyAsync(h_total, ws.off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st_small));
+            CU_TRY(ctx, cudaMemcpyAsync(ws.samples_h.p, ws.samples.p, (nsub + 1) * 16, cudaMemcpyDeviceToHost, st_small));
             if (n) {
                 CU_TRY(ctx, cudaMemcpyAsync(it.map ? it.t_len : J.oo.len + it.lo, ws.len.p, n * 4, cudaMemcpyDeviceToHost, st_small));
                 CU_TRY(ctx, cudaMemcpyAsync(it.map ? it.t_first : J.oo.first + 2 * it.lo, ws.first.p, n * 8, cudaMemcpyDeviceToHost, st_small));
@@ -1896,7 +2107,7 @@ int device_pipeline(AlignJob& J, int d) {
         rc_all = J.rc.load();
         if (rc_all) break;
         const double t0 = prof ? since() : 0;
-        rc_all = issue(s, c);
+        rc_all = issue(s, c, k);
         if (prof) fprintf(stderr, "[bgalign]   dev %d item %d (%llu pairs) issued %.2f .. %.2f ms\n", d, c, (unsigned long long)J.items[c].n, t0, since());
         if (rc_all) break;
         { std::lock_guard<std::mutex> lk(mu); taken.push_back(c); issued = k + 1; }
@@ -1906,7 +2117,8 @@ int device_pipeline(AlignJob& J, int d) {
     { std::lock_guard<std::mutex> lk(mu); issuer_done = true; }
     cv.notify_all();
     finisher.wait();
-    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_comp); cudaStreamSynchronize(st_small); cudaStreamSynchronize(st_arena);
+    if (prof) fprintf(stderr, "[bgalign] dev %d finisher done at %.2f ms\n", d, since());
+    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_plan); cudaStreamSynchronize(st_comp); cudaStreamSynchronize(st_small); cudaStreamSynchronize(st_arena);
     if (prof) {
         fprintf(stderr, "[bgalign] dev %d drained at %.2f ms\n", d, since());
         // GPU-side timeline of the kernels (events on the compute stream), relative to the first one
@@ -1923,8 +2135,8 @@ int device_pipeline(AlignJob& J, int d) {
     cudaStreamSynchronize(st_post);
     if (st_fill2) cudaStreamSynchronize(st_fill2);
     for (int s = 0; s < PIPE_DEPTH; ++s) {
-        dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr; dv.ws[s].fill2_stream = nullptr;
-        cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); cudaEventDestroy(ev_arena[s]);
+        dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr; dv.ws[s].fill2_stream = nullptr; dv.ws[s].launch_parity = -1;
+        cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); cudaEventDestroy(ev_arena[s]); cudaEventDestroy(ev_plan[s]);
     }
     return J.rc.load();
 }
@@ -1943,7 +2155,7 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, lo, hi, edit_chunks);
     const int nchunks = (int)cb.size() - 1;
     static const bool no_compact = getenv("BG_NO_COMPACT") != nullptr;
-    struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; };
+    struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; bool dev_plan = false, need_sort = false; PlanArgs pa; };
     std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one pool task per chunk, consumed as they finish
     static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
     const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues + off[2 * lo]);
@@ -2183,6 +2395,18 @@ int run_align_job(AlignJob& J) {
         J.pre[c].th = host_pool().submit([&J, c, ctx, ws_budget, wave_budget, stage_res] {
             WorkItem& it = J.items[c];
             Prebuilt& pb = J.pre[c];
+            // pipeline chunks are planned on the device from their offsets (k0_plan.cuh); the host only sizes the launches
+            pb.dev_plan = !J.long_mode && !ctx->host_plan && !J.pp->score_only && !it.map &&
+                          plan_from_stats(ctx, *J.scan, it.lo, it.lo + it.n, ws_budget, J.pp->half_maxabs, pb.plan, pb.pa, pb.need_sort);
+            if (pb.dev_plan) {
+                if (stage_res) {     // pageable caller memory: stage offsets and residues (see host_is_pageable)
+                    const uint64_t nb = it.off[2 * it.n] - it.off[0];
+                    if (!pb.stage.ensure((2 * it.n + 1) * 8) || !pb.res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
+                    memcpy(pb.stage.p, it.off, (2 * it.n + 1) * 8);
+                    memcpy(pb.res.p, it.res, nb);
+                }
+                return;
+            }
             if (!pb.stage.ensure(plan_desc_capacity(it.n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
             if (stage_res) {
                 const uint64_t nb = it.off[2 * it.n] - it.off[0];
@@ -2207,6 +2431,7 @@ int run_align_job(AlignJob& J) {
 
     if (!rc && J.want_strings && ops_mode) {
         std::unique_lock<std::mutex> lk(J.mu);
+        J.cv.wait(lk, [&] { return J.pending == 0; });
         if (J.long_mode) {   // items hold scattered pairs: lay the strings out in caller order now
             uint64_t cols = 0;
             for (uint64_t p = 0; p < N; ++p) { J.off[2 * p] = 2 * cols; cols += J.oo.len[p]; }
@@ -2227,6 +2452,11 @@ int run_align_job(AlignJob& J) {
 
 // Validates, prepares and sizes: the part bg_align_batch and bg_align_batch_ops share.
 int begin_align_call(bg_ctx* ctx, const bg_batch* in, const bg_params* p, BatchScan& scan, Prepared& pp) {
+    // the scan also counts what the device-side planner needs per kernel shape, which depends on whether the packed
+    // kernel is available for these parameters (pick_shape_m's half_ok)
+    scan.with_stats = !ctx->host_plan && !(p->flags & BG_F_SCORE_ONLY);
+    scan.half_ok = half_maxabs_of(p) > 0;
+    scan.force_si = ctx->force_L ? shape_index(Shape{ctx->force_L, ctx->force_C}) : -1;
     int rc = check_batch(ctx, in, &scan);
     if (rc) return rc;
     static const uint64_t zero_off[1] = {0};
@@ -2543,6 +2773,65 @@ int bg_debug_plan_long(const uint64_t* lens, uint64_t n_pairs, uint64_t budget_b
             if (next_off != ch.ckpt_elems) ++viol;
         }
     out[0] = launches; out[1] = ck_chunks; out[2] = max_nb; out[3] = P.cells_ckpt; out[4] = viol;
+    return BG_OK;
+}
+
+// Diagnostic: plans the whole batch as ONE pipeline item twice -- with the host planner (build_plan) and with the
+// device-side planner (k0_plan.cuh) -- and compares the two descriptor arrays field by field, class by class (the
+// device's descriptor ranges are sized from upper bounds, so its classes start at other slot numbers and end in
+// empty slots).  out[0] = 1 if the item is eligible for the device planner, out[1] = descriptors compared,
+// out[2] = descriptors that differ, out[3] = device slots beyond the host's count that are not empty.
+int bg_debug_plan_compare(bg_ctx* ctx, const bg_batch* in, const bg_params* p, uint64_t* out) {
+    if (!ctx || !in || !p || !out) return BG_EINVAL_ARG;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    BatchScan scan;
+    Prepared pp;
+    const bool saved = ctx->host_plan;
+    ctx->host_plan = false;
+    int rc = begin_align_call(ctx, in, p, scan, pp);
+    ctx->host_plan = saved;
+    if (rc) return rc;
+    const uint64_t N = in->n_pairs;
+    if (!N || scan.has_wide) return BG_OK;
+    const uint64_t budget = 1ull << 40;
+    Plan PD; PlanArgs A; bool need_sort = false;
+    if (!plan_from_stats(ctx, scan, 0, N, budget, pp.half_maxabs, PD, A, need_sort)) return BG_OK;
+    out[0] = 1;
+    std::vector<PairDesc> host_desc(plan_desc_capacity(N));
+    Plan PH;
+    rc = build_plan(ctx, in->seq_off, in->seq_off[0], N, true, budget, budget, pp.half_maxabs, PH, host_desc.data());
+    if (rc) return rc;
+    Device& dv = ctx->devs[0];
+    WorkSet& ws = dv.ws[0];
+    CU_TRY(ctx, cudaSetDevice(dv.ordinal));
+    const size_t scratch_bytes = plan_scratch_bytes((uint32_t)N, (uint32_t)PD.n_slots);
+    if (!ws.poff.ensure((2 * N + 1) * 8) || !ws.desc.ensure(std::max<size_t>(1, PD.n_slots) * sizeof(PairDesc)) || !ws.psort.ensure(scratch_bytes)) {
+        ctx->set_error("device allocation failed (planner buffers)"); return BG_ENOMEM;
+    }
+    CU_TRY(ctx, cudaMemcpyAsync(ws.poff.p, in->seq_off, (2 * N + 1) * 8, cudaMemcpyHostToDevice, ws.stream));
+    A.off = ws.poff.as<uint64_t>(); A.base = in->seq_off[0]; A.desc = ws.desc.as<PairDesc>();
+    CU_TRY(ctx, launch_plan(A, need_sort, (uint32_t)PD.n_slots, ws.psort.p, scratch_bytes, ws.stream));
+    std::vector<PairDesc> dev_desc(PD.n_slots);
+    CU_TRY(ctx, cudaMemcpyAsync(dev_desc.data(), ws.desc.p, PD.n_slots * sizeof(PairDesc), cudaMemcpyDeviceToHost, ws.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ws.stream));
+    if (PH.classes.size() != PD.classes.size()) { out[2] = ~0ull; return BG_OK; }
+    for (size_t k = 0; k < PH.classes.size(); ++k) {
+        const LaunchClass& h = PH.classes[k]; const LaunchClass& d = PD.classes[k];
+        if (h.chunks.size() != 1 || d.chunks.size() != 1 || h.sh.L != d.sh.L || h.sh.C != d.sh.C || h.half != d.half || h.long_walk != d.long_walk) { out[2] = ~0ull; return BG_OK; }
+        const uint32_t hb = h.chunks[0].slot_begin, hn = h.chunks[0].slot_end - hb, db = d.chunks[0].slot_begin, dn = d.chunks[0].slot_end - db;
+        if (hn > dn || h.chunks[0].trace_words > d.chunks[0].trace_words) { out[2] = ~0ull; return BG_OK; }
+        for (uint32_t j = 0; j < dn; ++j) {
+            const PairDesc& y = dev_desc[db + j];
+            if (j >= hn) { if (y.pair_id != 0xFFFFFFFFu || y.steps != 0) ++out[3]; continue; }
+            const PairDesc& x = host_desc[hb + j];
+            ++out[1];
+            bool same = x.pair_id == y.pair_id && x.steps == y.steps && x.trace_off == y.trace_off && x.pad_ == y.pad_;
+            if (same && x.pair_id != 0xFFFFFFFFu)
+                same = x.a_off == y.a_off && x.b_off == y.b_off && x.n == y.n && x.m == y.m && x.nbands == y.nbands &&
+                       x.pad_off - host_desc[hb].pad_off == y.pad_off - dev_desc[db].pad_off && (x.nbands <= 1 || x.bnd_off == y.bnd_off);
+            if (!same) ++out[2];
+        }
+    }
     return BG_OK;
 }
 

@@ -44,8 +44,8 @@ struct PlanArgs {
     uint32_t n_pairs, n_cls;
     uint32_t half_ok;                // as in pick_shape_m
     int32_t force_si;                // >= 0: every pair uses this shape (bg_set_shape)
-    uint64_t* keys;                  // [n] sort keys: class rank << 32 | (0x7fffffff - len1)
-    uint32_t* ids;                   // [n] pair ids in key order (nullptr: identity -- one class, one len1)
+    uint64_t* keys;                  // [2][n] sort keys: class rank << 32 | (0x7fffffff - len1)  (set by launch_plan)
+    uint32_t* ids;                   // [2][n] pair ids
     PairDesc* desc;
     int8_t rank_of_shape[16];        // shape number -> class rank in cls[] (-1: not present)
     PlanCls cls[PLAN_MAX_CLS];
@@ -130,7 +130,7 @@ struct PackOpsArgs {
     uint32_t n_slots;
     const uint8_t* pad;      // op slots written by the walkers
     const uint64_t* lens2;   // [2 * pairs + 1]: aligned length of pair p at [2p]
-    const uint64_t* woff;    // [pairs + 1]: exclusive scan of ceil(len / 16)
+    const ulonglong2* woff;  // [pairs + 1]: exclusive scan of {ceil(len / 16), len}
     uint32_t* len;           // [pairs]
     uint32_t* first;         // [2 * pairs]: (first_a, first_b) -- the strings start at seq1[first_a], seq2[first_b]
     uint32_t* ops;           // dense op words

@@ -634,11 +634,19 @@ __global__ void __launch_bounds__(128) k_gather(const GatherArgs A) {
 // moved to the front of a dense, word-aligned run -- out word j of pair p holds columns 16 j .. 16 j + 15, column 0
 // being the first alignment column -- next to its length and start cell.  About 0.3 B per column travels D2H
 // instead of 2 B; host_expand.cpp rebuilds the strings from the caller's own residues.
-//   words[p] = ceil(len / 16) is scanned by the caller between k_ops_words and k_pack_ops.
-__global__ void k_ops_words(const uint64_t* lens2, uint64_t n_pairs, uint64_t* words) {
+//   k_ops_counts: counts[p] = {ceil(len / 16), len}; the caller scans them (one scan of the pair) and k_pack_ops places
+//   the runs.  k_ops_sample: every `stride`-th entry of the scan plus the totals -- all the host needs to cut a chunk
+//   into independent expansion tasks (a task re-derives the offsets inside its own sub-block from the lengths).
+__global__ void k_ops_counts(const uint64_t* lens2, uint64_t n_pairs, ulonglong2* counts) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n_pairs) words[p] = (lens2[2 * p] + 15ull) >> 4;
-    if (p == n_pairs) words[p] = 0;
+    if (p < n_pairs) { const uint64_t len = lens2[2 * p]; counts[p] = make_ulonglong2((len + 15ull) >> 4, len); }
+    if (p == n_pairs) counts[p] = make_ulonglong2(0ull, 0ull);
+}
+__global__ void k_ops_sample(const ulonglong2* scan, uint64_t n_pairs, uint64_t stride, ulonglong2* samples) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nsub = (n_pairs + stride - 1) / stride;
+    if (i < nsub) samples[i] = scan[i * stride];
+    if (i == nsub) samples[i] = scan[n_pairs];        // totals: {op words, columns}
 }
 
 template <int G>   // lanes per slot
@@ -659,7 +667,7 @@ __global__ void __launch_bounds__(128) k_pack_ops(const PackOpsArgs A) {
         A.first[2ull * d.pair_id + 1] = slotw[1];
     }
     const uint32_t nw = (len + 15u) >> 4, w0 = pos0 >> 4, sh = (pos0 & 15u) * 2u;
-    uint32_t* dst = A.ops + A.woff[d.pair_id];
+    uint32_t* dst = A.ops + A.woff[d.pair_id].x;
     for (uint32_t j = lane; j < nw; j += G) {
         const uint32_t lo = __ldg(ops + w0 + j);
         const uint32_t hi = (sh && w0 + j + 1 < cap_words) ? __ldg(ops + w0 + j + 1) : 0u;

@@ -39,8 +39,18 @@ void launch_scores_only(const PairDesc* desc, const EndCell* end, uint32_t ns, i
     k_scores_only<<<(ns + 127) / 128, 128, 0, st>>>(desc, end, ns, score, flags, mode);
 }
 void launch_gather(const GatherArgs& a, cudaStream_t st) { k_gather<<<(unsigned)((a.n_slots + 3) / 4), 128, 0, st>>>(a); }
-void launch_ops_words(const uint64_t* lens2, uint64_t n_pairs, uint64_t* words, cudaStream_t st) {
-    k_ops_words<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(lens2, n_pairs, words);
+void launch_ops_counts(const uint64_t* lens2, uint64_t n_pairs, ulonglong2* counts, cudaStream_t st) {
+    k_ops_counts<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, st>>>(lens2, n_pairs, counts);
+}
+struct AddU2 {
+    __host__ __device__ ulonglong2 operator()(const ulonglong2& a, const ulonglong2& b) const { return make_ulonglong2(a.x + b.x, a.y + b.y); }
+};
+cudaError_t scan_counts(void* tmp, size_t& tmp_bytes, const ulonglong2* counts, ulonglong2* out, int count, cudaStream_t st) {
+    return cub::DeviceScan::ExclusiveScan(tmp, tmp_bytes, counts, out, AddU2(), make_ulonglong2(0ull, 0ull), count, st);
+}
+void launch_ops_sample(const ulonglong2* scan, uint64_t n_pairs, uint64_t stride, ulonglong2* samples, cudaStream_t st) {
+    const uint64_t nsub = (n_pairs + stride - 1) / stride;
+    k_ops_sample<<<(unsigned)((nsub + 1 + 255) / 256), 256, 0, st>>>(scan, n_pairs, stride, samples);
 }
 void launch_pack_ops(const PackOpsArgs& a, bool long_pairs, cudaStream_t st) {
     if (long_pairs) k_pack_ops<32><<<(unsigned)(((uint64_t)a.n_slots * 32 + 127) / 128), 128, 0, st>>>(a);

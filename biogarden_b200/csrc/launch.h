@@ -81,8 +81,8 @@ __host__ __device__ inline Shape pick_shape_m(uint32_t m, bool half_ok, bool c8)
 }
 
 // K0: launch descriptors built on the device (k0_plan.cuh)
-size_t plan_sort_tmp_bytes(uint32_t n);
-cudaError_t launch_plan(const PlanArgs& a, bool sort, void* tmp, size_t tmp_bytes, cudaStream_t st);
+size_t plan_scratch_bytes(uint32_t n_pairs, uint32_t n_slots);
+cudaError_t launch_plan(PlanArgs a, bool sort, uint32_t n_slots, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 // K1 / K1h / K2 fills
 void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a);
@@ -95,7 +95,9 @@ enum LongWalk { LW_SKEW = 0, LW_DIAG = 1 };
 void launch_long_walk(LongWalk kind, bool k2_geometry, uint32_t ns, cudaStream_t st, const WalkArgs& a);
 void launch_scores_only(const PairDesc* desc, const EndCell* end, uint32_t ns, int32_t* score, uint8_t* flags, int mode, cudaStream_t st);
 void launch_gather(const GatherArgs& a, cudaStream_t st);
-void launch_ops_words(const uint64_t* lens2, uint64_t n_pairs, uint64_t* words, cudaStream_t st);
+void launch_ops_counts(const uint64_t* lens2, uint64_t n_pairs, ulonglong2* counts, cudaStream_t st);
+cudaError_t scan_counts(void* tmp, size_t& tmp_bytes, const ulonglong2* counts, ulonglong2* out, int count, cudaStream_t st);
+void launch_ops_sample(const ulonglong2* scan, uint64_t n_pairs, uint64_t stride, ulonglong2* samples, cudaStream_t st);
 void launch_pack_ops(const PackOpsArgs& a, bool long_pairs, cudaStream_t st);
 void launch_rebase(uint64_t* off, uint64_t count, const uint64_t* base, cudaStream_t st);
 void launch_bump(uint64_t* base, const uint64_t* chunk_total_entry, uint64_t* chunk_total_out, cudaStream_t st);

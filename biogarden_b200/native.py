@@ -61,7 +61,7 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status",
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_set_host_plan", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status",
            "bg_align_batch_ops", "bg_ops_result_free", "bg_expand_ops", "bg_expand_kind"]
 
 _lib = None
@@ -113,6 +113,8 @@ def lib():
     L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
     L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
     L.bg_set_long_trace_budget.restype = ci; L.bg_set_long_trace_budget.argtypes = [vp, u64]
+    L.bg_set_host_plan.restype = ci; L.bg_set_host_plan.argtypes = [vp, ci]
+    L.bg_debug_plan_compare.restype = ci; L.bg_debug_plan_compare.argtypes = [vp, C.POINTER(bg_batch), C.POINTER(bg_params), vp]
     L.bg_score_table26.restype = C.POINTER(C.c_int8); L.bg_score_table26.argtypes = [C.c_char_p]
     L.bg_residue_histogram.restype = ci; L.bg_residue_histogram.argtypes = [C.POINTER(bg_batch), vp, vp]
     L.bg_ref_status.restype = ci; L.bg_ref_status.argtypes = [ci, u64, u64, i32, ci]
@@ -404,6 +406,16 @@ class Context:
 
     def set_trace_budget(self, nbytes):
         check(lib().bg_set_trace_budget(self.h, nbytes), self.h)
+
+    def set_host_plan(self, on: bool):
+        """True: launch plans are built on the host; False (default): pipeline chunks are planned on the device."""
+        check(lib().bg_set_host_plan(self.h, int(bool(on))), self.h)
+
+    def plan_compare(self, batch: Batch, params: Params):
+        """(eligible, descriptors compared, differing, non-empty surplus slots): host planner vs device planner."""
+        out = np.zeros(4, np.uint64)
+        check(lib().bg_debug_plan_compare(self.h, C.byref(batch.c), C.byref(params.c), out.ctypes.data), self.h)
+        return tuple(int(x) for x in out)
 
     def set_long_trace_budget(self, nbytes):
         """Trace memory per launch of the long-pair path; pairs that need more use bounded-memory traceback."""

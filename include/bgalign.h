@@ -223,6 +223,10 @@ int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes);
  * computed twice).  This replaces the reference's "six full matrices or nothing" (aligner.rs:594-602). */
 int bg_set_long_trace_budget(bg_ctx* ctx, uint64_t bytes);
 
+/* 1: build every launch plan on the host; 0 (default): the chunks of bg_align_batch are planned on the device from
+ * their sequence offsets (16 B per pair H2D instead of 64 B of descriptors, no per-pair host work). */
+int bg_set_host_plan(bg_ctx* ctx, int on);
+
 /* Page-lock / unlock caller memory (cudaHostRegister).  The host-buffer entry points read the caller's residue
  * arena directly: pinned, that is an asynchronous DMA overlapped with the kernels; pageable, the driver stages it
  * synchronously.  Results are always returned in library-owned pinned memory. */

@@ -629,3 +629,45 @@ def test_user_closure_scorer(aligner):
             problems += _cmp.diff(bt, eng, ora, "closure %s %s" % (mode, alpha[:4]))
             eng.close()
     assert not problems, "\n".join(problems)
+
+
+def test_device_planner_matches_host_planner(aligner):
+    """k0_plan.cuh (launch descriptors built on the GPU from the sequence offsets) against build_plan (the host
+    planner): the two descriptor arrays must agree field by field -- slot order (stable sort by class, len1
+    descending), K1h holes, step counts, trace / output / band-scratch offsets -- for uniform chunks (no sort), mixed
+    lengths (holes), protein classes, multi-band K1 pairs, pairs long enough for the warp walker's shape set, and
+    forced shapes; and the alignments must not depend on which planner ran."""
+    rng = random.Random(12)
+    batches = {
+        "cfg2": synth.make("cfg2_dna150_global", n_pairs=20000),
+        "cfg3": synth.make("cfg3_edit_100_300", n_pairs=70000),
+        "cfg4": synth.make("cfg4_protein_local", n_pairs=3000),
+        "ragged": _random_batch(rng, 5000, b"ACGT", 260),
+        "multiband": _mutated_long_pairs([(300, 1500), (1200, 1100), (2500, 4000), (100, 4096), (700, 700), (20000, 90), (17000, 300), (50, 50),
+                                          (1030, 1030), (1030, 1030), (1031, 1030)] * 3, 8),
+    }
+    ctx = aligner.context
+    for name, batch in batches.items():
+        for mode, scorer, a, b in (("global", "unit", -2, -1), ("local", "blosum62", -11, -1), ("semiglobal", "unit", -1, -1)):
+            if name == "cfg4" and scorer == "unit":
+                continue
+            for shape in (None, (8, 19), (32, 8)):
+                if shape and name not in ("ragged", "cfg3"):
+                    continue
+                if shape:
+                    ctx.set_shape(*shape)
+                try:
+                    params = aligner.make_params(batch, mode, _cmp.SCORERS[scorer], a, b)
+                    elig, compared, differing, surplus = ctx.plan_compare(batch, params)
+                    assert elig == 1, (name, mode, shape)
+                    assert compared >= batch.n_pairs and differing == 0 and surplus == 0, (name, mode, shape, compared, differing, surplus)
+                    ctx.set_host_plan(True)
+                    r_host = ctx.align_batch(batch, params)
+                    ctx.set_host_plan(False)
+                    r_dev = ctx.align_batch(batch, params)
+                    assert np.array_equal(r_host.score, r_dev.score) and np.array_equal(r_host.status, r_dev.status), (name, mode, shape)
+                    assert np.array_equal(r_host.off, r_dev.off) and np.array_equal(r_host.arena, r_dev.arena), (name, mode, shape)
+                    r_host.close(); r_dev.close()
+                finally:
+                    ctx.set_host_plan(False)
+                    ctx.set_shape(0, 0)

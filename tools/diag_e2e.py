@@ -1,15 +1,21 @@
-import sys, time, os
+"""Host-side timeline of the host-buffer path: one bg_align_batch call with BG_PROFILE_HOST=1 after warm-up.
+usage: BG_PROFILE_HOST=1 python tools/diag_e2e.py [workload] [pairs] [host_plan 0/1] [n_logical_devices]"""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from biogarden_b200 import native, score, synth
+from biogarden_b200 import score, synth
 from biogarden_b200.aligner import SequenceAligner
-batch = bench.pinned_batch(synth.make("cfg2_dna150_global", n_pairs=1000000))
-al = SequenceAligner([0]); ctx = al.context
-params = al.make_params(batch, "global", score.unit, -2, -1)
-for i in range(4):
-    t0 = time.perf_counter(); r = ctx.align_batch(batch, params); t1 = time.perf_counter(); r.close()
-    print("align_batch %.2f ms" % (1e3 * (t1 - t0)), flush=True)
-b3 = bench.pinned_batch(synth.make("cfg3_edit_100_300", n_pairs=1250000))
-for i in range(3):
-    t0 = time.perf_counter(); ctx.edit_distance_batch(b3); t1 = time.perf_counter()
-    print("edit_distance_batch %.2f ms" % (1e3 * (t1 - t0)), flush=True)
+wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+cfg_name, full = bench.WORKLOADS[wl]
+pairs = int(sys.argv[2]) if len(sys.argv) > 2 else full
+host_plan = len(sys.argv) > 3 and sys.argv[3] == "1"
+ndev = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+cfg = synth.CONFIGS[cfg_name]
+batch = bench.pinned_batch(bench.make_batch(cfg_name, pairs))
+al = SequenceAligner([0] * ndev)
+al.context.set_host_plan(host_plan)
+params = al.make_params(batch, cfg["mode"], getattr(score, cfg["scorer"]), cfg["a"], cfg["b"])
+ts = []
+for i in range(8):
+    t0 = time.perf_counter(); r = al.context.align_batch(batch, params); ts.append(time.perf_counter() - t0); r.close()
+print("calls (ms):", " ".join("%.2f" % (1e3 * x) for x in ts), "host_plan", host_plan, "ndev", ndev, file=sys.stderr)
