@@ -198,8 +198,10 @@ def pinned_batch(batch):
     on[:] = batch.seq_off
     nb = native.Batch.__new__(native.Batch)
     nb.residues, nb.seq_off, nb.n_pairs = rn, on, batch.n_pairs
+    nb.packing, nb.alphabet = batch.packing, batch.alphabet
     nb._keep = (r, o)
-    nb.c = native.bg_batch(nb.n_pairs, rn.ctypes.data, on.ctypes.data)
+    nb.c = native.bg_batch(nb.n_pairs, rn.ctypes.data, on.ctypes.data, nb.packing, 0,
+                           nb.alphabet.ctypes.data if nb.alphabet is not None else None)
     return nb
 
 
@@ -348,9 +350,31 @@ def measure(args, workload, steps, warmup, rank, world, local_rank, barrier, sam
     h2d = int(tt["h2d_bytes"])                # counted by the library from the copies it issued in the last call
     e2e_launches = int(tt["launches"])
     barrier()
+
+    # ---------------- the same end-to-end leg with PACKED host buffers (what bg_fasta_parse_packed emits) ----------------
+    packed_s = None
+    bits = 2 if cfg["alphabet"] == synth.DNA else 5
+    if "fixture" not in cfg:
+        plain = batch
+        batch = pinned_batch(rank_batch(cfg_name, pairs, rank).pack(bits))
+        if not is_edit:
+            params = al.make_params(batch, cfg["mode"], scorer, cfg["a"], cfg["b"])
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        packed_s = time.perf_counter() - w0
+        tp = ctx.timing()
+        packed_h2d, packed_d2h = int(tp["h2d_bytes"]), int(tp["d2h_bytes"])
+        batch = plain
+        barrier()
     ctx.close()
 
     dev_ms_max, e2e_ms_max, cells_total = reduce_over_ranks(dev_ms, e2e_s * 1e3, float(cells), world, "cuda")
+    packed_ms_max = reduce_over_ranks(0.0, (packed_s or 0.0) * 1e3, 0.0, world, "cuda")[1]
     if rank != 0:
         return None
     ms_per_step = dev_ms_max / steps
@@ -378,6 +402,10 @@ def measure(args, workload, steps, warmup, rank, world, local_rank, barrier, sam
                 "timed": "host wall clock around bg_align_batch / bg_edit_distance_batch: raw residue bytes in pinned host buffers in, "
                          "scores + status + offsets + aligned strings in host memory out (results cross the link as 2-bit ops and "
                          "are expanded by the library's host threads inside the call)"},
+        "e2e_packed": None if packed_s is None else {
+            "value": cells_total * steps / (packed_ms_max * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": packed_ms_max / steps,
+            "h2d_bytes_per_step": packed_h2d, "d2h_bytes_per_step": packed_d2h, "bits_per_residue": bits,
+            "timed": "as e2e, but the host batch holds %d-bit packed residues (bg_batch.packing; the form bg_fasta_parse_packed emits)" % bits},
         "gpu_launches": launches * steps,
         "clocks": clocks,
         "phases_ms_last_step": {"fill": fill_ms, "walk": walk_ms, "compact": compact_ms},
@@ -480,7 +508,7 @@ def main():
             r = measure(args, wl, st_, wu_, rank, world, local_rank, barrier, sampler)
             if rank == 0:
                 extra[wl] = {"value": r["value"], "unit": r["unit"], "metric": r["metric"], "ms_per_step": r["ms_per_step"], "steps": st_, "warmup": wu_,
-                             "e2e": r["e2e"], "roofline": {k: r["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "ops_per_cell", "gcups_fill_only")},
+                             "e2e": r["e2e"], "e2e_packed": r["e2e_packed"], "roofline": {k: r["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "ops_per_cell", "gcups_fill_only")},
                              "phases_ms_last_step": r["phases_ms_last_step"], "clocks": r["clocks"], "config": r["config"]}
         if rank == 0:
             line["configs"] = extra

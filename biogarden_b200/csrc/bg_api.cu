@@ -32,8 +32,12 @@
 
 #include "bg_args.cuh"
 #include "launch.h"
+#include "pack_util.h"
 
 namespace bg {
+// host_util.cpp: residues [first, first + count) of a packed arena -> bytes
+void make_unpack_lut2(const uint8_t* alphabet, uint32_t* lut);
+void unpack_residues(const uint8_t* packed, uint32_t bits, const uint8_t* alphabet, uint64_t first, uint64_t count, uint8_t* out, const uint32_t* lut2);
 // host_expand.cpp: 2-bit alignment ops -> the two aligned strings (AVX-512 VBMI2 or portable code)
 void expand_ops(const uint8_t* s1, const uint8_t* s2, const uint32_t* ops, uint64_t len, uint8_t* a_out, uint8_t* b_out);
 }
@@ -177,6 +181,7 @@ struct WorkSet {
     DevBuf ckpt, wstate, ckslots;                                      // K2 bounded-memory traceback: row checkpoints, suspended walks, launch table
     DevBuf run;                                                        // (unused by the alignment pipeline since results travel as ops)
     DevBuf len, first, ops;                                            // pipeline mode: compact results of the chunk (k_pack_ops)
+    DevBuf packed;                                                     // packed input: the chunk's packed bytes before k_unpack
     DevBuf samples;                                                    // pipeline mode: sampled offset scans of the chunk
     PinBuf samples_h;
     DevBuf poff, pkeys, pids, psort;                                   // pipeline mode: device-side planner (offsets of the chunk, sort keys / ids / scratch)
@@ -192,7 +197,7 @@ struct WorkSet {
     }
     void reset_events() { evs.clear(); ev_used = 0; }
     std::vector<DevBuf*> all_bufs() {
-        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots, &len, &first, &ops, &poff, &pkeys, &pids, &psort, &samples};
+        return {&trace, &trace2, &end, &bnd, &pad, &table, &codes, &err, &cubtmp, &progress, &cand, &residues, &desc, &score, &flags, &lens2, &off, &arena, &out64, &run, &assign, &ckpt, &wstate, &ckslots, &len, &first, &ops, &poff, &pkeys, &pids, &psort, &samples, &packed};
     }
 };
 
@@ -946,6 +951,9 @@ int check_batch(bg_ctx* ctx, const bg_batch* in, BatchScan* scan = nullptr) {
     if (!in || (in->n_pairs && (!in->seq_off || (!in->residues && in->seq_off[2 * in->n_pairs] != in->seq_off[0])))) {
         ctx->set_error("null batch pointers"); return BG_EINVAL_ARG;
     }
+    if (in->packing != BG_PACK_NONE && ((in->packing != BG_PACK_2BIT && in->packing != BG_PACK_5BIT) || !in->alphabet)) {
+        ctx->set_error("unknown residue packing, or packed batch without an alphabet"); return BG_EINVAL_ARG;
+    }
     if (scan) {
         scan_batch(in, *scan);
         if (!scan->monotone) { ctx->set_error("seq_off not monotone"); return BG_EINVAL_ARG; }
@@ -1023,6 +1031,36 @@ struct AlignIO {
     uint32_t* len = nullptr; uint32_t* first = nullptr; uint32_t* ops = nullptr;
     ulonglong2* samples = nullptr; uint64_t sample_stride = 0;   // every sample_stride-th entry of the {op words, columns} scan + totals
 };
+
+// Host bytes [b0, b1) of a batch's residue arena that hold residues [r0, r1).
+void host_byte_range(uint32_t packing, uint64_t r0, uint64_t r1, uint64_t& b0, uint64_t& b1) {
+    if (packing == BG_PACK_NONE) { b0 = r0; b1 = r1; }
+    else packed_byte_range(packing, r0, r1, b0, b1);
+}
+
+// Residues [r0, r1) of a host batch -> dst[0 .. r1 - r0) on the device, one byte per residue.  src points at host byte
+// b0 of host_byte_range(packing, r0, r1) (the caller's arena, or a pinned staging copy of exactly that range).
+// Packed batches: the packed bytes go to `staging` and k_unpack writes dst (same stream).
+int upload_residues(bg_ctx* ctx, const uint8_t* src, uint32_t packing, const uint8_t* alphabet, uint64_t r0, uint64_t r1,
+                    DevBuf& staging, uint8_t* dst, cudaStream_t st, uint64_t* h2d_bytes) {
+    if (r1 <= r0) return BG_OK;
+    uint64_t b0, b1;
+    host_byte_range(packing, r0, r1, b0, b1);
+    if (h2d_bytes) *h2d_bytes += b1 - b0;
+    if (packing == BG_PACK_NONE) {
+        CU_TRY(ctx, cudaMemcpyAsync(dst, src, b1 - b0, cudaMemcpyHostToDevice, st));
+        return BG_OK;
+    }
+    const uint64_t lead = b0 & 15;                      // keep the bytes' alignment mod 16 (128-bit loads in k_unpack2)
+    if (!staging.ensure(lead + (b1 - b0) + 64)) { ctx->set_error("device allocation failed (packed residues)"); return BG_ENOMEM; }
+    CU_TRY(ctx, cudaMemcpyAsync(staging.as<uint8_t>() + lead, src, b1 - b0, cudaMemcpyHostToDevice, st));
+    UnpackArgs ua;
+    ua.packed = staging.as<uint8_t>(); ua.bit0 = (uint64_t)packing * r0 - 8 * (b0 - lead); ua.count = r1 - r0; ua.bits = packing; ua.out = dst;
+    memcpy(ua.alphabet, alphabet, packing == BG_PACK_2BIT ? 4 : 32);
+    launch_unpack(ua, st);
+    CU_TRY(ctx, cudaGetLastError());
+    return BG_OK;
+}
 
 // Uploads the score table / code maps into the work set and clears its error flag.
 int upload_params(bg_ctx* ctx, WorkSet& ws, const Prepared& pp) {
@@ -1489,11 +1527,14 @@ int bg_batch_upload(bg_ctx* ctx, int dev_index, const bg_batch* in, bg_dbatch** 
     for (uint64_t s = 0; s <= 2 * in->n_pairs; ++s) B->seq_off[s] = in->n_pairs ? in->seq_off[s] - base : 0;
     B->n_residues = B->seq_off.back();
     if (!B->residues.ensure(B->n_residues + 16)) { delete B; ctx->set_error("device allocation for residues failed"); return BG_ENOMEM; }
+    ctx->h2d = 0;
     if (B->n_residues) {
-        cudaError_t e = cudaMemcpyAsync(B->residues.p, in->residues + base, B->n_residues, cudaMemcpyHostToDevice, ws.stream);
-        if (e != cudaSuccess) { B->residues.release(); delete B; ctx->set_error(cudaGetErrorString(e)); return BG_ECUDA; }
+        uint64_t b0, b1, moved = 0;
+        host_byte_range(in->packing, base, base + B->n_residues, b0, b1);
+        rc = upload_residues(ctx, in->residues + b0, in->packing, in->alphabet, base, base + B->n_residues, ws.packed, B->residues.as<uint8_t>(), ws.stream, &moved);
+        if (rc) { B->residues.release(); delete B; return rc; }
+        ctx->h2d = moved;
     }
-    ctx->h2d = B->n_residues;
     *out = B;
     return BG_OK;
 }
@@ -1764,7 +1805,9 @@ struct OpsOut {        // compact result arrays of the whole batch (pinned, call
 // into staging (long pairs dealt to devices by size; map[q] = caller index of local pair q).
 struct WorkItem {
     uint64_t lo = 0, n = 0;
-    const uint8_t* res = nullptr;       // host residues; sequence s of the item at res[off[s] - off[0]]
+    const uint8_t* res = nullptr;       // host residues of the item: byte b0 of host_byte_range(packing, off[0], off[2n]) onwards
+    uint32_t packing = BG_PACK_NONE;    // as in bg_batch (gathered long-mode items are unpacked while they are gathered)
+    const uint8_t* alphabet = nullptr;
     const uint64_t* off = nullptr;      // [2n + 1]
     const uint32_t* map = nullptr;
     uint64_t ops_base = 0, ops_cap = 0; // the item's region of OpsOut::ops (upper-bound layout), words
@@ -1794,7 +1837,24 @@ struct AlignJob {
     std::mutex mu; std::condition_variable cv;
     std::vector<char> arrived; int frontier = 0; uint64_t arena_base = 0;
     int pending = 0;                            // expansion tasks in flight
+    uint32_t lut2[256];                         // 2-bit packed input: packed byte -> four residue bytes
     void fail(int code) { int expect = BG_OK; rc.compare_exchange_strong(expect, code); }
+};
+
+// The residues the expansion of pair p reads: seq1 from first_a on, seq2 from first_b on -- the caller's bytes, or
+// (packed batches) unpacked into a buffer of the calling thread.
+struct PairResidues {
+    const uint8_t* s1; const uint8_t* s2;
+    PairResidues(const bg_batch* in, const uint32_t* lut2, uint64_t p, uint32_t first_a, uint32_t first_b) {
+        const uint64_t o0 = in->seq_off[2 * p], o1 = in->seq_off[2 * p + 1], o2 = in->seq_off[2 * p + 2];
+        if (in->packing == BG_PACK_NONE) { s1 = in->residues + o0 + first_a; s2 = in->residues + o1 + first_b; return; }
+        static thread_local std::vector<uint8_t> buf;
+        const uint64_t n1 = o1 - o0 - first_a, n2 = o2 - o1 - first_b;
+        if (buf.size() < n1 + n2 + 128) buf.resize(n1 + n2 + 128);
+        unpack_residues(in->residues, in->packing, in->alphabet, o0 + first_a, n1, buf.data(), lut2);
+        unpack_residues(in->residues, in->packing, in->alphabet, o1 + first_b, n2, buf.data() + n1 + 64, lut2);
+        s1 = buf.data(); s2 = buf.data() + n1 + 64;
+    }
 };
 
 // Expands pairs [p_lo, p_hi) (caller order): off[2p] holds the pair's a_align offset relative to `base`.
@@ -1805,8 +1865,8 @@ void expand_pairs(AlignJob& J, uint64_t p_lo, uint64_t p_hi, uint64_t base) {
         J.off[2 * p] = o; J.off[2 * p + 1] = o + len;
         if (!len) continue;
         if (o + 2 * len > J.arena_cap) { J.ctx->set_error("internal: arena bound exceeded"); J.fail(BG_ECUDA); return; }
-        expand_ops(in->residues + in->seq_off[2 * p] + J.oo.first[2 * p], in->residues + in->seq_off[2 * p + 1] + J.oo.first[2 * p + 1],
-                   J.oo.ops + J.oo.ops_off[p], len, J.arena + o, J.arena + o + len);
+        const PairResidues pr(in, J.lut2, p, J.oo.first[2 * p], J.oo.first[2 * p + 1]);
+        expand_ops(pr.s1, pr.s2, J.oo.ops + J.oo.ops_off[p], len, J.arena + o, J.arena + o + len);
     }
 }
 
@@ -1845,8 +1905,8 @@ void expand_sub(AlignJob& J, int c, uint64_t i, uint64_t arena_base, bool string
             J.off[2 * p] = o; J.off[2 * p + 1] = o + len;
             if (len) {
                 if (o + 2 * len > J.arena_cap) { J.ctx->set_error("internal: arena bound exceeded"); J.fail(BG_ECUDA); return; }
-                expand_ops(in->residues + in->seq_off[2 * p] + oo.first[2 * p], in->residues + in->seq_off[2 * p + 1] + oo.first[2 * p + 1],
-                           oo.ops + w, len, J.arena + o, J.arena + o + len);
+                const PairResidues pr(in, J.lut2, p, oo.first[2 * p], oo.first[2 * p + 1]);
+                expand_ops(pr.s1, pr.s2, oo.ops + w, len, J.arena + o, J.arena + o + len);
             }
         }
         w += (len + 15) >> 4; o += 2 * len;
@@ -2017,7 +2077,9 @@ int device_pipeline(AlignJob& J, int d) {
         const uint8_t* src = pb.res.p ? (const uint8_t*)pb.res.p : it.res;
         cudaEvent_t pe_a = nullptr;
         if (prof) { pe_a = ws.get_event(); cudaEventRecord(pe_a, st_h2d); }
-        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, src, nres, cudaMemcpyHostToDevice, st_h2d));
+        uint64_t res_bytes = 0;
+        rc = upload_residues(ctx, src, it.packing, it.alphabet, base, base + nres, ws.packed, ws.residues.as<uint8_t>(), st_h2d, &res_bytes);
+        if (rc) return rc;
         if (pb.dev_plan) {
             // the chunk's 16 B/pair offsets instead of 64 B/pair descriptors; the planner runs on its own high-priority
             // stream next to the previous chunk's fill and hands the descriptors to the compute stream
@@ -2035,12 +2097,12 @@ int device_pipeline(AlignJob& J, int d) {
             if (prof) { cudaEvent_t pp_b = ws.get_event(); cudaEventRecord(pp_b, st_plan); ws.evs.push_back(PhaseEv{pp_a, pp_b, 5}); }
             CU_TRY(ctx, cudaEventRecord(ev_plan[s], st_plan));
             CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_plan[s], 0));
-            ctx->h2d += nres + (2 * n + 1) * 8;
+            ctx->h2d += res_bytes + (2 * n + 1) * 8;
             ctx->launches += pb.need_sort ? 16 : 10;
         } else {
             if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pb.stage.p, P.n_slots * sizeof(PairDesc), cudaMemcpyHostToDevice, st_h2d));
             CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
-            ctx->h2d += nres + P.n_slots * sizeof(PairDesc);
+            ctx->h2d += res_bytes + P.n_slots * sizeof(PairDesc);
         }
         CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         rc = upload_params(ctx, ws, pp);
@@ -2158,13 +2220,14 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
     struct Prebuilt { Plan plan; PinBuf stage, res; int rc = BG_OK; TaskHandle th; bool dev_plan = false, need_sort = false; PlanArgs pa; };
     std::vector<Prebuilt> pre(nchunks);   // all chunk plans, one pool task per chunk, consumed as they finish
     static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
-    const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues + off[2 * lo]);
+    const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues);
     for (int c = 0; c < nchunks; ++c)
         pre[c].th = host_pool().submit([&, c] {
             const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
             if (!pre[c].stage.ensure(plan_desc_capacity(n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
             if (stage_res) {
-                const uint64_t b0 = off[2 * lo2], nb = off[2 * (lo2 + n)] - b0;
+                uint64_t b0, b1; host_byte_range(in->packing, off[2 * lo2], off[2 * (lo2 + n)], b0, b1);
+                const uint64_t nb = b1 - b0;
                 if (!pre[c].res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
                 memcpy(pre[c].res.p, in->residues + b0, nb);
             }
@@ -2250,11 +2313,17 @@ int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t 
         if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<size_t>(1, P.n_slots) * sizeof(PairDesc)) || !ws.out64.ensure(std::max<uint64_t>(1, n) * 8)) {
             ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM;
         }
-        if (nres) CU_TRY(ctx, cudaMemcpyAsync(ws.residues.p, stage_res ? (const uint8_t*)pre[c].res.p : in->residues + base, nres, cudaMemcpyHostToDevice, st_h2d));
+        uint64_t res_bytes = 0;
+        {
+            uint64_t hb0, hb1; host_byte_range(in->packing, base, base + nres, hb0, hb1);
+            int urc = upload_residues(ctx, stage_res ? (const uint8_t*)pre[c].res.p : in->residues + hb0, in->packing, in->alphabet, base, base + nres,
+                                      ws.packed, ws.residues.as<uint8_t>(), st_h2d, &res_bytes);
+            if (urc) return urc;
+        }
         const size_t slot_bytes = P.compact ? sizeof(MyersSlot) : sizeof(PairDesc);
         if (P.n_slots) CU_TRY(ctx, cudaMemcpyAsync(ws.desc.p, pre[c].stage.p, P.n_slots * slot_bytes, cudaMemcpyHostToDevice, st_h2d));
         CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
-        ctx->h2d += nres + P.n_slots * slot_bytes;
+        ctx->h2d += res_bytes + P.n_slots * slot_bytes;
         cudaStream_t st_comp = ws.stream;
         CU_TRY(ctx, cudaStreamWaitEvent(st_comp, ev_h2d[s], 0));
         int rc = run_edit(ctx, ws, ws.residues.as<uint8_t>(), ws.desc.as<PairDesc>(), P, ws.out64.as<uint64_t>(), lut);
@@ -2313,6 +2382,7 @@ int run_align_job(AlignJob& J) {
     // several devices the pairs are dealt by size instead -- largest first, each to the device with the least
     // work so far (1 000 pairs of 2.5e9 .. 1e10 cells: a contiguous split leaves the tail to chance).
     J.long_mode = scan.has_wide;
+    if (in->packing == BG_PACK_2BIT) make_unpack_lut2(in->alphabet, J.lut2);
     if (N == 0) { if (J.want_strings) J.off[0] = 0; return BG_OK; }
     if (!J.long_mode) {
         const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, 0, N, 0.0, nd);
@@ -2320,7 +2390,8 @@ int run_align_job(AlignJob& J) {
         for (size_t c = 0; c + 1 < cb.size(); ++c) {
             WorkItem& it = J.items[c];
             it.lo = cb[c]; it.n = cb[c + 1] - cb[c];
-            it.res = in->residues + off[2 * it.lo]; it.off = off + 2 * it.lo;
+            it.off = off + 2 * it.lo; it.packing = in->packing; it.alphabet = in->alphabet;
+            { uint64_t b0, b1; host_byte_range(in->packing, off[2 * it.lo], off[2 * cb[c + 1]], b0, b1); it.res = in->residues + b0; }
             // upper-bound layout of the op arena: B(p) = residues before pair p / 16 + p  (ceil((n + m) / 16) words per pair at most)
             it.ops_base = ((off[2 * it.lo] - off[0]) >> 4) + it.lo;
             it.ops_cap = ((off[2 * cb[c + 1]] - off[0]) >> 4) + cb[c + 1] - it.ops_base;
@@ -2328,7 +2399,8 @@ int run_align_job(AlignJob& J) {
     } else if (nd == 1) {
         J.items.resize(1);
         WorkItem& it = J.items[0];
-        it.lo = 0; it.n = N; it.res = in->residues + off[0]; it.off = off;
+        it.lo = 0; it.n = N; it.off = off; it.packing = in->packing; it.alphabet = in->alphabet;
+        { uint64_t b0, b1; host_byte_range(in->packing, off[0], off[2 * N], b0, b1); it.res = in->residues + b0; }
         it.ops_base = 0; it.ops_cap = ((off[2 * N] - off[0]) >> 4) + N;
         J.dev_items.assign(1, std::vector<int>{0});
     } else {
@@ -2372,7 +2444,8 @@ int run_align_job(AlignJob& J) {
             for (uint64_t q = 0; q < n; ++q) {
                 const uint64_t p = sets[d][q];
                 const uint64_t l1 = off[2 * p + 1] - off[2 * p], l2 = off[2 * p + 2] - off[2 * p + 1];
-                memcpy(base + w, in->residues + off[2 * p], l1 + l2);
+                if (in->packing == BG_PACK_NONE) memcpy(base + w, in->residues + off[2 * p], l1 + l2);
+                else unpack_residues(in->residues, in->packing, in->alphabet, off[2 * p], l1 + l2, base + w, in->packing == BG_PACK_2BIT ? J.lut2 : nullptr);
                 g_off[2 * q] = w; g_off[2 * q + 1] = w + l1; w += l1 + l2;
                 g_map[q] = (uint32_t)p;
             }
@@ -2389,7 +2462,7 @@ int run_align_job(AlignJob& J) {
     const uint64_t ws_budget = ctx->trace_budget_words;   // per work set; several fit the B200's 180 GB many times over
     const uint64_t wave_budget = ctx->long_budget_words ? ctx->long_budget_words : std::max<uint64_t>(ctx->trace_budget_words, (uint64_t)(0.8 * (double)ctx->devs[0].total_mem) / 4);
     static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
-    const bool stage_res = !no_stage && !J.long_mode && host_is_pageable(in->residues + off[0]);
+    const bool stage_res = !no_stage && !J.long_mode && host_is_pageable(J.items[0].res);
     J.pre = std::vector<Prebuilt>(nitems);
     for (int c = 0; c < nitems; ++c)
         J.pre[c].th = host_pool().submit([&J, c, ctx, ws_budget, wave_budget, stage_res] {
@@ -2400,7 +2473,8 @@ int run_align_job(AlignJob& J) {
                           plan_from_stats(ctx, *J.scan, it.lo, it.lo + it.n, ws_budget, J.pp->half_maxabs, pb.plan, pb.pa, pb.need_sort);
             if (pb.dev_plan) {
                 if (stage_res) {     // pageable caller memory: stage offsets and residues (see host_is_pageable)
-                    const uint64_t nb = it.off[2 * it.n] - it.off[0];
+                    uint64_t hb0, hb1; host_byte_range(it.packing, it.off[0], it.off[2 * it.n], hb0, hb1);
+                    const uint64_t nb = hb1 - hb0;
                     if (!pb.stage.ensure((2 * it.n + 1) * 8) || !pb.res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
                     memcpy(pb.stage.p, it.off, (2 * it.n + 1) * 8);
                     memcpy(pb.res.p, it.res, nb);
@@ -2409,7 +2483,8 @@ int run_align_job(AlignJob& J) {
             }
             if (!pb.stage.ensure(plan_desc_capacity(it.n) * sizeof(PairDesc))) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
             if (stage_res) {
-                const uint64_t nb = it.off[2 * it.n] - it.off[0];
+                uint64_t hb0, hb1; host_byte_range(it.packing, it.off[0], it.off[2 * it.n], hb0, hb1);
+                const uint64_t nb = hb1 - hb0;
                 if (!pb.res.ensure(nb + 16)) { ctx->set_error("pinned staging allocation failed"); pb.rc = BG_ENOMEM; return; }
                 memcpy(pb.res.p, it.res, nb);
             }
@@ -2575,7 +2650,11 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     // byte outside the sampled alphabet, in which case the batch is redone with the general kernel.
     uint8_t lut[256];
     bool use_lut = false;
-    if (in->n_pairs && !getenv("BG_NO_MYERS")) {
+    if (in->n_pairs && !getenv("BG_NO_MYERS") && in->packing == BG_PACK_2BIT) {
+        uint64_t hist[256] = {0};
+        for (int c = 0; c < 4; ++c) hist[in->alphabet[c]] = 1;      // a 2-bit batch has at most four letters by construction
+        use_lut = make_edit_lut(hist, lut);
+    } else if (in->n_pairs && !getenv("BG_NO_MYERS") && in->packing == BG_PACK_NONE) {
         const uint64_t b0 = in->seq_off[0], b1 = in->seq_off[2 * in->n_pairs];
         uint64_t hist[256] = {0};
         const uint64_t span = b1 - b0, take = std::min<uint64_t>(span, 1u << 16);   // (2 x 1 MiB of byte increments cost 2 ms)
@@ -2646,7 +2725,9 @@ int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
             stage.release(); return fail(BG_ENOMEM, "device allocation failed (hamming)");
         }
         cudaStream_t st = ws.stream;
-        cudaError_t e = cudaMemcpyAsync(ws.residues.p, in->residues + base, nres, cudaMemcpyHostToDevice, st);
+        uint64_t hb0, hb1, res_bytes = 0; host_byte_range(in->packing, base, base + nres, hb0, hb1);
+        if (upload_residues(ctx, in->residues + hb0, in->packing, in->alphabet, base, base + nres, ws.packed, ws.residues.as<uint8_t>(), st, &res_bytes)) { stage.release(); rcs[d] = BG_ECUDA; return; }
+        cudaError_t e = cudaSuccess;
         if (e == cudaSuccess) e = cudaMemcpyAsync(ws.off.p, h_off, (2 * n + 1) * 8, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(ws.lens2.p, h_first, (n + 1) * 8, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(ws.out64.p, 0, n * 8, st);
@@ -2669,7 +2750,7 @@ int bg_hamming_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { stage.release(); ctx->set_error(std::string("hamming: ") + cudaGetErrorString(e)); rcs[d] = BG_ECUDA; return; }
         memcpy(out + lo, h_out, n * 8);
-        ctx->h2d += nres + (3 * n + 2) * 8; ctx->d2h += n * 8;
+        ctx->h2d += res_bytes + (3 * n + 2) * 8; ctx->d2h += n * 8;
         stage.release();
     };
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;

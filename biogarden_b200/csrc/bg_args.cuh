@@ -51,6 +51,15 @@ struct PlanArgs {
     PlanCls cls[PLAN_MAX_CLS];
 };
 
+struct UnpackArgs {
+    const uint8_t* packed;    // device copy of the packed bytes, 16-byte aligned
+    uint64_t bit0;            // bit offset of the first residue to unpack
+    uint64_t count;           // residues
+    uint32_t bits;            // 2 or 5
+    uint8_t alphabet[32];     // code -> residue byte
+    uint8_t* out;             // [count]
+};
+
 // ---- K1h (k1h_fill.cuh) ----
 constexpr int32_t HB_BIAS = 1 << 15;
 constexpr int32_t HB_NEG = 1 << 8;       // biased "minus infinity": below every value a cell can take (>= 2^15 - 2*HB_RANGE - 3*HB_MAXABS)

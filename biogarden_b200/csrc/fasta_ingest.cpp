@@ -152,4 +152,20 @@ int bg_fasta_parse(const uint8_t* text, uint64_t len, int n_threads, bg_fasta* o
     return BG_OK;
 }
 
+int bg_fasta_parse_packed(const uint8_t* text, uint64_t len, int n_threads, int bits, bg_fasta* out) {
+    if (bits != 2 && bits != 5) return BG_EINVAL_ARG;
+    int rc = bg_fasta_parse(text, len, n_threads, out);
+    if (rc) return rc;
+    // second pass over the payload only (1 B read, 0.25 / 0.625 B written per residue), in parallel
+    const uint64_t n = out->n_records ? out->seq_off[out->n_records] : 0;
+    uint8_t* packed = (uint8_t*)malloc(bg_packed_bytes(n, bits));
+    if (!packed) { bg_fasta_free(out); return BG_ENOMEM; }
+    rc = bg_pack_residues(out->residues, n, bits, n_threads, packed, out->alphabet);
+    if (rc) { free(packed); bg_fasta_free(out); return rc; }
+    free(out->residues);
+    out->residues = packed;
+    out->packing = (uint32_t)bits;
+    return BG_OK;
+}
+
 }  // extern "C"

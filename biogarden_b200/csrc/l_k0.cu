@@ -3,6 +3,7 @@
 
 #include "launch.h"
 #include "k0_plan.cuh"
+#include "k0_unpack.cuh"
 
 namespace bg {
 
@@ -60,6 +61,12 @@ cudaError_t launch_plan(PlanArgs a, bool sort, uint32_t n_slots, void* scratch, 
     if (e != cudaSuccess) return e;
     k_plan_warp_write<<<(n_warps + 255) / 256, 256, 0, st>>>(a, woff, steps, n_warps);
     return cudaGetLastError();
+}
+
+void launch_unpack(const UnpackArgs& a, cudaStream_t st) {
+    if (!a.count) return;
+    if (a.bits == 2) k_unpack2<<<(unsigned)((a.count + 64 * 256 - 1) / (64 * 256)), 256, 0, st>>>(a);
+    else k_unpack_any<<<(unsigned)((a.count + 255) / 256), 256, 0, st>>>(a);
 }
 
 }  // namespace bg

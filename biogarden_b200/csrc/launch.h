@@ -84,6 +84,8 @@ __host__ __device__ inline Shape pick_shape_m(uint32_t m, bool half_ok, bool c8)
 size_t plan_scratch_bytes(uint32_t n_pairs, uint32_t n_slots);
 cudaError_t launch_plan(PlanArgs a, bool sort, uint32_t n_slots, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+void launch_unpack(const UnpackArgs& a, cudaStream_t st);
+
 // K1 / K1h / K2 fills
 void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a);
 bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a);

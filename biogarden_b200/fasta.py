@@ -74,17 +74,18 @@ def read_tile(path) -> Tile:
 
 
 # ---- native ingest: FASTA text -> the C ABI's batch layout (csrc/fasta_ingest.cpp) ---------------------
-def parse_batch(text: bytes, n_threads: int = 0):
+def parse_batch(text: bytes, n_threads: int = 0, bits: int = 0):
     """io::fasta::Reader::read_all over `text`, done by the native multi-threaded parser, straight into the layout
-    the alignment entry points take.  Returns (ids, residues uint8 array, seq_off uint64[n + 1]).  Raises IOError
-    ("Expected > at record start.") like the reference."""
+    the alignment entry points take.  Returns (ids, residues uint8 array, seq_off uint64[n + 1]); with bits = 2 / 5
+    the residues are packed (bg_fasta_parse_packed) and a fourth value, the alphabet (bytes), is returned.  Raises
+    IOError ("Expected > at record start.") like the reference."""
     import ctypes as C
     import numpy as np
     from . import native
     L = native.lib()
     f = native.bg_fasta()
     buf = bytes(text)
-    rc = L.bg_fasta_parse(buf, len(buf), n_threads, C.byref(f))
+    rc = L.bg_fasta_parse_packed(buf, len(buf), n_threads, bits, C.byref(f)) if bits else L.bg_fasta_parse(buf, len(buf), n_threads, C.byref(f))
     if rc == native.BG_EINVAL_FASTA:
         raise IOError("Expected > at record start.")
     native.check(rc)
@@ -93,17 +94,22 @@ def parse_batch(text: bytes, n_threads: int = 0):
         seq_off = np.ctypeslib.as_array(C.cast(f.seq_off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
         id_off = np.ctypeslib.as_array(C.cast(f.id_off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
         nres, nid = int(seq_off[n]), int(id_off[n])
+        alphabet = bytes(f.alphabet)
+        if bits:
+            nres = int(L.bg_packed_bytes(nres, bits))     # the packed arena incl. its padding
         residues = np.ctypeslib.as_array(C.cast(f.residues, C.POINTER(C.c_uint8)), shape=(max(nres, 1),))[:nres].copy()
         idbytes = bytes(np.ctypeslib.as_array(C.cast(f.ids, C.POINTER(C.c_uint8)), shape=(max(nid, 1),))[:nid])
         ids = [idbytes[int(id_off[r]):int(id_off[r + 1])].decode("utf-8", "replace") for r in range(n)]
     finally:
         L.bg_fasta_free(C.byref(f))
-    return ids, residues, seq_off
+    return (ids, residues, seq_off, alphabet) if bits else (ids, residues, seq_off)
 
 
-def read_batch(path, n_threads: int = 0):
-    """FASTA file -> native.Batch of pairs (record 2p, record 2p + 1) plus the record ids."""
+def read_batch(path, n_threads: int = 0, bits: int = 0):
+    """FASTA file -> native.Batch of pairs (record 2p, record 2p + 1) plus the record ids; bits = 2 / 5: packed residues."""
     from . import native
     with open(os.fspath(path), "rb") as fh:
-        ids, residues, seq_off = parse_batch(fh.read(), n_threads)
-    return native.Batch(residues, seq_off), ids
+        r = parse_batch(fh.read(), n_threads, bits)
+    if bits:
+        return native.Batch(r[1], r[2], bits, r[3]), r[0]
+    return native.Batch(r[1], r[2]), r[0]

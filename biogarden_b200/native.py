@@ -21,7 +21,11 @@ ST_OK, ST_REF_UNDEFINED = 0, 1
 
 
 class bg_batch(C.Structure):
-    _fields_ = [("n_pairs", C.c_uint64), ("residues", C.c_void_p), ("seq_off", C.c_void_p)]
+    _fields_ = [("n_pairs", C.c_uint64), ("residues", C.c_void_p), ("seq_off", C.c_void_p),
+                ("packing", C.c_uint32), ("reserved_", C.c_uint32), ("alphabet", C.c_void_p)]
+
+
+PACK_NONE, PACK_2BIT, PACK_5BIT = 0, 2, 5
 
 
 class bg_params(C.Structure):
@@ -42,7 +46,8 @@ class bg_ops_result(C.Structure):
 
 class bg_fasta(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("residues", C.c_void_p), ("seq_off", C.c_void_p),
-                ("ids", C.c_void_p), ("id_off", C.c_void_p)]
+                ("ids", C.c_void_p), ("id_off", C.c_void_p),
+                ("packing", C.c_uint32), ("reserved_", C.c_uint32), ("alphabet", C.c_uint8 * 32)]
 
 
 class bg_timing(C.Structure):
@@ -62,7 +67,8 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
            "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_set_host_plan", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status",
-           "bg_align_batch_ops", "bg_ops_result_free", "bg_expand_ops", "bg_expand_kind"]
+           "bg_align_batch_ops", "bg_ops_result_free", "bg_expand_ops", "bg_expand_kind",
+           "bg_fasta_parse_packed", "bg_packed_bytes", "bg_pack_residues", "bg_unpack_residues"]
 
 _lib = None
 
@@ -108,6 +114,10 @@ def lib():
     L.bg_p_distance_matrix.restype = ci; L.bg_p_distance_matrix.argtypes = [vp, vp, vp, u64, vp]
     L.bg_fasta_parse.restype = ci; L.bg_fasta_parse.argtypes = [vp, u64, ci, C.POINTER(bg_fasta)]
     L.bg_fasta_free.restype = None; L.bg_fasta_free.argtypes = [C.POINTER(bg_fasta)]
+    L.bg_fasta_parse_packed.restype = ci; L.bg_fasta_parse_packed.argtypes = [vp, u64, ci, ci, C.POINTER(bg_fasta)]
+    L.bg_packed_bytes.restype = u64; L.bg_packed_bytes.argtypes = [u64, ci]
+    L.bg_pack_residues.restype = ci; L.bg_pack_residues.argtypes = [vp, u64, ci, ci, vp, vp]
+    L.bg_unpack_residues.restype = ci; L.bg_unpack_residues.argtypes = [vp, ci, vp, u64, u64, vp]
     L.bg_pin_host.restype = ci; L.bg_pin_host.argtypes = [vp, u64]
     L.bg_unpin_host.restype = ci; L.bg_unpin_host.argtypes = [vp]
     L.bg_set_shape.restype = ci; L.bg_set_shape.argtypes = [vp, ci, ci]
@@ -148,13 +158,36 @@ def score_table26(name: str) -> np.ndarray:
 class Batch:
     """Host-side batch in the C ABI's layout (keeps the numpy arrays alive)."""
 
-    def __init__(self, residues: np.ndarray, seq_off: np.ndarray):
+    def __init__(self, residues: np.ndarray, seq_off: np.ndarray, packing: int = PACK_NONE, alphabet=None):
+        """packing != PACK_NONE: `residues` holds the packed bytes (bgalign.h BG_PACK_*), `alphabet` the code -> byte map."""
         self.residues = np.ascontiguousarray(residues, dtype=np.uint8)
         self.seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         assert self.seq_off.ndim == 1 and len(self.seq_off) % 2 == 1
         self.n_pairs = (len(self.seq_off) - 1) // 2
+        self.packing = int(packing)
+        self.alphabet = None if alphabet is None else np.ascontiguousarray(np.frombuffer(bytes(alphabet).ljust(32, b"\0"), np.uint8))
         self.c = bg_batch(self.n_pairs, self.residues.ctypes.data if self.residues.size else None,
-                          self.seq_off.ctypes.data)
+                          self.seq_off.ctypes.data, self.packing, 0,
+                          self.alphabet.ctypes.data if self.alphabet is not None else None)
+
+    def pack(self, bits: int) -> "Batch":
+        """The same pairs with the residues packed at `bits` per residue (bg_pack_residues)."""
+        assert self.packing == PACK_NONE
+        n = int(self.seq_off[-1]) if self.seq_off.size else 0
+        assert int(self.seq_off[0]) == 0, "pack() expects offsets that start at 0"
+        out = np.zeros(int(lib().bg_packed_bytes(n, bits)), np.uint8)
+        alpha = np.zeros(32, np.uint8)
+        check(lib().bg_pack_residues(self.residues.ctypes.data, n, bits, 0, out.ctypes.data, alpha.ctypes.data))
+        return Batch(out, self.seq_off, bits, bytes(alpha))
+
+    def unpacked_residues(self) -> np.ndarray:
+        """One byte per residue, whatever the packing."""
+        if self.packing == PACK_NONE:
+            return self.residues
+        n = int(self.seq_off[-1])
+        out = np.zeros(max(1, n), np.uint8)
+        check(lib().bg_unpack_residues(self.residues.ctypes.data, self.packing, self.alphabet.ctypes.data, 0, n, out.ctypes.data))
+        return out[:n]
 
     @classmethod
     def from_sequences(cls, seqs):

@@ -69,8 +69,21 @@ typedef enum { BG_ST_OK = 0, BG_ST_REF_UNDEFINED = 1 } bg_status;
 typedef struct {
     uint64_t n_pairs;
     const uint8_t* residues;
-    const uint64_t* seq_off; /* 2*n_pairs + 1 entries, non-decreasing */
+    const uint64_t* seq_off; /* 2*n_pairs + 1 entries, non-decreasing; residue indices in every packing */
+    /* Packed residues (what bg_fasta_parse_packed / bg_pack_residues produce): 4x / 1.6x fewer bytes over the host
+     * link and in host memory; the device unpacks them with 128-bit loads before the fill kernels read them.
+     *   BG_PACK_NONE  one byte per residue (Sequence::chain, ds/sequence.rs:10-13)
+     *   BG_PACK_2BIT  residue i = code at bits [2 (i & 3), +2) of residues[i >> 2]               (<= 4 letters: DNA)
+     *   BG_PACK_5BIT  residue i = code at bits [5 i, 5 i + 5) of the little-endian bit stream     (<= 32 letters: protein)
+     * alphabet[code] is the residue byte the code stands for (4 resp. 32 entries); results are identical to the
+     * unpacked batch's.  Zero-initialised trailing fields mean BG_PACK_NONE (API version 1 callers). */
+    uint32_t packing;
+    uint32_t reserved_;
+    const uint8_t* alphabet;
 } bg_batch;
+#define BG_PACK_NONE 0u
+#define BG_PACK_2BIT 2u
+#define BG_PACK_5BIT 5u
 
 #define BG_F_SCORE_ONLY 1u /* skip traceback: result.arena / off stay empty */
 
@@ -179,9 +192,24 @@ typedef struct bg_fasta {
     uint64_t* seq_off;    /* [n_records + 1] */
     uint8_t* ids;
     uint64_t* id_off;     /* [n_records + 1] */
+    uint32_t packing;     /* BG_PACK_*: how `residues` is stored (bg_fasta_parse: BG_PACK_NONE) */
+    uint32_t reserved_;
+    uint8_t alphabet[32]; /* packing != BG_PACK_NONE: code -> residue byte */
 } bg_fasta;
 int bg_fasta_parse(const uint8_t* text, uint64_t len, int n_threads, bg_fasta* out);
+/* The same records with the residues packed (bits = 2 or 5) -- the batch {n_records / 2, residues, seq_off, bits,
+ * alphabet} goes straight to bg_align_batch / bg_edit_distance_batch / bg_batch_upload.  bits = 2: the text may use
+ * at most 4 distinct residue bytes (codes in ascending byte order); bits = 5: 'A'..'Z' (code = byte - 'A', the
+ * index the shipped scorers use, score.rs:40).  Anything else: BG_EINVAL_RESIDUE. */
+int bg_fasta_parse_packed(const uint8_t* text, uint64_t len, int n_threads, int bits, bg_fasta* out);
 void bg_fasta_free(bg_fasta* f);
+
+/* Packing helpers for callers that hold bytes (a shim packs while it marshals its Tile).  bg_pack_residues: n residue
+ * bytes -> packed (capacity bg_packed_bytes(n, bits)); alphabet[32] is an output for bits = 2 (chosen from the data)
+ * and for bits = 5 (always 'A' + code).  bg_unpack_residues: residues [first, first + count) of a packed arena -> bytes. */
+uint64_t bg_packed_bytes(uint64_t n_residues, int bits);
+int bg_pack_residues(const uint8_t* residues, uint64_t n, int bits, int n_threads, uint8_t* packed, uint8_t* alphabet);
+int bg_unpack_residues(const uint8_t* packed, int bits, const uint8_t* alphabet, uint64_t first, uint64_t count, uint8_t* out);
 
 /* ---- next to the hot path: position-wise compares ----------------------- */
 /* analysis::seq::hamming_distance for every pair (seq.rs:74-83): out[p] = #positions where the two sequences

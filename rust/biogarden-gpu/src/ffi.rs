@@ -16,7 +16,11 @@ pub const BG_EINVAL_SIZE: c_int = 2;
 pub const BG_ST_OK: u8 = 0;
 
 #[repr(C)]
-pub struct bg_batch { pub n_pairs: u64, pub residues: *const u8, pub seq_off: *const u64 }
+pub struct bg_batch {
+    pub n_pairs: u64, pub residues: *const u8, pub seq_off: *const u64,
+    /// 0 = one byte per residue, 2 / 5 = packed (bgalign.h BG_PACK_*); `alphabet` maps code -> residue byte
+    pub packing: u32, pub reserved_: u32, pub alphabet: *const u8,
+}
 
 #[repr(C)]
 pub struct bg_params {

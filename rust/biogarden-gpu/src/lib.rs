@@ -68,7 +68,7 @@ impl SequenceAligner {
         let mut table = vec![0i32; nr * nc];
         for (i, x) in rows.iter().enumerate() { for (j, y) in cols.iter().enumerate() { table[i * nc + j] = score(x, y); } }
 
-        let batch = ffi::bg_batch { n_pairs: n_pairs as u64, residues: residues.as_ptr(), seq_off: off.as_ptr() };
+        let batch = ffi::bg_batch { n_pairs: n_pairs as u64, residues: residues.as_ptr(), seq_off: off.as_ptr(), packing: 0, reserved_: 0, alphabet: std::ptr::null() };
         let params = ffi::bg_params { mode: mode as i32, gap_open: a, gap_extend: b, flags: 0, table: table.as_ptr(),
                                       n_rows: nr as i32, n_cols: nc as i32, row_code: row_code.as_ptr(), col_code: col_code.as_ptr() };
         let mut res: ffi::bg_result = unsafe { std::mem::zeroed() };
@@ -101,7 +101,7 @@ impl SequenceAligner {
         let mut residues: Vec<u8> = Vec::new();
         let mut off: Vec<u64> = vec![0];
         for s in pairs { residues.extend_from_slice(&s.chain); off.push(residues.len() as u64); }
-        let batch = ffi::bg_batch { n_pairs: (pairs.len() / 2) as u64, residues: residues.as_ptr(), seq_off: off.as_ptr() };
+        let batch = ffi::bg_batch { n_pairs: (pairs.len() / 2) as u64, residues: residues.as_ptr(), seq_off: off.as_ptr(), packing: 0, reserved_: 0, alphabet: std::ptr::null() };
         let mut out = vec![0u64; pairs.len() / 2];
         let rc = unsafe { ffi::bg_edit_distance_batch(self.ctx, &batch, out.as_mut_ptr()) };
         assert!(rc == ffi::BG_OK);

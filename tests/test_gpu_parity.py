@@ -671,3 +671,45 @@ def test_device_planner_matches_host_planner(aligner):
                 finally:
                     ctx.set_host_plan(False)
                     ctx.set_shape(0, 0)
+
+
+def test_packed_batches_give_identical_results(aligner):
+    """Packed residues at the ABI (bg_batch::packing = 2 / 5 bit, what bg_fasta_parse_packed emits): every entry
+    point must return exactly what it returns for the byte batch -- alignment through the chunk pipeline (chunk
+    boundaries fall at arbitrary 2-bit offsets), compact ops results, long pairs, the device-resident path, edit
+    distance (bit-parallel and general kernel), hamming -- with the strings expanded from host-unpacked residues."""
+    rng = random.Random(41)
+    dna = synth.make("cfg3_edit_100_300", n_pairs=70000)
+    dna_p = dna.pack(2)
+    ctx = aligner.context
+    for mode, a, b in (("global", -2, -1), ("semiglobal", -1, -1), ("local", -3, -1)):
+        params = aligner.make_params(dna, mode, score_mod.unit, a, b)
+        params_p = aligner.make_params(dna_p, mode, score_mod.unit, a, b)
+        assert np.array_equal(params.table, params_p.table)
+        r0 = ctx.align_batch(dna, params); r1 = ctx.align_batch(dna_p, params_p)
+        assert np.array_equal(r0.score, r1.score) and np.array_equal(r0.status, r1.status)
+        assert np.array_equal(r0.off, r1.off) and np.array_equal(r0.arena, r1.arena), mode
+        r0.close(); r1.close()
+    prot = _random_batch(rng, 500, b"ACDEFGHIKLMNPQRSTVWY", 400)
+    prot_p = prot.pack(5)
+    r0 = _cmp.engine_align(aligner, prot, "local", "blosum62", -11, -1); r1 = _cmp.engine_align(aligner, prot_p, "local", "blosum62", -11, -1)
+    assert np.array_equal(r0.score, r1.score) and np.array_equal(r0.off, r1.off) and np.array_equal(r0.arena, r1.arena)
+    r0.close(); r1.close()
+    longb = _mutated_long_pairs([(5000, 4200), (301, 5003), (20001, 61), (149, 150), (4500, 4097)], 13)
+    long_p = longb.pack(2)
+    r0 = _cmp.engine_align(aligner, longb, "semiglobal", "unit", -1, -1); r1 = _cmp.engine_align(aligner, long_p, "semiglobal", "unit", -1, -1)
+    assert np.array_equal(r0.score, r1.score) and np.array_equal(r0.off, r1.off) and np.array_equal(r0.arena, r1.arena)
+    # device-resident path and compact results
+    params_p = aligner.make_params(long_p, "semiglobal", score_mod.unit, -1, -1)
+    db = ctx.upload(long_p); dres = ctx.align_device(db, params_p); r2 = ctx.download(dres)
+    assert np.array_equal(r0.score, r2.score) and np.array_equal(r0.arena, r2.arena)
+    r2.close(); ctx.free_result(dres); ctx.free_batch(db)
+    r0.close(); r1.close()
+    small = native.Batch(dna.residues[:int(dna.seq_off[2000])], dna.seq_off[:2001])
+    small_p = small.pack(2)
+    e0 = ctx.edit_distance_batch(dna); e1 = ctx.edit_distance_batch(dna_p)
+    assert np.array_equal(e0, e1)
+    assert np.array_equal(ctx.edit_distance_batch(prot), ctx.edit_distance_batch(prot_p))
+    eq = native.Batch.from_sequences([s for p in range(200) for s in (lambda x: (x, bytes(c if rng.random() < 0.9 else rng.choice(b"ACGT") for c in x)))(bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 300))))])
+    assert np.array_equal(ctx.hamming_distance_batch(eq), ctx.hamming_distance_batch(eq.pack(2)))
+    assert small_p.packing == 2

@@ -196,3 +196,40 @@ def test_host_expander_matches_definition():
             for impl in impls + [None]:
                 got = native.expand_ops(s1, s2, words, ln, impl)
                 assert got == (bytes(wa), bytes(wb)), (ln, bias, impl)
+
+
+def test_packed_residues_roundtrip_and_fasta():
+    """bg_pack_residues / bg_unpack_residues (2 bit and 5 bit per residue), bg_residue_histogram on packed batches and
+    bg_fasta_parse_packed: packing is lossless at every offset, a fifth letter (2 bit) / a non-letter (5 bit) is an
+    error, and the packed FASTA ingest yields the records the byte ingest yields."""
+    import ctypes as C
+    import random
+    from biogarden_b200 import fasta
+    rng = random.Random(9)
+    L = native.lib()
+    for bits, alpha in ((2, b"ACGT"), (2, b"AT"), (5, b"ACDEFGHIKLMNPQRSTVWY"), (5, b"ABCDEFGHIJKLMNOPQRSTUVWXYZ")):
+        seqs = [bytes(rng.choice(alpha) for _ in range(rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 9, 31, 150, 1001]))) for _ in range(60)]
+        b = native.Batch.from_sequences(seqs)
+        pk = b.pack(bits)
+        assert pk.packing == bits and np.array_equal(pk.unpacked_residues(), b.residues)
+        # any sub-range
+        total = int(b.seq_off[-1])
+        for _ in range(50):
+            first = rng.randrange(0, total + 1); count = rng.randrange(0, total - first + 1)
+            out = np.zeros(max(1, count), np.uint8)
+            native.check(L.bg_unpack_residues(pk.residues.ctypes.data, bits, pk.alphabet.ctypes.data, first, count, out.ctypes.data))
+            assert np.array_equal(out[:count], b.residues[first:first + count])
+        ha, hb = b.histograms(); pa, pb = pk.histograms()
+        assert np.array_equal(ha, pa) and np.array_equal(hb, pb)
+    bad = native.Batch.from_sequences([b"ACGTN", b"ACGT"])
+    with pytest.raises(EngineError):
+        bad.pack(2)
+    with pytest.raises(EngineError):
+        native.Batch.from_sequences([b"AC-T", b"ACGT"]).pack(5)
+    for name, bits in (("semiglobal_alignment", 2), ("local_alignment", 5), ("edit_distance", 5)):
+        path = os.path.join(ROOT, "tests", "golden", "fasta", "input", name + ".fasta")
+        plain, ids = fasta.read_batch(path)
+        packed, ids2 = fasta.read_batch(path, bits=bits)
+        assert ids == ids2 and np.array_equal(plain.seq_off, packed.seq_off)
+        assert packed.packing == bits and np.array_equal(packed.unpacked_residues(), plain.residues)
+        assert packed.residues.size < plain.residues.size
