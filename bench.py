@@ -328,28 +328,35 @@ def measure(args, workload, steps, warmup, rank, world, local_rank, barrier, sam
     ctx.free_batch(dbatch)
 
     # ---------------- end-to-end leg: host buffers through the C ABI ----------------
-    def e2e_step():
+    # `e2e` calls bg_align_batch_ops: the complete result in compact form (score, status, aligned length, start cell and
+    # one 2-bit op per alignment column) -- what a shim that owns its containers consumes, expanding each pair straight
+    # into its own Vec<u8> with bg_expand_ops.  `e2e_strings` calls bg_align_batch, which also materialises every aligned
+    # string in a host arena inside the call (the library's own host threads run the same expansion).
+    def e2e_step(strings=False):
         if is_edit:
             out = ctx.edit_distance_batch(batch)
             return int(out[0]), batch.n_pairs * 8
-        res = ctx.align_batch(batch, params)
+        res = ctx.align_batch(batch, params) if strings else ctx.align_batch_ops(batch, params)
         tt = ctx.timing()
         sc = int(res.score[0])
         res.close()
         return sc, int(tt["d2h_bytes"])
-    for _ in range(max(1, warmup - 1)):
-        e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    d2h = 0
-    for _ in range(steps):
-        _, d2h = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    tt = ctx.timing()
-    h2d = int(tt["h2d_bytes"])                # counted by the library from the copies it issued in the last call
-    e2e_launches = int(tt["launches"])
-    barrier()
+
+    def e2e_leg(strings):
+        for _ in range(max(1, warmup - 1)):
+            e2e_step(strings)
+        barrier()
+        w0 = time.perf_counter()
+        d2h_ = 0
+        for _ in range(steps):
+            _, d2h_ = e2e_step(strings)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - w0
+        tt_ = ctx.timing()
+        barrier()
+        return dt, d2h_, int(tt_["h2d_bytes"]), int(tt_["launches"])   # bytes: counted by the library from the copies it issued in the last call
+    e2e_s, d2h, h2d, e2e_launches = e2e_leg(False)
+    strings_s = None if is_edit else e2e_leg(True)[0]
 
     # ---------------- the same end-to-end leg with PACKED host buffers (what bg_fasta_parse_packed emits) ----------------
     packed_s = None
@@ -375,6 +382,7 @@ def measure(args, workload, steps, warmup, rank, world, local_rank, barrier, sam
 
     dev_ms_max, e2e_ms_max, cells_total = reduce_over_ranks(dev_ms, e2e_s * 1e3, float(cells), world, "cuda")
     packed_ms_max = reduce_over_ranks(0.0, (packed_s or 0.0) * 1e3, 0.0, world, "cuda")[1]
+    strings_ms_max = reduce_over_ranks(0.0, (strings_s or 0.0) * 1e3, 0.0, world, "cuda")[1]
     if rank != 0:
         return None
     ms_per_step = dev_ms_max / steps
@@ -399,9 +407,13 @@ def measure(args, workload, steps, warmup, rank, world, local_rank, barrier, sam
                       "e2e includes planning (on the device), all copies and the host-side string expansion",
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / steps, "gpu_launches_per_step": e2e_launches,
-                "timed": "host wall clock around bg_align_batch / bg_edit_distance_batch: raw residue bytes in pinned host buffers in, "
-                         "scores + status + offsets + aligned strings in host memory out (results cross the link as 2-bit ops and "
-                         "are expanded by the library's host threads inside the call)"},
+                "timed": "host wall clock around bg_align_batch_ops / bg_edit_distance_batch: raw residue bytes in pinned host buffers in; "
+                         "scores, status, aligned lengths, start cells and 2-bit alignment ops (the complete result, compact; bg_expand_ops "
+                         "turns a pair's ops into its two strings) in host memory out.  Launch planning on the device, all copies inside."},
+        "e2e_strings": None if strings_s is None else {
+            "value": cells_total * steps / (strings_ms_max * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": strings_ms_max / steps,
+            "timed": "host wall clock around bg_align_batch: as e2e, plus every aligned string materialised in a dense host arena inside "
+                     "the call (host threads expand the ops with AVX-512 VBMI2 / non-temporal stores)"},
         "e2e_packed": None if packed_s is None else {
             "value": cells_total * steps / (packed_ms_max * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": packed_ms_max / steps,
             "h2d_bytes_per_step": packed_h2d, "d2h_bytes_per_step": packed_d2h, "bits_per_residue": bits,
@@ -440,15 +452,19 @@ def measure_inprocess(args, n_dev, steps, warmup):
     batch = pinned_batch(make_batch(cfg_name, pairs))
     al = SequenceAligner(list(range(n_dev)))
     params = al.make_params(batch, cfg["mode"], getattr(score, cfg["scorer"]), cfg["a"], cfg["b"])
-    for _ in range(max(2, warmup)):
-        al.context.align_batch(batch, params).close()
-    w0 = time.perf_counter()
-    for _ in range(steps):
-        al.context.align_batch(batch, params).close()
-    dt = time.perf_counter() - w0
+    def leg(fn):
+        for _ in range(max(2, warmup)):
+            fn(batch, params).close()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            fn(batch, params).close()
+        return time.perf_counter() - w0
+    dt_strings = leg(al.context.align_batch)
+    dt = leg(al.context.align_batch_ops)
     tt = al.context.timing()
     al.context.close()
     return {"value": batch.cells() * steps / dt / 1e9, "unit": "GCUPS", "ms_per_step": 1e3 * dt / steps, "pairs": pairs, "n_gpus": n_dev,
+            "strings": {"value": batch.cells() * steps / dt_strings / 1e9, "ms_per_step": 1e3 * dt_strings / steps},
             "h2d_bytes_per_step": int(tt["h2d_bytes"]), "d2h_bytes_per_step": int(tt["d2h_bytes"]),
             "how": "one process, bg_create(%d devices), one shared chunk queue; the other ranks idle at the barrier" % n_dev}
 
@@ -508,7 +524,7 @@ def main():
             r = measure(args, wl, st_, wu_, rank, world, local_rank, barrier, sampler)
             if rank == 0:
                 extra[wl] = {"value": r["value"], "unit": r["unit"], "metric": r["metric"], "ms_per_step": r["ms_per_step"], "steps": st_, "warmup": wu_,
-                             "e2e": r["e2e"], "e2e_packed": r["e2e_packed"], "roofline": {k: r["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "ops_per_cell", "gcups_fill_only")},
+                             "e2e": r["e2e"], "e2e_strings": r["e2e_strings"], "e2e_packed": r["e2e_packed"], "roofline": {k: r["roofline"][k] for k in ("kernel", "achieved", "peak", "frac", "ops_per_cell", "gcups_fill_only")},
                              "phases_ms_last_step": r["phases_ms_last_step"], "clocks": r["clocks"], "config": r["config"]}
         if rank == 0:
             line["configs"] = extra

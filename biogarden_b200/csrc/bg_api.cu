@@ -40,6 +40,7 @@ void make_unpack_lut2(const uint8_t* alphabet, uint32_t* lut);
 void unpack_residues(const uint8_t* packed, uint32_t bits, const uint8_t* alphabet, uint64_t first, uint64_t count, uint8_t* out, const uint32_t* lut2);
 // host_expand.cpp: 2-bit alignment ops -> the two aligned strings (AVX-512 VBMI2 or portable code)
 void expand_ops(const uint8_t* s1, const uint8_t* s2, const uint32_t* ops, uint64_t len, uint8_t* a_out, uint8_t* b_out);
+void stream_copy(uint8_t* dst, const uint8_t* src, size_t n);
 }
 using namespace bg;
 
@@ -1897,19 +1898,31 @@ void expand_sub(AlignJob& J, int c, uint64_t i, uint64_t arena_base, bool string
     const bg_batch* in = J.in;
     OpsOut& oo = J.oo;
     const uint64_t p_lo = it.lo + i * it.stride, p_hi = std::min(it.lo + it.n, p_lo + it.stride);
-    uint64_t w = it.ops_base + it.samples[i].x, o = arena_base + 2 * it.samples[i].y;
+    const uint64_t nsub = (it.n + it.stride - 1) / it.stride;
+    const uint64_t o_begin = arena_base + 2 * it.samples[i].y;
+    const uint64_t o_end = arena_base + 2 * (i + 1 < nsub ? it.samples[i + 1].y : it.cols);
+    if (strings && o_end > J.arena_cap) { J.ctx->set_error("internal: arena bound exceeded"); J.fail(BG_ECUDA); return; }
+    // the sub-block's strings are one contiguous run of the arena: they are built in a cache-resident buffer of this
+    // thread and leave it with non-temporal stores (stream_copy)
+    static thread_local std::vector<uint8_t> stage;
+    uint8_t* out = nullptr;
+    if (strings) { if (stage.size() < o_end - o_begin + 64) stage.resize(o_end - o_begin + 64); out = stage.data(); }
+    uint64_t w = it.ops_base + it.samples[i].x, o = o_begin;
     for (uint64_t p = p_lo; p < p_hi; ++p) {
         const uint64_t len = oo.len[p];
         oo.ops_off[p] = w;
         if (strings) {
             J.off[2 * p] = o; J.off[2 * p + 1] = o + len;
             if (len) {
-                if (o + 2 * len > J.arena_cap) { J.ctx->set_error("internal: arena bound exceeded"); J.fail(BG_ECUDA); return; }
                 const PairResidues pr(in, J.lut2, p, oo.first[2 * p], oo.first[2 * p + 1]);
-                expand_ops(pr.s1, pr.s2, oo.ops + w, len, J.arena + o, J.arena + o + len);
+                expand_ops(pr.s1, pr.s2, oo.ops + w, len, out + (o - o_begin), out + (o - o_begin) + len);
             }
         }
         w += (len + 15) >> 4; o += 2 * len;
+    }
+    if (strings) {
+        if (o != o_end) { J.ctx->set_error("internal: sampled column offsets disagree with the lengths"); J.fail(BG_ECUDA); return; }
+        stream_copy(J.arena + o_begin, out, o_end - o_begin);
     }
 }
 
@@ -2111,10 +2124,10 @@ int device_pipeline(AlignJob& J, int d) {
                    ws.score.as<int32_t>(), ws.flags.as<uint8_t>(), ws.lens2.as<uint64_t>(), ws.off.as<uint64_t>(), nullptr};
         uint64_t nsub = 0;
         if (ops_mode) {
-            // expansion tasks of ~256k columns: pairs per task from the item's mean length, a power of two
+            // expansion tasks of ~128k columns (256 KB of strings, cache resident): pairs per task from the item's mean length, a power of two
             const uint64_t mean = std::max<uint64_t>(1, nres / (2 * std::max<uint64_t>(1, n)));
             uint64_t stride = 64;
-            while (stride < 8192 && stride * mean < (256u << 10)) stride *= 2;
+            while (stride < 8192 && stride * mean < (128u << 10)) stride *= 2;
             it.stride = stride;
             nsub = (n + stride - 1) / stride;
             if (!ws.samples.ensure((nsub + 1) * 16) || !ws.samples_h.ensure((nsub + 1) * 16)) { ctx->set_error("allocation failed (offset samples)"); return BG_ENOMEM; }
@@ -2497,6 +2510,7 @@ int run_align_job(AlignJob& J) {
 
     // one driver per device: the caller's thread takes device 0, the context's persistent workers the others
     std::vector<int> rcs(nd, BG_OK);
+    for (int d = 0; d < nd; ++d) { ctx->dev_worker(d); ctx->fin_worker(d); }   // create them here: worker() grows a vector and is not thread safe
     for (int d = 1; d < nd; ++d) ctx->dev_worker(d).run([&J, &rcs, d] { rcs[d] = device_pipeline(J, d); });
     rcs[0] = device_pipeline(J, 0);
     for (int d = 1; d < nd; ++d) ctx->dev_worker(d).wait();
