@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs
             }
             rcur = r;
             if (active) {
-                int32_t diagA = MdiagA, leftA = MlA, Y = Yl;
+                int32_t leftA = MlA, Y = Yl;
                 uint32_t w[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) w[k] = 0;
@@ -242,44 +242,41 @@ __global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs
                 if (PROF4) sel = r * 0x1111u + 0x8880u;
                 else rowp = reinterpret_cast<const unsigned char*>(s_tab) + r * (uint32_t)(ncol1 * 4);
                 uint32_t rowkey = 0;
+                // diagonal terms first, while the previous row's M is still in MuA[]: the cell loop then overwrites MuA[c]
+                // in place (carrying the old value along as the next column's diagonal made ptxas rotate the register
+                // array: one extra move per cell)
+                int32_t dg[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    int32_t sb_;   // s - a
+                    if (PROF4) sb_ = prmt_sx(cprof[c], sel);
+                    else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
+                    dg[c] = fma_add(c ? MuA[c - 1] : MdiagA, one, sb_);
+                }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     uint32_t& wk = w[c >> 3];
                     const uint32_t sh = 4u * (c & 7);
                     const int32_t upA = MuA[c];
                     if (IS_LOCAL) {
-                        int32_t sb_;   // s - a
-                        if (PROF4) sb_ = prmt_sx(cprof[c], sel);
-                        else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
                         int32_t mx;
-                        local_cell(wk, sh, upA, Xu[c], Y, leftA, fma_add(diagA, one, sb_), b, one, k32, 31u - c, rowkey, mx);
-                        const int32_t mxA = fma_add(mx, one, a);
-                        diagA = upA; leftA = mxA;
-                        MuA[c] = mxA;
+                        local_cell(wk, sh, upA, Xu[c], Y, leftA, dg[c], b, one, k32, 31u - c, rowkey, mx);
+                        leftA = fma_add(mx, one, a);
+                        MuA[c] = leftA;
                         continue;
                     }
-                    // aligner.rs:443-444 / 477-480: xo = M[i-1][j] + a is the register itself
-                    int32_t X = __viaddmax_s32(Xu[c], b, upA);
+                    // aligner.rs:443-444: xo = M[i-1][j] + a is the register itself
+                    const int32_t X = __viaddmax_s32(Xu[c], b, upA);
                     acc_if_eq(wk, X, upA, one, TR_XOPEN << sh);
-                    // aligner.rs:447-448 / 483-486: yo = M[i][j-1] + a likewise
+                    // aligner.rs:447-448: yo = M[i][j-1] + a likewise
                     Y = __viaddmax_s32(Y, b, leftA);
                     acc_if_eq(wk, Y, leftA, one, TR_YOPEN << sh);
-                    if (IS_LOCAL) { X = max(X, 0); Y = max(Y, 0); }
-                    // aligner.rs:451-466 / 489-506
-                    int32_t sb_;   // s - a
-                    if (PROF4) sb_ = prmt_sx(cprof[c], sel);
-                    else sb_ = *reinterpret_cast<const int32_t*>(rowp + cprof[c]);
-                    const int32_t mx = __vimax3_s32(fma_add(diagA, one, sb_), X, Y);
+                    // aligner.rs:451-466
+                    const int32_t mx = __vimax3_s32(dg[c], X, Y);
                     acc_if_eq(wk, mx, Y, one, TR_YEQ << sh);
-                    if (IS_LOCAL) {
-                        acc_local_bit0(wk, mx, X, Y, one, TR_XEQ << sh);   // STOP when M == 0 (A.3)
-                        if (mx > best) { best = mx; bi = i0 + 1; bj = jbase + c + 1; }
-                    } else {
-                        acc_if_eq(wk, mx, X, one, TR_XEQ << sh);
-                    }
-                    const int32_t mxA = fma_add(mx, one, a);
-                    diagA = upA; leftA = mxA;
-                    MuA[c] = mxA; Xu[c] = X;
+                    acc_if_eq(wk, mx, X, one, TR_XEQ << sh);
+                    leftA = fma_add(mx, one, a);
+                    MuA[c] = leftA; Xu[c] = X;
                 }
                 MlastA = leftA; Ylast = Y; MdiagA = MlA;
                 if (IS_LOCAL) {   // first maximum of this row's cells; strictly greater than everything above

@@ -227,20 +227,26 @@ __global__ void __launch_bounds__(128, MINB) k1h_fill(const FillArgs A) {
             Yl = (Yl & ~first_lane) | (hb_pack(HB_NEG) & first_lane);
             rcur = r;
             if (i0 < n_max) {
-                uint32_t diagA = MdiagA, leftA = MlA, Y = Yl;
+                uint32_t leftA = MlA, Y = Yl;
                 const unsigned char* rowp = reinterpret_cast<const unsigned char*>(s_pack) + r * 64u;
+                // diagonal terms first, HB_DG columns at a time, while the previous row's M is still in MuA[]: the cell
+                // loop can then overwrite MuA[c] in place (carrying the old value along as "diag of the next column"
+                // made ptxas rotate the whole register array: one extra move per cell)
+                uint32_t dg[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t s2 = *reinterpret_cast<const uint32_t*>(rowp + cc[c]);
+                    dg[c] = hb_add(c ? MuA[c - 1] : MdiagA, one, s2);
+                }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const uint32_t sh = 4u * rr;   // this step's nibble inside the column word (compile-time after unrolling)
-                    const uint32_t upA = MuA[c];
-                    const uint32_t X = hb_max_acc<HB_PIPES & 3>(upA, Xu[c], w[c], one, TR_XOPEN << sh);
+                    const uint32_t X = hb_max_acc<HB_PIPES & 3>(MuA[c], Xu[c], w[c], one, TR_XOPEN << sh);
                     Y = hb_max_acc<(HB_PIPES >> 2) & 3>(leftA, Y, w[c], one, TR_YOPEN << sh);
-                    const uint32_t s2 = *reinterpret_cast<const uint32_t*>(rowp + cc[c]);
-                    const uint32_t m1 = hb_max_acc<(HB_PIPES >> 4) & 3>(X, hb_add(diagA, one, s2), w[c], one, TR_XEQ << sh);
+                    const uint32_t m1 = hb_max_acc<(HB_PIPES >> 4) & 3>(X, dg[c], w[c], one, TR_XEQ << sh);
                     const uint32_t mx = hb_max_acc<(HB_PIPES >> 6) & 3>(Y, m1, w[c], one, TR_YEQ << sh);
-                    const uint32_t mxA = hb_add(mx, one, amb2);
-                    diagA = upA; leftA = mxA;
-                    MuA[c] = mxA; Xu[c] = X;
+                    leftA = hb_add(mx, one, amb2);
+                    MuA[c] = leftA; Xu[c] = X;
                 }
                 MlastA = leftA; Ylast = Y; MdiagA = MlA;
                 if (TRACK) {
