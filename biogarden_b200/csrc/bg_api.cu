@@ -156,6 +156,7 @@ struct Plan {
     int max_Q = 1;
     uint32_t max_n = 0, max_m = 0;
     int32_t half_maxabs = 0;          // > 0: short classes were laid out for K1h (packed 16 x 2) with this max |score|
+    bool wave_overlap = false;        // K2 launches were cut for TWO trace buffers: the walk of launch c runs next to the fill of launch c + 1
     bool myers = false;               // edit distance: pairs with len2 <= 320 laid out one per thread for K4b
     bool compact = false;             // host pipeline, all classes K4b: the staged descriptors are MyersSlot (16 B), not PairDesc
     bool built = false;
@@ -579,6 +580,21 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 k += S;
             }
         }
+        // Opt-in (BG_WAVE_OVERLAP=1), measured and NOT a win: several K2 launches and no bounded-memory group -> cut the
+        // launches for HALF the budget, so that two launches' traces are resident at once and the walk of launch c runs
+        // next to the fill of launch c + 1 instead of after it.  cfg5, 125 pairs: 5 launches instead of 3, fill 616 -> 715 ms
+        // (more launch tails, and the walk's warps compete with the persistent cooperative grid), walks 61 -> 104 ms:
+        // 1 060 -> 964 GCUPS.
+        uint64_t class_budget_eff = class_budget;
+        if (wave && with_trace && ck_group.empty() && cn > 1 && getenv("BG_WAVE_OVERLAP")) {
+            uint64_t total = 0, top = 0;
+            for (size_t k = 0; k < cn; ++k) {
+                const uint64_t nb_ = (len_m(cid[k]) + band_cols - 1) / band_cols;
+                const uint64_t wds = nb_ * ((uint64_t)len_n(cid[k]) + sh.L - 1) * K * 32ull;
+                total += wds; if (k < 8) top += wds;
+            }
+            if (total > class_budget && top <= class_budget / 2) { class_budget_eff = class_budget / 2; P.wave_overlap = true; }
+        }
         lap("class prologue");
         // (a 32-bit division per pair is a third of the plan's cost: most classes have a single band)
         const bool single_band = cls_max_m[si] <= band_cols;
@@ -605,7 +621,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             // K2 launches run one pair per resident cluster at a time: close a chunk at a multiple of the
             // cluster count once memory is nearly used up, so that the (length-sorted) pairs of a launch finish together
             const bool wave_round = wave && ch.trace_words > 0 && ((nd - ch.slot_begin) % wave_clusters) == 0 &&
-                                    ch.trace_words + warp_words * wave_clusters > class_budget;
+                                    ch.trace_words + warp_words * wave_clusters > class_budget_eff;
             // bounded-memory groups (decided above): a chunk of their own, block-sized traces
             const uint32_t grp = (wave && !ck_group.empty()) ? ck_group[w] : 0u;
             const bool grp_first = grp && (w == 0 || ck_group[w - 1] != grp);
@@ -619,7 +635,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                 ch = Chunk(); ch.slot_begin = ch.slot_end = (uint32_t)nd; ch.trace_words = 0;
             }
             if (!grp)
-            if (with_trace && ch.trace_words > 0 && (wave_round || ch.trace_words + warp_words > class_budget)) {
+            if (with_trace && ch.trace_words > 0 && (wave_round || ch.trace_words + warp_words > class_budget_eff)) {
                 ch.slot_end = (uint32_t)nd;
                 lc.chunks.push_back(ch);
                 P.max_trace_words = std::max(P.max_trace_words, ch.trace_words);
@@ -1116,7 +1132,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
     // Measured on B200 (cfg2): overlapping buys 2 % (17.9 vs 18.3 ms/step) -- both kernels just time-share the
     // SMs -- and it blurs the per-kernel event timings the roofline is computed from, so it is opt-in.
     static const bool want_overlap = [] { const char* e = getenv("BG_OVERLAP"); return e && atoi(e) != 0; }();
-    const bool overlap = want_overlap && !split && !pp.score_only && n_chunks >= 2 && P.max_wave_slots == 0;   // K2 traces need the memory of both buffers
+    const bool overlap = !split && !pp.score_only && n_chunks >= 2 && ((want_overlap && P.max_wave_slots == 0) || P.wave_overlap);
     if (overlap && !ws.trace2.ensure(std::max<uint64_t>(1, P.max_trace_words) * 4)) { ctx->set_error("device allocation failed (second trace buffer)"); return BG_ENOMEM; }
     cudaStream_t wst = overlap ? ws.walk_stream : split ? ws.post_stream : st;
     cudaStream_t pst = split ? ws.post_stream : st;
