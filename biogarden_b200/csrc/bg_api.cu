@@ -137,6 +137,7 @@ struct PinBuf {   // pinned host block from the global cache
 struct Chunk {
     uint32_t slot_begin, slot_end; uint64_t trace_words;
     std::vector<WaveAssign> assign; uint32_t n_rounds = 0, max_Q = 1;   // K2 launches only
+    uint32_t fine_bands = 0;              // > 0: K2f launch (k2f_fine.cuh, one column per lane) -- the widest pair's warps
     // bounded-memory traceback (k2_wave.cuh): pairs whose whole traces do not fit the budget; trace_words then
     // covers one row block of every pair
     uint32_t ckpt_nb = 0;                 // > 0: bounded-memory chunk, every pair cut into this many row blocks
@@ -270,6 +271,8 @@ struct bg_ctx {
     uint64_t trace_budget_words = 0;
     uint64_t long_budget_words = 0;   // K2 pairs; 0 = automatic (most of the device)
     int force_L = 0, force_C = 0;
+    int fine_max_pairs = 0;           // K2-class launches of at most this many pairs run on K2f (one column per lane); 0 (default): never --
+                                      // K2f is bit-exact but, measured on cfg1, no faster than K2 yet (7.8 vs 6.5 ms; see k2f_fine.cuh)
     bool host_plan = false;           // build every launch plan on the host (default: pipeline chunks are planned on the device, k0_plan.cuh)
     int num_sms = 148;
     void set_error(const std::string& s) { std::lock_guard<std::mutex> lk(err_mu); last_error = s; }
@@ -710,6 +713,12 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             const uint32_t n_cta = (uint32_t)std::max(1, ctx->num_sms);
             for (Chunk& wc : lc.chunks) {
                 const uint32_t ns = wc.slot_end - wc.slot_begin;
+                // very few pairs in the launch: one column per lane (K2f) spreads a lone pair over hundreds of warps
+                if (ns && !wc.ckpt_nb && (int)ns <= ctx->fine_max_pairs) {
+                    uint32_t maxb = 0;
+                    for (uint32_t x = 0; x < ns; ++x) maxb = std::max(maxb, (dst[wc.slot_begin + x].m + 31u) / 32u);
+                    if (maxb <= (uint32_t)std::max(1, ctx->num_sms) * 32u) wc.fine_bands = std::max(1u, maxb);
+                }
                 double total = 0;
                 for (uint32_t x = 0; x < ns; ++x) total += (double)dst[wc.slot_begin + x].n * (double)dst[wc.slot_begin + x].m;
                 const double ideal = std::max(1.0, total / n_cta);                 // cells per CTA if the launch were perfectly balanced
@@ -1211,7 +1220,24 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 ctx->launches += 1 + 2 * (uint64_t)NB;
                 continue;
             }
-            if (lc.wave) {
+            if (lc.wave && ch.fine_bands) {
+                // ---- K2f: one column per lane; W warps per CTA so that the pair's warps cover as many SMs as they can ----
+                static const int fine_w = [] { const char* e = getenv("BG_FINE_WARPS"); return e ? std::max(1, std::min(32, atoi(e))) : 0; }();
+                const uint32_t B = ch.fine_bands;
+                const int Wc = fine_w ? fine_w : (int)std::min<uint32_t>(32u, std::max<uint32_t>(8u, (B + (uint32_t)ctx->num_sms - 1) / (uint32_t)ctx->num_sms));
+                const int n_cta = (int)((B + Wc - 1) / Wc);
+                const size_t cand_bytes = (size_t)ns * B * sizeof(WaveCand);
+                const size_t ctr_bytes = ((size_t)ns + 2 * (size_t)n_cta + 8) * 4;
+                if (!ws.cand.ensure(cand_bytes) || !ws.progress.ensure(ctr_bytes) || !ws.assign.ensure((size_t)n_cta * FINE_RING_G * sizeof(int2))) {
+                    ctx->set_error("device allocation failed (K2f scratch)"); return BG_ENOMEM;
+                }
+                CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, ctr_bytes, st));
+                FineArgs fx; fx.f = fa; fx.cand = ws.cand.as<WaveCand>(); fx.cand_stride = B;
+                fx.done = ws.progress.as<uint32_t>(); fx.cons_g = fx.done + ns + 2;
+                fx.ring_g = ws.assign.as<unsigned long long>();
+                Phase ph(ws, 1);
+                CU_TRY(ctx, launch_k2f(pp.local, pp.prof4, n_cta, Wc, pp.smem, st, fx));
+            } else if (lc.wave) {
                 const uint64_t nw = (uint64_t)ch.max_Q * K2_WARPS;
                 const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
                 CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + (2 * (uint64_t)ns + 4) * 4, st));
@@ -1434,6 +1460,7 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
     ctx->trace_budget_words = budget_mb * (1024ull * 1024ull / 4ull);
     if (const char* e = getenv("BG_LONG_TRACE_BUDGET_MB")) ctx->long_budget_words = strtoull(e, nullptr, 10) * (1024ull * 1024ull / 4ull);
     if (const char* e = getenv("BG_HOST_PLAN")) ctx->host_plan = atoi(e) != 0;
+    if (const char* e = getenv("BG_FINE_PAIRS")) ctx->fine_max_pairs = std::max(0, atoi(e));
     if (const char* e = getenv("BG_FORCE_SHAPE")) {   // "L,C" -- experiments / tests
         int l = 0, c = 0;
         if (sscanf(e, "%d,%d", &l, &c) == 2) { ctx->force_L = l; ctx->force_C = c; }
@@ -1459,6 +1486,12 @@ int bg_set_shape(bg_ctx* ctx, int L, int C) {   // 0,0 = automatic
 int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes) {
     if (!ctx || bytes < 4096) return BG_EINVAL_ARG;
     ctx->trace_budget_words = bytes / 4;
+    return BG_OK;
+}
+
+int bg_set_fine_pairs(bg_ctx* ctx, int max_pairs) {
+    if (!ctx || max_pairs < 0) return BG_EINVAL_ARG;
+    ctx->fine_max_pairs = max_pairs;
     return BG_OK;
 }
 

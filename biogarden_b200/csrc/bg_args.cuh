@@ -104,6 +104,18 @@ struct WaveArgs {
 constexpr int K2_MAX_Q = 13;        // CTAs per pair (196 bands of a 100 kbp pair / 16 warps)
 constexpr int K2_WARPS = 16;        // warps per CTA
 
+// ---- K2f (k2f_fine.cuh): one column per lane, for launches of very few long pairs ----
+constexpr uint32_t FINE_RING = 64;        // rows of a boundary column in flight between two warps of a CTA (shared memory)
+constexpr uint32_t FINE_RING_G = 256;     // ... between the last warp of a CTA and the first of the next (global memory)
+struct FineArgs {
+    FillArgs f;
+    WaveCand* cand;          // [slot][cand_stride]: one record per warp of the pair
+    uint32_t* done;          // [slot] warps that have finished the pair (zeroed before launch)
+    uint32_t cand_stride;
+    unsigned long long* ring_g;   // [CTAs][FINE_RING_G] boundary column of the CTA's last warp: (M + a, Y, generation tag) per row
+    uint32_t* cons_g;        // [CTAs] rows the next CTA has consumed
+};
+
 // ---- K3 (k3_walk.cuh) ----
 struct WalkArgs {
     const PairDesc* desc;

@@ -5,6 +5,7 @@
 // 33 resident clusters instead of 37 groups -- measured, see profiles/.)
 #include "launch.h"
 #include "k2_wave.cuh"
+#include "k2f_fine.cuh"
 
 namespace bg {
 
@@ -37,6 +38,29 @@ cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream
     }
     if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_cta, smem, st, a);
     return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_cta, smem, st, a);
+}
+
+template <class Kern>
+static cudaError_t launch_k2f_impl(Kern kern, int n_cta, int warps, size_t smem, cudaStream_t st, const FineArgs& a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_cta);
+    cfg.blockDim = dim3((unsigned)warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+cudaError_t launch_k2f(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const FineArgs& a) {
+    if (local) {
+        if (prof4) return launch_k2f_impl(k2f_fine<true, true>, n_cta, warps_per_cta, smem, st, a);
+        return launch_k2f_impl(k2f_fine<true, false>, n_cta, warps_per_cta, smem, st, a);
+    }
+    if (prof4) return launch_k2f_impl(k2f_fine<false, true>, n_cta, warps_per_cta, smem, st, a);
+    return launch_k2f_impl(k2f_fine<false, false>, n_cta, warps_per_cta, smem, st, a);
 }
 
 }  // namespace bg

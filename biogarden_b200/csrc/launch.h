@@ -91,6 +91,8 @@ void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaS
 bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a);
 cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false);
 
+cudaError_t launch_k2f(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const FineArgs& a);
+
 // K3 walks + string assembly
 void dispatch_walk(Shape sh, bool half, uint32_t ns, cudaStream_t st, const WalkArgs& a);
 enum LongWalk { LW_SKEW = 0, LW_DIAG = 1 };

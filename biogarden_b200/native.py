@@ -66,7 +66,7 @@ SYMBOLS = ["bg_create", "bg_destroy", "bg_strerror", "bg_last_error", "bg_versio
            "bg_result_free", "bg_edit_distance_batch", "bg_hamming_distance_batch", "bg_p_distance_matrix", "bg_batch_upload", "bg_dbatch_free", "bg_align_device",
            "bg_edit_distance_device", "bg_dresult_download", "bg_dresult_download_u64", "bg_dresult_free",
            "bg_sync", "bg_stream", "bg_device_ordinal", "bg_last_timing", "bg_batch_prepare", "bg_set_shape",
-           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_set_host_plan", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status",
+           "bg_set_trace_budget", "bg_set_long_trace_budget", "bg_set_host_plan", "bg_set_fine_pairs", "bg_fasta_parse", "bg_fasta_free", "bg_pin_host", "bg_unpin_host", "bg_score_table26", "bg_residue_histogram", "bg_ref_status",
            "bg_align_batch_ops", "bg_ops_result_free", "bg_expand_ops", "bg_expand_kind",
            "bg_fasta_parse_packed", "bg_packed_bytes", "bg_pack_residues", "bg_unpack_residues"]
 
@@ -124,6 +124,7 @@ def lib():
     L.bg_set_trace_budget.restype = ci; L.bg_set_trace_budget.argtypes = [vp, u64]
     L.bg_set_long_trace_budget.restype = ci; L.bg_set_long_trace_budget.argtypes = [vp, u64]
     L.bg_set_host_plan.restype = ci; L.bg_set_host_plan.argtypes = [vp, ci]
+    L.bg_set_fine_pairs.restype = ci; L.bg_set_fine_pairs.argtypes = [vp, ci]
     L.bg_debug_plan_compare.restype = ci; L.bg_debug_plan_compare.argtypes = [vp, C.POINTER(bg_batch), C.POINTER(bg_params), vp]
     L.bg_score_table26.restype = C.POINTER(C.c_int8); L.bg_score_table26.argtypes = [C.c_char_p]
     L.bg_residue_histogram.restype = ci; L.bg_residue_histogram.argtypes = [C.POINTER(bg_batch), vp, vp]
@@ -439,6 +440,10 @@ class Context:
 
     def set_trace_budget(self, nbytes):
         check(lib().bg_set_trace_budget(self.h, nbytes), self.h)
+
+    def set_fine_pairs(self, max_pairs: int):
+        """Long-pair launches of at most max_pairs pairs run on the fine-grained wavefront kernel (0: never)."""
+        check(lib().bg_set_fine_pairs(self.h, int(max_pairs)), self.h)
 
     def set_host_plan(self, on: bool):
         """True: launch plans are built on the host; False (default): pipeline chunks are planned on the device."""

@@ -251,6 +251,12 @@ int bg_set_trace_budget(bg_ctx* ctx, uint64_t bytes);
  * computed twice).  This replaces the reference's "six full matrices or nothing" (aligner.rs:594-602). */
 int bg_set_long_trace_budget(bg_ctx* ctx, uint64_t bytes);
 
+/* Launches of the long-pair path (pairs wider than 4096 columns) with at most `max_pairs` pairs use the fine-grained
+ * wavefront kernel -- one column per lane, a lone 10 kbp pair spread over ~270 warps -- instead of 512-column bands
+ * (0 = never, the default: the kernel is bit-exact but not yet faster than the banded one, see k2f_fine.cuh).
+ * Results are identical either way (tests force both). */
+int bg_set_fine_pairs(bg_ctx* ctx, int max_pairs);
+
 /* 1: build every launch plan on the host; 0 (default): the chunks of bg_align_batch are planned on the device from
  * their sequence offsets (16 B per pair H2D instead of 64 B of descriptors, no per-pair host work). */
 int bg_set_host_plan(bg_ctx* ctx, int on);

@@ -713,3 +713,27 @@ def test_packed_batches_give_identical_results(aligner):
     eq = native.Batch.from_sequences([s for p in range(200) for s in (lambda x: (x, bytes(c if rng.random() < 0.9 else rng.choice(b"ACGT") for c in x)))(bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 300))))])
     assert np.array_equal(ctx.hamming_distance_batch(eq), ctx.hamming_distance_batch(eq.pack(2)))
     assert small_p.packing == 2
+
+
+def test_fine_wavefront_kernel_vs_oracle_and_k2():
+    """K2f (k2f_fine.cuh: one column per lane, shared-memory hand-over between warps, direction codes transposed into
+    K2's trace layout) against the lean oracle in every mode, forced onto launches of many pairs (pairs run one after
+    the other inside the launch), with several warps-per-CTA settings so that both the shared-memory and the
+    global-memory hand-over carry the boundary columns; and byte-identical to K2 (fine kernel switched off)."""
+    batch = _mutated_long_pairs([(5000, 4200), (3000, 9000), (300, 5000), (4500, 4097), (9000, 17000), (33, 4100), (4100, 4099), (1, 5000), (0, 4200)], 77)
+    al = SequenceAligner()
+    problems = []
+    for mode, scorer, a, b in [("semiglobal", "unit", -1, -1), ("local", "blosum62", -11, -1), ("global", "unit", -2, -1),
+                               ("overlap", "unit", -2, -2), ("fitting", "unit", -1, -1), ("semiglobal", "blosum62", -1, -2)]:
+        bt = _fitting_domain(batch) if mode == "fitting" else batch
+        al.context.set_fine_pairs(0)
+        k2 = _cmp.engine_align(al, bt, mode, scorer, a, b)
+        al.context.set_fine_pairs(64)
+        fine = _cmp.engine_align(al, bt, mode, scorer, a, b)
+        ora = _cmp.oracle_align(bt, mode, scorer, a, b, lean=True)
+        problems += _cmp.diff(bt, fine, ora, "K2f %s/%s" % (mode, scorer))
+        assert np.array_equal(k2.score, fine.score) and np.array_equal(k2.status, fine.status), mode
+        assert np.array_equal(k2.off, fine.off) and np.array_equal(k2.arena, fine.arena), mode
+        k2.close(); fine.close()
+    assert not problems, "\\n".join(problems)
+    al.context.set_fine_pairs(0)
