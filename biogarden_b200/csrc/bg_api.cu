@@ -868,13 +868,15 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
 
 // Pipeline chunks for pairs [lo, hi) at SCAN_BLOCK granularity, roughly equal cell counts.
 // nd > 1: the chunks feed a queue that nd devices share -- nd times as many chunks, and the ramp goes by rounds of nd.
-std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi, double nchunk_override = 0.0, int nd = 1) {
+// ramp_down: the chunks shrink towards the end (what follows the GPU's last kernel -- the string expansion of the last
+// chunk on the host, formerly its D2H -- is proportional to the last chunk's size); compact-result calls have no such tail.
+std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, uint64_t hi, double nchunk_override = 0.0, int nd = 1, bool ramp_down = true) {
     std::vector<uint64_t> b{lo};
     if (hi == lo) { b.push_back(hi); return b; }
     const uint64_t blk_lo = lo / SCAN_BLOCK, blk_hi = (hi + SCAN_BLOCK - 1) / SCAN_BLOCK;
     double total = 0;
     for (uint64_t k = blk_lo; k < blk_hi; ++k) total += S.block_cost[k];
-    static const double nchunk_target = [] { const char* e = getenv("BG_PIPE_CHUNKS"); return e ? std::max(1.0, atof(e)) : 5.0; }();
+    static const double nchunk_target = [] { const char* e = getenv("BG_PIPE_CHUNKS"); return e ? std::max(1.0, atof(e)) : 4.0; }();   // (cfg2, compact results: 3 / 4 / 5 / 6 -> 12.5 / 12.5 / 12.9 / 13.6 ms per call)
     const double target = nchunk_override > 0 ? std::max(total / nchunk_override, 1.0e8) : std::max(total / (nchunk_target * nd), 1.0e9);
     const uint64_t max_pairs = 262144;
     // every length class of a chunk becomes its own launch: keep >= ~4 waves of warps per launch
@@ -893,7 +895,7 @@ std::vector<uint64_t> chunk_bounds_from_scan(const BatchScan& S, uint64_t lo, ui
         static const double ramp[] = {0.125, 0.1875, 0.25, 0.375, 0.5, 0.75};
         const double scale = nb <= 6 ? ramp[nb - 1] : 1.0;
         const double left = total - done_cost;
-        const double want = std::min(target * scale, std::max(left * 0.5, target * 0.25));
+        const double want = ramp_down ? std::min(target * scale, std::max(left * 0.5, target * 0.25)) : target * scale;
         if ((acc >= want && (double)(end - start) >= (double)min_pairs * scale) || (double)(end - start) >= (double)max_pairs * scale) {
             b.push_back(end); start = end; done_cost += acc; acc = 0;
         }
@@ -1455,7 +1457,7 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
                 cudaEventCreateWithFlags(&ws.ev_scan, cudaEventDisableTiming) != cudaSuccess) { bg_destroy(ctx); return BG_ECUDA; }
         }
     }
-    uint64_t budget_mb = 8192;
+    uint64_t budget_mb = 4096;   // (device-resident cfg2: 1 / 2 / 4 / 8 GiB per launch -> 2215 / 2229 / 2229 / 2189 GCUPS: more launches hide more of the walks)
     if (const char* e = getenv("BG_TRACE_BUDGET_MB")) budget_mb = strtoull(e, nullptr, 10);
     ctx->trace_budget_words = budget_mb * (1024ull * 1024ull / 4ull);
     if (const char* e = getenv("BG_LONG_TRACE_BUDGET_MB")) ctx->long_budget_words = strtoull(e, nullptr, 10) * (1024ull * 1024ull / 4ull);
@@ -2447,7 +2449,7 @@ int run_align_job(AlignJob& J) {
     if (in->packing == BG_PACK_2BIT) make_unpack_lut2(in->alphabet, J.lut2);
     if (N == 0) { if (J.want_strings) J.off[0] = 0; return BG_OK; }
     if (!J.long_mode) {
-        const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, 0, N, 0.0, nd);
+        const std::vector<uint64_t> cb = chunk_bounds_from_scan(scan, 0, N, 0.0, nd, J.want_strings || !J.oo.len);
         J.items.resize(cb.size() - 1);
         for (size_t c = 0; c + 1 < cb.size(); ++c) {
             WorkItem& it = J.items[c];
