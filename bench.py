@@ -56,13 +56,15 @@ def ncu_traffic(kernel_prefix):
     """DRAM bytes per cell of the dominant kernel from the committed `ncu --set full` summary
     (profiles/ncu_traffic_r01.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch and the
     cells that launch processed); None when no capture of that kernel is on file."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    try:
-        for e in json.load(open(p))["kernels"]:
-            if e["kernel"].startswith(kernel_prefix):
-                return (e["dram_bytes_read"] + e["dram_bytes_write"]) / e["cells"], e
-    except Exception:
-        pass
+    for name in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            for e in json.load(open(p))["kernels"]:
+                if e["kernel"].startswith(kernel_prefix):
+                    e = dict(e); e["file"] = name
+                    return (e["dram_bytes_read"] + e["dram_bytes_write"]) / e["cells"], e
+        except Exception:
+            pass
     return None, None
 
 
@@ -431,8 +433,8 @@ def measure(args, workload, steps, warmup, rank, world, local_rank, barrier, sam
             "peak_source": peak_src,
             "frac_of_alu_plus_fma_issue": (achieved / (2 * peak)) if achieved else None,
             "traffic": (bytes_per_cell * cells / fill_launches) if bytes_per_cell else None,
-            "traffic_source": ("profiles/ncu_traffic_r01.json: %s, %.3f B/cell DRAM read+write in one ncu --set full launch, scaled to this "
-                               "run's cells per launch" % (cap["kernel"], bytes_per_cell)) if bytes_per_cell else None,
+            "traffic_source": ("profiles/%s: %s, %.3f B/cell DRAM read+write in one ncu --set full launch, scaled to this "
+                               "run's cells per launch" % (cap["file"], cap["kernel"], bytes_per_cell)) if bytes_per_cell else None,
             "hbm": {"trace_bytes_per_launch_set": trace_bytes,
                     "achieved_gbs": trace_bytes / (fill_ms * 1e-3) / 1e9 if fill_ms > 0 else None,
                     "peak_gbs": hbm, "peak_source": hbm_src},

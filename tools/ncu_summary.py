@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Summarise .ncu-rep captures (ncu --set full) into profiles/: one text block per kernel with the
-metrics DESIGN.md / bench.py quote, and profiles/ncu_traffic_r01.json (DRAM bytes per launch).
+metrics DESIGN.md / bench.py quote, and profiles/ncu_traffic_r02.json (DRAM bytes per launch; BG_TRAFFIC_FILE overrides).
 
   python tools/ncu_summary.py OUT.txt REPORT.ncu-rep:CELLS[:NOTE] ...
 """
@@ -32,7 +32,7 @@ TO_BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 def main():
     out = sys.argv[1]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    tpath = os.path.join(root, "profiles", "ncu_traffic_r01.json")
+    tpath = os.path.join(root, "profiles", os.environ.get("BG_TRAFFIC_FILE", "ncu_traffic_r02.json"))
     traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from `ncu --set full --clock-control none`; "
                        "cells = DP cells that launch processed (bench.py scales bytes/cell to its own launches)", "kernels": []}
     if os.path.exists(tpath):
