@@ -1457,7 +1457,9 @@ int bg_create(const int* devices, int n_dev, bg_ctx** out) {
                 cudaEventCreateWithFlags(&ws.ev_scan, cudaEventDisableTiming) != cudaSuccess) { bg_destroy(ctx); return BG_ECUDA; }
         }
     }
-    uint64_t budget_mb = 4096;   // (device-resident cfg2: 1 / 2 / 4 / 8 GiB per launch -> 2215 / 2229 / 2229 / 2189 GCUPS: more launches hide more of the walks)
+    uint64_t budget_mb = 8192;   // (device-resident cfg2: 1 / 2 / 4 / 8 GiB per launch -> 2215 / 2229 / 2229 / 2189 GCUPS: more launches hide more of the
+                                 //  walks behind fills, +1.8 % overall, but the fills then share the SMs with walks for longer and the fill phase --
+                                 //  what the roofline fraction is computed from -- stretches from 8.53 to 8.97 ms: kept at 8 GiB)
     if (const char* e = getenv("BG_TRACE_BUDGET_MB")) budget_mb = strtoull(e, nullptr, 10);
     ctx->trace_budget_words = budget_mb * (1024ull * 1024ull / 4ull);
     if (const char* e = getenv("BG_LONG_TRACE_BUDGET_MB")) ctx->long_budget_words = strtoull(e, nullptr, 10) * (1024ull * 1024ull / 4ull);

@@ -23,6 +23,7 @@
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -125,23 +126,36 @@ class SequenceAligner {
         for (size_t i = 0; i < rows.size(); ++i)
             for (size_t j = 0; j < cols.size(); ++j) table[i * nc + j] = sc((uint8_t)rows[i], (uint8_t)cols[j]);
         bg_params prm{(int32_t)mode, a, b, 0u, table.data(), nr, nc, rc.data(), cc.data()};
-        bg_result r{};
-        const int err = bg_align_batch(ctx_, &batch, &prm, &r);
+        // compact results + expansion straight into the Sequences this function has to allocate anyway (no arena in between):
+        // what the Rust shim does too (rust/biogarden-gpu/src/lib.rs)
+        bg_ops_result r{};
+        const int err = bg_align_batch_ops(ctx_, &batch, &prm, &r);
         if (err == BG_EINVAL_RANGE) throw BioError(BioError::InvalidArgumentRange, "The provided has is within an unsupported range!");
         if (err == BG_EINVAL_SIZE) throw BioError(BioError::InvalidInputSize, "Provided inputs have invalid size!");
         if (err != BG_OK) throw BioError(BioError::Engine, std::string(bg_strerror(err)) + ": " + bg_last_error(ctx_));
-        std::vector<Aligned> out;
-        out.reserve(r.n_pairs);
-        for (uint64_t p = 0; p < r.n_pairs; ++p) {
-            ds::Sequence x(std::vector<uint8_t>(r.arena + r.off[2 * p], r.arena + r.off[2 * p + 1]));
-            ds::Sequence y(std::vector<uint8_t>(r.arena + r.off[2 * p + 1], r.arena + r.off[2 * p + 2]));
-            out.emplace_back(r.score[p], std::move(x), std::move(y));
+        std::vector<Aligned> out(r.n_pairs);
+        auto expand = [&](uint64_t lo, uint64_t hi) {
+            for (uint64_t p = lo; p < hi; ++p) {
+                const uint64_t len = r.len[p];
+                std::vector<uint8_t> x(len), y(len);
+                bg_expand_ops(res.data() + off[2 * p] + r.first[2 * p], res.data() + off[2 * p + 1] + r.first[2 * p + 1],
+                              r.ops + r.ops_off[p], len, x.data(), y.data());
+                out[p] = Aligned(r.score[p], ds::Sequence(std::move(x)), ds::Sequence(std::move(y)));
+            }
+        };
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(hw, r.n_pairs / 4096));
+        if (nt == 1) expand(0, r.n_pairs);
+        else {
+            std::vector<std::thread> th;
+            for (uint64_t t = 0; t < nt; ++t) th.emplace_back(expand, r.n_pairs * t / nt, r.n_pairs * (t + 1) / nt);
+            for (auto& t : th) t.join();
         }
         if (status) status->assign(r.status, r.status + r.n_pairs);
         else
             for (uint64_t p = 0; p < r.n_pairs; ++p)
-                if (r.status[p] != BG_ST_OK) { bg_result_free(&r); throw BioError(BioError::ReferenceUndefined, "the reference panics or never returns on this input"); }
-        bg_result_free(&r);
+                if (r.status[p] != BG_ST_OK) { bg_ops_result_free(&r); throw BioError(BioError::ReferenceUndefined, "the reference panics or never returns on this input"); }
+        bg_ops_result_free(&r);
         return out;
     }
 

@@ -35,7 +35,18 @@ pub struct bg_result {
     pub owner_: *mut c_void,
 }
 
+/// Compact results (bgalign.h): one 2-bit op per alignment column instead of the aligned strings.
+#[repr(C)]
+pub struct bg_ops_result {
+    pub n_pairs: u64, pub score: *mut i32, pub status: *mut u8, pub len: *mut u32, pub first: *mut u32,
+    pub ops: *mut u32, pub ops_off: *mut u64, pub owner_: *mut c_void,
+}
+
 extern "C" {
+    pub fn bg_align_batch_ops(ctx: *mut bg_ctx, input: *const bg_batch, p: *const bg_params, out: *mut bg_ops_result) -> c_int;
+    pub fn bg_ops_result_free(r: *mut bg_ops_result);
+    /// ops -> the two aligned strings (`len` bytes each); AVX-512 VBMI2 when the host has it.
+    pub fn bg_expand_ops(seq1_from: *const u8, seq2_from: *const u8, ops: *const u32, len: u64, a_out: *mut u8, b_out: *mut u8) -> c_int;
     pub fn bg_create(devices: *const c_int, n_dev: c_int, out: *mut *mut bg_ctx) -> c_int;
     pub fn bg_destroy(ctx: *mut bg_ctx);
     pub fn bg_strerror(err: c_int) -> *const c_char;

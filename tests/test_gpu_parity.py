@@ -389,7 +389,7 @@ def test_full_size_properties_cfg2(aligner):
     try:
         eng2 = _cmp.engine_align(aligner, batch, "global", "unit", -2, -1)
     finally:
-        aligner.context.set_trace_budget(4 << 30)
+        aligner.context.set_trace_budget(8 << 30)
     a2 = eng2.arena
     assert np.array_equal(eng2.score, score_full)
     assert (int(np.sum(a2.astype(np.uint64) * (np.arange(len(a2), dtype=np.uint64) % 1000003))), len(a2)) == digest_full
@@ -485,7 +485,7 @@ def test_cfg5_real_size_pairs_vs_oracle():
 def test_cfg4_full_size_sample_and_chunk_invariance(aligner):
     """Config #4 at full size (100 000 protein pairs, 200-1000 aa, local, blosum62 -11/-1): 5 000 random pairs
     against the lean oracle (scores + every string), and the whole output byte-identical under a different chunking
-    (trace budget 1 GiB instead of 4: several launches per length class)."""
+    (trace budget 1 GiB instead of 8: several launches per length class)."""
     n_pairs = 100_000
     batch = synth.make("cfg4_protein_local", n_pairs=n_pairs)
     eng = _cmp.engine_align(aligner, batch, "local", "blosum62", -11, -1)
@@ -507,7 +507,7 @@ def test_cfg4_full_size_sample_and_chunk_invariance(aligner):
     try:
         eng2 = _cmp.engine_align(aligner, batch, "local", "blosum62", -11, -1)
     finally:
-        aligner.context.set_trace_budget(4 << 30)
+        aligner.context.set_trace_budget(8 << 30)
     assert np.array_equal(eng2.score, score_full) and np.array_equal(eng2.off, off_full) and np.array_equal(eng2.arena, arena_full)
     eng2.close()
 
