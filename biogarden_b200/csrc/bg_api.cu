@@ -2054,9 +2054,15 @@ int device_pipeline(AlignJob& J, int d) {
     static const bool no_split = getenv("BG_NO_SPLIT") != nullptr;
     cudaStream_t st_post = (long_mode || no_split) ? st_comp : dv.ws[1].walk_stream;
     cudaStream_t saved[PIPE_DEPTH];
+    // every launch of an item gets its own trace region (so that its walk runs next to the next fill) as long as the items
+    // in flight together stay within 45 % of the device: cfg4's chunks need ~12 GB each (six length classes, 0.5 MB per
+    // 1000 x 1000 pair); with the old fixed 6 GB cap they ran fill -> walk -> fill on one stream, 52 instead of 43 ms per call
+    const uint64_t cap_saved = dv.ws[0].split_cap_words;
+    const uint64_t split_cap = (uint64_t)(0.45 * (double)dv.total_mem) / 4 / (uint64_t)std::max(1, std::min(PIPE_DEPTH, nitems));
     for (int s = 0; s < PIPE_DEPTH; ++s) {
         saved[s] = dv.ws[s].stream; dv.ws[s].stream = st_comp; dv.ws[s].reset_events();
         dv.ws[s].post_stream = (st_post == st_comp) ? nullptr : st_post;
+        dv.ws[s].split_cap_words = std::max(cap_saved, split_cap);
     }
     static const bool no_fill2 = getenv("BG_NO_FILL2") != nullptr;
     cudaStream_t st_fill2 = (PIPE_DEPTH > 3 && !no_fill2 && st_post != st_comp) ? saved[3] : nullptr;   // an otherwise idle work-set stream
@@ -2264,6 +2270,7 @@ int device_pipeline(AlignJob& J, int d) {
     if (st_fill2) cudaStreamSynchronize(st_fill2);
     for (int s = 0; s < PIPE_DEPTH; ++s) {
         dv.ws[s].stream = saved[s]; dv.ws[s].post_stream = nullptr; dv.ws[s].fill2_stream = nullptr; dv.ws[s].launch_parity = -1;
+        dv.ws[s].split_cap_words = cap_saved;
         cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); cudaEventDestroy(ev_arena[s]); cudaEventDestroy(ev_plan[s]);
     }
     return J.rc.load();
