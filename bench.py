@@ -502,6 +502,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # a CPU-side group for the phase in which rank 0 alone drives all GPUs: an NCCL barrier would park a spinning kernel on
+    # every waiting rank's GPU (and a spinning host thread beside it), i.e. on the very devices rank 0 is measuring
+    idle_pg = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -538,6 +541,7 @@ def main():
                 line["e2e_inprocess"] = measure_inprocess(args, world, 5, 3)
             except Exception as exc:   # the headline line must survive
                 line["e2e_inprocess"] = {"error": str(exc)[:300]}
+        dist.barrier(group=idle_pg)    # the other ranks wait here on a socket, GPUs and cores idle
         barrier()
     sampler.close()
     if rank == 0:

@@ -819,10 +819,12 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
             const uint64_t q_hi = std::min(N, (blk + 1) * SCAN_BLOCK);
             double cost = 0;
             ClassStat* cs = S.with_stats ? &S.block_cls[blk * BG_N_SHAPES] : nullptr;
-            for (uint64_t q = blk * SCAN_BLOCK; q < q_hi; ++q) {
-                const uint64_t o0 = off[2 * q], o1 = off[2 * q + 1], o2 = off[2 * q + 2];
-                if (o1 < o0 || o2 < o1) { P.monotone = false; continue; }
-                const uint64_t n = o1 - o0, m = o2 - o1;
+            // runs of pairs with the same two lengths (read sets are mostly uniform) are accounted once
+            uint64_t run_n = ~0ull, run_m = ~0ull, run_len = 0;
+            auto flush = [&] {
+                if (!run_len) return;
+                const uint64_t n = run_n, m = run_m, k = run_len;
+                run_len = 0;
                 if (n < m) P.fitting_violation = true;
                 if (m > WAVE_MIN_COLS) P.has_wide = true;
                 if (cs && m <= WAVE_MIN_COLS && n < 0x7FFFFFF0ull) {
@@ -833,9 +835,9 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                         st_si = shape_index(sh); st_band = (uint32_t)(sh.L * sh.C);
                     }
                     ClassStat& c = cs[st_si];
-                    c.count++; c.cells += n * m;
-                    c.pad_bytes += 2ull * ((n + m + 3ull) & ~3ull) + 16ull;
-                    if (m > st_band) c.bnd_elems += n;
+                    c.count += k; c.cells += k * n * m;
+                    c.pad_bytes += k * (2ull * ((n + m + 3ull) & ~3ull) + 16ull);
+                    if (m > st_band) c.bnd_elems += k * n;
                     c.min_n = std::min<uint32_t>(c.min_n, (uint32_t)n); c.max_n = std::max<uint32_t>(c.max_n, (uint32_t)n);
                     c.max_m = std::max<uint32_t>(c.max_m, (uint32_t)m);
                 }
@@ -845,8 +847,17 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                                            m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
                 }
                 P.max_len_sum = std::max(P.max_len_sum, n + m);
-                cost += (double)n * (double)m + 64.0;
+                cost += (double)k * ((double)n * (double)m + 64.0);
+            };
+            for (uint64_t q = blk * SCAN_BLOCK; q < q_hi; ++q) {
+                const uint64_t o0 = off[2 * q], o1 = off[2 * q + 1], o2 = off[2 * q + 2];
+                if (o1 < o0 || o2 < o1) { P.monotone = false; continue; }
+                const uint64_t n = o1 - o0, m = o2 - o1;
+                if (n == run_n && m == run_m) { ++run_len; continue; }
+                flush();
+                run_n = n; run_m = m; run_len = 1;
             }
+            flush();
             S.block_cost[blk] = cost;
         }
     };
