@@ -221,6 +221,7 @@ struct Prepared {
     uint8_t codes[512];
     int64_t maxabs = 0;
     int32_t half_maxabs = 0;   // > 0: K1h (packed 16 x 2) may be used for short classes
+    bool half_prof8 = false;   // ... in its byte-profile form: every s - a - b (and -a - b) fits a signed byte
 };
 
 }  // namespace
@@ -1053,6 +1054,12 @@ int prepare_params(bg_ctx* ctx, const bg_params* p, const uint64_t* off, uint64_
     if (pp.smem > 48 * 1024) { ctx->set_error("score table too large for shared memory"); return BG_EUNSUPPORTED; }
     pp.prof4 = fits8 && p->n_rows <= 4;
     pp.half_maxabs = half_maxabs_of(p);
+    pp.half_prof8 = !getenv("BG_NO_HALF_PROF");
+    {
+        const int64_t ab = (int64_t)p->gap_open + p->gap_extend;
+        if (-ab < -128 || -ab > 127) pp.half_prof8 = false;
+        for (int32_t v : pp.table) if (v - ab < -128 || v - ab > 127) pp.half_prof8 = false;
+    }
     memcpy(pp.codes, p->row_code, 256); memcpy(pp.codes + 256, p->col_code, 256);
     for (int i = 0; i < 256; ++i) {
         if (pp.codes[i] != 0xFF && pp.codes[i] >= p->n_rows) { ctx->set_error("row_code entry out of range"); return BG_EINVAL_ARG; }
@@ -1267,7 +1274,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 fst = (st2 && ((chunk_no + parity) & 1)) ? st2 : st;
                 Phase ph(ws, 1, fst);
                 const uint32_t nw2 = (ns + 2 * G - 1) / (2 * G);
-                if (!dispatch_k1h(lc.sh, pp.mode != BG_GLOBAL, dim3((nw2 + 3) / 4), fst, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
+                if (!dispatch_k1h(lc.sh, pp.mode != BG_GLOBAL, pp.half_prof8, dim3((nw2 + 3) / 4), fst, fa)) { ctx->set_error("internal: K1h shape not compiled"); return BG_ECUDA; }
             } else {
                 fst = (st2 && ((chunk_no + parity) & 1)) ? st2 : st;
                 Phase ph(ws, 1, fst);

@@ -24,9 +24,16 @@
 //     accumulations per cell pair are split between the ALU pipe (VIADD) and the FMA pipe (IMAD) by
 //     HB_PIPES so that both pipes carry ~8 instructions per cell pair (ncu of the first version, all
 //     on the FMA pipe: fmaheavy 78 % busy, ALU 41 %);
-//   * the substitution score pair comes from one LDS into a 256-entry table indexed by
-//     (row residue A, row residue B, column residue A, column residue B), pre-biased by -(a + b).
-// 16 instructions per TWO cells (4 VIMNMX.U16x2, 8 accumulations, 2 adds, 1 address, 1 LDS).
+//   * the substitution score pair (s - a - b of pair A | of pair B):
+//       PROF (every s - a - b fits a signed byte -- the usual case): once per ROW one LDS.64 fetches the row's two
+//       byte profiles (scores of row residue A / B against the four column codes); per cell ONE PRMT whose selector
+//       is the column's constant picks byte cA of profile A and byte cB of profile B and replicates their sign
+//       bits into the upper bytes, i.e. builds the sign-extended 16 x 2 pair; VIADD.16x2 adds it to the diagonal
+//       (a packed add: a negative low half must not borrow from the high half);
+//       otherwise: one LDS into a 256-entry table indexed by (row residue A, row residue B, column residue A,
+//       column residue B), pre-biased by -(a + b) with the borrow folded in, and an IMAD.
+// PROF: 15 instructions per TWO cells (4 VIMNMX.U16x2, 8 accumulations, PRMT, VIADD.16x2, IMAD), no shared-memory
+// access in the cell loop; table form: 16 (... 2 adds, 1 address, 1 LDS).
 //
 // Trace layout ("row blocks"): a lane keeps one accumulator per COLUMN and collects HB_TB = 4
 // systolic steps in it -- pair A's nibbles in bits 0..15, pair B's in bits 16..31 -- then writes its
@@ -98,24 +105,47 @@ __device__ __forceinline__ uint32_t hb_add(uint32_t x, uint32_t one, uint32_t y)
     return d;
 }
 
+__device__ __forceinline__ uint32_t hb_add16x2(uint32_t x, uint32_t y) {   // VIADD.16x2
+    uint32_t d;
+    asm("add.u16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(y));
+    return d;
+}
+__device__ __forceinline__ uint32_t hb_prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+}
+
 // Launch geometry: a warp holds 32/L lane groups, each with two pairs: slots (2g, 2g+1) of the warp's
 // 2*(32/L) consecutive slots.  TRACK: the last-column / last-row end-cell scans of semiglobal, fitting
 // and overlap are compiled in (global only needs the corner cell).
-template <int L, int C, bool TRACK, int HB_PIPES, int MINB>
+template <int L, int C, bool TRACK, int HB_PIPES, int MINB, bool PROF>
 __global__ void __launch_bounds__(128, MINB) k1h_fill(const FillArgs A) {
     constexpr int GP = 32 / L;
     constexpr int CW = (C + 3) & ~3;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint8_t s_row[256];
     __shared__ uint8_t s_col[256];
-    __shared__ uint32_t s_pack[256];   // [(rA*4 + rB) * 16 + (cA*4 + cB)] = (sA - a - b) + (sB - a - b) * 65536
+    // !PROF: [(rA*4 + rB) * 16 + (cA*4 + cB)] = (sA - a - b) + (sB - a - b) * 65536
+    // PROF:  [(rA*4 + rB) * 2 + h] = the four bytes (s(r_h, c) - a - b) & 0xff, c = 0..3: the row's score profile
+    __shared__ __align__(8) uint32_t s_pack[PROF ? 32 : 256];
 
     for (int x = threadIdx.x; x < 256; x += blockDim.x) {
         s_row[x] = A.row_code[x]; s_col[x] = A.col_code[x];
-        const int rA = (x >> 6) & 3, rB = (x >> 4) & 3, cA = (x >> 2) & 3, cB = x & 3;
-        const int32_t sA = ((rA < A.n_rows && cA < A.n_cols) ? A.table[rA * A.n_cols + cA] : 0) - A.a - A.b;
-        const int32_t sB = ((rB < A.n_rows && cB < A.n_cols) ? A.table[rB * A.n_cols + cB] : 0) - A.a - A.b;
-        s_pack[x] = (uint32_t)(sA + sB * 65536);
+        if (!PROF) {
+            const int rA = (x >> 6) & 3, rB = (x >> 4) & 3, cA = (x >> 2) & 3, cB = x & 3;
+            const int32_t sA = ((rA < A.n_rows && cA < A.n_cols) ? A.table[rA * A.n_cols + cA] : 0) - A.a - A.b;
+            const int32_t sB = ((rB < A.n_rows && cB < A.n_cols) ? A.table[rB * A.n_cols + cB] : 0) - A.a - A.b;
+            s_pack[x] = (uint32_t)(sA + sB * 65536);
+        } else if (x < 32) {
+            const int r = (x & 1) ? ((x >> 1) & 3) : ((x >> 3) & 3);
+            uint32_t v = 0;
+            for (int c = 0; c < 4; ++c) {
+                const int32_t sc = ((r < A.n_rows && c < A.n_cols) ? A.table[r * A.n_cols + c] : 0) - A.a - A.b;
+                v |= ((uint32_t)sc & 0xffu) << (8 * c);
+            }
+            s_pack[x] = v;
+        }
     }
     __syncthreads();
 
@@ -177,7 +207,9 @@ __global__ void __launch_bounds__(128, MINB) k1h_fill(const FillArgs A) {
                 if (code[h] > 3u) { bad_residue = 1; code[h] = 0; }
             }
         }
-        cc[c] = (code[0] * 4u + code[1]) * 4u;
+        // PROF: PRMT selector -- byte 0 <- profile A [cA], byte 1 <- its sign, byte 2 <- profile B [cB], byte 3 <- its sign
+        cc[c] = PROF ? (code[0] | ((code[0] | 8u) << 4) | ((code[1] | 4u) << 8) | ((code[1] | 12u) << 12))
+                     : (code[0] * 4u + code[1]) * 4u;
         MuA[c] = to_state(border_row(row_gap, a, b, j0 + 1), 0, j0 + 1);
         Xu[c] = hb_pack(HB_NEG);
     }
@@ -229,14 +261,22 @@ __global__ void __launch_bounds__(128, MINB) k1h_fill(const FillArgs A) {
             if (i0 < n_max) {
                 uint32_t leftA = MlA, Y = Yl;
                 const unsigned char* rowp = reinterpret_cast<const unsigned char*>(s_pack) + r * 64u;
+                uint2 rprof = make_uint2(0u, 0u);
+                if (PROF) rprof = *reinterpret_cast<const uint2*>(s_pack + 2u * r);
                 // diagonal terms first, HB_DG columns at a time, while the previous row's M is still in MuA[]: the cell
                 // loop can then overwrite MuA[c] in place (carrying the old value along as "diag of the next column"
                 // made ptxas rotate the whole register array: one extra move per cell)
                 uint32_t dg[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const uint32_t s2 = *reinterpret_cast<const uint32_t*>(rowp + cc[c]);
-                    dg[c] = hb_add(c ? MuA[c - 1] : MdiagA, one, s2);
+                    if (PROF) {
+                        // one PRMT builds the sign-extended score pair from the row's two byte profiles; the packed
+                        // add keeps the halves apart (a negative low half would otherwise borrow from the high one)
+                        dg[c] = hb_add16x2(c ? MuA[c - 1] : MdiagA, hb_prmt(rprof.x, rprof.y, cc[c]));
+                    } else {
+                        const uint32_t s2 = *reinterpret_cast<const uint32_t*>(rowp + cc[c]);
+                        dg[c] = hb_add(c ? MuA[c - 1] : MdiagA, one, s2);
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {

@@ -44,7 +44,7 @@ __host__ __device__ inline bool shape_has_half(Shape s) {
 // Short pairs use few lanes per pair (the systolic pipeline costs L-1 fill/drain steps per pair) and many columns
 // per lane; wide pairs use a full warp, and pairs wider than 1024 columns loop over bands of the L=32 shape that
 // wastes the fewest padded columns.  half_ok: the packed 16 x 2 kernel is available for the call (16 lanes x 10
-// columns at 6 blocks/SM then beats 8 x 19).  c8: only shapes with C % 8 == 0 (an eight-column block is one trace
+// columns at 6 blocks/SM then beats 8 x 24 at 3 for 153-160 columns; up to 152 columns 8 x 19 at 4 blocks/SM is fastest).  c8: only shapes with C % 8 == 0 (an eight-column block is one trace
 // word, which the long-pair walker's window loader relies on) -- for pairs with len1 + len2 > LONG_WALK_LEN.
 __host__ __device__ inline Shape pick_shape_m(uint32_t m, bool half_ok, bool c8) {
     if (c8) {
@@ -56,7 +56,7 @@ __host__ __device__ inline Shape pick_shape_m(uint32_t m, bool half_ok, bool c8)
         if (m <= 768) return Shape{32, 24};
         if (m <= 1024) return Shape{32, 32};
     } else {
-        if (half_ok && m > 128 && m <= 160) return Shape{16, 10};
+        if (half_ok && m > 152 && m <= 160) return Shape{16, 10};
         if (m <= 64) return Shape{8, 8};
         if (m <= 96) return Shape{8, 12};
         if (m <= 128) return Shape{8, 16};
@@ -88,7 +88,7 @@ void launch_unpack(const UnpackArgs& a, cudaStream_t st);
 
 // K1 / K1h / K2 fills
 void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a);
-bool dispatch_k1h(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a);
+bool dispatch_k1h(Shape sh, bool track, bool prof8, dim3 grid, cudaStream_t st, const FillArgs& a);
 cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false);
 
 cudaError_t launch_k2f(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const FineArgs& a);

@@ -101,6 +101,8 @@ PARAMS = [
     ("semiglobal", "unit", -1, -1), ("semiglobal", "blosum62", -1, -2), ("semiglobal", "unit", 1, -1),
     ("fitting", "unit", -1, -1), ("fitting", "blosum62", -11, -1),
     ("overlap", "unit", -2, -2), ("overlap", "blosum62", -3, -1),
+    # -a - b > 127: the packed kernel takes its score pairs from the shared-memory table, not from byte profiles
+    ("global", "unit", -100, -60), ("semiglobal", "unit", -90, -50),
 ]
 
 
