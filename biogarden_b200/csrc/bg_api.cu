@@ -137,6 +137,7 @@ struct PinBuf {   // pinned host block from the global cache
 struct Chunk {
     uint32_t slot_begin, slot_end; uint64_t trace_words;
     std::vector<WaveAssign> assign; uint32_t n_rounds = 0, max_Q = 1;   // K2 launches only
+    uint32_t wpc = K2_WARPS;              // K2: warps per CTA of this launch (fewer when it has fewer bands than the machine has warps)
     uint32_t fine_bands = 0;              // > 0: K2f launch (k2f_fine.cuh, one column per lane) -- the widest pair's warps
     // bounded-memory traceback (k2_wave.cuh): pairs whose whole traces do not fit the budget; trace_words then
     // covers one row block of every pair
@@ -154,7 +155,7 @@ struct Plan {
     uint64_t cells_ckpt = 0;                    // of `cells`: pairs on the bounded-memory path (filled twice)
     uint64_t max_wave_slots = 0;      // largest K2 launch (slots), for the progress / candidate scratch
     uint64_t ckpt_elems = 0;          // bounded-memory traceback: int2 elements of the largest checkpoint array
-    int max_Q = 1;
+    uint64_t max_nw = K2_WARPS;   // K2: most workers (warps) any pair of any launch has
     uint32_t max_n = 0, max_m = 0;
     int32_t half_maxabs = 0;          // > 0: short classes were laid out for K1h (packed 16 x 2) with this max |score|
     bool wave_overlap = false;        // K2 launches were cut for TWO trace buffers: the walk of launch c runs next to the fill of launch c + 1
@@ -721,7 +722,14 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     if (maxb <= (uint32_t)std::max(1, ctx->num_sms) * 32u) wc.fine_bands = std::max(1u, maxb);
                 }
                 double total = 0;
-                for (uint32_t x = 0; x < ns; ++x) total += (double)dst[wc.slot_begin + x].n * (double)dst[wc.slot_begin + x].m;
+                uint64_t total_bands = 0;
+                for (uint32_t x = 0; x < ns; ++x) {
+                    total += (double)dst[wc.slot_begin + x].n * (double)dst[wc.slot_begin + x].m;
+                    total_bands += dst[wc.slot_begin + x].nbands;
+                }
+                // warps per CTA: the launch's bands spread over all SMs (a lone 10 kbp pair: 17 bands -> 17 CTAs of one warp)
+                static const int wpc_env = [] { const char* e = getenv("BG_K2_WPC"); return e ? std::max(1, std::min((int)K2_WARPS, atoi(e))) : 0; }();
+                wc.wpc = wpc_env ? (uint32_t)wpc_env : (uint32_t)std::min<uint64_t>(K2_WARPS, std::max<uint64_t>(1, (total_bands + n_cta - 1) / n_cta));
                 const double ideal = std::max(1.0, total / n_cta);                 // cells per CTA if the launch were perfectly balanced
                 std::vector<double> avail(n_cta, 0.0);
                 std::vector<std::vector<WaveAssign>> lists(n_cta);
@@ -732,11 +740,11 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                     // one warp per band: the whole pair is in flight at once (n + 64 * bands steps), and a warp whose pair
                     // has no band left moves on to its CTA's next pair.  Measured on cfg5 (31 pairs per launch): groups
                     // sized in proportion to the cells (one pair per group, ~5 CTAs) fill in 772 ms, 12 CTAs per pair in 682 ms.
-                    uint32_t q = std::max<uint32_t>(1, (d.nbands + K2_WARPS - 1) / K2_WARPS);
+                    uint32_t q = std::max<uint32_t>(1, (d.nbands + wc.wpc - 1) / wc.wpc);
                     (void)ideal;
-                    uint32_t q_cap = K2_MAX_Q;
+                    uint32_t q_cap = (wc.wpc == K2_WARPS) ? K2_MAX_Q : n_cta;
                     if (wc.ckpt_nb && ns == 1) {   // a single huge pair may own the machine; its boundary ring (q * 16 + 1 columns of n rows) is kept below 2 GiB
-                        const uint64_t ring_q = ((2ull << 30) / sizeof(int2)) / ((((uint64_t)d.n + 31ull) & ~31ull) * K2_WARPS);
+                        const uint64_t ring_q = ((2ull << 30) / sizeof(int2)) / ((((uint64_t)d.n + 31ull) & ~31ull) * wc.wpc);
                         q_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_cta, ring_q));
                     }
                     q = std::min<uint32_t>(std::min<uint32_t>(q, q_cap), n_cta);
@@ -751,14 +759,14 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
                         avail[order[r]] = start + cells / q;
                     }
                     wc.max_Q = std::max(wc.max_Q, q);
-                    d.bnd_off = bnd_off; bnd_off += ((uint64_t)q * K2_WARPS + 1) * (((uint64_t)d.n + 31ull) & ~31ull);
+                    d.bnd_off = bnd_off; bnd_off += ((uint64_t)q * wc.wpc + 1) * (((uint64_t)d.n + 31ull) & ~31ull);
                 }
                 wc.n_rounds = 0;
                 for (auto& l : lists) wc.n_rounds = std::max<uint32_t>(wc.n_rounds, (uint32_t)l.size());
                 wc.assign.assign((size_t)wc.n_rounds * n_cta, WaveAssign{0, 0, 0});
                 for (uint32_t c = 0; c < n_cta; ++c)
                     for (size_t r = 0; r < lists[c].size(); ++r) wc.assign[r * n_cta + c] = lists[c][r];
-                P.max_Q = std::max<int>(P.max_Q, (int)wc.max_Q);
+                P.max_nw = std::max<uint64_t>(P.max_nw, (uint64_t)wc.max_Q * wc.wpc);
             }
         }
         lap("class slots");
@@ -1137,7 +1145,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
         ok = ok && ws.pad.ensure(std::max<uint64_t>(1, P.pad_bytes));
     }
     if (P.max_wave_slots) {
-        const uint64_t nw = (uint64_t)P.max_Q * K2_WARPS;
+        const uint64_t nw = P.max_nw;
         // progress counters, then one "workers done" counter per pair
         ok = ok && ws.progress.ensure(P.max_wave_slots * (nw + 1) * 8 + (2 * P.max_wave_slots + 4) * 4) && ws.cand.ensure(P.max_wave_slots * nw * sizeof(WaveCand));
     }
@@ -1207,7 +1215,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 CU_TRY(ctx, cudaMemsetAsync(ws.wstate.p, 0, ns * sizeof(WalkState), st));
                 CU_TRY(ctx, cudaMemcpyAsync(ws.assign.p, ch.assign.data(), ch.assign.size() * sizeof(WaveAssign), cudaMemcpyHostToDevice, st));
                 CU_TRY(ctx, cudaMemcpyAsync(ws.ckslots.p, ch.ck_table.data(), ch.ck_table.size() * sizeof(CkptSlot), cudaMemcpyHostToDevice, st));
-                const uint64_t nw = (uint64_t)ch.max_Q * K2_WARPS;
+                const uint64_t nw = (uint64_t)ch.max_Q * ch.wpc;
                 const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
                 WaveArgs wa; wa.f = fa; wa.progress = ws.progress.as<unsigned long long>(); wa.cand = ws.cand.as<WaveCand>();
                 wa.assign = ws.assign.as<WaveAssign>(); wa.n_rounds = ch.n_rounds;
@@ -1227,7 +1235,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                         CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + (2 * (uint64_t)ns + 4) * 4, st));
                         wa.cks = ws.ckslots.as<CkptSlot>() + (size_t)l * ns;
                         wa.f.want_trace = l ? 1 : 0; wa.ckpt_write = l ? 0 : 1; wa.write_end = l ? 0 : 1;
-                        CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, pp.smem, st, wa, true));
+                        CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, (int)ch.wpc, pp.smem, st, wa, true));
                     }
                     if (l) {
                         Phase ph(ws, 2);
@@ -1258,7 +1266,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 Phase ph(ws, 1);
                 CU_TRY(ctx, launch_k2f(pp.local, pp.prof4, n_cta, Wc, pp.smem, st, fx));
             } else if (lc.wave) {
-                const uint64_t nw = (uint64_t)ch.max_Q * K2_WARPS;
+                const uint64_t nw = (uint64_t)ch.max_Q * ch.wpc;
                 const uint64_t prog_bytes = (uint64_t)ns * (nw + 1) * 8;
                 CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + (2 * (uint64_t)ns + 4) * 4, st));
                 if (!ws.assign.ensure(std::max<size_t>(1, ch.assign.size()) * sizeof(WaveAssign))) { ctx->set_error("device allocation failed (K2 assignment)"); return BG_ENOMEM; }
@@ -1269,7 +1277,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 wa.done = reinterpret_cast<uint32_t*>(ws.progress.as<unsigned char>() + prog_bytes);
                 wa.next_band = wa.done + ns + 2;
                 Phase ph(ws, 1);
-                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, pp.smem, st, wa));
+                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, (int)ch.wpc, pp.smem, st, wa));
             } else if (lc.half) {
                 fst = (st2 && ((chunk_no + parity) & 1)) ? st2 : st;
                 Phase ph(ws, 1, fst);

@@ -13,6 +13,10 @@
 //     star, at band granularity, with the diagonal tiles staged through registers / L2;
 //   * the launch is cooperative, so all workers are co-resident and the spin waits cannot deadlock;
 //     the last worker to finish a pair merges the workers' end-cell candidates;
+//   * a launch with fewer bands than 16 warps per SM (a lone 10 kbp pair has 17) uses fewer warps per CTA, down to
+//     one, so that the bands spread over the SMs: 16 warps on one SM share its four schedulers (19 instructions per
+//     cell x 4 warps per scheduler = ~80 cycles per cell and warp), a warp alone on its scheduler runs at the
+//     latency of the dependent chain;
 //   * the grid is persistent (one CTA per SM) and every CTA walks its own list of (pair, group rank,
 //     group size) assignments built by the host (WaveAssign): groups are sized in proportion to the
 //     pairs' cell counts so that the pairs of a launch finish together, and a CTA moves on to its next
@@ -78,8 +82,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
     const WaveAssign as = W.assign[(uint64_t)rd * gridDim.x + blockIdx.x];
     if (as.Q == 0) continue;
     const uint32_t slot = as.slot;
-    const uint32_t Q = as.Q, NW = Q * K2_WARPS, R = NW + 1;
-    const uint32_t wk = (uint32_t)as.rank * K2_WARPS + (threadIdx.x >> 5);
+    const uint32_t wpc = blockDim.x >> 5;   // warps per CTA: K2_WARPS, fewer when the launch has fewer bands than the machine has warps
+    const uint32_t Q = as.Q, NW = Q * wpc, R = NW + 1;
+    const uint32_t wk = (uint32_t)as.rank * wpc + (threadIdx.x >> 5);
     const PairDesc d = A.desc[slot];
     CkptSlot cs; cs.ck_off = 0; cs.ck_stride = cs.row0 = cs.nrows = 0; cs.every = 1;
     if (CKPT) cs = W.cks[slot];

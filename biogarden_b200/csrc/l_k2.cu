@@ -10,10 +10,10 @@
 namespace bg {
 
 template <class Kern>
-static cudaError_t launch_k2_impl(Kern kern, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a) {
+static cudaError_t launch_k2_impl(Kern kern, int n_cta, int wpc, size_t smem, cudaStream_t st, const WaveArgs& a) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_cta);          // one CTA per SM (launch bounds: 1 block of 16 warps per SM)
-    cfg.blockDim = dim3(K2_WARPS * 32);
+    cfg.blockDim = dim3((unsigned)wpc * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -23,21 +23,21 @@ static cudaError_t launch_k2_impl(Kern kern, int n_cta, size_t smem, cudaStream_
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt) {
+cudaError_t launch_k2(bool local, bool prof4, int n_cta, int wpc, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt) {
     if (ckpt) {
         if (local) {
-            if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true, true>, n_cta, smem, st, a);
-            return launch_k2_impl(k2_wave<WAVE_C, true, false, true>, n_cta, smem, st, a);
+            if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true, true>, n_cta, wpc, smem, st, a);
+            return launch_k2_impl(k2_wave<WAVE_C, true, false, true>, n_cta, wpc, smem, st, a);
         }
-        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true, true>, n_cta, smem, st, a);
-        return launch_k2_impl(k2_wave<WAVE_C, false, false, true>, n_cta, smem, st, a);
+        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true, true>, n_cta, wpc, smem, st, a);
+        return launch_k2_impl(k2_wave<WAVE_C, false, false, true>, n_cta, wpc, smem, st, a);
     }
     if (local) {
-        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_cta, smem, st, a);
-        return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_cta, smem, st, a);
+        if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true>, n_cta, wpc, smem, st, a);
+        return launch_k2_impl(k2_wave<WAVE_C, true, false>, n_cta, wpc, smem, st, a);
     }
-    if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_cta, smem, st, a);
-    return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_cta, smem, st, a);
+    if (prof4) return launch_k2_impl(k2_wave<WAVE_C, false, true>, n_cta, wpc, smem, st, a);
+    return launch_k2_impl(k2_wave<WAVE_C, false, false>, n_cta, wpc, smem, st, a);
 }
 
 template <class Kern>

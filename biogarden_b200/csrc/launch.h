@@ -89,7 +89,7 @@ void launch_unpack(const UnpackArgs& a, cudaStream_t st);
 // K1 / K1h / K2 fills
 void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a);
 bool dispatch_k1h(Shape sh, bool track, bool prof8, dim3 grid, cudaStream_t st, const FillArgs& a);
-cudaError_t launch_k2(bool local, bool prof4, int n_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false);
+cudaError_t launch_k2(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false);
 
 cudaError_t launch_k2f(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const FineArgs& a);
 
