@@ -175,6 +175,7 @@ struct WorkSet {
     uint64_t split_cap_words = (6ull << 30) / 4;   // all launches of a plan get their own trace region up to this total
     int launch_parity = -1;               // host-buffer pipeline: >= 0 -> this item's first fill goes to the main (0) or the second (1) fill stream, so that
                                           // the fills of consecutive items alternate and the tail of one overlaps the head of the next
+    cudaStream_t aux[2] = {nullptr, nullptr};   // edit-distance pipeline: the K4b launches of a chunk's three classes run side by side (created on first use)
     cudaStream_t fill2_stream = nullptr;  // host-buffer pipeline: every other fill launch of a chunk goes here, so that the tail of
                                           // one length class's launch overlaps the head of the next (their traces are disjoint)
     BlockCache* cache = nullptr;
@@ -804,7 +805,7 @@ struct ClassStat {
 struct BatchScan {
     bool monotone = true, fitting_violation = false, has_wide = false;
     uint32_t class_mask = 0;          // length classes present (by len2)
-    uint64_t max_len_sum = 0;
+    uint64_t max_len_sum = 0, max_m = 0;
     std::vector<double> block_cost;   // per SCAN_BLOCK pairs
     bool with_stats = false;          // block_cls filled (alignment calls with traceback)
     bool half_ok = false; int force_si = -1;
@@ -856,6 +857,7 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                                            m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
                 }
                 P.max_len_sum = std::max(P.max_len_sum, n + m);
+                P.max_m = std::max(P.max_m, m);
                 cost += (double)k * ((double)n * (double)m + 64.0);
             };
             for (uint64_t q = blk * SCAN_BLOCK; q < q_hi; ++q) {
@@ -883,6 +885,7 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
         S.has_wide = S.has_wide || P.has_wide;
         S.class_mask |= P.class_mask;
         S.max_len_sum = std::max(S.max_len_sum, P.max_len_sum);
+        S.max_m = std::max(S.max_m, P.max_m);
     }
 }
 
@@ -1319,7 +1322,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 if (overlap) ev_walk_done[buf] = pb;
             }
             CU_TRY(ctx, cudaGetLastError());
-            ctx->launches += 2;
+            ctx->launches += 3;
         }
     }
     if (overlap)
@@ -1387,7 +1390,7 @@ int run_edit(bg_ctx* ctx, WorkSet& ws, const uint8_t* residues, const PairDesc* 
                 MyersArgs ma;
                 ma.desc = desc + ch.slot_begin; ma.n_slots = ns; ma.residues = residues; ma.lut = ws.codes.as<uint8_t>();
                 ma.cdesc = P.compact ? reinterpret_cast<const MyersSlot*>(desc) + ch.slot_begin : nullptr;
-                ma.out = out; ma.err_flag = ws.err.as<uint32_t>();
+                ma.out = out; ma.err_flag = ws.err.as<uint32_t>(); ma.cls_count = nullptr; ma.cls = 0;
                 launch_myers(lc.myers_W, ns, ws.stream, ma);
             } else {
                 ea.desc = desc + ch.slot_begin; ea.n_slots = ns;
@@ -1446,6 +1449,7 @@ void bg_destroy(bg_ctx* ctx) {
             for (auto e : ws.ev_pool) cudaEventDestroy(e);
             if (ws.ev_scan) cudaEventDestroy(ws.ev_scan);
             if (ws.walk_stream) cudaStreamDestroy(ws.walk_stream);
+            for (cudaStream_t a : ws.aux) if (a) cudaStreamDestroy(a);
             if (ws.stream) cudaStreamDestroy(ws.stream);
         }
         if (dv.cache) { dv.cache->trim(); delete dv.cache; dv.cache = nullptr; }
@@ -2304,6 +2308,230 @@ int device_pipeline(AlignJob& J, int d) {
 
 constexpr int EDIT_RETRY_GENERAL = -77;   // internal: a byte outside the sampled 4-symbol alphabet turned up
 
+
+// bg_edit_distance_batch when every pair fits the bit-parallel kernel (<= 4 distinct bytes, len2 <= 320): the chunk's
+// launch slots are built on the device from its offsets (k0_eplan.cuh), so the host does nothing per pair after the
+// scan.  Per chunk: H2D (residues, packed or not, + 16 B/pair offsets) | K0e + the three K4b launches on the work
+// set's own stream (chunks overlap on the GPU) | D2H of 8 B/pair.  With the host planner (edit_pipeline below, still
+// used for richer alphabets and longer pairs) cfg3 was bound by ~35 ns per pair and core of planning.
+int edit_pipeline_dev(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, uint64_t* out, const uint8_t* lut) {
+    Device& dv = ctx->devs[d];
+    if (cudaSetDevice(dv.ordinal) != cudaSuccess) { ctx->set_error("cudaSetDevice failed"); return BG_ECUDA; }
+    const uint64_t* off = in->seq_off;
+    // Chunks: equal pair counts (the host does not read the offsets on this path).  A chunk's K4b launches take ~0.7-0.9 ms
+    // whatever its size below one wave of threads (one thread per pair, 300 k thread slots): few, large chunks -- the first one
+    // half size so that the GPU starts early.
+    static const int edit_chunks = [] { const char* e = getenv("BG_EDIT_CHUNKS_DEV"); return e ? std::max(1, atoi(e)) : 12; }();
+    std::vector<uint64_t> cb{lo};
+    {
+        const uint64_t n_all = hi - lo;
+        const uint64_t k = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)edit_chunks, (n_all + 32767) / 32768));
+        const uint64_t per = std::max<uint64_t>(1, (2 * n_all + 2 * k - 2) / (2 * k - 1));   // first chunk per / 2, then k - 1 chunks of per
+        uint64_t at = lo + std::min(n_all, std::max<uint64_t>(1, per / 2));
+        while (at < hi) { cb.push_back(at); at += per; }
+        cb.push_back(hi);
+    }
+    // sanity of the chunk boundaries (the pairs in between are validated on the device): monotone, and no chunk so large
+    // that it cannot be a batch of short pairs -- anything else goes to the general path, which scans the offsets
+    for (size_t c = 0; c + 1 < cb.size(); ++c) {
+        const uint64_t o_lo = off[2 * cb[c]], o_hi = off[2 * cb[c + 1]];
+        if (o_hi < o_lo || o_hi - o_lo > (cb[c + 1] - cb[c]) * 65536ull + (1ull << 20)) return EDIT_RETRY_GENERAL;
+    }
+    const int nchunks = (int)cb.size() - 1;
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    static const bool no_stage = getenv("BG_NO_STAGE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    // pageable caller memory is staged into pinned buffers by pool tasks, chunk by chunk (see host_is_pageable)
+    const bool stage_res = !no_stage && hi > lo && host_is_pageable(in->residues);
+    // len1 ranges of the device-side counting sort: 64 ranges up to ~1.25 x the longest len1 of a sample (longer ones share the last range)
+    uint32_t n_shift = 0;
+    {
+        uint64_t max_n = 1;
+        const uint64_t n_all = hi - lo, stride = std::max<uint64_t>(1, n_all / 512);
+        for (uint64_t q = lo; q < hi; q += stride) max_n = std::max(max_n, off[2 * q + 1] - off[2 * q]);
+        max_n += max_n / 4;
+        while (n_shift < 32 && (max_n >> n_shift) >= 64) ++n_shift;
+    }
+    const bool stage_off = !no_stage && hi > lo && host_is_pageable(off);
+    struct Staged { PinBuf off, res; int rc = BG_OK; TaskHandle th; };
+    std::vector<Staged> pre(nchunks);
+    if (stage_res || stage_off)
+        for (int c = 0; c < nchunks; ++c)
+            pre[c].th = host_pool().submit([&, c] {
+                const uint64_t lo2 = cb[c], n = cb[c + 1] - cb[c];
+                if (stage_off) {
+                    if (!pre[c].off.ensure((2 * n + 1) * 8)) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+                    memcpy(pre[c].off.p, off + 2 * lo2, (2 * n + 1) * 8);
+                }
+                if (stage_res) {
+                    uint64_t b0, b1; host_byte_range(in->packing, off[2 * lo2], off[2 * (lo2 + n)], b0, b1);
+                    if (!pre[c].res.ensure(b1 - b0 + 16)) { ctx->set_error("pinned staging allocation failed"); pre[c].rc = BG_ENOMEM; return; }
+                    memcpy(pre[c].res.p, in->residues + b0, b1 - b0);
+                }
+            });
+    cudaStream_t st_h2d = dv.ws[0].walk_stream, st_d2h = dv.ws[1].walk_stream;
+    for (int s = 0; s < PIPE_DEPTH; ++s) dv.ws[s].reset_events();
+    cudaEvent_t ev_h2d[PIPE_DEPTH], ev_comp[PIPE_DEPTH];
+    for (int s = 0; s < PIPE_DEPTH; ++s) {
+        cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_comp[s], cudaEventDisableTiming);
+    }
+    PinBuf host_out[PIPE_DEPTH];      // `out` is caller memory of unknown kind: results are staged in pinned memory per work set
+    PinBuf lut_pin;
+    if (!lut_pin.ensure(256)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+    memcpy(lut_pin.p, lut, 256);
+
+    std::mutex mu; std::condition_variable cv;
+    int issued = 0, finished = 0; bool issuer_done = false;
+    std::atomic<int> rc_shared{BG_OK};
+    std::thread finisher([&] {
+        cudaSetDevice(dv.ordinal);
+        for (int c = 0;; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return issued > c || issuer_done; });
+                if (issued <= c) break;
+            }
+            const int s = c % PIPE_DEPTH;
+            WorkSet& ws = dv.ws[s];
+            int rc = BG_OK;
+            if (cudaEventSynchronize(ws.ev_scan) != cudaSuccess) { ctx->set_error("cudaEventSynchronize failed"); rc = BG_ECUDA; }
+            const uint32_t* sc = reinterpret_cast<const uint32_t*>(ws.scalars.as<uint64_t>() + 1);
+            // a byte outside the alphabet, offsets that are not monotone, or a pair K4b / the 16-byte slot cannot take:
+            // the general path (which scans the offsets on the host and reports errors) redoes the batch
+            if (!rc && ((sc[0] & 6u) || sc[1])) rc = EDIT_RETRY_GENERAL;
+            if (!rc) {
+                const uint64_t c_lo = cb[c], c_n = cb[c + 1] - cb[c];
+                memcpy(out + c_lo, host_out[s].p, c_n * 8);
+                ctx->d2h += c_n * 8;
+                const uint64_t cells = ws.scalars.as<uint64_t>()[2];
+                static std::mutex timing_mu;   // several devices' finishers add to the same counters
+                std::lock_guard<std::mutex> lk(timing_mu);
+                ctx->timing.cells += cells; ctx->timing.cells_bitparallel += cells;
+            } else {
+                int expect = BG_OK; rc_shared.compare_exchange_strong(expect, rc);
+            }
+            if (prof) fprintf(stderr, "[bgalign]   edit chunk %d results on the host at %.2f ms\n", c, since());
+            { std::lock_guard<std::mutex> lk(mu); finished = c + 1; }
+            cv.notify_all();
+        }
+    });
+
+    auto issue = [&](int s, int c) -> int {
+        WorkSet& ws = dv.ws[s];
+        const uint64_t c_lo = cb[c], n = cb[c + 1] - cb[c];
+        const uint64_t base = off[2 * c_lo], nres = off[2 * (c_lo + n)] - base;
+        if (n >= 0x7FFFFFF0ull) { ctx->set_error("too many pairs in one pipeline chunk"); return BG_EINVAL_ARG; }
+        const size_t scratch_bytes = edit_plan_scratch_bytes((uint32_t)n);
+        if (!host_out[s].ensure(std::max<uint64_t>(1, n) * 8) || !ws.scalars.ensure(32)) { ctx->set_error("pinned staging allocation failed"); return BG_ENOMEM; }
+        if (pre[c].th.joinable()) pre[c].th.join();
+        if (pre[c].rc) return pre[c].rc;
+        if (!ws.residues.ensure(nres + 16) || !ws.desc.ensure(std::max<uint64_t>(1, n) * sizeof(MyersSlot)) || !ws.out64.ensure(std::max<uint64_t>(1, n) * 8) ||
+            !ws.poff.ensure((2 * n + 1) * 8) || !ws.psort.ensure(scratch_bytes) || !ws.err.ensure(32) || !ws.codes.ensure(512)) {
+            ctx->set_error("device allocation failed (pipeline buffers)"); return BG_ENOMEM;
+        }
+        if (c < PIPE_DEPTH) CU_TRY(ctx, cudaMemcpyAsync(ws.codes.p, lut_pin.p, 256, cudaMemcpyHostToDevice, st_h2d));   // once per work set and call
+        uint64_t res_bytes = 0;
+        {
+            uint64_t hb0, hb1; host_byte_range(in->packing, base, base + nres, hb0, hb1);
+            int urc = upload_residues(ctx, stage_res ? (const uint8_t*)pre[c].res.p : in->residues + hb0, in->packing, in->alphabet, base, base + nres,
+                                      ws.packed, ws.residues.as<uint8_t>(), st_h2d, &res_bytes);
+            if (urc) return urc;
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(ws.poff.p, stage_off ? (const void*)pre[c].off.p : (const void*)(off + 2 * c_lo), (2 * n + 1) * 8, cudaMemcpyHostToDevice, st_h2d));
+        CU_TRY(ctx, cudaEventRecord(ev_h2d[s], st_h2d));
+        ctx->h2d += res_bytes + (2 * n + 1) * 8;
+        cudaStream_t st = ws.stream;
+        CU_TRY(ctx, cudaStreamWaitEvent(st, ev_h2d[s], 0));
+        // err words: [0] K4b's flags, [1..4] the planner's class histogram ([4] = pairs that do not fit)
+        // (no memsets / small copies on the compute streams: they may be queued on a copy engine behind the next chunks' uploads)
+        uint32_t* errw = ws.err.as<uint32_t>();
+        {
+            Phase ph(ws, 5);
+            EditPlanArgs pa;
+            pa.off = ws.poff.as<uint64_t>(); pa.base = base; pa.n_pairs = (uint32_t)n; pa.hist = nullptr; pa.cursor = nullptr;
+            pa.n_shift = n_shift; pa.slots = ws.desc.as<MyersSlot>(); pa.cls_count = errw + 1;
+            CU_TRY(ctx, launch_edit_plan(pa, ws.psort.p, scratch_bytes, errw, st));
+            ctx->launches += 3;
+        }
+        {
+            // the three classes are independent and each is a partial wave of a latency-bound kernel (one thread per pair):
+            // they run side by side on the work set's stream and its two auxiliary streams
+            for (cudaStream_t& a : ws.aux)
+                if (!a && cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess) { ctx->set_error("cudaStreamCreate failed"); return BG_ECUDA; }
+            MyersArgs ma;
+            ma.desc = nullptr; ma.cdesc = ws.desc.as<MyersSlot>(); ma.n_slots = (uint32_t)n; ma.residues = ws.residues.as<uint8_t>();
+            ma.lut = ws.codes.as<uint8_t>(); ma.out = ws.out64.as<uint64_t>(); ma.err_flag = errw; ma.cls_count = errw + 1;
+            static const int Ws[3] = {4, 8, 10};
+            cudaEvent_t ev_plan = ws.get_event();
+            CU_TRY(ctx, cudaEventRecord(ev_plan, st));
+            for (uint32_t k = 0; k < 3; ++k) {
+                cudaStream_t sk = k ? ws.aux[k - 1] : st;
+                if (k) CU_TRY(ctx, cudaStreamWaitEvent(sk, ev_plan, 0));
+                {
+                    Phase ph(ws, 1, sk);
+                    ma.cls = k;
+                    launch_myers(Ws[k], (uint32_t)n, sk, ma);
+                }
+                ctx->launches++;
+                if (k) {
+                    cudaEvent_t ev_k = ws.get_event();
+                    CU_TRY(ctx, cudaEventRecord(ev_k, sk));
+                    CU_TRY(ctx, cudaStreamWaitEvent(st, ev_k, 0));
+                }
+            }
+            CU_TRY(ctx, cudaGetLastError());
+        }
+        CU_TRY(ctx, cudaEventRecord(ev_comp[s], st));
+        CU_TRY(ctx, cudaStreamWaitEvent(st_d2h, ev_comp[s], 0));
+        if (n) CU_TRY(ctx, cudaMemcpyAsync(host_out[s].p, ws.out64.p, n * 8, cudaMemcpyDeviceToHost, st_d2h));
+        uint32_t* sc = reinterpret_cast<uint32_t*>(ws.scalars.as<uint64_t>() + 1);
+        CU_TRY(ctx, cudaMemcpyAsync(sc, errw, 4, cudaMemcpyDeviceToHost, st_d2h));
+        CU_TRY(ctx, cudaMemcpyAsync(sc + 1, errw + 4, 4, cudaMemcpyDeviceToHost, st_d2h));
+        CU_TRY(ctx, cudaMemcpyAsync(ws.scalars.as<uint64_t>() + 2, ws.psort.as<uint32_t>() + 254, 8, cudaMemcpyDeviceToHost, st_d2h));   // the chunk's cells (k_eplan_count)
+        CU_TRY(ctx, cudaEventRecord(ws.ev_scan, st_d2h));
+        return BG_OK;
+    };
+
+    int rc_all = BG_OK;
+    for (int c = 0; c < nchunks && rc_all == BG_OK; ++c) {
+        const int s = c % PIPE_DEPTH;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return finished >= c - PIPE_DEPTH + 1; });
+        }
+        rc_all = rc_shared.load();
+        if (rc_all) break;
+        const double t0 = prof ? since() : 0;
+        rc_all = issue(s, c);
+        if (prof) fprintf(stderr, "[bgalign]   edit chunk %d (%llu pairs, device plan) issued %.2f .. %.2f ms\n", c, (unsigned long long)(cb[c + 1] - cb[c]), t0, since());
+        if (rc_all) break;
+        { std::lock_guard<std::mutex> lk(mu); issued = c + 1; }
+        cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); issuer_done = true; }
+    cv.notify_all();
+    finisher.join();
+    if (rc_all == BG_OK) rc_all = rc_shared.load();
+    cudaStreamSynchronize(st_h2d); cudaStreamSynchronize(st_d2h);
+    for (int s = 0; s < PIPE_DEPTH; ++s) cudaStreamSynchronize(dv.ws[s].stream);
+    if (prof && !dv.ws[0].evs.empty()) {   // GPU-side timeline of the kernels, relative to the first one
+        cudaEvent_t e0 = dv.ws[0].evs.front().a;
+        for (int s = 0; s < PIPE_DEPTH; ++s)
+            for (auto& ev : dv.ws[s].evs) {
+                float t_a = 0, dur = 0;
+                cudaEventElapsedTime(&t_a, e0, ev.a); cudaEventElapsedTime(&dur, ev.a, ev.b);
+                fprintf(stderr, "[bgalign]   gpu ws%d phase %d: start %.3f ms, %.3f ms\n", s, ev.phase, t_a, dur);
+            }
+    }
+    for (auto& h : host_out) h.release();
+    lut_pin.release();
+    for (auto& pb : pre) { if (pb.th.joinable()) pb.th.join(); pb.off.release(); pb.res.release(); }
+    for (int s = 0; s < PIPE_DEPTH; ++s) { cudaEventDestroy(ev_h2d[s]); cudaEventDestroy(ev_comp[s]); }
+    return rc_all;
+}
+
 int edit_pipeline(bg_ctx* ctx, int d, const bg_batch* in, uint64_t lo, uint64_t hi, const BatchScan& scan, uint64_t* out, const uint8_t* lut) {
     // Same three-stage structure as align_pipeline (H2D stream | compute stream | D2H stream, issuer + finisher
     // threads); the path is bound by the H2D copy of the residues (4 B of input per ~45 cells).
@@ -2737,12 +2965,11 @@ void bg_ops_result_free(bg_ops_result* r) {
 
 int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     if (!ctx || !in || (!out && in->n_pairs)) return BG_EINVAL_ARG;
-    BatchScan scan;
-    int rc = check_batch(ctx, in, &scan);
-    if (rc) return rc;
+    static const bool prof = getenv("BG_PROFILE_HOST") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto since_call = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
     const int nd = (int)ctx->devs.size();
-    const std::vector<uint64_t> bounds = (in->n_pairs < 8ull * SCAN_BLOCK * nd) ? shard_bounds(in, nd) : shard_bounds_from_scan(scan, in->n_pairs, nd);
-    rc = bg_sync(ctx);
+    int rc = bg_sync(ctx);
     if (rc) return rc;
     ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0;
     ctx->timing.cells = 0; ctx->timing.trace_bytes = 0; ctx->timing.cells_packed16 = 0; ctx->timing.cells_bitparallel = 0; ctx->timing.cells_refilled = 0;
@@ -2750,11 +2977,12 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
     // byte outside the sampled alphabet, in which case the batch is redone with the general kernel.
     uint8_t lut[256];
     bool use_lut = false;
-    if (in->n_pairs && !getenv("BG_NO_MYERS") && in->packing == BG_PACK_2BIT) {
+    if (in->n_pairs && !getenv("BG_NO_MYERS") && in->packing == BG_PACK_2BIT && in->alphabet) {
         uint64_t hist[256] = {0};
         for (int c = 0; c < 4; ++c) hist[in->alphabet[c]] = 1;      // a 2-bit batch has at most four letters by construction
         use_lut = make_edit_lut(hist, lut);
-    } else if (in->n_pairs && !getenv("BG_NO_MYERS") && in->packing == BG_PACK_NONE) {
+    } else if (in->n_pairs && !getenv("BG_NO_MYERS") && in->packing == BG_PACK_NONE && in->seq_off && in->residues &&
+               in->seq_off[2 * in->n_pairs] >= in->seq_off[0]) {
         const uint64_t b0 = in->seq_off[0], b1 = in->seq_off[2 * in->n_pairs];
         uint64_t hist[256] = {0};
         const uint64_t span = b1 - b0, take = std::min<uint64_t>(span, 1u << 16);   // (2 x 1 MiB of byte increments cost 2 ms)
@@ -2762,6 +2990,44 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
         for (uint64_t x = 0; x < take; ++x) hist[in->residues[b1 - 1 - x]]++;
         use_lut = span > 0 && make_edit_lut(hist, lut);
     }
+    // Fast path (<= 4 letters, every len2 <= 320): the host does not even read the offsets -- the device validates them,
+    // buckets the pairs and counts the cells (k0_eplan.cuh); anything it cannot take comes back as a retry and the batch
+    // goes through the general path below, which scans on the host and reports errors.
+    bool fast = use_lut && !ctx->host_plan && in->seq_off && in->residues;
+    if (fast) {   // a look at 512 pairs: batches with longer second sequences go straight to the general path
+        const uint64_t stride = std::max<uint64_t>(1, in->n_pairs / 512);
+        for (uint64_t q = 0; q < in->n_pairs && fast; q += stride) {
+            const uint64_t o0 = in->seq_off[2 * q], o1 = in->seq_off[2 * q + 1], o2 = in->seq_off[2 * q + 2];
+            fast = o0 <= o1 && o1 <= o2 && o2 - o1 <= 320;
+        }
+    }
+    if (fast) {
+        std::vector<uint64_t> eq(nd + 1);
+        for (int d = 0; d <= nd; ++d) eq[d] = in->n_pairs * (uint64_t)d / (uint64_t)nd;
+        std::vector<int> rcs(nd, BG_OK);
+        auto work = [&](int d) { rcs[d] = eq[d + 1] > eq[d] ? edit_pipeline_dev(ctx, d, in, eq[d], eq[d + 1], out, lut) : BG_OK; };
+        if (nd == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
+            for (auto& t : th) t.join();
+        }
+        if (prof) fprintf(stderr, "[bgalign] edit: device-planned pipelines done at %.2f ms\n", since_call());
+        bool retry = false;
+        for (int r : rcs) {
+            if (r == EDIT_RETRY_GENERAL) retry = true;
+            else if (r) return r;
+        }
+        if (!retry) return BG_OK;
+        rc = bg_sync(ctx);
+        if (rc) return rc;
+        ctx->h2d = 0; ctx->d2h = 0; ctx->launches = 0; ctx->timing.cells = 0; ctx->timing.cells_bitparallel = 0;
+    }
+    BatchScan scan;
+    rc = check_batch(ctx, in, &scan);
+    if (rc) return rc;
+    if (prof) fprintf(stderr, "[bgalign] edit: scan done at %.2f ms\n", since_call());
+    const std::vector<uint64_t> bounds = (in->n_pairs < 8ull * SCAN_BLOCK * nd) ? shard_bounds(in, nd) : shard_bounds_from_scan(scan, in->n_pairs, nd);
     for (int attempt = 0; attempt < 2; ++attempt) {
         std::vector<int> rcs(nd, BG_OK);
         auto work = [&](int d) { rcs[d] = edit_pipeline(ctx, d, in, bounds[d], bounds[d + 1], scan, out, use_lut ? lut : nullptr); };
@@ -2771,6 +3037,7 @@ int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out) {
             for (int d = 0; d < nd; ++d) th.emplace_back(work, d);
             for (auto& t : th) t.join();
         }
+        if (prof) fprintf(stderr, "[bgalign] edit: pipelines done at %.2f ms\n", since_call());
         bool retry = false;
         for (int r : rcs) {
             if (r == EDIT_RETRY_GENERAL) retry = true;

@@ -176,10 +176,26 @@ struct MyersArgs {
     const PairDesc* desc;
     const MyersSlot* cdesc;  // != nullptr: compact slots instead of desc
     uint32_t n_slots;
+    const uint32_t* cls_count;   // != nullptr (device-side plan, k0_eplan.cuh): [3] slots per class; this launch handles
+    uint32_t cls;                //   class `cls`, i.e. slots [sum(cls_count[0 .. cls)), + cls_count[cls]) of cdesc
     const uint8_t* residues;
     const uint8_t* lut;      // [256] byte -> code 0..3, 0xFF = not in the 4-symbol alphabet (device)
     uint64_t* out;           // [pair]
     uint32_t* err_flag;      // bit 1: a byte outside the alphabet was met (the caller then reruns with K4)
+};
+
+// K0e (k0_eplan.cuh): MyersSlot array of a pipeline chunk built on the device
+struct EditPlanArgs {
+    const uint64_t* off;     // [2n + 1] sequence offsets of the chunk (device copy of the caller's slice)
+    uint64_t base;           // off[0]: the chunk's residues start at device offset 0
+    uint32_t n_pairs;
+    uint32_t n_shift;        // len1 >> n_shift < 64 for (nearly) every pair: the len1 ranges of the counting sort
+    uint32_t* hist;          // [193] zeroed by the launcher: pairs per bucket (class x len1 range; [192]: pairs that do not fit K4b)
+    uint32_t* cursor;        // [193] zeroed by the launcher
+    MyersSlot* slots;        // [n] out
+    uint32_t* cls_count;     // [4] out: slots per class (W = 4, 8, 10); [3]: pairs that do not fit
+    unsigned long long* cells;   // out (zeroed by the launcher): sum of len1 * len2 over the pairs that fit
+    uint32_t* err_flag;      // bit 2: an offset pair that is not monotone
 };
 
 // ---- K5 (k5_distance.cuh) ----

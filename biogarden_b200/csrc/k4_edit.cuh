@@ -117,8 +117,13 @@ __global__ void __launch_bounds__(128) k4_myers(const MyersArgs A) {
     __shared__ uint8_t s_lut[256];
     for (int x = threadIdx.x; x < 256; x += blockDim.x) s_lut[x] = A.lut[x];
     __syncthreads();
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= A.n_slots) return;
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.cls_count) {   // device-side plan: this class's slot range comes from the histogram
+        uint32_t begin = 0;
+        for (uint32_t k = 0; k < A.cls; ++k) begin += A.cls_count[k];
+        if (slot >= A.cls_count[A.cls]) return;
+        slot += begin;
+    } else if (slot >= A.n_slots) return;
     struct { uint64_t a_off, b_off; uint32_t n, m, pair_id; } d;
     if (A.cdesc) {
         const MyersSlot c = A.cdesc[slot];

@@ -4,6 +4,7 @@
 #include "launch.h"
 #include "k0_plan.cuh"
 #include "k0_unpack.cuh"
+#include "k0_eplan.cuh"
 
 namespace bg {
 
@@ -60,6 +61,23 @@ cudaError_t launch_plan(PlanArgs a, bool sort, uint32_t n_slots, void* scratch, 
     e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const unsigned long long*)words, woff, (int)n_warps + 1, st);
     if (e != cudaSuccess) return e;
     k_plan_warp_write<<<(n_warps + 255) / 256, 256, 0, st>>>(a, woff, steps, n_warps);
+    return cudaGetLastError();
+}
+
+// K0e scratch: [hist 193 u32][cursor 193 u32], padded to 256 each; the cell counter lives in the last 8 bytes of the hist block
+size_t edit_plan_scratch_bytes(uint32_t) { return 2048; }
+cudaError_t launch_edit_plan(EditPlanArgs a, void* scratch, size_t scratch_bytes, uint32_t* err_flag, cudaStream_t st) {
+    if (!a.n_pairs) { k_eplan_zero<<<1, 32, 0, st>>>(a.cls_count, 4, err_flag); return cudaGetLastError(); }
+    static_assert(EPLAN_BUCKETS <= 254, "scratch layout");
+    if (scratch_bytes < 2048) return cudaErrorInvalidValue;
+    a.hist = reinterpret_cast<uint32_t*>(scratch);
+    a.cursor = a.hist + 256;
+    a.cells = reinterpret_cast<unsigned long long*>(a.hist + 254);
+    a.err_flag = err_flag;
+    k_eplan_zero<<<1, 256, 0, st>>>(a.hist, 512, err_flag);
+    const unsigned grid = (a.n_pairs + 255) / 256;
+    k_eplan_count<<<grid, 256, 0, st>>>(a);
+    k_eplan_scatter<<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -84,6 +84,9 @@ __host__ __device__ inline Shape pick_shape_m(uint32_t m, bool half_ok, bool c8)
 size_t plan_scratch_bytes(uint32_t n_pairs, uint32_t n_slots);
 cudaError_t launch_plan(PlanArgs a, bool sort, uint32_t n_slots, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+size_t edit_plan_scratch_bytes(uint32_t n_pairs);
+cudaError_t launch_edit_plan(EditPlanArgs a, void* scratch, size_t scratch_bytes, uint32_t* err_flag, cudaStream_t st);   // also clears *err_flag   // K0e (k0_eplan.cuh)
+
 void launch_unpack(const UnpackArgs& a, cudaStream_t st);
 
 // K1 / K1h / K2 fills

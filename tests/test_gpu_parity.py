@@ -560,6 +560,35 @@ def test_edit_distance_bit_parallel_and_fallback():
     r = ctx.edit_distance_device(db)
     assert np.array_equal(ctx.download_u64(r, batch.n_pairs), want)
     ctx.free_result(r); ctx.free_batch(db)
+    # every len2 <= 320: the chunk's launch slots are built on the device (k0_eplan.cuh); same results as with the
+    # host planner, for raw and for 2-bit packed residues, with empty sequences and len1 up to 700
+    seqs2 = []
+    for k in range(0, len(seqs), 2):
+        a_, b_ = seqs[k], seqs[k + 1]
+        seqs2 += [a_, b_] if len(b_) <= 320 else ([b_, a_] if len(a_) <= 320 else [a_[:300], b_[:320]])
+    batch2 = native.Batch.from_sequences(seqs2 * 6)     # 18 000 pairs: several pipeline chunks
+    assert int(np.diff(batch2.seq_off.astype(np.int64))[1::2].max()) <= 320
+    want3, _ = orc.edit_distance_batch(batch2.residues, batch2.seq_off, threads=orc.hw_threads(), lean=True)
+    got_dev = ctx.edit_distance_batch(batch2)
+    assert np.array_equal(got_dev, want3)
+    assert np.array_equal(ctx.edit_distance_batch(batch2.pack(2)), want3)
+    ctx.set_host_plan(True)
+    try:
+        assert np.array_equal(ctx.edit_distance_batch(batch2), want3)
+    finally:
+        ctx.set_host_plan(False)
+    # the device-planned path does not read the offsets on the host: a single long pair (len2 > 320) or a broken offset
+    # hidden between the pairs the host samples must be caught on the device and go through the general path
+    seqs3 = list(seqs2 * 6)
+    seqs3[2 * 7], seqs3[2 * 7 + 1] = seqs3[2 * 7] + b"ACGT" * 100, (seqs3[2 * 7 + 1] + b"TTGACA" * 80)
+    batch3 = native.Batch.from_sequences(seqs3)
+    want4, _ = orc.edit_distance_batch(batch3.residues, batch3.seq_off, threads=orc.hw_threads(), lean=True)
+    assert np.array_equal(ctx.edit_distance_batch(batch3), want4)
+    bad_off = batch2.seq_off.copy()
+    bad_off[2 * 11 + 1] = bad_off[2 * 11] - 1 if bad_off[2 * 11] > 0 else bad_off[2 * 11 + 2] + 1
+    from biogarden_b200.error import EngineError
+    with pytest.raises(EngineError):
+        ctx.edit_distance_batch(native.Batch(batch2.residues, bad_off))
     # fallback
     big = synth.make("cfg3_edit_100_300", n_pairs=30000)
     res = big.residues.copy()
