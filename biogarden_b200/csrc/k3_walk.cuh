@@ -56,14 +56,34 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     };
     const uint32_t CW = LT ? (HALF ? (uint32_t)((CT + 3) & ~3) : 0u) : (uint32_t)A.CW;
     uint64_t quad_idx = ~0ull; uint4 quad = make_uint4(0, 0, 0, 0);
+    // INC (K1h layout with compile-time geometry, the short-read case): the cell's coordinates in the trace -- lane wp,
+    // column wc of the lane, systolic step wt -- follow the walk incrementally, and the word index is kept as the sum of
+    // a term that changes with the 4-step row block (every 4th step), one that changes with the lane (every C-th
+    // column) and the column.  Recomputing the address from (k, l) every step (two divisions by the geometry, 64-bit
+    // multiplies) was most of the ~160 thread instructions a step cost (ncu: issue slots 54 % busy in a kernel that
+    // should only wait for memory).
+    constexpr bool INC = (LT != 0) && HALF;
+    uint32_t wc = 0, wt = 0, w_lane = 0, w_blk = 0, quad_i = 0xffffffffu;   // word offsets are relative to the pair's trace block (32 bits)
+    const uint32_t tgs = (uint32_t)A.tg_shift;
+    const uint4* const tquad = reinterpret_cast<const uint4*>(A.trace + (INC ? d.trace_off : 0));   // 16-byte aligned: the fill stores uint4 there
+    auto set_blk = [&]() {
+        const uint32_t tb = wt >> 2;
+        w_blk = (((tb >> tgs) * (32u * CW)) << tgs) + (tb & ((1u << tgs) - 1u)) * CW;
+    };
     auto nib_at = [&](uint32_t i, uint32_t j) -> uint32_t {   // i, j >= 1
+        if (INC) {
+            const uint32_t idx = w_lane + w_blk + wc;
+            const uint32_t q = idx >> 2;
+            if (q != quad_i) { quad_i = q; quad = __ldg(tquad + q); }
+            const uint32_t lo2 = (idx & 1u) ? quad.y : quad.x, hi2 = (idx & 1u) ? quad.w : quad.z;
+            return (((idx & 2u) ? hi2 : lo2) >> ((wt & 3u) * 4u + half * 16u)) & 15u;
+        }
         const uint32_t j0 = j - 1;
         if (CW) {   // K1h row blocks: a diagonal move goes to the previous word of the same 16-byte quad, which
                     // is kept in registers (2048 walks per SM touch 5 lines each: L1 cannot hold them, ncu 13 % hits)
             const uint32_t p = j0 / C, c = j0 - p * C;
             const uint32_t t = (i - 1) + p;
             const uint32_t tb = t >> 2;
-            const uint32_t tgs = (uint32_t)A.tg_shift;
             const uint64_t idx = d.trace_off + ((((uint64_t)(tb >> tgs) * 32u + lane_base + p) * CW) << tgs) + (tb & ((1u << tgs) - 1u)) * CW + c;
             const uint64_t q = idx >> 2;
             if (q != quad_idx) { quad_idx = q; quad = __ldg(reinterpret_cast<const uint4*>(A.trace) + q); }
@@ -78,10 +98,28 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     };
 
     uint32_t k = e.k, l = e.l, flags = 0;
+    // one row up / one column left, with the trace coordinates following (they are only read while k, l >= 1)
+    auto step_up = [&]() {
+        --k;
+        if (INC) { const uint32_t t0 = wt; --wt; if ((t0 & 3u) == 0u) set_blk(); }
+    };
+    auto step_left = [&]() {
+        --l;
+        if (INC) {
+            if (wc) --wc;
+            else { wc = C - 1u; w_lane -= CW << tgs; const uint32_t t0 = wt; --wt; if ((t0 & 3u) == 0u) set_blk(); }
+        }
+    };
     const bool colbr = (e.flags & 1u) != 0;
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:389-404
         if (colbr) { for (uint32_t i = n; i > k; --i) push(1u); }
         else       { for (uint32_t i = m; i > l; --i) push(2u); }
+    }
+    if (INC && k != 0 && l != 0) {
+        const uint32_t j0 = l - 1, wp = j0 / C;
+        wc = j0 - wp * C; wt = (k - 1) + wp;
+        w_lane = ((lane_base + wp) * CW) << tgs;
+        set_blk();
     }
     uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
     const uint32_t bound = 2u * (n + m) + 8u;
@@ -103,17 +141,17 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
             uint32_t t;   // 0 'R', 1 'X', 2 'Y'; m_trace borders: column 0 'X', then row 0 'Y' (aligner.rs:107-108)
             if (l == 0) t = 1; else if (k == 0) t = 2; else t = (nib & TR_YEQ) ? 2u : (nib & TR_XEQ);
             push(t);
-            if (t == 0) { --k; --l; }
-            else if (t == 1) { --k; cur = 1; }
-            else { --l; cur = 2; }
+            if (t == 0) { step_up(); step_left(); }
+            else if (t == 1) { step_up(); cur = 1; }
+            else { step_left(); cur = 2; }
         } else if (cur == 1) {
             if (interior && (nib & TR_XOPEN)) cur = 0;                 // x_trace borders stay 'I' (aligner.rs:52)
             else if (k == 0) { flags |= WALK_UNDERFLOW; break; }      // reference: seq1[usize::MAX] -> panic
-            else { push(1u); --k; }
+            else { push(1u); step_up(); }
         } else {
             if (interior && (nib & TR_YOPEN)) cur = 0;
             else if (l == 0) { flags |= WALK_UNDERFLOW; break; }
-            else { push(2u); --l; }
+            else { push(2u); step_left(); }
         }
     }
     if (mode == M_SEMIGLOBAL) {   // aligner.rs:417-428
