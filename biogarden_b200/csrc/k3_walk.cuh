@@ -74,9 +74,13 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
         if (INC) {
             const uint32_t idx = w_lane + w_blk + wc;
             const uint32_t q = idx >> 2;
-            if (q != quad_i) { quad_i = q; quad = __ldg(tquad + q); }
+            if (q != quad_i) {   // the pair's half of every word is moved down once per quad, not once per step
+                quad_i = q; quad = __ldg(tquad + q);
+                const uint32_t h16 = (threadIdx.x & 1u) * 16u;    // == half * 16 (H == 2): not kept in a register across the loop
+                quad.x >>= h16; quad.y >>= h16; quad.z >>= h16; quad.w >>= h16;
+            }
             const uint32_t lo2 = (idx & 1u) ? quad.y : quad.x, hi2 = (idx & 1u) ? quad.w : quad.z;
-            return (((idx & 2u) ? hi2 : lo2) >> ((wt & 3u) * 4u + half * 16u)) & 15u;
+            return (((idx & 2u) ? hi2 : lo2) >> ((wt & 3u) * 4u)) & 15u;
         }
         const uint32_t j0 = j - 1;
         if (CW) {   // K1h row blocks: a diagonal move goes to the previous word of the same 16-byte quad, which
@@ -124,6 +128,33 @@ __global__ void __launch_bounds__(128, K3_MINB) k3_walk(const WalkArgs A) {
     uint32_t cur = 0;   // 0 = 'M', 1 = 'X', 2 = 'Y'
     const uint32_t bound = 2u * (n + m) + 8u;
     uint32_t it = 0;
+    if (INC) {
+        // Interior cells, branch-free: the 32 walks of a warp are in different states, and the state machine below, written
+        // with branches, makes the warp run every arm in turn (ncu: 25 k warp instructions per warp of ~170-step walks,
+        // issue slots 54 % busy).  Here every step is the same instruction stream: the transition as selects, the op push
+        // and the coordinate updates predicated.  Borders (k == 0 or l == 0) and the end of the walk are left to the
+        // general loop, which continues from whatever state this one stops in.
+        const uint32_t lane_step = CW << tgs;
+        // (K1h never runs local mode, so there is no stop test; every second iteration at least emits, so the loop ends
+        //  after at most 2 (n + m) iterations without a hang counter)
+        while (k != 0 && l != 0) {
+            const uint32_t nib = nib_at(k, l);
+            const bool s0 = cur == 0;
+            const uint32_t op_m = (nib & TR_YEQ) ? 2u : (nib & TR_XEQ);           // aligner.rs:519-531: Y tested first
+            const bool open = ((cur == 1 ? TR_XOPEN : TR_YOPEN) & nib) != 0;     // aligner.rs:541, 566: the gap was opened here
+            const bool emit = s0 || !open;
+            const uint32_t op = s0 ? op_m : cur;
+            if (emit) push(op);
+            const uint32_t dk = (emit && op != 2u) ? 1u : 0u, dl = (emit && op != 1u) ? 1u : 0u;
+            const uint32_t wrap = (dl && wc == 0u) ? 1u : 0u;                     // leaving the lane: column C - 1 of the lane to the left, one step earlier
+            k -= dk; l -= dl;
+            wc = wrap ? C - 1u : wc - dl;
+            w_lane -= wrap ? lane_step : 0u;
+            wt -= dk + wrap;
+            set_blk();
+            cur = s0 ? op_m : (open ? 0u : cur);
+        }
+    }
     for (;; ++it) {
         if (it > bound) { flags |= WALK_HANG; break; }
         const bool interior = (k != 0 && l != 0);
