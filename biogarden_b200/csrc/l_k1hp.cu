@@ -14,6 +14,8 @@ constexpr int k1hp_minb(int C, bool track) { return C <= 10 ? 6 : C <= 12 ? 4 : 
 // -DBG_HBP_SWEEP and set BG_HBP_PIPES to repeat it):
 //   (8, 19) at 4 blocks/SM: 0x00 7.87 ms, 0x05 7.49, 0x15 7.43, 0x55 7.41, 0x44 7.40, 0x45 7.35, 0xD5 7.57, 0xFF 8.34
 //   (16, 10) at 6 blocks/SM: 0x00 9.20, 0x05 8.56, 0x15 8.34, 0x55 8.31, 0x57 8.45, 0x5F 8.72, 0xFF 9.49
+// Tried and dropped on (8, 19): the diagonal add as an IMAD on the FMA pipe (valid when every s - a - b >= 0): best split
+// 7.46 ms; M^ + (a - b) as VIADD.16x2 on the ALU pipe: best 7.78 ms -- it sits on the cell-to-cell dependency chain.
 constexpr int k1hp_pipes(int C) { return C >= 16 ? 0x45 : 0x55; }
 
 bool dispatch_k1hp(Shape sh, bool track, dim3 grid, cudaStream_t st, const FillArgs& a) {
