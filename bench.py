@@ -56,7 +56,7 @@ def ncu_traffic(kernel_prefix):
     """DRAM bytes per cell of the dominant kernel from the committed `ncu --set full` summary
     (profiles/ncu_traffic_r01.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch and the
     cells that launch processed); None when no capture of that kernel is on file."""
-    for name in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+    for name in ("ncu_traffic_r02b.json", "ncu_traffic_r02.json", "ncu_traffic_r01.json"):
         p = os.path.join(ROOT, "profiles", name)
         try:
             for e in json.load(open(p))["kernels"]:

@@ -994,6 +994,12 @@ bool plan_from_stats(const bg_ctx* ctx, const BatchScan& S, uint64_t lo, uint64_
     P.built = true;
     (void)ctx;
     need_sort = !(n_present == 1 && uniform_n);
+    // one class, one len1, and -- every len2 <= max_m, so equal sums mean equal terms -- one len2
+    static const bool no_uniform = getenv("BG_NO_UNIFORM_PLAN") != nullptr;
+    A.uniform = 0;
+    if (!need_sort && !no_uniform && A.n_cls == 1)
+        for (int si = 0; si < BG_N_SHAPES; ++si)
+            if (cls[si].count && cls[si].max_n > 0 && cls[si].cells == cls[si].count * (uint64_t)cls[si].max_n * (uint64_t)cls[si].max_m) A.uniform = 1;
     return true;
 }
 

@@ -44,6 +44,8 @@ struct PlanArgs {
     uint32_t n_pairs, n_cls;
     uint32_t half_ok;                // as in pick_shape_m
     int32_t force_si;                // >= 0: every pair uses this shape (bg_set_shape)
+    uint32_t uniform;                // 1: one class and every pair has the same len1 and the same len2 (read sets): descriptors are a
+                                     //    closed form of the pair index, written by ONE kernel (k_plan_uniform) instead of ten launches
     uint64_t* keys;                  // [2][n] sort keys: class rank << 32 | (0x7fffffff - len1)  (set by launch_plan)
     uint32_t* ids;                   // [2][n] pair ids
     PairDesc* desc;

@@ -98,6 +98,43 @@ __global__ void k_plan_write(const PlanArgs A, const uint64_t* keys, const uint3
     A.desc[c.slot_begin + (k - c.sorted_begin) + (s.holes - holes0)] = d;
 }
 
+// Uniform item (one class, one len1, one len2 -- a read set): no sort, no holes except behind the last pair, and every
+// running sum is index x constant.  One launch writes what k_plan_clear .. k_plan_warp_write produce (descriptor by
+// descriptor the same: bg_debug_plan_compare).  The ten launches of the general planner each wait for SM slots between
+// the blocks of the fill that runs next to them: 0.4-0.9 ms per item against ~0.1 ms of kernel time.
+__global__ void k_plan_uniform(const PlanArgs A) {
+    const PlanCls& c = A.cls[0];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.slot_cap) return;
+    PairDesc d;
+    d.a_off = d.b_off = d.trace_off = d.bnd_off = d.pad_off = 0; d.n = d.m = d.steps = d.nbands = 0; d.pair_id = 0xFFFFFFFFu; d.pad_ = 1u;
+    const uint32_t L = (uint32_t)c.L, C = (uint32_t)c.C, K = (C + 7u) / 8u, band_cols = L * C;
+    // lengths from pair 0 (all pairs are alike)
+    const uint64_t n0 = A.off[1] - A.off[0], m0 = A.off[2] - A.off[1];
+    const uint32_t nb0 = m0 ? (uint32_t)((m0 + band_cols - 1) / band_cols) : 0u;
+    if (s < c.count) {
+        const uint64_t o0 = A.off[2ull * s], o1 = A.off[2ull * s + 1];
+        d.a_off = o0 - A.base; d.b_off = o1 - A.base;
+        d.n = (uint32_t)n0; d.m = (uint32_t)m0; d.nbands = nb0;
+        d.pair_id = s;
+        d.pad_off = (uint64_t)s * (2ull * ((n0 + m0 + 3ull) & ~3ull) + 16ull);
+        d.bnd_off = (nb0 > 1u) ? (uint64_t)s * n0 : 0ull;
+    }
+    const uint32_t w = s / c.G2;
+    if (w * c.G2 < c.count) {        // the warp has at least one pair: every slot of it carries the warp's step count and trace offset
+        uint32_t steps; unsigned long long ww;
+        if (c.half) {
+            steps = (((uint32_t)n0 + L - 1u + HB_TB - 1u) / HB_TB) * HB_TB;
+            ww = (unsigned long long)((steps / HB_TB + HB_TG_MAX - 1u) / HB_TG_MAX) * HB_TG_MAX * 32ull * hb_words_per_lane_block((int)C);
+        } else {
+            steps = (uint32_t)n0 + L - 1u;
+            ww = (unsigned long long)nb0 * steps * K * 32ull;
+        }
+        if (steps) { d.steps = steps; d.trace_off = (unsigned long long)w * ww; }
+    }
+    A.desc[c.slot_begin + s] = d;
+}
+
 // warp w of the item (classes back to back, slot_cap / G2 warps each) -> (class, first slot)
 __device__ __forceinline__ bool plan_warp_locate(const PlanArgs& A, uint32_t w, uint32_t& cls, uint32_t& slot0) {
     uint32_t first = 0;

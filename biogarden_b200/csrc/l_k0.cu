@@ -42,6 +42,10 @@ cudaError_t launch_plan(PlanArgs a, bool sort, uint32_t n_slots, void* scratch, 
     uint32_t* steps = reinterpret_cast<uint32_t*>(p); p += al256((size_t)n_slots * 4);
     void* tmp = p;
     size_t tmp_bytes = scratch_bytes - (size_t)(p - reinterpret_cast<unsigned char*>(scratch));
+    if (a.uniform && a.n_cls == 1 && !sort) {
+        k_plan_uniform<<<(a.cls[0].slot_cap + 255) / 256, 256, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     a.keys = keys; a.ids = ids;
     k_plan_keys<<<(n + 255) / 256, 256, 0, st>>>(a);
     const uint64_t* ks = keys; const uint32_t* is = ids;

@@ -671,6 +671,9 @@ def test_device_planner_matches_host_planner(aligner):
     rng = random.Random(12)
     batches = {
         "cfg2": synth.make("cfg2_dna150_global", n_pairs=20000),
+        "cfg2_odd": synth.make("cfg2_dna150_global", n_pairs=20001),     # uniform chunk (k_plan_uniform), a hole behind the last pair
+        "uniform_multiband": native.synth_pairs(9, 0, 37, b"ACGT", 1500, 1500, True),  # uniform, two bands per pair (band scratch offsets)
+        "uniform_protein": native.synth_pairs(4, 0, 999, synth.PROTEIN, 300, 300, True),
         "cfg3": synth.make("cfg3_edit_100_300", n_pairs=70000),
         "cfg4": synth.make("cfg4_protein_local", n_pairs=3000),
         "ragged": _random_batch(rng, 5000, b"ACGT", 260),
@@ -680,7 +683,7 @@ def test_device_planner_matches_host_planner(aligner):
     ctx = aligner.context
     for name, batch in batches.items():
         for mode, scorer, a, b in (("global", "unit", -2, -1), ("local", "blosum62", -11, -1), ("semiglobal", "unit", -1, -1)):
-            if name == "cfg4" and scorer == "unit":
+            if name in ("cfg4", "uniform_protein") and scorer == "unit":
                 continue
             for shape in (None, (8, 19), (32, 8)):
                 if shape and name not in ("ragged", "cfg3"):
