@@ -442,6 +442,7 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
     uint32_t cls_min_n[MAX_SHAPES], cls_max_n[MAX_SHAPES] = {0}, cls_max_m[MAX_SHAPES] = {0};
     for (int s = 0; s < MAX_SHAPES; ++s) cls_min_n[s] = 0xFFFFFFFFu;
     uint32_t last_m = 0xFFFFFFFFu; int last_si = -1; bool last_long = false;
+    uint64_t wave_bands16 = 0, wave_cells = 0;    // K2 class: bands at WAVE_C columns per lane, cells
     for (uint64_t p = 0; p < n_pairs; ++p) {
         const uint64_t n = off[2 * p + 1] - off[2 * p], m = off[2 * p + 2] - off[2 * p + 1];
         if (n > 0x7FFFFFF0ull || m > 0x7FFFFFF0ull) { ctx->set_error("sequence longer than 2^31"); return BG_EUNSUPPORTED; }
@@ -454,12 +455,22 @@ int build_plan(bg_ctx* ctx, const uint64_t* off, uint64_t base, uint64_t n_pairs
             if (last_si < 0) { ctx->set_error("forced kernel shape is not compiled in"); return BG_EINVAL_ARG; }
         }
         cls[p] = (uint8_t)last_si; count[last_si]++;
+        if (last_si == wave_si) { wave_bands16 += (m + 32ull * WAVE_C - 1) / (32ull * WAVE_C); wave_cells += n * m; }
         P.cells += n * m;
         cls_min_n[last_si] = std::min<uint32_t>(cls_min_n[last_si], (uint32_t)n);
         cls_max_n[last_si] = std::max<uint32_t>(cls_max_n[last_si], (uint32_t)n);
         cls_max_m[last_si] = std::max<uint32_t>(cls_max_m[last_si], (uint32_t)m);
     }
     for (int s = 0; s < nshape; ++s) { P.max_n = std::max(P.max_n, cls_max_n[s]); P.max_m = std::max(P.max_m, cls_max_m[s]); }
+    // K2 with few long pairs (config #1: ONE pair of 17 bands): bands of 8 columns per lane instead of 16 -- twice the warps,
+    // half the work per step of each (a lone warp per SM runs at the latency of its cell-to-cell chain, so the step time is
+    // what counts).  Only when all of it fits one launch without the bounded-memory path, which is compiled for WAVE_C alone.
+    if (count[wave_si]) {
+        static const int narrow_env = [] { const char* e = getenv("BG_K2_NARROW"); return e ? atoi(e) : -1; }();
+        const bool fits = wave_cells / 8 + (1ull << 22) < wave_budget_words / 2;
+        const bool narrow = narrow_env >= 0 ? narrow_env != 0 : (wave_bands16 * 2 <= (uint64_t)std::max(1, ctx->num_sms));
+        if (narrow && fits && (int)count[wave_si] > ctx->fine_max_pairs) shapes[wave_si] = Shape{32, WAVE_C_NARROW};
+    }
     lap("pass 1");
     // pass 2: bucket pair ids per class
     std::vector<uint32_t>& ids = scratch.s->ids;
@@ -1244,13 +1255,13 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                         CU_TRY(ctx, cudaMemsetAsync(ws.progress.p, 0, prog_bytes + (2 * (uint64_t)ns + 4) * 4, st));
                         wa.cks = ws.ckslots.as<CkptSlot>() + (size_t)l * ns;
                         wa.f.want_trace = l ? 1 : 0; wa.ckpt_write = l ? 0 : 1; wa.write_end = l ? 0 : 1;
-                        CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, (int)ch.wpc, pp.smem, st, wa, true));
+                        CU_TRY(ctx, launch_k2(pp.local, pp.prof4, lc.sh.C, ctx->num_sms, (int)ch.wpc, pp.smem, st, wa, true));
                     }
                     if (l) {
                         Phase ph(ws, 2);
                         wk.cks = wa.cks; wk.last_launch = (l == NB) ? 1u : 0u;
                         static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
-                        launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, true, ns, st, wk);
+                        launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, WAVE_C, ns, st, wk);
                     }
                     CU_TRY(ctx, cudaGetLastError());
                 }
@@ -1286,7 +1297,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                 wa.done = reinterpret_cast<uint32_t*>(ws.progress.as<unsigned char>() + prog_bytes);
                 wa.next_band = wa.done + ns + 2;
                 Phase ph(ws, 1);
-                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, ctx->num_sms, (int)ch.wpc, pp.smem, st, wa));
+                CU_TRY(ctx, launch_k2(pp.local, pp.prof4, lc.sh.C, ctx->num_sms, (int)ch.wpc, pp.smem, st, wa));
             } else if (lc.half) {
                 fst = (st2 && ((chunk_no + parity) & 1)) ? st2 : st;
                 Phase ph(ws, 1, fst);
@@ -1318,7 +1329,7 @@ int run_align(bg_ctx* ctx, WorkSet& ws, const AlignIO& io, const Prepared& pp) {
                     // long pairs: one warp per pair with a trace window in shared memory; short pairs: one thread per pair
                     if (lc.long_walk) {
                         static const bool old_diag = [] { const char* e = getenv("BG_LONG_WALK"); return e && !strcmp(e, "diag"); }();
-                        launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, lc.sh.L == 32 && lc.sh.C == WAVE_C, ns, wst, wa);
+                        launch_long_walk(old_diag ? LW_DIAG : LW_SKEW, (lc.sh.L == 32 && (lc.sh.C == WAVE_C || lc.sh.C == WAVE_C_NARROW)) ? lc.sh.C : 0, ns, wst, wa);
                     }
                     else dispatch_walk(lc.sh, lc.half, ns, wst, wa);
                 }

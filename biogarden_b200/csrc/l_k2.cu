@@ -23,7 +23,17 @@ static cudaError_t launch_k2_impl(Kern kern, int n_cta, int wpc, size_t smem, cu
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-cudaError_t launch_k2(bool local, bool prof4, int n_cta, int wpc, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt) {
+cudaError_t launch_k2(bool local, bool prof4, int C, int n_cta, int wpc, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt) {
+    if (C == WAVE_C_NARROW) {
+        if (ckpt) return cudaErrorInvalidValue;        // the host never plans a bounded-memory launch on narrow bands
+        if (local) {
+            if (prof4) return launch_k2_impl(k2_wave<WAVE_C_NARROW, true, true>, n_cta, wpc, smem, st, a);
+            return launch_k2_impl(k2_wave<WAVE_C_NARROW, true, false>, n_cta, wpc, smem, st, a);
+        }
+        if (prof4) return launch_k2_impl(k2_wave<WAVE_C_NARROW, false, true>, n_cta, wpc, smem, st, a);
+        return launch_k2_impl(k2_wave<WAVE_C_NARROW, false, false>, n_cta, wpc, smem, st, a);
+    }
+    if (C != WAVE_C) return cudaErrorInvalidValue;
     if (ckpt) {
         if (local) {
             if (prof4) return launch_k2_impl(k2_wave<WAVE_C, true, true, true>, n_cta, wpc, smem, st, a);

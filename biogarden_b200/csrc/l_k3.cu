@@ -21,16 +21,19 @@ void dispatch_walk(Shape sh, bool half, uint32_t ns, cudaStream_t st, const Walk
     k3_walk<0, 0, false><<<grid, 128, 0, st>>>(a);
 }
 
-// Long pairs: one warp per pair.  k2_geometry: the (32 lanes x WAVE_C columns) geometry as compile-time constants.
-void launch_long_walk(LongWalk kind, bool k2_geometry, uint32_t ns, cudaStream_t st, const WalkArgs& a) {
+// Long pairs: one warp per pair.  k2_C: WAVE_C / WAVE_C_NARROW -> the (32 lanes x k2_C columns) geometry as compile-time
+// constants; 0 -> any geometry with C % 8 == 0.
+void launch_long_walk(LongWalk kind, int k2_C, uint32_t ns, cudaStream_t st, const WalkArgs& a) {
+    const unsigned gs = (ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, gd = (ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS;
     switch (kind) {
     case LW_SKEW:
-        if (k2_geometry) k3_walk_skew<WAVE_C><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, st>>>(a);
-        else k3_walk_skew<0><<<(ns + WALK_SKEW_WARPS - 1) / WALK_SKEW_WARPS, WALK_SKEW_WARPS * 32, 0, st>>>(a);
+        if (k2_C == WAVE_C) k3_walk_skew<WAVE_C><<<gs, WALK_SKEW_WARPS * 32, 0, st>>>(a);
+        else if (k2_C == WAVE_C_NARROW) k3_walk_skew<WAVE_C_NARROW><<<gs, WALK_SKEW_WARPS * 32, 0, st>>>(a);
+        else k3_walk_skew<0><<<gs, WALK_SKEW_WARPS * 32, 0, st>>>(a);
         break;
     case LW_DIAG:
-        if (k2_geometry) k3_walk_diag<WAVE_C><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(a);
-        else k3_walk_diag<0><<<(ns + WALK_DIAG_WARPS - 1) / WALK_DIAG_WARPS, WALK_DIAG_WARPS * 32, 0, st>>>(a);
+        if (k2_C == WAVE_C) k3_walk_diag<WAVE_C><<<gd, WALK_DIAG_WARPS * 32, 0, st>>>(a);
+        else k3_walk_diag<0><<<gd, WALK_DIAG_WARPS * 32, 0, st>>>(a);
         break;
     }
 }

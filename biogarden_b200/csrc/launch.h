@@ -15,6 +15,7 @@ struct Shape { int L, C; };
 // ... of which have a packed 16 x 2 instantiation (K1h)
 #define BG_HALF_SHAPES(X) X(8, 8) X(8, 12) X(8, 16) X(8, 19) X(8, 24) X(16, 10) X(16, 16) X(32, 12) X(32, 16) X(32, 20) X(32, 24) X(32, 32)
 constexpr int WAVE_C = 16;   // columns per lane of the K2 wavefront kernel (bands of 32 * WAVE_C columns)
+constexpr int WAVE_C_NARROW = 8;   // ... for launches with so few bands that most SMs would idle (a lone 10 kbp pair)
 constexpr int BG_N_SHAPES = 14;
 constexpr uint64_t LONG_WALK_LEN = 16384;   // len1 + len2 above which a pair is walked by a warp (k3_walk_skew) instead of a thread
 
@@ -92,14 +93,14 @@ void launch_unpack(const UnpackArgs& a, cudaStream_t st);
 // K1 / K1h / K2 fills
 void dispatch_k1(Shape sh, bool local, bool prof4, dim3 grid, size_t smem, cudaStream_t st, const FillArgs& a);
 bool dispatch_k1h(Shape sh, bool track, bool prof8, dim3 grid, cudaStream_t st, const FillArgs& a);
-cudaError_t launch_k2(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false);
+cudaError_t launch_k2(bool local, bool prof4, int C, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const WaveArgs& a, bool ckpt = false);
 
 cudaError_t launch_k2f(bool local, bool prof4, int n_cta, int warps_per_cta, size_t smem, cudaStream_t st, const FineArgs& a);
 
 // K3 walks + string assembly
 void dispatch_walk(Shape sh, bool half, uint32_t ns, cudaStream_t st, const WalkArgs& a);
 enum LongWalk { LW_SKEW = 0, LW_DIAG = 1 };
-void launch_long_walk(LongWalk kind, bool k2_geometry, uint32_t ns, cudaStream_t st, const WalkArgs& a);
+void launch_long_walk(LongWalk kind, int k2_C, uint32_t ns, cudaStream_t st, const WalkArgs& a);   // k2_C: 16 / 8 = K2 geometry compiled in, 0 = generic
 void launch_scores_only(const PairDesc* desc, const EndCell* end, uint32_t ns, int32_t* score, uint8_t* flags, int mode, cudaStream_t st);
 void launch_gather(const GatherArgs& a, cudaStream_t st);
 void launch_ops_counts(const uint64_t* lens2, uint64_t n_pairs, ulonglong2* counts, cudaStream_t st);
