@@ -12,3 +12,5 @@ print('cfg2', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), round(d['e
 print('cpu', d['cpu_baseline'])
 for k,v in d['configs'].items(): print(k, round(v['value'],1), 'ms', round(v['ms_per_step'],2), 'e2e', round(v['e2e']['value'],1), round(v['e2e']['ms_per_step'],2), 'packed', (round(v['e2e_packed']['ms_per_step'],2) if v.get('e2e_packed') else None), 'frac', round(v['roofline']['frac'],3) if v.get('roofline') else None)"
 tail -n 1 $O/bench_ref.log | cut -c 1-400
+python tools/diag_midlen.py > $O/midlen.log 2>&1; BG_NO_HALF_PROF=1 python tools/diag_midlen.py > $O/midlen_table.log 2>&1
+cat $O/midlen.log
