@@ -468,7 +468,26 @@ def measure_inprocess(args, n_dev, steps, warmup):
     return {"value": batch.cells() * steps / dt / 1e9, "unit": "GCUPS", "ms_per_step": 1e3 * dt / steps, "pairs": pairs, "n_gpus": n_dev,
             "strings": {"value": batch.cells() * steps / dt_strings / 1e9, "ms_per_step": 1e3 * dt_strings / steps},
             "h2d_bytes_per_step": int(tt["h2d_bytes"]), "d2h_bytes_per_step": int(tt["d2h_bytes"]),
-            "how": "one process, bg_create(%d devices), one shared chunk queue; the other ranks idle at the barrier" % n_dev}
+            "how": "one fresh process without the launcher's environment, bg_create(%d devices), one shared chunk queue; "
+                   "the torchrun ranks idle at a socket barrier meanwhile" % n_dev}
+
+
+def inprocess_in_child(args, n_dev):
+    """measure_inprocess() in a fresh interpreter WITHOUT the launcher's environment: the library sizes its host thread
+    pool from LOCAL_WORLD_SIZE (one process per GPU shares the cores), and the pool is created once per process -- inside
+    rank 0 the single process that drives all GPUs would be left with an eighth of the cores (measured: strings expanded by
+    4 threads, 149 ms per step instead of ~50).  The other ranks wait on their socket barrier meanwhile."""
+    import subprocess
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("LOCAL_WORLD_SIZE", "WORLD_SIZE", "RANK", "LOCAL_RANK", "GROUP_RANK", "ROLE_RANK", "ROLE_WORLD_SIZE",
+                        "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "OMP_NUM_THREADS")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--inprocess-child", str(n_dev)]
+    if args.pairs:
+        cmd += ["--pairs", str(args.pairs)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    if out.returncode != 0:
+        raise RuntimeError("in-process child failed: " + out.stderr[-300:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
 
 
 def main():
@@ -483,7 +502,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="only the headline workload (skip the other BASELINE configs)")
     ap.add_argument("--shape", default="", help="force kernel shape L,C (experiments)")
+    ap.add_argument("--inprocess-child", type=int, default=0, help=argparse.SUPPRESS)   # internal: see inprocess_in_child()
     args = ap.parse_args()
+    if args.inprocess_child:
+        print(json.dumps(measure_inprocess(args, args.inprocess_child, 5, 3)), flush=True)
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -538,7 +561,7 @@ def main():
         barrier()
         if rank == 0:
             try:
-                line["e2e_inprocess"] = measure_inprocess(args, world, 5, 3)
+                line["e2e_inprocess"] = inprocess_in_child(args, world)
             except Exception as exc:   # the headline line must survive
                 line["e2e_inprocess"] = {"error": str(exc)[:300]}
         dist.barrier(group=idle_pg)    # the other ranks wait here on a socket, GPUs and cores idle
