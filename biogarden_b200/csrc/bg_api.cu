@@ -822,7 +822,27 @@ struct BatchScan {
     bool half_ok = false; int force_si = -1;
     std::vector<ClassStat> block_cls; // [block][BG_N_SHAPES]
 };
+// Kernel shape and class-mask bit by len2, tabulated once per process: the scan of a batch with varying lengths asks for
+// them once per pair, and pick_shape_m + shape_index (a chain of ~30 compares) was most of its ~35 ns per pair.
+struct ScanTables {
+    uint8_t si[2][2][WAVE_MIN_COLS + 1];       // [half kernel available][pair long enough for the warp walker][len2] -> shape number
+    uint16_t band[BG_N_SHAPES];                // columns of one band of the shape
+    uint8_t mask_bit[WAVE_MIN_COLS + 1];       // BatchScan::class_mask bit of len2
+    ScanTables() {
+        for (int h = 0; h < 2; ++h)
+            for (int lg = 0; lg < 2; ++lg)
+                for (uint32_t m = 0; m <= WAVE_MIN_COLS; ++m)
+                    si[h][lg][m] = (uint8_t)shape_index(pick_shape_m(m, h && !lg, lg != 0));
+        for (int k = 0; k < BG_N_SHAPES; ++k) { const Shape sh = shape_at(k); band[k] = (uint16_t)(sh.L * sh.C); }
+        for (uint32_t m = 0; m <= WAVE_MIN_COLS; ++m)
+            mask_bit[m] = (uint8_t)(m <= 64 ? 0 : m <= 96 ? 1 : m <= 128 ? 2 : m <= 160 ? 3 : m <= 192 ? 4 : m <= 256 ? 5 : m <= 384 ? 6 :
+                                    m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
+    }
+};
+const ScanTables& scan_tables() { static const ScanTables* t = new ScanTables(); return *t; }
+
 void scan_batch(const bg_batch* in, BatchScan& S) {
+    const ScanTables& T = scan_tables();
     const uint64_t N = in->n_pairs;
     const uint64_t nblocks = (N + SCAN_BLOCK - 1) / SCAN_BLOCK;
     S.block_cost.assign(nblocks, 0.0);
@@ -852,8 +872,8 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                     const bool is_long = n + m > LONG_WALK_LEN;
                     if (m != st_m || is_long != st_long) {
                         st_m = m; st_long = is_long;
-                        const Shape sh = S.force_si >= 0 ? shape_at(S.force_si) : pick_shape_m((uint32_t)m, S.half_ok && !is_long, is_long);
-                        st_si = shape_index(sh); st_band = (uint32_t)(sh.L * sh.C);
+                        st_si = S.force_si >= 0 ? S.force_si : (int)T.si[S.half_ok ? 1 : 0][is_long ? 1 : 0][m];
+                        st_band = T.band[st_si];
                     }
                     ClassStat& c = cs[st_si];
                     c.count += k; c.cells += k * n * m;
@@ -864,8 +884,7 @@ void scan_batch(const bg_batch* in, BatchScan& S) {
                 }
                 if (m != last_m) {
                     last_m = m;
-                    P.class_mask |= 1u << (m <= 64 ? 0 : m <= 96 ? 1 : m <= 128 ? 2 : m <= 160 ? 3 : m <= 192 ? 4 : m <= 256 ? 5 : m <= 384 ? 6 :
-                                           m <= 512 ? 7 : m <= 640 ? 8 : m <= 768 ? 9 : m <= 1024 ? 10 : 11);
+                    P.class_mask |= 1u << (m <= WAVE_MIN_COLS ? T.mask_bit[m] : 11);
                 }
                 P.max_len_sum = std::max(P.max_len_sum, n + m);
                 P.max_m = std::max(P.max_m, m);
@@ -3246,6 +3265,23 @@ int bg_debug_plan_long(const uint64_t* lens, uint64_t n_pairs, uint64_t budget_b
 // device's descriptor ranges are sized from upper bounds, so its classes start at other slot numbers and end in
 // empty slots).  out[0] = 1 if the item is eligible for the device planner, out[1] = descriptors compared,
 // out[2] = descriptors that differ, out[3] = device slots beyond the host's count that are not empty.
+// The host's one pass over a batch's offsets (scan_batch), without a device: out = {monotone, class mask, max len1 + len2,
+// max len2, has pairs wider than the K1 classes, sum of the block costs, nanoseconds the scan took}.  Host-logic tests
+// and timing on machines without a GPU.
+int bg_debug_scan(const bg_batch* in, int with_stats, int half_ok, uint64_t* out) {
+    if (!in || !out || (in->n_pairs && !in->seq_off)) return BG_EINVAL_ARG;
+    BatchScan S;
+    S.with_stats = with_stats != 0; S.half_ok = half_ok != 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    scan_batch(in, S);
+    const auto t1 = std::chrono::steady_clock::now();
+    double cost = 0;
+    for (double c : S.block_cost) cost += c;
+    out[0] = S.monotone ? 1 : 0; out[1] = S.class_mask; out[2] = S.max_len_sum; out[3] = S.max_m; out[4] = S.has_wide ? 1 : 0;
+    out[5] = (uint64_t)cost; out[6] = (uint64_t)std::chrono::duration<double, std::nano>(t1 - t0).count();
+    return BG_OK;
+}
+
 int bg_debug_plan_compare(bg_ctx* ctx, const bg_batch* in, const bg_params* p, uint64_t* out) {
     if (!ctx || !in || !p || !out) return BG_EINVAL_ARG;
     out[0] = out[1] = out[2] = out[3] = 0;

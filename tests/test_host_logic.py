@@ -233,3 +233,48 @@ def test_packed_residues_roundtrip_and_fasta():
         assert ids == ids2 and np.array_equal(plain.seq_off, packed.seq_off)
         assert packed.packing == bits and np.array_equal(packed.unpacked_residues(), plain.residues)
         assert packed.residues.size < plain.residues.size
+
+
+def test_batch_scan_matches_numpy():
+    """The host's one pass over a batch's offsets (scan_batch: validity, length statistics, the cost of every block of
+    4096 pairs, the length classes present) against the same quantities computed with numpy -- uniform read sets (runs
+    of equal pairs are accounted once), mixed lengths, pairs wider than the K1 classes, and a broken offset."""
+    import ctypes as C
+    L = native.lib()
+    L.bg_debug_scan.restype = C.c_int
+    L.bg_debug_scan.argtypes = [C.POINTER(native.bg_batch), C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.RandomState(5)
+
+    def mask_bit(m):
+        for k, hi in enumerate((64, 96, 128, 160, 192, 256, 384, 512, 640, 768, 1024)):
+            if m <= hi:
+                return k
+        return 11
+
+    cases = {
+        "uniform": np.full(2 * 70000, 150, np.uint64),
+        "mixed": rng.randint(0, 1200, 2 * 50000).astype(np.uint64),
+        "runs": np.repeat(rng.randint(1, 400, 2 * 300).astype(np.uint64).reshape(-1, 2), 177, axis=0).reshape(-1),
+        "wide": np.concatenate([rng.randint(50, 300, 2 * 9000), [9000, 5000, 100, 4097]]).astype(np.uint64),
+    }
+    for name, lens in cases.items():
+        off = np.concatenate([[7], 7 + np.cumsum(lens)]).astype(np.uint64)
+        batch = native.Batch(np.zeros(1, np.uint8), off)          # the scan never touches the residues
+        n, m = lens[0::2].astype(np.float64), lens[1::2].astype(np.float64)
+        for with_stats in (0, 1):
+            out = np.zeros(8, np.uint64)
+            assert L.bg_debug_scan(C.byref(batch.c), with_stats, 1, out.ctypes.data) == 0
+            assert out[0] == 1, name
+            want_mask = 0
+            for v in np.unique(lens[1::2]):
+                want_mask |= 1 << mask_bit(int(v))
+            assert int(out[1]) == want_mask, (name, hex(int(out[1])), hex(want_mask))
+            assert int(out[2]) == int((lens[0::2] + lens[1::2]).max()), name
+            assert int(out[3]) == int(lens[1::2].max()), name
+            assert int(out[4]) == int((lens[1::2] > 4096).any()), name
+            assert int(out[5]) == int((n * m + 64.0).sum()), name
+    bad = np.concatenate([[0], np.cumsum(np.full(2 * 40000, 100))]).astype(np.uint64)
+    bad[2 * 31234 + 1] = bad[2 * 31234] - np.uint64(1)
+    out = np.zeros(8, np.uint64)
+    assert L.bg_debug_scan(C.byref(native.Batch(np.zeros(1, np.uint8), bad).c), 1, 1, out.ctypes.data) == 0
+    assert out[0] == 0
