@@ -7,7 +7,8 @@
 
 namespace bg {
 
-// blocks per SM: without the end-cell scans 19 / 20 columns per lane fit 128 registers (4 blocks)
+// blocks per SM: without the end-cell scans 19 / 20 columns per lane fit 128 registers (4 blocks).  (More than 16 warps per SM
+// would need <= 96 registers whatever the block size: each SM sub-partition holds 16 384 registers, i.e. four warps of 116.)
 constexpr int k1hp_minb(int C, bool track) { return C <= 10 ? 6 : C <= 12 ? 4 : (C <= 20 && !track) ? 4 : C <= 24 ? 3 : 2; }
 // Pipe split of the 8 trace-bit accumulations per cell pair (HB_PIPES, k1h_fill.cuh).  The ALU pipe already carries
 // 4 VIMNMX + PRMT + VIADD.16x2, the FMA pipe one IMAD.  Measured on cfg2 (10^6 pairs of 150 bp, fill time; build with
