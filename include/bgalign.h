@@ -178,7 +178,10 @@ int bg_expand_ops(const uint8_t* seq1_from, const uint8_t* seq2_from, const uint
 const char* bg_expand_kind(void);
 
 /* analysis::seq::edit_distance for every pair (seq.rs:105-130): out[p] = distance.  Never
- * fails on any byte content (the reference never errs). */
+ * fails on any byte content (the reference never errs).  Batches of <= 4 distinct bytes whose second sequences are
+ * <= 320 long (read sets, raw or 2-bit packed) take the bit-parallel kernel with launch slots built on the device: the
+ * host then does not read seq_off at all; offsets are validated on the device, and a batch it cannot take (a longer
+ * pair, a fifth byte value, offsets that are not monotone -> BG_EINVAL_ARG as always) is redone by the general path. */
 int bg_edit_distance_batch(bg_ctx* ctx, const bg_batch* in, uint64_t* out);
 
 /* ---- before the hot path: FASTA text -> batch layout -------------------- */
