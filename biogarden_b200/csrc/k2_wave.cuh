@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
         uint32_t rcur = 0;
         uint32_t cur_blk = 0;
         int2 in_blk = make_int2(a, NEG_INF);    // boundary rows [t0, t0+32) of the band to the left
-        int2 out_blk = make_int2(0, 0);         // this band's last column, rows collected over 32 steps
         uint32_t next_ck = cs.every, ck_no = 0;  // CKPT pass 1: next checkpoint row of this lane, its index
 
         for (uint32_t t = 0; t < steps; ++t) {
@@ -204,10 +203,15 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
             uint32_t r = __shfl_up_sync(FULL, rcur, 1);
             const uint32_t i0 = t - (uint32_t)p;
             const bool active = i0 < n;
-            if (p == 0) {
-                r = r0;
-                if (bd == 0) { MlA = border_col(col_gap, a, b, row0 + i0 + 1) + a; Yl = NEG_INF; }
-                else { MlA = inM; Yl = inY; }
+            {
+                // lane 0 takes the row residue from the block and the left border / the neighbour band's column instead of a
+                // left neighbour -- as selects: a branch here made the warp run lane 0's arm on its own every step
+                const bool first = (p == 0);
+                const int32_t bM = (bd == 0) ? border_col(col_gap, a, b, row0 + i0 + 1) + a : inM;   // bd is uniform in the warp
+                const int32_t bY = (bd == 0) ? NEG_INF : inY;
+                r = first ? r0 : r;
+                MlA = first ? bM : MlA;
+                Yl = first ? bY : Yl;
             }
             rcur = r;
             if (active) {
@@ -283,14 +287,11 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_wave(const WaveArgs W) {
                 }
             }
             if (has_next) {
-                // collect lane 31's (row t-31) boundary value in lane tq; flush every 32 steps
-                const int32_t oM = __shfl_sync(FULL, MlastA, 31);
-                const int32_t oY = __shfl_sync(FULL, Ylast, 31);
-                if (lane == (int)tq) out_blk = make_int2(oM, oY);
+                // lane 31 finishes row t - 31 in this step: its (M + a, Y) go straight to the ring (8 bytes per step; collecting 32
+                // rows in the lanes for one coalesced store cost two shuffles and two selects per step); the counter is
+                // published every 32 steps
+                if (lane == 31 && active) bnd_wr[i0] = make_int2(MlastA, Ylast);
                 if (tq == 31u || t + 1 == steps) {
-                    const uint32_t t0 = t & ~31u;
-                    const int64_t row = (int64_t)t0 + lane - 31;       // lane q holds the value of step t0 + q
-                    if (row >= 0 && row < (int64_t)n && (uint32_t)lane <= tq) bnd_wr[row] = out_blk;
                     __syncwarp();
                     if (lane == 0) {
                         long long done = (long long)t - 30;             // rows 0 .. t-31 are out
