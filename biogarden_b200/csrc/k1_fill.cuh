@@ -224,13 +224,19 @@ __global__ void __launch_bounds__(128, (C <= 20 ? 4 : 3)) k1_fill(const FillArgs
             uint32_t r = __shfl_up_sync(FULL, rcur, 1, L);
             const uint32_t i0 = t - (uint32_t)p;          // 0-based row; wraps (inactive) while t < p
             const bool active = band_on && i0 < n;
-            if (p == 0) {
-                r = r0;
-                if (bd == 0) { MlA = border_col(col_gap, a, b, i0 + 1) + a; Yl = NEG_INF; }
+            {
+                // lane 0 of a group: row residue from the block, left border (band 0) or the previous band's last column instead
+                // of a left neighbour -- as selects; a branch on p == 0 made the warp run lane 0's arm on its own every step
+                const bool first = (p == 0);
+                int32_t bM, bY;
+                if (bd == 0) { bM = border_col(col_gap, a, b, i0 + 1) + a; bY = NEG_INF; }      // bd is uniform in the warp
                 else {
-                    MlA = bnd_in.x; Yl = bnd_in.y;
-                    if (band_on && i0 + 1 < n) bnd_in = __ldcg(A.bnd + d.bnd_off + i0 + 1);
+                    bM = bnd_in.x; bY = bnd_in.y;
+                    if (first && band_on && i0 + 1 < n) bnd_in = __ldcg(A.bnd + d.bnd_off + i0 + 1);
                 }
+                r = first ? r0 : r;
+                MlA = first ? bM : MlA;
+                Yl = first ? bY : Yl;
             }
             rcur = r;
             if (active) {
